@@ -1,0 +1,114 @@
+"""ctypes binding of libbfsr_b200.so (the C ABI declared in include/bfsr_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails
+the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbfsr_b200.so")
+
+
+class BfsrError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class SRFlowDesc(C.Structure):
+    _fields_ = [("scale", C.c_int32), ("nf", C.c_int32), ("nb", C.c_int32), ("gc", C.c_int32), ("K", C.c_int32),
+                ("L", C.c_int32), ("n_no_affine", C.c_int32), ("hidden", C.c_int32), ("n_blocks", C.c_int32),
+                ("blocks", C.c_int32 * 8), ("split_enable", C.c_int32), ("tile_chunk", C.c_int32),
+                ("precision", C.c_int32)]
+
+
+class UNetDesc(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("depth", C.c_int32), ("dim", C.c_int32), ("bilinear", C.c_int32),
+                ("n_latents", C.c_int32), ("latent_ch", C.c_int32 * 4), ("in_chans", C.c_int32),
+                ("precision", C.c_int32)]
+
+
+_lib = None
+
+# every symbol include/bfsr_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_I = C.c_int32
+SYMBOLS = {
+    "bfsr_last_error": (C.c_char_p, []),
+    "bfsr_version": (C.c_char_p, []),
+    "bfsr_launch_count": (C.c_int64, [C.c_int]),
+    "bfsr_srflow_create": (C.c_int, [C.POINTER(_P), C.POINTER(SRFlowDesc), C.POINTER(Tensor), _I, _I]),
+    "bfsr_srflow_destroy": (None, [_P]),
+    "bfsr_srflow_num_latents": (C.c_int, [_P]),
+    "bfsr_srflow_latent_shape": (C.c_int, [_P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "bfsr_srflow_encode": (C.c_int, [_P, _P, _P, _I, _I, _I, C.POINTER(_P), _P]),
+    "bfsr_srflow_decode": (C.c_int, [_P, _P, C.POINTER(_P), _I, _I, _I, _P, _P]),
+    "bfsr_srflow_lp_sr": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "bfsr_srflow_lp_sr_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "bfsr_srflow_workspace_bytes": (C.c_int64, [_P]),
+    "bfsr_unet_create": (C.c_int, [C.POINTER(_P), C.POINTER(UNetDesc), C.POINTER(Tensor), _I, _I]),
+    "bfsr_unet_destroy": (None, [_P]),
+    "bfsr_unet_forward_srflow": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_P), _P]),
+    "bfsr_op_conv2d": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "bfsr_op_squeeze2d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+}
+
+
+def lib():
+    """Load libbfsr_b200.so (once).  Raises if it has not been built (`make -C bfsr_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BfsrError(f"{LIB_PATH} not found: build it with `make -C bfsr_b200/csrc` "
+                            "(or `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BfsrError(lib().bfsr_last_error().decode("utf-8", "replace"))
+
+
+def tensor_table(sd):
+    """state_dict -> (ctypes array of Tensor, keep-alive list).  Non-fp32 entries (BatchNorm counters) are skipped."""
+    keep = []
+    items = []
+    for k, v in sd.items():
+        if not torch.is_tensor(v) or not v.dtype.is_floating_point:
+            continue
+        t = v.detach().to("cpu", torch.float32).contiguous()
+        keep.append(t)
+        kb = k.encode()
+        keep.append(kb)
+        tt = Tensor()
+        tt.name = kb
+        tt.data = t.data_ptr()
+        tt.ndim = t.dim()
+        if t.dim() > 4:
+            raise BfsrError(f"tensor {k} has rank {t.dim()} > 4")
+        for i, s in enumerate(t.shape):
+            tt.shape[i] = s
+        items.append(tt)
+    arr = (Tensor * len(items))(*items)
+    return arr, keep
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

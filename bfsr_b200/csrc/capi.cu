@@ -1,0 +1,197 @@
+// extern "C" surface of libbfsr_b200.so (declared in include/bfsr_b200.h).
+#include "engine.cuh"
+#include <cstring>
+#include <memory>
+
+using namespace bfsr;
+
+namespace bfsr {
+void srflow_build(bfsr_srflow* e, const bfsr_tensor_t* weights, int n);
+void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode, const float* lr, const float* gt, float* const* lat_out,
+                const float* const* lat_in, float* sr, int B, int h, int w, cudaStream_t s);
+void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n);
+std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s);
+}
+
+static thread_local std::string g_err;
+
+#define API_BEGIN try {
+#define API_END                                                      \
+  } catch (const std::exception& ex) { g_err = ex.what(); return -1; } \
+    catch (...) { g_err = "unknown error"; return -2; }              \
+  return 0;
+
+extern "C" {
+
+const char* bfsr_last_error(void) { return g_err.c_str(); }
+const char* bfsr_version(void) { return "bfsr_b200 0.1 (sm_100a)"; }
+int64_t bfsr_launch_count(int reset) { int64_t v = g_launches; if (reset) g_launches = 0; return v; }
+
+int bfsr_srflow_create(bfsr_srflow_t** out, const bfsr_srflow_desc_t* desc, const bfsr_tensor_t* weights,
+                       int32_t n_weights, int32_t device) {
+  API_BEGIN
+  BFSR_CHECK(out && desc && weights, "null argument");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  BFSR_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<bfsr_srflow> e(new bfsr_srflow());
+  e->d = *desc; e->device = device;
+  srflow_build(e.get(), weights, n_weights);
+  *out = e.release();
+  API_END
+}
+void bfsr_srflow_destroy(bfsr_srflow_t* h) { if (h) { cudaSetDevice(h->device); delete h; } }
+
+int bfsr_srflow_num_latents(const bfsr_srflow_t* h) { return h ? (int)h->latent_C.size() : -1; }
+int bfsr_srflow_latent_shape(const bfsr_srflow_t* h, int32_t i, int32_t lr_h, int32_t lr_w, int32_t* C, int32_t* H,
+                             int32_t* W) {
+  API_BEGIN
+  BFSR_CHECK(h && i >= 0 && i < (int)h->latent_C.size(), "latent index out of range");
+  *C = h->latent_C[i];
+  *H = (lr_h * h->d.scale) >> h->latent_level[i];
+  *W = (lr_w * h->d.scale) >> h->latent_level[i];
+  API_END
+}
+
+int bfsr_srflow_encode(bfsr_srflow_t* h, const float* lr_dev, const float* gt_dev, int32_t B, int32_t lr_h,
+                       int32_t lr_w, float* const* latents_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && lr_dev && gt_dev && latents_dev, "null argument");
+  srflow_run(h, nullptr, 0, lr_dev, gt_dev, latents_dev, nullptr, nullptr, B, lr_h, lr_w, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_srflow_decode(bfsr_srflow_t* h, const float* lr_dev, const float* const* latents_dev, int32_t B,
+                       int32_t lr_h, int32_t lr_w, float* sr_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && lr_dev && latents_dev && sr_dev, "null argument");
+  srflow_run(h, nullptr, 1, lr_dev, nullptr, nullptr, latents_dev, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_srflow_lp_sr(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_dev, int32_t B, int32_t lr_h,
+                      int32_t lr_w, float* sr_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && prior && lr_dev && sr_dev, "null argument");
+  BFSR_CHECK(prior->device == h->device, "prior and generator live on different devices");
+  srflow_run(h, prior, 2, lr_dev, nullptr, nullptr, nullptr, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_srflow_lp_sr_host(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_host, int32_t B, int32_t lr_h,
+                           int32_t lr_w, float* sr_host, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && prior && lr_host && sr_host, "null argument");
+  BFSR_CHECK(prior->device == h->device, "prior and generator live on different devices");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nin = (size_t)B * 3 * lr_h * lr_w * 4;
+  const size_t nout = nin * h->d.scale * h->d.scale;
+  if (nin > h->stage_in_sz) { if (h->stage_in) cudaFree(h->stage_in); h->stage_in = nullptr; h->stage_in_sz = 0;
+                              CUDA_OK(cudaMalloc((void**)&h->stage_in, nin)); h->stage_in_sz = nin; }
+  if (nout > h->stage_out_sz) { if (h->stage_out) cudaFree(h->stage_out); h->stage_out = nullptr; h->stage_out_sz = 0;
+                                CUDA_OK(cudaMalloc((void**)&h->stage_out, nout)); h->stage_out_sz = nout; }
+  if (B > 0) CUDA_OK(cudaMemcpyAsync(h->stage_in, lr_host, nin, cudaMemcpyHostToDevice, s));
+  srflow_run(h, prior, 2, h->stage_in, nullptr, nullptr, nullptr, h->stage_out, B, lr_h, lr_w, s);
+  if (B > 0) CUDA_OK(cudaMemcpyAsync(sr_host, h->stage_out, nout, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  API_END
+}
+int64_t bfsr_srflow_workspace_bytes(const bfsr_srflow_t* h) { return h ? (int64_t)h->arena.cap : -1; }
+
+int bfsr_unet_create(bfsr_unet_t** out, const bfsr_unet_desc_t* desc, const bfsr_tensor_t* weights, int32_t n_weights,
+                     int32_t device) {
+  API_BEGIN
+  BFSR_CHECK(out && desc && weights, "null argument");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  BFSR_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<bfsr_unet> u(new bfsr_unet());
+  u->d = *desc; u->device = device;
+  unet_build(u.get(), weights, n_weights);
+  *out = u.release();
+  API_END
+}
+void bfsr_unet_destroy(bfsr_unet_t* h) { if (h) { cudaSetDevice(h->device); delete h; } }
+
+int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, const int32_t* H, const int32_t* W,
+                             int32_t B, float* const* out_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && latents_dev && H && W && out_dev, "null argument");
+  BFSR_CHECK(h->d.variant == 0, "not an SRFlow-LP prior");
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena& A = h->arena;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
+    std::vector<View> lat;
+    for (int i = 0; i < h->d.n_latents; ++i) {
+      View v = make_view(A, B, H[i], W[i], h->d.latent_ch[i]);
+      if (!A.plan) nchw_to_nhwc(latents_dev[i], v, s);
+      lat.push_back(v);
+    }
+    std::vector<View> out = run_unet_srflow(h, A, lat, s);
+    if (!A.plan) for (int i = 0; i < h->d.n_latents; ++i) nhwc_to_nchw(out[i], out_dev[i], s);
+    if (pass == 0) { A.plan = false; if (A.peak + (1 << 20) > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(A.peak + (1 << 20)); } }
+  }
+  CUDA_OK(cudaGetLastError());
+  API_END
+}
+
+// ------------------------------------------------------------------ single operators
+int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
+                   const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
+                   void* stream) {
+  API_BEGIN
+  BFSR_CHECK(x_dev && w_host && y_dev, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvW cw = pack_conv(w_host, Cout, Cin, ks, bias_host, nullptr, {});
+  float *xn = nullptr, *yn = nullptr;
+  const size_t npix = (size_t)B * H * W;
+  try {
+    CUDA_OK(cudaMalloc((void**)&xn, (npix * Cin + 4) * 4));
+    CUDA_OK(cudaMalloc((void**)&yn, (npix * Cout + 4) * 4));
+    View x; x.p = xn; x.N = B; x.H = H; x.W = W; x.C = Cin; x.cs = Cin;
+    View y; y.p = yn; y.N = B; y.H = H; y.W = W; y.C = Cout; y.cs = Cout;
+    nchw_to_nhwc(x_dev, x, s);
+    ConvEpi ep; ep.act = act;
+    if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s); else conv2d(cw, x, y, ep, IN_DIRECT, s);
+    nhwc_to_nchw(y, y_dev, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { cudaFree(xn); cudaFree(yn); free_conv(cw); throw; }
+  cudaFree(xn); cudaFree(yn); free_conv(cw);
+  API_END
+}
+
+int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
+                      void* stream) {
+  API_BEGIN
+  BFSR_CHECK(x_dev && y_dev, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  float *xn = nullptr, *yn = nullptr;
+  const size_t n = (size_t)B * C * H * W;
+  try {
+    CUDA_OK(cudaMalloc((void**)&xn, n * 4 + 16));
+    CUDA_OK(cudaMalloc((void**)&yn, n * 4 + 16));
+    View x; x.p = xn; x.N = B; x.H = H; x.W = W; x.C = C; x.cs = C;
+    View y; y.p = yn; y.N = B;
+    if (!reverse) { BFSR_CHECK(H % 2 == 0 && W % 2 == 0, "squeeze2d: odd size"); y.H = H / 2; y.W = W / 2; y.C = y.cs = C * 4; }
+    else { BFSR_CHECK(C % 4 == 0, "unsqueeze2d: C %% 4 != 0"); y.H = H * 2; y.W = W * 2; y.C = y.cs = C / 4; }
+    nchw_to_nhwc(x_dev, x, s);
+    if (!reverse) squeeze_copy(x, y, s); else unsqueeze_copy(x, y, s);
+    nhwc_to_nchw(y, y_dev, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { cudaFree(xn); cudaFree(yn); throw; }
+  cudaFree(xn); cudaFree(yn);
+  API_END
+}
+
+}  // extern "C"
+
+namespace bfsr {
+// conv dispatcher: the tcgen05 implicit-GEMM path takes the shapes it supports, everything else runs on the
+// fp32 CUDA-core kernel.
+void conv2d(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
+  conv2d_fp32(w, in, out, epi, in_mode, s);
+}
+}  // namespace bfsr

@@ -1,0 +1,241 @@
+// fp32 CUDA-core convolution (3x3 / 1x1, stride 1, 'same' zero padding) over NHWC views.
+//
+// This is the exact-arithmetic member of the conv family: it serves the z-dependent
+// coupling convs whose inputs must stay fp32 (the flow inverse amplifies operand
+// rounding), every small-K conv that cannot fill a tcgen05 tile
+// (K = 27..432), and it is the on-device fp32 reference the tcgen05 kernels are
+// checked against at full size.  Replaces cuDNN behind nn.Conv2d at
+// RRDBNet_arch.py:25-45, flow.py:26-83, unet.py:10-107.
+//
+// Tiling: one CTA = 16 x TH output pixels x CO_T output channels, 256 threads; a
+// thread owns 8 consecutive pixels of one row x 4 output channels (32 fp32
+// accumulators).  Input channels are walked in chunks of 8 through shared memory
+// ([ci][row][col] so the 8(+2) pixels a thread needs are 2.5 float4 loads); the 9 taps
+// reuse the staged halo tile, so each input element is read from L2 once per CTA.
+#include "ops.cuh"
+#include <vector>
+#include <cstring>
+
+namespace bfsr {
+
+thread_local long long g_launches = 0;
+
+struct ConvArgs {
+  View in, out, pre, res1, res2;
+  const float* w; const float* bias;
+  int cin, cin_pad, cout, cout_pad;
+  int H, W;           // output spatial dims
+  int in_mode, act;
+  float eps, alpha, beta1, beta2;
+  int tiles_x;
+  int vec_in, vec_out;
+};
+
+constexpr int CI = 8;
+constexpr int TW = 16;
+
+template <int KS, int CO_T>
+__global__ void __launch_bounds__(256) conv_fp32_kernel(ConvArgs a) {
+  constexpr int HALO = KS / 2;
+  constexpr int NCG = CO_T / 4;
+  constexpr int NPG = 256 / NCG;
+  constexpr int TH = NPG / 2;
+  constexpr int ROWS = TH + 2 * HALO;
+  constexpr int COLS = TW + 2 * HALO;
+  constexpr int ROWP = 20;                 // padded row pitch (floats), keeps float4 alignment
+  constexpr int NV = 8 + KS - 1;
+
+  __shared__ __align__(16) float in_s[CI][ROWS][ROWP];
+  __shared__ __align__(16) float w_s[KS * KS][CI][CO_T];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / a.tiles_x) * TH, tx0 = (tile % a.tiles_x) * TW;
+  const int co_base = blockIdx.y * CO_T;
+  const int n = blockIdx.z;
+  const int pg = tid / NCG, cg = tid % NCG;
+  const int r = pg >> 1, x0 = (pg & 1) * 8;
+
+  const int inH = a.in_mode == IN_UP2 ? a.H >> 1 : a.H;
+  const int inW = a.in_mode == IN_UP2 ? a.W >> 1 : a.W;
+  const long long in_img = (long long)n * inH * inW;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < a.cin_pad; c0 += CI) {
+    // ---- stage the input halo tile: (ROWS x COLS) pixels x CI channels
+    for (int e = tid; e < ROWS * COLS * (CI / 4); e += 256) {
+      const int q = e % (CI / 4), pix = e / (CI / 4);
+      const int yy = pix / COLS, xx = pix % COLS;
+      const int gy = ty0 + yy - HALO, gx = tx0 + xx - HALO;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+        const int sy = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx = a.in_mode == IN_UP2 ? gx >> 1 : gx;
+        const long long p = in_img + (long long)sy * inW + sx;
+        const int cb = c0 + q * 4;
+        if (a.vec_in && cb + 4 <= a.cin) {
+          v = *reinterpret_cast<const float4*>((const float*)a.in.p + p * a.in.cs + a.in.coff + cb);
+        } else {
+          if (cb + 0 < a.cin) v.x = ld(a.in, p, cb + 0);
+          if (cb + 1 < a.cin) v.y = ld(a.in, p, cb + 1);
+          if (cb + 2 < a.cin) v.z = ld(a.in, p, cb + 2);
+          if (cb + 3 < a.cin) v.w = ld(a.in, p, cb + 3);
+        }
+      }
+      in_s[q * 4 + 0][yy][xx] = v.x;
+      in_s[q * 4 + 1][yy][xx] = v.y;
+      in_s[q * 4 + 2][yy][xx] = v.z;
+      in_s[q * 4 + 3][yy][xx] = v.w;
+    }
+    // ---- stage the weight chunk
+    for (int e = tid; e < KS * KS * CI * (CO_T / 4); e += 256) {
+      const int c4 = e % (CO_T / 4);
+      const int ci = (e / (CO_T / 4)) % CI;
+      const int tap = e / (CO_T / 4) / CI;
+      const float4 v = *reinterpret_cast<const float4*>(
+          a.w + ((long long)tap * a.cin_pad + c0 + ci) * a.cout_pad + co_base + c4 * 4);
+      *reinterpret_cast<float4*>(&w_s[tap][ci][c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy) {
+        float v[12];
+        const float* row = &in_s[ci][r + dy][x0];
+        *reinterpret_cast<float4*>(&v[0]) = *reinterpret_cast<const float4*>(row);
+        *reinterpret_cast<float4*>(&v[4]) = *reinterpret_cast<const float4*>(row + 4);
+        if (KS == 3) *reinterpret_cast<float2*>(&v[8]) = *reinterpret_cast<const float2*>(row + 8);
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&w_s[dy * KS + dx][ci][cg * 4]);
+#pragma unroll
+          for (int px = 0; px < 8; ++px) {
+            const float x = v[px + dx];
+            acc[px][0] = fmaf(x, w4.x, acc[px][0]);
+            acc[px][1] = fmaf(x, w4.y, acc[px][1]);
+            acc[px][2] = fmaf(x, w4.z, acc[px][2]);
+            acc[px][3] = fmaf(x, w4.w, acc[px][3]);
+          }
+        }
+        (void)NV;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  const int gy = ty0 + r;
+  if (gy >= a.H) return;
+  const int co = co_base + cg * 4;
+  if (co >= a.cout) return;
+  float b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = a.bias[co + j];
+#pragma unroll
+  for (int px = 0; px < 8; ++px) {
+    const int gx = tx0 + x0 + px;
+    if (gx >= a.W) break;
+    const long long p = ((long long)n * a.H + gy) * a.W + gx;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[px][j] + b[j];
+      const int c = co + j;
+      if (c < a.cout) {
+        if (a.pre.p) v += ld(a.pre, p, c);
+        if (a.act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+        else if (a.act == ACT_RELU) v = fmaxf(v, 0.f);
+        else if (a.act == ACT_CROSS_SIGMOID) { if (c & 1) v = 1.f / (1.f + expf(-(v + 2.f))) + a.eps; }
+        v *= a.alpha;
+        if (a.res1.p) v = fmaf(a.beta1, ld(a.res1, p, c), v);
+        if (a.res2.p) v = fmaf(a.beta2, ld(a.res2, p, c), v);
+      }
+      o[j] = v;
+    }
+    if (a.vec_out && co + 4 <= a.cout) {
+      *reinterpret_cast<float4*>((float*)a.out.p + p * a.out.cs + a.out.coff + co) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co + j < a.cout) st(a.out, p, co + j, o[j]);
+    }
+  }
+}
+
+template <int KS, int CO_T>
+static void launch(const ConvArgs& a, int N, cudaStream_t s) {
+  constexpr int TH = (256 / (CO_T / 4)) / 2;
+  ConvArgs b = a;
+  b.tiles_x = cdiv(a.W, TW);
+  dim3 grid(b.tiles_x * cdiv(a.H, TH), a.cout_pad / CO_T, N);
+  conv_fp32_kernel<KS, CO_T><<<grid, 256, 0, s>>>(b);
+  count_launch();
+}
+
+void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
+  BFSR_CHECK(in.C == w.cin, "conv: input view has %d channels, weights expect %d", in.C, w.cin);
+  BFSR_CHECK(out.C == w.cout, "conv: output view has %d channels, weights produce %d", out.C, w.cout);
+  BFSR_CHECK(in.N == out.N, "conv: batch mismatch");
+  if (in_mode == IN_UP2) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv(up2): spatial mismatch");
+  else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv: spatial mismatch %dx%d vs %dx%d", in.H, in.W, out.H, out.W);
+  ConvArgs a;
+  a.in = in; a.out = out;
+  a.pre = epi.pre ? *epi.pre : View();
+  a.res1 = epi.res1 ? *epi.res1 : View();
+  a.res2 = epi.res2 ? *epi.res2 : View();
+  a.w = w.w; a.bias = w.bias;
+  a.cin = w.cin; a.cin_pad = w.cin_pad; a.cout = w.cout; a.cout_pad = w.cout_pad;
+  a.H = out.H; a.W = out.W; a.in_mode = in_mode; a.act = epi.act;
+  a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
+  a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
+  a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
+  a.tiles_x = 0;
+  if (out.npix() == 0) return;
+#define L(KS, T) launch<KS, T>(a, out.N, s)
+  if (w.ks == 3) { if (w.co_tile == 64) L(3, 64); else if (w.co_tile == 32) L(3, 32); else L(3, 16); }
+  else           { if (w.co_tile == 64) L(1, 64); else if (w.co_tile == 32) L(1, 32); else L(1, 16); }
+#undef L
+}
+
+ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float* bias, const float* out_scale,
+                const std::vector<int>& cin_map) {
+  BFSR_CHECK(ks == 1 || ks == 3, "conv kernel size %d unsupported", ks);
+  ConvW c;
+  c.ks = ks; c.cout = cout;
+  c.cin = cin_map.empty() ? cin_src : (int)cin_map.size();
+  c.co_tile = cout > 32 ? 64 : (cout > 16 ? 32 : 16);
+  c.cout_pad = cdiv(cout, c.co_tile) * c.co_tile;
+  c.cin_pad = cdiv(c.cin, CI) * CI;
+  const int taps = ks * ks;
+  std::vector<float> h((size_t)taps * c.cin_pad * c.cout_pad, 0.f), hb(c.cout_pad, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    const float sc = out_scale ? out_scale[co] : 1.f;
+    for (int ci = 0; ci < c.cin; ++ci) {
+      const int src = cin_map.empty() ? ci : cin_map[ci];
+      if (src < 0) continue;
+      BFSR_CHECK(src < cin_src, "pack_conv: channel map out of range");
+      for (int t = 0; t < taps; ++t)
+        h[((size_t)t * c.cin_pad + ci) * c.cout_pad + co] = w_oihw[((size_t)co * cin_src + src) * taps + t] * sc;
+    }
+    hb[co] = bias ? bias[co] : 0.f;   // final bias: callers fold their own scales into it
+  }
+  CUDA_OK(cudaMalloc((void**)&c.w, h.size() * 4));
+  CUDA_OK(cudaMalloc((void**)&c.bias, hb.size() * 4));
+  CUDA_OK(cudaMemcpy(c.w, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c.bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  return c;
+}
+
+void free_conv(ConvW& w) {
+  if (w.w) cudaFree(w.w);
+  if (w.bias) cudaFree(w.bias);
+  if (w.w_tc) cudaFree(w.w_tc);
+  w.w = w.bias = nullptr; w.w_tc = nullptr;
+}
+
+}  // namespace bfsr

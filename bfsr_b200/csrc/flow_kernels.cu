@@ -1,0 +1,358 @@
+// HBM-bound kernels of the conditional flow: the fused FlowStep (both directions),
+// Split2d, latent normalisation, Squeeze2d index maps, layout and resampling.
+//
+// One launch per FlowStep: ActNorm, InvertibleConv1x1 and both affine couplings are
+// fused so the flow state z makes exactly one HBM round trip per step
+// (reference: ~15 ATen kernels per step, FlowStep.py:88-129; plus an fp64
+// torch.inverse per step per call, Permutations.py:41 — here W^-1 is folded with the
+// ActNorm scale once at load time).  Squeeze2d / Unsqueeze2d (flow.py:122-152) never
+// run as copies: they are index maps in the load (encode) or store (decode) of the
+// adjacent step.
+//
+// Per-CTA scheme: a tile of PIX pixels x C channels is staged in shared memory with
+// coalesced NHWC reads (the elementwise coupling math is applied on the way in), the
+// C x C channel mix runs from shared memory with 4 output channels per thread, and the
+// result is written with coalesced stores.
+#include "ops.cuh"
+
+namespace bfsr {
+
+// ------------------------------------------------------------------ fused flow steps
+struct StepArgs {
+  View zin, zout, h, hF;
+  const float* M;      // [C][C] row-major (out, in)
+  const float* cvec;   // [C]
+  int C, H, W;         // dims of the squeezed (level) tensor
+  long long npix;
+  int squeeze_in, unsqueeze_out, has_h, has_hF;
+  int pix_per_block;
+};
+
+// element (pix, c) of the level tensor read from the un-squeezed source: c = 4c' + 2fh + fw
+__device__ __forceinline__ float ld_squeezed(const View& v, int H, int W, long long pix, int c) {
+  const int j = (int)(pix % W); const long long t = pix / W; const int i = (int)(t % H); const long long b = t / H;
+  const int cc = c >> 2, fh = (c >> 1) & 1, fw = c & 1;
+  const long long sp = (b * (2 * H) + (2 * i + fh)) * (2 * W) + (2 * j + fw);
+  return ld(v, sp, cc);
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256) flowstep_kernel(StepArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = a.C, C4 = C >> 2, ZP = C + 1;
+  float* Mt = sm;                      // [C][C] transposed: Mt[ci*C + co]
+  float* zs = sm + C * C;              // [PIX][C+1]
+  const int tid = threadIdx.x, P = a.pix_per_block;
+  const long long p0 = (long long)blockIdx.x * P;
+
+  for (int e = tid; e < C * C; e += 256) { const int co = e / C, ci = e % C; Mt[ci * C + co] = a.M[e]; }
+
+  // ---- phase 1: gather z, apply the elementwise part that precedes the channel mix
+  for (int e = tid; e < P * C; e += 256) {
+    const int p = e / C, c = e % C;
+    const long long pix = p0 + p;
+    float z = 0.f;
+    if (pix < a.npix) {
+      z = a.squeeze_in ? ld_squeezed(a.zin, a.H, a.W, pix, c) : ld(a.zin, pix, c);
+      if (a.has_h && c >= C / 2) {
+        const int j = c - C / 2;
+        const float shift = ld(a.h, pix, 2 * j), scale = ld(a.h, pix, 2 * j + 1);
+        z = INV ? z / scale - shift : (z + shift) * scale;
+      }
+      if (INV && a.has_hF) {
+        const float shiftF = ld(a.hF, pix, 2 * c), scaleF = ld(a.hF, pix, 2 * c + 1);
+        z = z / scaleF - shiftF;
+      }
+    }
+    zs[p * ZP + c] = z;
+  }
+  __syncthreads();
+
+  // ---- phase 2: channel mix, 4 outputs per thread
+  for (int e = tid; e < P * C4; e += 256) {
+    const int p = e / C4, g = e % C4;
+    const long long pix = p0 + p;
+    if (pix >= a.npix) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* zr = zs + p * ZP;
+    const float* mr = Mt + 4 * g;
+#pragma unroll 4
+    for (int ci = 0; ci < C; ++ci) {
+      const float zv = zr[ci];
+      const float4 m = *reinterpret_cast<const float4*>(mr + ci * C);
+      acc.x = fmaf(m.x, zv, acc.x); acc.y = fmaf(m.y, zv, acc.y);
+      acc.z = fmaf(m.z, zv, acc.z); acc.w = fmaf(m.w, zv, acc.w);
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * g + j;
+      if (INV) o[j] -= a.cvec[c];
+      else {
+        o[j] += a.cvec[c];
+        if (a.has_hF) { const float shiftF = ld(a.hF, pix, 2 * c), scaleF = ld(a.hF, pix, 2 * c + 1); o[j] = (o[j] + shiftF) * scaleF; }
+      }
+    }
+    if (a.unsqueeze_out) {
+      const int jx = (int)(pix % a.W); const long long t = pix / a.W; const int iy = (int)(t % a.H); const long long b = t / a.H;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int fh = j >> 1, fw = j & 1;
+        const long long dp = (b * (2 * a.H) + (2 * iy + fh)) * (2 * a.W) + (2 * jx + fw);
+        st(a.zout, dp, g, o[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st(a.zout, pix, 4 * g + j, o[j]);
+    }
+  }
+}
+
+static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, const View* h, const View* hF,
+                        const View& zout, bool unsq_out, cudaStream_t s) {
+  StepArgs a;
+  a.C = w.C;
+  BFSR_CHECK(w.C % 4 == 0, "flow step: C=%d not divisible by 4", w.C);
+  if (sq_in) {
+    BFSR_CHECK(zin.C * 4 == w.C && zout.C == w.C && zin.H == 2 * zout.H && zin.W == 2 * zout.W, "flowstep: squeeze shapes");
+    a.H = zout.H; a.W = zout.W; a.npix = zout.npix();
+  } else {
+    BFSR_CHECK(zin.C == w.C, "flowstep: z has %d channels, step expects %d", zin.C, w.C);
+    a.H = zin.H; a.W = zin.W; a.npix = zin.npix();
+    if (unsq_out) BFSR_CHECK(zout.C * 4 == w.C && zout.H == 2 * zin.H && zout.W == 2 * zin.W, "flowstep: unsqueeze shapes");
+    else BFSR_CHECK(zout.C == w.C && zout.npix() == zin.npix(), "flowstep: output shape");
+  }
+  if (h) BFSR_CHECK(h->C == (w.C - w.C / 2) * 2 && h->npix() == a.npix, "flowstep: h shape");
+  if (hF) BFSR_CHECK(hF->C == 2 * w.C && hF->npix() == a.npix, "flowstep: hF shape");
+  a.zin = zin; a.zout = zout;
+  a.h = h ? *h : View(); a.hF = hF ? *hF : View();
+  a.has_h = h != nullptr; a.has_hF = hF != nullptr;
+  a.M = inv ? w.Mi : w.Mf; a.cvec = inv ? w.ci : w.cf;
+  a.squeeze_in = sq_in; a.unsqueeze_out = unsq_out;
+  a.pix_per_block = w.C <= 24 ? 256 : (w.C <= 96 ? 64 : 32);
+  if (a.npix == 0) return;
+  const size_t smem = ((size_t)w.C * w.C + (size_t)a.pix_per_block * (w.C + 1)) * 4;
+  const int grid = cdiv(a.npix, a.pix_per_block);
+  if (inv) {
+    CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    flowstep_kernel<true><<<grid, 256, smem, s>>>(a);
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    flowstep_kernel<false><<<grid, 256, smem, s>>>(a);
+  }
+  count_launch();
+}
+
+void flowstep_fwd(const StepW& w, const View& z_in, bool squeeze_in, const View* h_prev, const View* hF,
+                  const View& z_out, cudaStream_t s) {
+  launch_step(false, w, z_in, squeeze_in, h_prev, hF, z_out, false, s);
+}
+void flowstep_inv(const StepW& w, const View& z_in, const View* h, const View* hF, const View& z_out,
+                  bool unsqueeze_out, cudaStream_t s) {
+  launch_step(true, w, z_in, false, h, hF, z_out, unsqueeze_out, s);
+}
+
+// ------------------------------------------------------------------ small elementwise flow ops
+__global__ void coupling_finish_kernel(View z, View h, View out, long long n, int C) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long long pix = e / C; const int c = (int)(e % C);
+  float v = ld(z, pix, c);
+  if (c >= C / 2) { const int j = c - C / 2; v = (v + ld(h, pix, 2 * j)) * ld(h, pix, 2 * j + 1); }
+  st(out, pix, c, v);
+}
+void coupling_finish(const View& z, const View& h, const View& z_out, cudaStream_t s) {
+  const long long n = z.npix() * z.C;
+  if (!n) return;
+  coupling_finish_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, h, z_out, n, z.C);
+  count_launch();
+}
+
+__global__ void split_fwd_kernel(View z, View h, View z1, View eps, long long n, int Cp, int Cc) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int C = Cp + Cc;
+  const long long pix = e / C; const int c = (int)(e % C);
+  const float v = ld(z, pix, c);
+  if (c < Cp) { st(z1, pix, c, v); return; }
+  const int j = c - Cp;
+  const float mean = ld(h, pix, 2 * j), logs = ld(h, pix, 2 * j + 1);
+  st(eps, pix, j, (v - mean) / expf(logs));
+}
+void split_fwd(const View& z, const View& h, const View& z1_out, const View& eps_out, cudaStream_t s) {
+  const long long n = z.npix() * z.C;
+  if (!n) return;
+  split_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, h, z1_out, eps_out, n, z1_out.C, eps_out.C);
+  count_launch();
+}
+
+__global__ void split_inv_kernel(View z1, View h, View eps, View out, long long n, int Cp, int Cc) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int C = Cp + Cc;
+  const long long pix = e / C; const int c = (int)(e % C);
+  if (c < Cp) { st(out, pix, c, ld(z1, pix, c)); return; }
+  const int j = c - Cp;
+  const float mean = ld(h, pix, 2 * j), logs = ld(h, pix, 2 * j + 1);
+  st(out, pix, c, mean + expf(logs) * ld(eps, pix, j));
+}
+void split_inv(const View& z1, const View& h, const View& eps, const View& z_out, cudaStream_t s) {
+  const long long n = z_out.npix() * z_out.C;
+  if (!n) return;
+  split_inv_kernel<<<cdiv(n, 256), 256, 0, s>>>(z1, h, eps, z_out, n, z1.C, eps.C);
+  count_launch();
+}
+
+__global__ void normalise_kernel(View e, View out, long long npix, int C) {
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += ld(e, pix, c);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int c = 0; c < C; ++c) { const float d = ld(e, pix, c) - mean; q = fmaf(d, d, q); }
+  const float sd = sqrtf(q / (C - 1)) + 1e-8f;
+  for (int c = 0; c < C; ++c) st(out, pix, c, (ld(e, pix, c) - mean) / sd);
+}
+void normalise_latent(const View& e, const View& out, cudaStream_t s) {
+  if (!e.npix()) return;
+  normalise_kernel<<<cdiv(e.npix(), 128), 128, 0, s>>>(e, out, e.npix(), e.C);
+  count_launch();
+}
+
+__global__ void squeeze_copy_kernel(View src, View dst, long long n, int C, int H, int W, int dir) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  // (pix, c) indexes the SQUEEZED tensor (C channels, H x W)
+  const long long pix = e / C; const int c = (int)(e % C);
+  const int j = (int)(pix % W); const long long t = pix / W; const int i = (int)(t % H); const long long b = t / H;
+  const int cc = c >> 2, fh = (c >> 1) & 1, fw = c & 1;
+  const long long up = (b * (2 * H) + (2 * i + fh)) * (2 * W) + (2 * j + fw);
+  if (dir == 0) st(dst, pix, c, ld(src, up, cc));
+  else st(dst, up, cc, ld(src, pix, c));
+}
+void squeeze_copy(const View& src, const View& dst, cudaStream_t s) {
+  const long long n = dst.npix() * dst.C;
+  if (!n) return;
+  squeeze_copy_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, dst.C, dst.H, dst.W, 0);
+  count_launch();
+}
+void unsqueeze_copy(const View& src, const View& dst, cudaStream_t s) {
+  const long long n = src.npix() * src.C;
+  if (!n) return;
+  squeeze_copy_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, src.C, src.H, src.W, 1);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* src, View dst, long long n, int C, int HW) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long long pix = e / C; const int c = (int)(e % C);
+  const long long b = pix / HW, r = pix % HW;
+  st(dst, pix, c, src[(b * C + c) * HW + r]);
+}
+void nchw_to_nhwc(const float* src, const View& dst, cudaStream_t s) {
+  const long long n = dst.npix() * dst.C;
+  if (!n) return;
+  nchw_to_nhwc_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, dst.C, dst.H * dst.W);
+  count_launch();
+}
+__global__ void nhwc_to_nchw_kernel(View src, float* dst, long long n, int C, int HW) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  // e indexes the NCHW output so the stores coalesce
+  const long long r = e % HW; const long long t = e / HW; const int c = (int)(t % C); const long long b = t / C;
+  dst[e] = ld(src, b * HW + r, c);
+}
+void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s) {
+  const long long n = src.npix() * src.C;
+  if (!n) return;
+  nhwc_to_nchw_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, src.C, src.H * src.W);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ resampling
+__global__ void resample_kernel(View src, View dst, long long n, int mode, int oy, int ox) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int C = dst.C;
+  const long long pix = e / C; const int c = (int)(e % C);
+  const int x = (int)(pix % dst.W); const long long t = pix / dst.W; const int y = (int)(t % dst.H); const long long b = t / dst.H;
+  const long long sb = b * src.H * src.W;
+  float v;
+  if (mode == RS_COPY) v = c < src.C ? ld(src, pix, c) : 0.f;   // extra dst channels are zero padding
+  else if (mode == RS_NEAREST_UP2) v = ld(src, sb + (long long)(y >> 1) * src.W + (x >> 1), c);
+  else if (mode == RS_NEAREST_DOWN2) v = ld(src, sb + (long long)(2 * y) * src.W + 2 * x, c);
+  else if (mode == RS_AVG_DOWN2) {
+    // bilinear x0.5, align_corners=False, recompute_scale_factor=True (RRDBNet_arch.py:134): every weight is 0.5
+    const long long p = sb + (long long)(2 * y) * src.W + 2 * x;
+    const float t0 = 0.5f * ld(src, p, c) + 0.5f * ld(src, p + 1, c);
+    const float t1 = 0.5f * ld(src, p + src.W, c) + 0.5f * ld(src, p + src.W + 1, c);
+    v = 0.5f * t0 + 0.5f * t1;
+  } else if (mode == RS_MAXPOOL2) {
+    const long long p = sb + (long long)(2 * y) * src.W + 2 * x;
+    v = fmaxf(fmaxf(ld(src, p, c), ld(src, p + 1, c)), fmaxf(ld(src, p + src.W, c), ld(src, p + src.W + 1, c)));
+  } else {  // RS_BILINEAR_UP2_AC: nn.Upsample(x2, bilinear, align_corners=True) then F.pad to dst (unet.py:80-91)
+    const int uy = y - oy, ux = x - ox, UH = 2 * src.H, UW = 2 * src.W;
+    if (uy < 0 || uy >= UH || ux < 0 || ux >= UW) v = 0.f;
+    else {
+      const float sh = UH > 1 ? (float)(src.H - 1) / (float)(UH - 1) : 0.f;
+      const float sw = UW > 1 ? (float)(src.W - 1) / (float)(UW - 1) : 0.f;
+      const float fy = sh * uy, fx = sw * ux;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < src.H - 1 ? 1 : 0), x1 = x0 + (x0 < src.W - 1 ? 1 : 0);
+      const float ly = fy - y0, lx = fx - x0;
+      const float a00 = ld(src, sb + (long long)y0 * src.W + x0, c), a01 = ld(src, sb + (long long)y0 * src.W + x1, c);
+      const float a10 = ld(src, sb + (long long)y1 * src.W + x0, c), a11 = ld(src, sb + (long long)y1 * src.W + x1, c);
+      v = (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11);
+    }
+  }
+  st(dst, pix, c, v);
+}
+void resample(const View& src, const View& dst, int mode, cudaStream_t s) {
+  BFSR_CHECK((src.C == dst.C || (mode == RS_COPY && src.C < dst.C)) && src.N == dst.N,
+             "resample: channel/batch mismatch (%d vs %d)", src.C, dst.C);
+  int oy = 0, ox = 0;
+  switch (mode) {
+    case RS_COPY: BFSR_CHECK(src.H == dst.H && src.W == dst.W, "resample copy: shape"); break;
+    case RS_NEAREST_UP2: BFSR_CHECK(dst.H == 2 * src.H && dst.W == 2 * src.W, "resample up2: shape"); break;
+    case RS_NEAREST_DOWN2: case RS_AVG_DOWN2:
+      BFSR_CHECK(src.H == 2 * dst.H && src.W == 2 * dst.W, "resample down2: shape"); break;
+    case RS_MAXPOOL2: BFSR_CHECK(dst.H == src.H / 2 && dst.W == src.W / 2, "maxpool2: shape"); break;
+    case RS_BILINEAR_UP2_AC:
+      BFSR_CHECK(dst.H >= 2 * src.H && dst.W >= 2 * src.W, "bilinear up2: dst smaller than upsampled src");
+      oy = (dst.H - 2 * src.H) / 2; ox = (dst.W - 2 * src.W) / 2; break;
+    default: BFSR_CHECK(false, "resample: bad mode %d", mode);
+  }
+  const long long n = dst.npix() * dst.C;
+  if (!n) return;
+  resample_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, mode, oy, ox);
+  count_launch();
+}
+
+// F.interpolate(lr, scale_factor=s, mode='bilinear', align_corners=False)  — SRFlow-LP/code/test.py:137
+__global__ void bilinear_up_nchw_kernel(const float* src, int C, int h, int w, int scale, View dst, long long n) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long long pix = e / C; const int c = (int)(e % C);
+  const int x = (int)(pix % dst.W); const long long t = pix / dst.W; const int y = (int)(t % dst.H); const long long b = t / dst.H;
+  const float rs = 1.f / (float)scale;
+  float fy = rs * (y + 0.5f) - 0.5f, fx = rs * (x + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const float* sp = src + (b * C + c) * (long long)h * w;
+  const float a00 = sp[y0 * w + x0], a01 = sp[y0 * w + x1], a10 = sp[y1 * w + x0], a11 = sp[y1 * w + x1];
+  st(dst, pix, c, (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11));
+}
+void bilinear_up_nchw(const float* src, int N, int C, int h, int w, int scale, const View& dst, cudaStream_t s) {
+  BFSR_CHECK(dst.N == N && dst.C == C && dst.H == h * scale && dst.W == w * scale, "bilinear_up: shape");
+  const long long n = dst.npix() * C;
+  if (!n) return;
+  bilinear_up_nchw_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, C, h, w, scale, dst, n);
+  count_launch();
+}
+
+}  // namespace bfsr

@@ -1,0 +1,76 @@
+// Kernel launchers shared by the engines (SRFlow-LP, LINF-LP) and the per-op C ABI.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace bfsr {
+
+// ------------------------------------------------------------------ convolution
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2,
+                 ACT_CROSS_SIGMOID = 3 };  // odd channels -> sigmoid(v+2)+eps (thops 'cross' split, FlowAffineCouplingsAblation.py:108-119)
+enum InMode : int { IN_DIRECT = 0, IN_UP2 = 1 /* nearest x2 folded into the loader */ };
+
+// Packed conv weights (device).  fp32 layout: [tap][cin_pad][cout_pad], tap = ky*ks+kx.
+struct ConvW {
+  int ks = 3, cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, co_tile = 64;
+  float* w = nullptr;      // fp32 packed
+  float* bias = nullptr;   // [cout_pad] (zeros if the conv has none)
+  // split-bf16 packing for the tcgen05 path (built lazily by conv_tc.cu)
+  void* w_tc = nullptr;
+  int tc_kchunks = 0, tc_npad = 0;
+};
+
+struct ConvEpi {
+  int act = ACT_NONE;
+  float eps = 1e-4f;            // ACT_CROSS_SIGMOID epsilon
+  const View* pre = nullptr;    // added before the activation
+  float alpha = 1.f;            // out = act(acc+bias+pre)*alpha + beta1*res1 + beta2*res2
+  const View* res1 = nullptr; float beta1 = 0.f;
+  const View* res2 = nullptr; float beta2 = 0.f;
+};
+
+// out(N,H,W,Cout) = conv_ks(in) ; `in` has spatial dims (H,W) or (H/2,W/2) for IN_UP2.
+void conv2d(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
+void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
+
+// Host-side packing: src is OIHW fp32 [cout][cin_src][ks][ks]; `out_scale` (optional) multiplies the weights per
+// output channel, `bias` is the FINAL bias (already scaled); the input-channel gather map makes packed input channel
+// i read source channel map[i] (-1 = zero) so callers can split / pad / reorder concatenated inputs.
+ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float* bias, const float* out_scale,
+                const std::vector<int>& cin_map);
+void free_conv(ConvW& w);
+
+// ------------------------------------------------------------------ layout / resampling
+void nchw_to_nhwc(const float* src, const View& dst, cudaStream_t s);
+void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);
+enum Resample : int { RS_COPY = 0, RS_NEAREST_UP2, RS_NEAREST_DOWN2, RS_AVG_DOWN2, RS_MAXPOOL2,
+                      RS_BILINEAR_UP2_AC /* align_corners=True x2 + zero pad to dst size (unet.py:80-91) */ };
+void resample(const View& src, const View& dst, int mode, cudaStream_t s);
+// F.interpolate(x, scale_factor=s, mode='bilinear', align_corners=False) on NCHW input -> NHWC view
+void bilinear_up_nchw(const float* src, int N, int C, int h, int w, int scale, const View& dst, cudaStream_t s);
+
+// ------------------------------------------------------------------ flow
+struct StepW {      // one FlowStep (device pointers, fp32)
+  int C = 0; bool coupling = false;
+  float* Mf = nullptr;  float* cf = nullptr;   // forward: y = Mf z + cf   (W diag(e^logs), W (b*e^logs))
+  float* Mi = nullptr;  float* ci = nullptr;   // inverse: z = Mi y - ci   (diag(e^-logs) W^-1, bias)
+};
+// encode half-step: [finish previous coupling with h_prev] -> actnorm -> invconv -> [ft-affine with hF]
+//   squeeze_in: z_in is the un-squeezed tensor (N,2H,2W,C/4) read through the Squeeze2d index map (flow.py:122-134)
+void flowstep_fwd(const StepW& w, const View& z_in, bool squeeze_in, const View* h_prev, const View* hF,
+                  const View& z_out, cudaStream_t s);
+// z2 = (z2 + shift) * scale with (shift,scale) pairs in h   (FlowAffineCouplingsAblation.py:72-76)
+void coupling_finish(const View& z, const View& h, const View& z_out, cudaStream_t s);
+// decode step: coupling^-1 (h) -> ft-affine^-1 (hF) -> invconv^-1 -> actnorm^-1 ; unsqueeze_out folds Unsqueeze2d
+void flowstep_inv(const StepW& w, const View& z_in, const View* h, const View* hF, const View& z_out,
+                  bool unsqueeze_out, cudaStream_t s);
+// Split2d (Split.py:49-77): h holds (mean,logs) pairs
+void split_fwd(const View& z, const View& h, const View& z1_out, const View& eps_out, cudaStream_t s);
+void split_inv(const View& z1, const View& h, const View& eps, const View& z_out, cudaStream_t s);
+// per-pixel channel normalisation (test.py:141-145)
+void normalise_latent(const View& e, const View& out, cudaStream_t s);
+// squeeze / unsqueeze as plain copies (used only where they cannot be folded)
+void squeeze_copy(const View& src, const View& dst, cudaStream_t s);
+void unsqueeze_copy(const View& src, const View& dst, cudaStream_t s);
+
+}  // namespace bfsr

@@ -1,0 +1,503 @@
+// SRFlow-LP inference engine: weight packing and the execution plan of
+// encoder -> feature-only coupling convs (shared by both flow directions) -> flow encode ->
+// latent normalisation -> learned prior -> flow decode.
+//
+// Restructurings relative to the reference graph (all exact in real arithmetic):
+//  * ActNorm after flow.Conv2d, the exp(3*logs) of Conv2dZeros and eval-mode BatchNorm are folded
+//    into the conv weights at load time (flow.py:41-83, unet.py:38-56);
+//  * fAffine's first conv is split by linearity into a z-part and an ft-part
+//    (FlowAffineCouplingsAblation.py:114-116): the ft-part and all of fFeatures depend only on the LR
+//    encoder output, so they are computed ONCE per level, batched over the level's K steps, and reused
+//    by encode and decode (the reference recomputes them, and the encoder, in each pass);
+//  * inverse(W) of every InvertibleConv1x1 is computed once in fp64 (Permutations.py:41 does it per call);
+//  * dead encoder heads (upconv2/HRconv/conv_last for 4x, RRDBNet_arch.py:108-125) and the logdet chain
+//    (discarded by get_sr/get_encode_z, SRFlow_model.py:199,204) are not computed;
+//  * torch.cat never materialises: producers write channel slices of preallocated NHWC buffers.
+#include "engine.cuh"
+#include <cmath>
+#include <cstring>
+
+using namespace bfsr;
+
+bfsr_srflow::~bfsr_srflow() {
+  free_conv(rrdb.conv_first); free_conv(rrdb.trunk_conv);
+  for (auto& c : rrdb.rdb) free_conv(c);
+  for (auto& c : rrdb.upconv) free_conv(c);
+  for (auto& l : layers) {
+    if (l.step.Mf) cudaFree(l.step.Mf);
+    if (l.step.cf) cudaFree(l.step.cf);
+    if (l.step.Mi) cudaFree(l.step.Mi);
+    if (l.step.ci) cudaFree(l.step.ci);
+    free_conv(l.cp.fF2); free_conv(l.cp.fF4); free_conv(l.cp.fA0z); free_conv(l.cp.fA2); free_conv(l.cp.fA4);
+    free_conv(l.split_conv);
+  }
+  for (auto& l : levels) { free_conv(l.fF0_all); free_conv(l.fA0ft_all); }
+  if (stage_in) cudaFree(stage_in);
+  if (stage_out) cudaFree(stage_out);
+}
+
+namespace bfsr {
+
+static float* to_device(const std::vector<float>& v) {
+  float* d = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d, v.size() * 4));
+  CUDA_OK(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+
+// fp64 Gauss-Jordan inverse with partial pivoting (stands in for torch.inverse(W.double()), Permutations.py:41)
+static std::vector<double> invert(const float* W, int n) {
+  std::vector<double> a((size_t)n * 2 * n, 0.0);
+  for (int i = 0; i < n; ++i) { for (int j = 0; j < n; ++j) a[(size_t)i * 2 * n + j] = W[i * n + j]; a[(size_t)i * 2 * n + n + i] = 1.0; }
+  for (int c = 0; c < n; ++c) {
+    int piv = c; double best = std::fabs(a[(size_t)c * 2 * n + c]);
+    for (int r = c + 1; r < n; ++r) { double v = std::fabs(a[(size_t)r * 2 * n + c]); if (v > best) { best = v; piv = r; } }
+    BFSR_CHECK(best > 1e-300, "InvertibleConv1x1 weight is singular");
+    if (piv != c) for (int j = 0; j < 2 * n; ++j) std::swap(a[(size_t)c * 2 * n + j], a[(size_t)piv * 2 * n + j]);
+    const double d = 1.0 / a[(size_t)c * 2 * n + c];
+    for (int j = 0; j < 2 * n; ++j) a[(size_t)c * 2 * n + j] *= d;
+    for (int r = 0; r < n; ++r) if (r != c) {
+      const double f = a[(size_t)r * 2 * n + c];
+      if (f != 0.0) for (int j = 0; j < 2 * n; ++j) a[(size_t)r * 2 * n + j] -= f * a[(size_t)c * 2 * n + j];
+    }
+  }
+  std::vector<double> inv((size_t)n * n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) inv[(size_t)i * n + j] = a[(size_t)i * 2 * n + n + j];
+  return inv;
+}
+
+static StepW pack_step(const Weights& W, const std::string& p, int C, bool coupling) {
+  StepW s; s.C = C; s.coupling = coupling;
+  const float* b = W.data(p + ".actnorm.bias", {1, C, 1, 1});
+  const float* l = W.data(p + ".actnorm.logs", {1, C, 1, 1});
+  const float* w = W.data(p + ".invconv.weight", {C, C});
+  std::vector<float> Mf((size_t)C * C), cf(C), Mi((size_t)C * C), ci(C);
+  for (int o = 0; o < C; ++o) {
+    double acc = 0.0;
+    for (int i = 0; i < C; ++i) {
+      const double e = std::exp((double)l[i]);
+      Mf[(size_t)o * C + i] = (float)((double)w[o * C + i] * e);
+      acc += (double)w[o * C + i] * (double)b[i] * e;
+    }
+    cf[o] = (float)acc;
+  }
+  std::vector<double> inv = invert(w, C);
+  for (int o = 0; o < C; ++o) {
+    const double e = std::exp(-(double)l[o]);
+    for (int i = 0; i < C; ++i) Mi[(size_t)o * C + i] = (float)(inv[(size_t)o * C + i] * e);
+    ci[o] = b[o];
+  }
+  s.Mf = to_device(Mf); s.cf = to_device(cf); s.Mi = to_device(Mi); s.ci = to_device(ci);
+  return s;
+}
+
+// flow.Conv2d (bias-free conv + ActNorm): W' = W*e^logs, b' = b_an*e^logs   (flow.py:41-65)
+static ConvW pack_conv_actnorm(const Weights& W, const std::string& p, int cout, int cin_src, int ks,
+                               const std::vector<int>& cin_map, bool with_bias) {
+  const float* w = W.data(p + ".weight", {cout, cin_src, ks, ks});
+  const float* ab = W.data(p + ".actnorm.bias", {1, cout, 1, 1});
+  const float* al = W.data(p + ".actnorm.logs", {1, cout, 1, 1});
+  std::vector<float> sc(cout), bi(cout);
+  for (int i = 0; i < cout; ++i) { sc[i] = std::exp(al[i]); bi[i] = with_bias ? ab[i] * sc[i] : 0.f; }
+  return pack_conv(w, cout, cin_src, ks, bi.data(), sc.data(), cin_map);
+}
+// flow.Conv2dZeros: (conv + b) * exp(3*logs)   (flow.py:68-83)
+static ConvW pack_conv_zeros(const Weights& W, const std::string& p, int cout, int cin) {
+  const float* w = W.data(p + ".weight", {cout, cin, 3, 3});
+  const float* b = W.data(p + ".bias", {cout});
+  const float* l = W.data(p + ".logs", {cout, 1, 1});
+  std::vector<float> sc(cout), bi(cout);
+  for (int i = 0; i < cout; ++i) { sc[i] = std::exp(3.f * l[i]); bi[i] = b[i] * sc[i]; }
+  return pack_conv(w, cout, cin, 3, bi.data(), sc.data(), {});
+}
+static ConvW pack_plain(const Weights& W, const std::string& p, int cout, int cin, int ks) {
+  return pack_conv(W.data(p + ".weight", {cout, cin, ks, ks}), cout, cin, ks, W.data(p + ".bias", {cout}), nullptr, {});
+}
+
+static void build_srflow(bfsr_srflow* e, const Weights& W) {
+  const bfsr_srflow_desc_t& d = e->d;
+  BFSR_CHECK(d.scale == 4 || d.scale == 8, "scale %d unsupported (4 or 8)", d.scale);
+  BFSR_CHECK(d.nf == 64 && d.gc == 32, "nf=%d gc=%d unsupported", d.nf, d.gc);
+  BFSR_CHECK(d.n_blocks >= 0 && d.n_blocks <= 8, "too many stackRRDB blocks");
+  const int nf = d.nf, gc = d.gc, Hd = d.hidden;
+  e->n_cond = (d.n_blocks + 1) * nf;
+  BFSR_CHECK(e->n_cond == 320, "conditioning width %d: CondAffineSeparatedAndCond hard-codes 320 "
+             "(FlowAffineCouplingsAblation.py:30)", e->n_cond);
+  // ---- encoder
+  e->rrdb.conv_first = pack_plain(W, "RRDB.conv_first", nf, 3, 3);
+  for (int i = 0; i < d.nb; ++i)
+    for (int r = 1; r <= 3; ++r)
+      for (int c = 1; c <= 5; ++c) {
+        const std::string p = "RRDB.RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r) + ".conv" + std::to_string(c);
+        e->rrdb.rdb.push_back(pack_plain(W, p, c < 5 ? gc : nf, nf + (c - 1) * gc, 3));
+      }
+  e->rrdb.trunk_conv = pack_plain(W, "RRDB.trunk_conv", nf, nf, 3);
+  int log2s = d.scale == 4 ? 2 : 3;
+  const int n_up = log2s - 1;   // level 1 runs at scale/2: upconv1 (.. upconv2 for 8x)
+  for (int u = 1; u <= n_up; ++u) e->rrdb.upconv.push_back(pack_plain(W, "RRDB.upconv" + std::to_string(u), nf, nf, 3));
+  // ---- flow topology (FlowUpsamplerNet.py:94-115)
+  e->levels.resize(d.L + 1);
+  int C = 3, idx = 0;
+  for (int level = 1; level <= d.L; ++level) {
+    C *= 4;
+    { LayerW l; l.kind = 0; l.C = C; l.level = level; e->layers.push_back(l); ++idx; }
+    for (int k = 0; k < d.n_no_affine; ++k) {
+      LayerW l; l.kind = 1; l.C = C; l.level = level;
+      l.step = pack_step(W, "flowUpsamplerNet.layers." + std::to_string(idx), C, false);
+      e->layers.push_back(l); ++idx;
+    }
+    LevelW& lv = e->levels[level];
+    lv.C = C; lv.n_coupling = d.K;
+    std::vector<float> wF((size_t)d.K * Hd * 320 * 9), sF(d.K * Hd), bF(d.K * Hd);
+    std::vector<float> wA((size_t)d.K * Hd * 320 * 9), sA(d.K * Hd), bA(d.K * Hd);
+    for (int k = 0; k < d.K; ++k) {
+      LayerW l; l.kind = 2; l.C = C; l.level = level; l.k_in_level = k;
+      const std::string p = "flowUpsamplerNet.layers." + std::to_string(idx);
+      l.step = pack_step(W, p, C, true);
+      const int Cn = C / 2, Cc = C - Cn;
+      // fFeatures.0 (ft only) -> batched
+      {
+        const float* w = W.data(p + ".affine.fFeatures.0.weight", {Hd, 320, 3, 3});
+        const float* ab = W.data(p + ".affine.fFeatures.0.actnorm.bias", {1, Hd, 1, 1});
+        const float* al = W.data(p + ".affine.fFeatures.0.actnorm.logs", {1, Hd, 1, 1});
+        memcpy(&wF[(size_t)k * Hd * 320 * 9], w, (size_t)Hd * 320 * 9 * 4);
+        for (int i = 0; i < Hd; ++i) { sF[k * Hd + i] = std::exp(al[i]); bF[k * Hd + i] = ab[i] * sF[k * Hd + i]; }
+      }
+      // fAffine.0: input = [z1 (Cn) | ft (320)]  (FlowAffineCouplingsAblation.py:115)
+      {
+        const float* w = W.data(p + ".affine.fAffine.0.weight", {Hd, Cn + 320, 3, 3});
+        const float* ab = W.data(p + ".affine.fAffine.0.actnorm.bias", {1, Hd, 1, 1});
+        const float* al = W.data(p + ".affine.fAffine.0.actnorm.logs", {1, Hd, 1, 1});
+        for (int o = 0; o < Hd; ++o) {
+          memcpy(&wA[((size_t)(k * Hd + o) * 320) * 9], &w[((size_t)o * (Cn + 320) + Cn) * 9], (size_t)320 * 9 * 4);
+          sA[k * Hd + o] = std::exp(al[o]); bA[k * Hd + o] = ab[o] * sA[k * Hd + o];
+        }
+        std::vector<int> zmap(Cn); for (int i = 0; i < Cn; ++i) zmap[i] = i;
+        l.cp.fA0z = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, zmap, /*with_bias=*/false);
+      }
+      l.cp.fF2 = pack_conv_actnorm(W, p + ".affine.fFeatures.2", Hd, Hd, 1, {}, true);
+      l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
+      l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
+      l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
+      e->layers.push_back(l); ++idx;
+    }
+    lv.fF0_all = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), {});
+    lv.fA0ft_all = pack_conv(wA.data(), d.K * Hd, 320, 3, bA.data(), sA.data(), {});
+    if (d.split_enable && level < d.L - 1) {
+      LayerW l; l.kind = 3; l.C = C; l.level = level;
+      const int cons = (int)std::lround(C * 0.5), pass = C - cons;
+      l.split_conv = pack_conv_zeros(W, "flowUpsamplerNet.layers." + std::to_string(idx) + ".conv", 2 * cons, pass);
+      e->layers.push_back(l); ++idx;
+      e->latent_C.push_back(cons); e->latent_level.push_back(level);
+      C = pass;
+    }
+  }
+  e->latent_C.push_back(C); e->latent_level.push_back(d.L);
+}
+
+// ===================================================================== execution
+struct Run {
+  bfsr_srflow* e; cudaStream_t s; Arena& A;
+  int B, h, w;
+  std::vector<View> ft;                    // per level (index 1..L), 320 channels
+  std::vector<View> bufA;                  // per level: n_coupling*64 pre-activations of fAffine.0 (ft part)
+  std::vector<std::vector<View>> hF;       // per level, per step: (shiftFt, scaleFt) pairs, 2C channels
+  bool plan() const { return A.plan; }
+  int lvH(int level) const { return (h * e->d.scale) >> level; }
+  int lvW(int level) const { return (w * e->d.scale) >> level; }
+};
+#define K_(...) do { if (!r.A.plan) { __VA_ARGS__; } } while (0)
+
+// RRDBNet.forward(get_steps=True) + SRFlowNet.rrdbPreprocessing (RRDBNet_arch.py:89-148, SRFlowNet_arch.py:118-138)
+static void run_encoder(Run& r, const View& x) {
+  bfsr_srflow* e = r.e; const auto& d = e->d;
+  const int B = r.B, h = r.h, w = r.w, nf = d.nf, gc = d.gc, L = d.L;
+  const int log2s = d.scale == 4 ? 2 : 3;
+  r.ft.assign(L + 1, View());
+  for (int lv = 1; lv <= L; ++lv) r.ft[lv] = make_view(r.A, B, r.lvH(lv), r.lvW(lv), e->n_cond);
+  const int lv0 = log2s;                           // level whose features live at LR resolution ('fea_up1')
+  BFSR_CHECK(lv0 <= L, "L=%d too small for scale %d", L, d.scale);
+  View& ft0 = r.ft[lv0];
+  const size_t mark = r.A.off;
+  View D[3];
+  for (int i = 0; i < 3; ++i) D[i] = make_view(r.A, B, h, w, nf + 4 * gc);
+  ConvEpi lrelu; lrelu.act = ACT_LRELU;
+  K_(conv2d(e->rrdb.conv_first, x, D[0].slice(0, nf), ConvEpi(), IN_DIRECT, r.s));
+  int tap = 0;
+  for (int i = 0; i < d.nb; ++i) {
+    for (int rb = 0; rb < 3; ++rb) {
+      View& cur = D[rb]; View& nxt = D[(rb + 1) % 3];
+      const ConvW* cw = &e->rrdb.rdb[(size_t)(i * 3 + rb) * 5];
+      for (int c = 0; c < 4; ++c)
+        K_(conv2d(cw[c], cur.slice(0, nf + c * gc), cur.slice(nf + c * gc, gc), lrelu, IN_DIRECT, r.s));
+      ConvEpi ep;
+      View x_rdb = cur.slice(0, nf), x_rrdb = D[0].slice(0, nf);
+      if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &x_rdb; ep.beta1 = 1.f; }                      // x5*0.2 + x
+      else { ep.alpha = 0.04f; ep.res1 = &x_rdb; ep.beta1 = 0.2f; ep.res2 = &x_rrdb; ep.beta2 = 1.f; }  // (x5*0.2+x)*0.2 + x_rrdb
+      K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), nxt.slice(0, nf), ep, IN_DIRECT, r.s));
+    }
+    for (int b = 0; b < d.n_blocks; ++b)
+      if (d.blocks[b] == i) {   // block_{i} tap -> its slot in the conditioning tensor (order of stackRRDB.blocks)
+        K_(resample(D[0].slice(0, nf), ft0.slice(nf * (1 + b), nf), RS_COPY, r.s));
+        ++tap;
+      }
+  }
+  BFSR_CHECK(tap == d.n_blocks, "stackRRDB.blocks reference RRDB indices outside [0, nb)");
+  {  // last_lr_fea = fea + trunk_conv(fea)
+    ConvEpi ep; View fea = D[0].slice(0, nf); ep.res1 = &fea; ep.beta1 = 1.f;
+    K_(conv2d(e->rrdb.trunk_conv, fea, ft0.slice(0, nf), ep, IN_DIRECT, r.s));
+  }
+  r.A.off = mark;
+  // finer levels: fea_up2 = lrelu(upconv1(nearest2x(last_lr_fea))) etc. (post-activation: in-place LeakyReLU aliasing)
+  for (int lv = lv0 - 1, u = 0; lv >= 1; --lv, ++u) {
+    K_(conv2d(e->rrdb.upconv[u], r.ft[lv + 1].slice(0, nf), r.ft[lv].slice(0, nf), lrelu, IN_UP2, r.s));
+    K_(resample(r.ft[lv + 1].slice(nf, e->n_cond - nf), r.ft[lv].slice(nf, e->n_cond - nf), RS_NEAREST_UP2, r.s));
+  }
+  // coarser level: fea_up0 = bilinear x0.5 (== 2x2 mean), taps nearest x0.5
+  for (int lv = lv0 + 1; lv <= L; ++lv) {
+    BFSR_CHECK(lv == lv0 + 1, "levels below fea_up0 are not supported");
+    K_(resample(ft0.slice(0, nf), r.ft[lv].slice(0, nf), RS_AVG_DOWN2, r.s));
+    K_(resample(ft0.slice(nf, e->n_cond - nf), r.ft[lv].slice(nf, e->n_cond - nf), RS_NEAREST_DOWN2, r.s));
+  }
+}
+
+// feature-only halves of every coupling step of every level
+static void run_ft_convs(Run& r) {
+  bfsr_srflow* e = r.e; const auto& d = e->d;
+  const int Hd = d.hidden;
+  r.bufA.assign(d.L + 1, View());
+  r.hF.assign(d.L + 1, {});
+  for (int lv = 1; lv <= d.L; ++lv) {
+    const LevelW& L = e->levels[lv];
+    const int H = r.lvH(lv), W = r.lvW(lv);
+    r.bufA[lv] = make_view(r.A, r.B, H, W, L.n_coupling * Hd);
+    for (int k = 0; k < L.n_coupling; ++k) r.hF[lv].push_back(make_view(r.A, r.B, H, W, 2 * L.C));
+  }
+  for (int lv = 1; lv <= d.L; ++lv) {
+    const LevelW& L = e->levels[lv];
+    const int H = r.lvH(lv), W = r.lvW(lv);
+    const size_t mark = r.A.off;
+    View bufF = make_view(r.A, r.B, H, W, L.n_coupling * Hd);
+    View t = make_view(r.A, r.B, H, W, Hd);
+    ConvEpi relu; relu.act = ACT_RELU;
+    ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
+    K_(conv2d(L.fF0_all, r.ft[lv], bufF, relu, IN_DIRECT, r.s));
+    K_(conv2d(L.fA0ft_all, r.ft[lv], r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));
+    for (const LayerW& l : e->layers) {
+      if (l.kind != 2 || l.level != lv) continue;
+      K_(conv2d(l.cp.fF2, bufF.slice(l.k_in_level * Hd, Hd), t, relu, IN_DIRECT, r.s));
+      K_(conv2d(l.cp.fF4, t, r.hF[lv][l.k_in_level], cs, IN_DIRECT, r.s));
+    }
+    r.A.off = mark;
+  }
+}
+
+// z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
+static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& t1, const View& t2, const View& hout) {
+  const int Hd = r.e->d.hidden;
+  View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
+  ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
+  K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  ConvEpi relu; relu.act = ACT_RELU;
+  K_(conv2d(l.cp.fA2, t1, t2, relu, IN_DIRECT, r.s));
+  ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
+  K_(conv2d(l.cp.fA4, t2, hout, cs, IN_DIRECT, r.s));
+}
+
+// Per-level scratch: the flow state ping-pongs between two buffers; the affine-net intermediates are reused by
+// every step of the level (all work is ordered on one stream).
+struct LevelBufs {
+  View z[2], t1, t2, h; int pp = 0;
+  void alloc(Run& r, int H, int W, int C) {
+    const int Hd = r.e->d.hidden;
+    z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
+    t1 = make_view(r.A, r.B, H, W, Hd); t2 = make_view(r.A, r.B, H, W, Hd);
+    h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
+    pp = 0;
+  }
+  View& next() { View& v = z[pp]; pp ^= 1; return v; }
+};
+
+// FlowUpsamplerNet.encode (FlowUpsamplerNet.py:217-251).  gt: (B, sh, sw, 3) NHWC.  Returns latent views.
+static std::vector<View> run_encode(Run& r, const View& gt) {
+  bfsr_srflow* e = r.e;
+  std::vector<View> lat;
+  View z = gt;                    // current flow state
+  bool pending = false;           // coupling whose second half has not been applied to z yet
+  LevelBufs lb; int cur_level = 0;
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    const LayerW& l = e->layers[i];
+    if (l.kind == 0) continue;    // squeeze: folded into the next step's load
+    const int H = r.lvH(l.level), W = r.lvW(l.level);
+    if (l.kind == 1 || l.kind == 2) {
+      if (l.level != cur_level) { lb.alloc(r, H, W, l.C); cur_level = l.level; }
+      const bool sq = e->layers[i - 1].kind == 0;
+      BFSR_CHECK(!(sq && pending), "internal: pending coupling across a squeeze");
+      View zo = lb.next();
+      const View* hF = l.kind == 2 ? &r.hF[l.level][l.k_in_level] : nullptr;
+      K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s));
+      pending = false;
+      z = zo;
+      if (l.kind == 2) { run_affine_net(r, l, z, lb.t1, lb.t2, lb.h); pending = true; }
+      const bool level_end = (i + 1 == e->layers.size()) || e->layers[i + 1].kind == 0 || e->layers[i + 1].kind == 3;
+      if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
+    } else {   // Split2d forward (Split.py:49-61)
+      const int cons = (int)std::lround(l.C * 0.5), pass = l.C - cons;
+      View hs = make_view(r.A, r.B, H, W, 2 * cons);
+      View z1 = make_view(r.A, r.B, H, W, pass), eps = make_view(r.A, r.B, H, W, cons);
+      K_(conv2d_fp32(l.split_conv, z.slice(0, pass), hs, ConvEpi(), IN_DIRECT, r.s));
+      K_(split_fwd(z, hs, z1, eps, r.s));
+      lat.push_back(eps);
+      z = z1;
+    }
+  }
+  lat.push_back(z);
+  return lat;
+}
+
+// FlowUpsamplerNet.decode (FlowUpsamplerNet.py:267-296).  Returns SR as NHWC (B, sh, sw, 3).
+static View run_decode(Run& r, const std::vector<View>& lat) {
+  bfsr_srflow* e = r.e;
+  int li = (int)lat.size() - 1;
+  View z = lat[li--];
+  LevelBufs lb; int cur_level = 0;
+  for (int i = (int)e->layers.size() - 1; i >= 0; --i) {
+    const LayerW& l = e->layers[i];
+    if (l.kind == 0) continue;   // unsqueeze: folded into the previous step's store
+    const int H = r.lvH(l.level), W = r.lvW(l.level);
+    if (l.kind == 3) {
+      const int cons = (int)std::lround(l.C * 0.5);
+      BFSR_CHECK(li >= 0, "decode: not enough latents");
+      View hs = make_view(r.A, r.B, H, W, 2 * cons);
+      View zo = make_view(r.A, r.B, H, W, l.C);
+      K_(conv2d_fp32(l.split_conv, z, hs, ConvEpi(), IN_DIRECT, r.s));
+      K_(split_inv(z, hs, lat[li], zo, r.s));
+      --li; z = zo;
+      continue;
+    }
+    if (l.level != cur_level) { lb.alloc(r, H, W, l.C); cur_level = l.level; }
+    const bool unsq = e->layers[i - 1].kind == 0;
+    View zo = unsq ? make_view(r.A, r.B, 2 * H, 2 * W, l.C / 4) : lb.next();
+    if (l.kind == 2) {
+      run_affine_net(r, l, z, lb.t1, lb.t2, lb.h);
+      K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s));
+    } else {
+      K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s));
+    }
+    z = zo;
+  }
+  BFSR_CHECK(z.C == 3, "decode: final tensor has %d channels", z.C);
+  return z;
+}
+
+}  // namespace bfsr
+
+// ===================================================================== UNet prior (defined in unet_engine.cu)
+namespace bfsr {
+std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s);
+}
+
+// ===================================================================== entry points used by capi.cu
+namespace bfsr {
+
+void srflow_build(bfsr_srflow* e, const bfsr_tensor_t* weights, int n) {
+  Weights W(weights, n);
+  build_srflow(e, W);
+}
+
+static void check_dims(const bfsr_srflow* e, int B, int h, int w) {
+  BFSR_CHECK(B >= 0 && h > 0 && w > 0, "bad input shape (%d,3,%d,%d)", B, h, w);
+  const int div = 1 << e->d.L;
+  BFSR_CHECK((h * e->d.scale) % div == 0 && (w * e->d.scale) % div == 0,
+             "LR size %dx%d: scale*size must be divisible by 2^L=%d (the reference pads to even, test.py:126-130)", h, w, div);
+}
+
+enum Mode { M_ENCODE, M_DECODE, M_LP };
+
+// One chunk of tiles through the workspace.  Pointers are NCHW device buffers already offset to the chunk.
+static void run_chunk(bfsr_srflow* e, bfsr_unet* prior, Mode mode, const float* lr, const float* gt,
+                      float* const* lat_out, const float* const* lat_in, float* sr, int B, int h, int w,
+                      cudaStream_t s) {
+  Arena& A = e->arena;
+  A.reset();
+  Run r{e, s, A, B, h, w};
+  const int S = e->d.scale;
+  View x = make_view(A, B, h, w, 3);
+  K_(nchw_to_nhwc(lr, x, s));
+  run_encoder(r, x);
+  run_ft_convs(r);
+  std::vector<View> lat;
+  const int nl = (int)e->latent_C.size();
+  if (mode == M_ENCODE || mode == M_LP) {
+    View g = make_view(A, B, S * h, S * w, 3);
+    if (mode == M_LP) K_(bilinear_up_nchw(lr, B, 3, h, w, S, g, s));
+    else K_(nchw_to_nhwc(gt, g, s));
+    lat = run_encode(r, g);
+    BFSR_CHECK((int)lat.size() == nl, "internal: latent count");
+    if (mode == M_ENCODE) {
+      for (int i = 0; i < nl; ++i) K_(nhwc_to_nchw(lat[i], lat_out[i], s));
+      return;
+    }
+    std::vector<View> nrm;
+    for (int i = 0; i < nl; ++i) {
+      View o = make_view(A, B, lat[i].H, lat[i].W, lat[i].C);
+      K_(normalise_latent(lat[i], o, s));
+      nrm.push_back(o);
+    }
+    lat = run_unet_srflow(prior, A, nrm, s);
+  } else {
+    for (int i = 0; i < nl; ++i) {
+      const int lv = e->latent_level[i];
+      View v = make_view(A, B, r.lvH(lv), r.lvW(lv), e->latent_C[i]);
+      K_(nchw_to_nhwc(lat_in[i], v, s));
+      lat.push_back(v);
+    }
+  }
+  View out = run_decode(r, lat);
+  K_(nhwc_to_nchw(out, sr, s));
+}
+
+void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode_i, const float* lr, const float* gt,
+                float* const* lat_out, const float* const* lat_in, float* sr, int B, int h, int w, cudaStream_t s) {
+  const Mode mode = (Mode)mode_i;
+  check_dims(e, B, h, w);
+  if (mode == M_LP) BFSR_CHECK(prior != nullptr && prior->d.variant == 0, "lp_sr needs an SRFlow-LP prior handle");
+  if (mode == M_LP) {
+    BFSR_CHECK(prior->d.n_latents == (int)e->latent_C.size(), "prior expects %d latents, flow produces %zu",
+               prior->d.n_latents, e->latent_C.size());
+    for (size_t i = 0; i < e->latent_C.size(); ++i)
+      BFSR_CHECK(prior->d.latent_ch[i] == e->latent_C[i], "prior latent %zu has %d channels, flow produces %d", i,
+                 prior->d.latent_ch[i], e->latent_C[i]);
+  }
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  const int chunk = e->d.tile_chunk > 0 ? e->d.tile_chunk : 8;
+  const int S = e->d.scale;
+  const int nl = (int)e->latent_C.size();
+  // plan pass: measure the workspace of the largest chunk
+  {
+    Arena& A = e->arena;
+    const size_t peak0 = A.peak;
+    A.plan = true; A.peak = 0;
+    run_chunk(e, prior, mode, nullptr, nullptr, nullptr, nullptr, nullptr, B < chunk ? B : chunk, h, w, s);
+    A.plan = false;
+    const size_t need = A.peak + (1 << 20);
+    A.peak = peak0 > need ? peak0 : need;
+    if (need > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(need); }
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    std::vector<float*> lo(nl, nullptr); std::vector<const float*> li(nl, nullptr);
+    for (int i = 0; i < nl; ++i) {
+      const int lv = e->latent_level[i];
+      const size_t per = (size_t)e->latent_C[i] * ((h * S) >> lv) * ((w * S) >> lv);
+      if (lat_out) lo[i] = lat_out[i] + per * b0;
+      if (lat_in) li[i] = lat_in[i] + per * b0;
+    }
+    run_chunk(e, prior, mode, lr + (size_t)b0 * 3 * h * w, gt ? gt + (size_t)b0 * 3 * S * h * S * w : nullptr,
+              lo.data(), li.data(), sr ? sr + (size_t)b0 * 3 * S * h * S * w : nullptr, nb, h, w, s);
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace bfsr

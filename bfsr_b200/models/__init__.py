@@ -1,0 +1,4 @@
+"""`models` registry surface of the reference (SRFlow-LP/code/models/__init__.py:24, LINF-LP/models/__init__.py)."""
+from .models import make, register, models  # noqa: F401
+from . import unet  # noqa: F401  (registers 'unet')
+from .srflow import SRFlowNetEngine, define_Flow  # noqa: F401

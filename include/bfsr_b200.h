@@ -1,0 +1,120 @@
+/* bfsr_b200 — C ABI of the Blackwell-native flow-SR inference engine.
+ *
+ * The reference (liyuantsao/BFSR) has no FFI: its operator API for the inference hot
+ * path is two Python call surfaces.  Each entry point below names the
+ * reference interface it stands behind; paths are relative to /root/reference.
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative code; the message is in the
+ *    thread-local bfsr_last_error().  Nothing throws across the ABI.
+ *  - Tensors at the boundary are contiguous fp32 NCHW, exactly what the reference's
+ *    callers hold.  `*_dev` pointers are device memory on the handle's device,
+ *    `*_host` pointers are host memory (pinned for best speed).  The library owns only
+ *    its packed weights and one grow-only workspace per handle.
+ *  - Work is enqueued on the caller's stream (cudaStream_t passed as void*); device
+ *    entry points do not synchronise, `*_host` entry points return after the result
+ *    is in host memory.
+ *  - A handle is bound to one device and is not re-entrant.
+ */
+#ifndef BFSR_B200_H
+#define BFSR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One named fp32 tensor of a state_dict (host memory), in the reference's checkpoint layout
+ * (SRFlow-LP/code/models/base_model.py:95-124; LINF-LP/train.py:234-248). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} bfsr_tensor_t;
+
+const char* bfsr_last_error(void);
+const char* bfsr_version(void);
+/* kernels launched by this thread since the last call with reset!=0 */
+int64_t bfsr_launch_count(int reset);
+
+/* ------------------------------------------------------------------ SRFlow generator
+ * Stands behind SRFlowNet.forward (SRFlow-LP/code/models/modules/SRFlowNet_arch.py:60-82),
+ * i.e. behind SRFlowModel.get_encode_z / get_sr (models/SRFlow_model.py:198-222). */
+typedef struct {
+  int32_t scale;            /* opt['scale']: 4 or 8 */
+  int32_t nf, nb, gc;       /* network_G.nf / nb, growth channels (64, 23, 32) */
+  int32_t K, L;             /* network_G.flow.K / L */
+  int32_t n_no_affine;      /* network_G.flow.additionalFlowNoAffine */
+  int32_t hidden;           /* coupling hidden channels (64) */
+  int32_t n_blocks;         /* len(network_G.flow.stackRRDB.blocks) */
+  int32_t blocks[8];        /* stackRRDB.blocks */
+  int32_t split_enable;     /* network_G.flow.split.enable */
+  int32_t tile_chunk;       /* LR tiles processed per pass through the workspace (0 = default) */
+  int32_t precision;        /* 0 = fp32-accurate (parity mode), 1 = bf16 fast mode */
+} bfsr_srflow_desc_t;
+
+typedef struct bfsr_srflow bfsr_srflow_t;
+typedef struct bfsr_unet bfsr_unet_t;
+
+int bfsr_srflow_create(bfsr_srflow_t** out, const bfsr_srflow_desc_t* desc, const bfsr_tensor_t* weights,
+                       int32_t n_weights, int32_t device);
+void bfsr_srflow_destroy(bfsr_srflow_t* h);
+/* number of latent tensors an encode returns and the shape of latent i for an LR input of (h, w) */
+int bfsr_srflow_num_latents(const bfsr_srflow_t* h);
+int bfsr_srflow_latent_shape(const bfsr_srflow_t* h, int32_t i, int32_t lr_h, int32_t lr_w, int32_t* C, int32_t* H,
+                             int32_t* W);
+
+/* netG(gt=gt, lr=lr, reverse=False, epses=[], add_gt_noise=False): SRFlowNet.normal_flow
+ * (SRFlowNet_arch.py:83-116) + FlowUpsamplerNet.encode (FlowUpsamplerNet.py:217-251).
+ * lr: (B,3,h,w); gt: (B,3,s*h,s*w); latents[i]: device buffers in the order the reference appends
+ * them (Split2d eps first, final z last). */
+int bfsr_srflow_encode(bfsr_srflow_t* h, const float* lr_dev, const float* gt_dev, int32_t B, int32_t lr_h,
+                       int32_t lr_w, float* const* latents_dev, void* stream);
+/* netG(lr=lr, z=None, eps_std=None, reverse=True, epses=latents): SRFlowNet.reverse_flow
+ * (SRFlowNet_arch.py:145-158) + FlowUpsamplerNet.decode (FlowUpsamplerNet.py:267-296). sr: (B,3,s*h,s*w). */
+int bfsr_srflow_decode(bfsr_srflow_t* h, const float* lr_dev, const float* const* latents_dev, int32_t B,
+                       int32_t lr_h, int32_t lr_w, float* sr_dev, void* stream);
+/* The whole LP inference path of SRFlow-LP/code/test.py:135-148 in one call:
+ * lr_up = bilinear(lr) -> encode -> per-pixel latent normalisation -> prior -> decode (pre-clamp SR).
+ * The LR encoder and every feature-only conv run once and are shared by both flow directions. */
+int bfsr_srflow_lp_sr(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_dev, int32_t B, int32_t lr_h,
+                      int32_t lr_w, float* sr_dev, void* stream);
+/* Same with host buffers: H2D copy of lr, compute, D2H copy of sr, synchronises the stream. */
+int bfsr_srflow_lp_sr_host(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_host, int32_t B, int32_t lr_h,
+                           int32_t lr_w, float* sr_host, void* stream);
+/* bytes of workspace currently reserved by the handle */
+int64_t bfsr_srflow_workspace_bytes(const bfsr_srflow_t* h);
+
+/* ------------------------------------------------------------------ learned prior (UNet)
+ * variant 0: SRFlow-LP UNet.forward(epses) (SRFlow-LP/code/models/unet.py:109-181), one branch per latent;
+ * variant 1: LINF-LP UNet.forward(x, lr)   (LINF-LP/models/unet.py:105-167). */
+typedef struct {
+  int32_t variant;
+  int32_t depth, dim, bilinear;
+  int32_t n_latents;        /* variant 0 */
+  int32_t latent_ch[4];     /* variant 0: channels of each latent (6, 96) */
+  int32_t in_chans;         /* variant 1: 27 */
+  int32_t precision;
+} bfsr_unet_desc_t;
+
+int bfsr_unet_create(bfsr_unet_t** out, const bfsr_unet_desc_t* desc, const bfsr_tensor_t* weights, int32_t n_weights,
+                     int32_t device);
+void bfsr_unet_destroy(bfsr_unet_t* h);
+/* variant 0: prior_model(epses) -> [z0, z1]; latent i is (B, latent_ch[i], H[i], W[i]) NCHW */
+int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, const int32_t* H, const int32_t* W,
+                             int32_t B, float* const* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ single operators (parity tests, P1 in SURVEY.md §8c)
+ * fp32 NCHW in / out on the device; weights in the reference's per-module layout (host). */
+/* nn.Conv2d(ks in {1,3}, stride 1, 'same') + bias + activation (0 none, 1 LeakyReLU(0.2), 2 ReLU) */
+int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
+                   const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
+                   void* stream);
+/* flow.squeeze2d / unsqueeze2d (flow.py:122-152) */
+int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFSR_B200_H */

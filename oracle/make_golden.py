@@ -8,7 +8,7 @@ Run (build container only — /root/reference does not exist on the GPU box):
 The reference is imported from /root/reference with the stub modules under
 oracle/stubs/ on sys.path (missing offline deps) and `.cuda()`
 neutralised; no reference file is modified or copied.  The synthetic SRFlow
-checkpoints come from oracle/synth.py and are loaded with strict=True, which also
+checkpoints come from tools/synth.py and are loaded with strict=True, which also
 pins the state_dict key/shape layout.  Fixtures hold only inputs and outputs
 (weights are regenerated from their seed by the tests).
 """
@@ -36,7 +36,7 @@ def _ref_srflow_modules():
 
 
 def golden_srflow():
-    from oracle import synth
+    from tools import synth
     networks, ref_models, option = _ref_srflow_modules()
     torch.manual_seed(0)
     torch.set_num_threads(8)

@@ -22,7 +22,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .synth import SRFlowTopo
+from tools.synth import SRFlowTopo
 
 
 # ----------------------------------------------------------------- RRDB encoder

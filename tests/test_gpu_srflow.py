@@ -1,0 +1,140 @@
+"""GPU parity tests of the SRFlow-LP path: CUDA engine (through the C ABI) vs the CPU oracle and the golden
+fixtures recorded from the unmodified reference.  Tolerances: bit-exact for index ops; fp32 conv/coupling
+<= 1e-4 relative (BASELINE.json north_star), in practice ~1e-6."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import SMALL, golden, max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bfsr_b200 import _lib
+    return _lib
+
+
+def _small():
+    from tools import synth
+    from bfsr_b200 import models
+    t = synth.SRFlowTopo(**SMALL)
+    sd = synth.synth_srflow_state_dict(t, seed=11)
+    usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(), seed=12)
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(sd, strict=True)
+    prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
+    return t, sd, usd, net, prior
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 6), (1, 12, 4, 4), (3, 96, 2, 10)])
+def test_squeeze_bit_exact(lib, shape):
+    from oracle import srflow_oracle as O
+    x = torch.randn(*shape)
+    xd = x.cuda()
+    B, Cc, H, W = shape
+    y = torch.empty(B, Cc * 4, H // 2, W // 2, device="cuda")
+    lib.check(lib.lib().bfsr_op_squeeze2d(xd.data_ptr(), B, Cc, H, W, 0, y.data_ptr(), None))
+    assert torch.equal(y.cpu(), O.squeeze2d(x))
+    if Cc % 4 == 0:
+        u = torch.empty(B, Cc // 4, H * 2, W * 2, device="cuda")
+        lib.check(lib.lib().bfsr_op_squeeze2d(xd.data_ptr(), B, Cc, H, W, 1, u.data_ptr(), None))
+        assert torch.equal(u.cpu(), O.unsqueeze2d(x))
+        assert torch.equal(O.unsqueeze2d(O.squeeze2d(x)), x)
+
+
+@pytest.mark.parametrize("cin,cout,ks,H,W,act", [
+    (3, 64, 3, 17, 23, 0), (64, 32, 3, 16, 16, 1), (70, 64, 3, 9, 31, 1), (6, 12, 3, 20, 12, 0),
+    (64, 64, 1, 13, 7, 2), (192, 64, 3, 32, 32, 0), (320, 128, 3, 8, 24, 2), (64, 48, 3, 40, 40, 0),
+    (96, 27, 1, 5, 5, 0)])
+def test_conv2d_fp32(lib, cin, cout, ks, H, W, act):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=ks // 2)
+    ref = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.2), 2: F.relu}[act](ref)
+    y = torch.empty(2, cout, H, W, device="cuda")
+    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, ks, act, 0,
+                                      y.data_ptr(), None))
+    assert rel_l2(ref, y) < 2e-6
+
+
+def test_encode_decode_small_vs_golden():
+    from oracle import srflow_oracle as O
+    t, sd, usd, net, prior = _small()
+    g = golden("srflow_small")
+    lr = torch.from_numpy(g["lr"])
+    lr_up = F.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=False)
+    epses = []
+    out, nll, logdet = net(gt=lr_up, lr=lr, reverse=False, epses=epses, add_gt_noise=False)
+    assert out is epses and len(epses) == 2            # appended in place, reference order
+    for i, e in enumerate(epses):
+        assert rel_l2(g[f"eps_lr{i}"], e) < 1e-4, i
+    # decode of the reference's learned latents reproduces the reference SR
+    learned = [torch.from_numpy(g[f"learned{i}"]) for i in range(2)]
+    keep = list(learned)
+    sr, _ = net(lr=lr, z=None, eps_std=None, reverse=True, epses=learned, reverse_with_grad=True)
+    assert len(learned) == 2 and all(a is b for a, b in zip(keep, learned))   # caller's list untouched
+    assert rel_l2(g["sr"], sr) < 1e-4
+    # invertibility (P2): decode(encode(x)) == x
+    rt, _ = net(lr=lr, reverse=True, epses=epses)
+    assert max_abs(lr_up, rt) < 5e-5
+
+
+def test_prior_small_vs_oracle():
+    from oracle import srflow_oracle as O
+    t, sd, usd, net, prior = _small()
+    g = golden("srflow_small")
+    eps = O.normalise_latents([torch.from_numpy(g[f"eps_lr{i}"]) for i in range(2)])
+    got = prior(eps)
+    for i in range(2):
+        assert rel_l2(g[f"learned{i}"], got[i]) < 1e-4
+
+
+@pytest.mark.parametrize("name,kw", [("srflow_small", SMALL), ("srflow_full40", {})])
+def test_lp_sr_vs_golden(name, kw):
+    """Whole LP path (test.py:135-148) through bfsr_srflow_lp_sr vs the reference's recorded output (P3)."""
+    from tools import synth
+    from bfsr_b200 import models
+    g = golden(name)
+    B, h, w, wseed, iseed = [int(v) for v in g["meta"]]
+    t = synth.SRFlowTopo(**kw)
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(synth.synth_srflow_state_dict(t, seed=wseed), strict=True)
+    usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(), seed=wseed + 1)
+    prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
+    lr = torch.from_numpy(g["lr"])
+    sr = net.lp_sr(lr, prior)
+    assert torch.isfinite(sr).all()
+    assert rel_l2(g["sr"], sr) < 1e-4
+    # host-buffer entry point gives the same bits
+    sr_h = net.lp_sr_host(lr.contiguous(), prior)
+    assert torch.equal(sr_h, sr.cpu())
+
+
+def test_lp_sr_ragged_batch_chunks():
+    """Batch not a multiple of the tile chunk, non-square tiles; chunked result == per-tile result."""
+    from tools import synth
+    from bfsr_b200 import models
+    t, sd, usd, _, prior = _small()
+    net = models.define_Flow(t.opt(), tile_chunk=2)
+    net.load_state_dict(sd, strict=True)
+    lr = synth.img(5, 16, 24, 77)
+    sr = net.lp_sr(lr, prior)
+    for i in (0, 4):
+        one = net.lp_sr(lr[i:i + 1], prior)
+        assert torch.equal(one, sr[i:i + 1])
+    empty = net.lp_sr(lr[:0], prior)
+    assert empty.shape == (0, 3, 64, 96)
+
+
+def test_rejects_odd_lr_size():
+    from bfsr_b200 import BfsrError
+    t, sd, usd, net, prior = _small()
+    with pytest.raises(BfsrError):
+        net.lp_sr(torch.rand(1, 3, 11, 12), prior)

@@ -1,7 +1,8 @@
-"""Deterministic synthetic inputs and checkpoints in the reference's layouts.
+"""Deterministic synthetic workloads: inputs and checkpoints in the reference's layouts.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md): nothing here is imported by the
-product path (`bfsr_b200/`).  The reference ships no SRFlow weights
+Neutral workload generator shared by the tests, bench.py and the oracle scripts; it
+contains no model arithmetic and is never imported by the product package
+(`bfsr_b200/`).  The reference ships no SRFlow weights
 (SRFlow-LP/setup.sh:32-38 downloads them; no network here), so every SRFlow
 configuration is exercised with synthetic checkpoints written in the reference's
 own state_dict layout:
