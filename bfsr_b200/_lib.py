@@ -44,6 +44,8 @@ SYMBOLS = {
     "bfsr_last_error": (C.c_char_p, []),
     "bfsr_version": (C.c_char_p, []),
     "bfsr_launch_count": (C.c_int64, [C.c_int]),
+    "bfsr_prof_enable": (C.c_int, [C.c_int]),
+    "bfsr_prof_summary": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bfsr_srflow_create": (C.c_int, [C.POINTER(_P), C.POINTER(SRFlowDesc), C.POINTER(Tensor), _I, _I]),
     "bfsr_srflow_destroy": (None, [_P]),
     "bfsr_srflow_num_latents": (C.c_int, [_P]),

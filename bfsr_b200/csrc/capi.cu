@@ -57,21 +57,21 @@ int bfsr_srflow_latent_shape(const bfsr_srflow_t* h, int32_t i, int32_t lr_h, in
 int bfsr_srflow_encode(bfsr_srflow_t* h, const float* lr_dev, const float* gt_dev, int32_t B, int32_t lr_h,
                        int32_t lr_w, float* const* latents_dev, void* stream) {
   API_BEGIN
-  BFSR_CHECK(h && lr_dev && gt_dev && latents_dev, "null argument");
+  BFSR_CHECK(h && latents_dev && (B == 0 || (lr_dev && gt_dev)), "null argument");
   srflow_run(h, nullptr, 0, lr_dev, gt_dev, latents_dev, nullptr, nullptr, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
 }
 int bfsr_srflow_decode(bfsr_srflow_t* h, const float* lr_dev, const float* const* latents_dev, int32_t B,
                        int32_t lr_h, int32_t lr_w, float* sr_dev, void* stream) {
   API_BEGIN
-  BFSR_CHECK(h && lr_dev && latents_dev && sr_dev, "null argument");
+  BFSR_CHECK(h && latents_dev && (B == 0 || (lr_dev && sr_dev)), "null argument");
   srflow_run(h, nullptr, 1, lr_dev, nullptr, nullptr, latents_dev, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
 }
 int bfsr_srflow_lp_sr(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_dev, int32_t B, int32_t lr_h,
                       int32_t lr_w, float* sr_dev, void* stream) {
   API_BEGIN
-  BFSR_CHECK(h && prior && lr_dev && sr_dev, "null argument");
+  BFSR_CHECK(h && prior && (B == 0 || (lr_dev && sr_dev)), "null argument");
   BFSR_CHECK(prior->device == h->device, "prior and generator live on different devices");
   srflow_run(h, prior, 2, lr_dev, nullptr, nullptr, nullptr, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
@@ -79,7 +79,7 @@ int bfsr_srflow_lp_sr(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_dev,
 int bfsr_srflow_lp_sr_host(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_host, int32_t B, int32_t lr_h,
                            int32_t lr_w, float* sr_host, void* stream) {
   API_BEGIN
-  BFSR_CHECK(h && prior && lr_host && sr_host, "null argument");
+  BFSR_CHECK(h && prior && (B == 0 || (lr_host && sr_host)), "null argument");
   BFSR_CHECK(prior->device == h->device, "prior and generator live on different devices");
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;

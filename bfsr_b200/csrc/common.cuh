@@ -99,4 +99,16 @@ inline void count_launch(int n = 1) { g_launches += n; }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------- per-kernel-class device timing (bench.py roofline)
+// When enabled, launchers bracket each launch with CUDA events on the launching stream; bfsr_prof_summary()
+// returns the summed device time and algorithmic work (flops for convs, bytes for flow steps) per class.
+enum ProfKind : int { PK_CONV_FP32 = 0, PK_CONV_TC = 1, PK_FLOWSTEP = 2, PK_OTHER = 3, PK_COUNT = 4 };
+void prof_begin(int kind, double work, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(int kind, double work, cudaStream_t st) : s(st) { prof_begin(kind, work, st); }
+  ~ProfScope() { prof_end(s); }
+};
+
 }  // namespace bfsr

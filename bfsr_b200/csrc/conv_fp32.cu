@@ -196,6 +196,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   a.tiles_x = 0;
   if (out.npix() == 0) return;
+  ProfScope prof(PK_CONV_FP32, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
 #define L(KS, T) launch<KS, T>(a, out.N, s)
   if (w.ks == 3) { if (w.co_tile == 64) L(3, 64); else if (w.co_tile == 32) L(3, 32); else L(3, 16); }
   else           { if (w.co_tile == 64) L(1, 64); else if (w.co_tile == 32) L(1, 32); else L(1, 16); }

@@ -133,6 +133,8 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   if (a.npix == 0) return;
   const size_t smem = ((size_t)w.C * w.C + (size_t)a.pix_per_block * (w.C + 1)) * 4;
   const int grid = cdiv(a.npix, a.pix_per_block);
+  // algorithmic HBM bytes: z in + z out (+ h: C, + hF: 2C) fp32 per level-pixel
+  ProfScope prof(PK_FLOWSTEP, 4.0 * (double)a.npix * w.C * (2 + (h ? 1 : 0) + (hF ? 2 : 0)), s);
   if (inv) {
     CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     flowstep_kernel<true><<<grid, 256, smem, s>>>(a);

@@ -1,0 +1,54 @@
+// Optional per-launch device timing with CUDA events (used by bench.py for the roofline numbers; off by default).
+#include "common.cuh"
+#include <vector>
+
+namespace bfsr {
+
+struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_recs;
+static thread_local std::vector<cudaEvent_t> g_pool;
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); return e;
+}
+
+void prof_begin(int kind, double work, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r; r.a = get_event(); r.b = get_event(); r.kind = kind; r.work = work;
+  CUDA_OK(cudaEventRecord(r.a, s));
+  g_recs.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof_on || g_recs.empty()) return;
+  cudaEventRecord(g_recs.back().b, s);
+}
+
+}  // namespace bfsr
+
+using namespace bfsr;
+
+extern "C" {
+int bfsr_prof_enable(int on) {
+  g_prof_on = on != 0;
+  for (auto& r : g_recs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+  g_recs.clear();
+  return 0;
+}
+// Synchronises the device, then reports the sum over recorded launches of class `kind`.
+int bfsr_prof_summary(int kind, double* total_ms, double* total_work, int64_t* count) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  double ms = 0, work = 0; int64_t n = 0;
+  for (auto& r : g_recs) {
+    if (r.kind != kind) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return -1;
+    ms += t; work += r.work; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  if (count) *count = n;
+  return 0;
+}
+}

@@ -37,6 +37,11 @@ const char* bfsr_version(void);
 /* kernels launched by this thread since the last call with reset!=0 */
 int64_t bfsr_launch_count(int reset);
 
+/* Per-kernel-class device timing for the roofline report (off by default; adds two event records per launch).
+ * kind: 0 fp32 conv, 1 tcgen05 conv, 2 fused flow step, 3 other.  work = algorithmic FLOPs (convs) or bytes (flow steps). */
+int bfsr_prof_enable(int on);
+int bfsr_prof_summary(int kind, double* total_ms, double* total_work, int64_t* count);
+
 /* ------------------------------------------------------------------ SRFlow generator
  * Stands behind SRFlowNet.forward (SRFlow-LP/code/models/modules/SRFlowNet_arch.py:60-82),
  * i.e. behind SRFlowModel.get_encode_z / get_sr (models/SRFlow_model.py:198-222). */

@@ -267,11 +267,15 @@ def synth_unet_state_dict(shapes, seed: int = 1):
             std = math.sqrt(2.0 / fan_in)
             if "input_proj" in k or "lr_proj" in k:
                 std *= 0.5
+            if k.startswith("outc"):
+                # an untrained prior must stay near the flow's mode: O(1) random latents drive the untrained inverse
+                # into its exploding regime (scale -> 1e-4 saturation; inf on ~1/4 of 160x160 tiles when undamped)
+                std *= 0.1
             v = rs.randn(*shp) * std
         elif k.endswith(".weight"):  # BN gamma
             v = 1.0 + rs.randn(*shp) * 0.1
         else:  # biases / BN beta
-            v = rs.randn(*shp) * 0.05
+            v = rs.randn(*shp) * (0.005 if k.startswith("outc") else 0.05)
         sd[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
     return sd
 
