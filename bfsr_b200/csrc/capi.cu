@@ -58,6 +58,7 @@ int bfsr_srflow_encode(bfsr_srflow_t* h, const float* lr_dev, const float* gt_de
                        int32_t lr_w, float* const* latents_dev, void* stream) {
   API_BEGIN
   BFSR_CHECK(h && latents_dev && (B == 0 || (lr_dev && gt_dev)), "null argument");
+  g_conv_mode = h->d.precision;
   srflow_run(h, nullptr, 0, lr_dev, gt_dev, latents_dev, nullptr, nullptr, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
 }
@@ -65,6 +66,7 @@ int bfsr_srflow_decode(bfsr_srflow_t* h, const float* lr_dev, const float* const
                        int32_t lr_h, int32_t lr_w, float* sr_dev, void* stream) {
   API_BEGIN
   BFSR_CHECK(h && latents_dev && (B == 0 || (lr_dev && sr_dev)), "null argument");
+  g_conv_mode = h->d.precision;
   srflow_run(h, nullptr, 1, lr_dev, nullptr, nullptr, latents_dev, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
 }
@@ -73,6 +75,7 @@ int bfsr_srflow_lp_sr(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr_dev,
   API_BEGIN
   BFSR_CHECK(h && prior && (B == 0 || (lr_dev && sr_dev)), "null argument");
   BFSR_CHECK(prior->device == h->device, "prior and generator live on different devices");
+  g_conv_mode = h->d.precision;
   srflow_run(h, prior, 2, lr_dev, nullptr, nullptr, nullptr, sr_dev, B, lr_h, lr_w, (cudaStream_t)stream);
   API_END
 }
@@ -90,6 +93,7 @@ int bfsr_srflow_lp_sr_host(bfsr_srflow_t* h, bfsr_unet_t* prior, const float* lr
   if (nout > h->stage_out_sz) { if (h->stage_out) cudaFree(h->stage_out); h->stage_out = nullptr; h->stage_out_sz = 0;
                                 CUDA_OK(cudaMalloc((void**)&h->stage_out, nout)); h->stage_out_sz = nout; }
   if (B > 0) CUDA_OK(cudaMemcpyAsync(h->stage_in, lr_host, nin, cudaMemcpyHostToDevice, s));
+  g_conv_mode = h->d.precision;
   srflow_run(h, prior, 2, h->stage_in, nullptr, nullptr, nullptr, h->stage_out, B, lr_h, lr_w, s);
   if (B > 0) CUDA_OK(cudaMemcpyAsync(sr_host, h->stage_out, nout, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
@@ -122,6 +126,7 @@ int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, co
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   Arena& A = h->arena;
+  g_conv_mode = h->d.precision;
   for (int pass = 0; pass < 2; ++pass) {
     A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
     std::vector<View> lat;
@@ -155,7 +160,13 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
     View y; y.p = yn; y.N = B; y.H = H; y.W = W; y.C = Cout; y.cs = Cout;
     nchw_to_nhwc(x_dev, x, s);
     ConvEpi ep; ep.act = act;
-    if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s); else conv2d(cw, x, y, ep, IN_DIRECT, s);
+    if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s);
+    else {   // 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass
+      const int saved = g_conv_mode;
+      g_conv_mode = impl == 1 ? 0 : 1;
+      try { conv2d_tc(cw, x, y, ep, IN_DIRECT, s); } catch (...) { g_conv_mode = saved; throw; }
+      g_conv_mode = saved;
+    }
     nhwc_to_nchw(y, y_dev, s);
     CUDA_OK(cudaStreamSynchronize(s));
   } catch (...) { cudaFree(xn); cudaFree(yn); free_conv(cw); throw; }
@@ -192,6 +203,7 @@ namespace bfsr {
 // conv dispatcher: the tcgen05 implicit-GEMM path takes the shapes it supports, everything else runs on the
 // fp32 CUDA-core kernel.
 void conv2d(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
-  conv2d_fp32(w, in, out, epi, in_mode, s);
+  if (conv_tc_eligible(w, in, out)) conv2d_tc(w, in, out, epi, in_mode, s);
+  else conv2d_fp32(w, in, out, epi, in_mode, s);
 }
 }  // namespace bfsr

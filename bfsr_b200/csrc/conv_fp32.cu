@@ -229,6 +229,7 @@ ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float*
   CUDA_OK(cudaMalloc((void**)&c.bias, hb.size() * 4));
   CUDA_OK(cudaMemcpy(c.w, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(c.bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  pack_conv_tc(c, h);   // split-bf16 image for the tcgen05 path when the shape is eligible
   return c;
 }
 

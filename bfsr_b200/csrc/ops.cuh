@@ -32,6 +32,12 @@ struct ConvEpi {
 // out(N,H,W,Cout) = conv_ks(in) ; `in` has spatial dims (H,W) or (H/2,W/2) for IN_UP2.
 void conv2d(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
 void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
+// tcgen05 path (conv_tc.cu).  g_conv_mode: 0 = split-bf16 x3 (fp32-accurate), 1 = bf16 single pass (fast),
+// 2 = never use the tensor-core path (all convs on the fp32 CUDA-core kernel).
+extern thread_local int g_conv_mode;
+void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed);
+bool conv_tc_eligible(const ConvW& w, const View& in, const View& out);
+void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
 
 // Host-side packing: src is OIHW fp32 [cout][cin_src][ks][ks]; `out_scale` (optional) multiplies the weights per
 // output channel, `bias` is the FINAL bias (already scaled); the input-channel gather map makes packed input channel

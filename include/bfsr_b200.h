@@ -55,7 +55,8 @@ typedef struct {
   int32_t blocks[8];        /* stackRRDB.blocks */
   int32_t split_enable;     /* network_G.flow.split.enable */
   int32_t tile_chunk;       /* LR tiles processed per pass through the workspace (0 = default) */
-  int32_t precision;        /* 0 = fp32-accurate (parity mode), 1 = bf16 fast mode */
+  int32_t precision;        /* 0 = fp32-accurate: split-bf16 x3 on tcgen05 (parity mode); 1 = bf16 single pass (fast);
+                               2 = every conv on the fp32 CUDA-core kernel */
 } bfsr_srflow_desc_t;
 
 typedef struct bfsr_srflow bfsr_srflow_t;
@@ -111,7 +112,8 @@ int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, co
 
 /* ------------------------------------------------------------------ single operators (parity tests, P1 in SURVEY.md §8c)
  * fp32 NCHW in / out on the device; weights in the reference's per-module layout (host). */
-/* nn.Conv2d(ks in {1,3}, stride 1, 'same') + bias + activation (0 none, 1 LeakyReLU(0.2), 2 ReLU) */
+/* nn.Conv2d(ks in {1,3}, stride 1, 'same') + bias + activation (0 none, 1 LeakyReLU(0.2), 2 ReLU);
+ * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass (3x3, Cin >= 32 only) */
 int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                    const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
                    void* stream);

@@ -138,3 +138,25 @@ def test_rejects_odd_lr_size():
     t, sd, usd, net, prior = _small()
     with pytest.raises(BfsrError):
         net.lp_sr(torch.rand(1, 3, 11, 12), prior)
+
+
+@pytest.mark.parametrize("cin,cout,H,W,act", [
+    (64, 32, 16, 8, 0), (64, 64, 32, 24, 1), (96, 32, 17, 23, 1), (192, 64, 40, 40, 0), (160, 32, 33, 9, 2),
+    (320, 128, 24, 16, 2), (72, 64, 20, 12, 0), (64, 24, 16, 16, 3), (352, 64, 8, 8, 0), (64, 192, 10, 10, 3)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
+    """tcgen05 implicit-GEMM conv: split-bf16 x3 (impl 1) must be fp32-accurate; single-pass bf16 (impl 2) is the fast mode."""
+    g = torch.Generator().manual_seed(cin * 1000 + cout + H)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if act == 3:   # 'cross' sigmoid on odd channels
+        ref = ref.clone(); ref[:, 1::2] = torch.sigmoid(ref[:, 1::2] + 2.0) + 1e-4
+    else:
+        ref = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.2), 2: F.relu}[act](ref)
+    y = torch.empty(2, cout, H, W, device="cuda")
+    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 3, act, impl,
+                                      y.data_ptr(), None))
+    err = rel_l2(ref, y)
+    assert err < (2e-5 if impl == 1 else 1e-2), err
