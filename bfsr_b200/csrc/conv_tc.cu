@@ -1,29 +1,33 @@
 // tcgen05 implicit-GEMM 3x3 convolution for sm_100a (replaces cuDNN behind every wide nn.Conv2d of the path:
 // RRDBNet_arch.py:25-45, the feature-only coupling convs of FlowAffineCouplingsAblation.py:45-55, unet.py:10-107).
 //
-// GEMM view per CTA: M = 128 output pixels (8 wide x 16 tall), N = NT <= 64 output channels, K = 9 taps x Cin.
+// Persistent, warp-specialised kernel.  One CTA per SM walks a static round-robin list of work tiles; a work tile is a
+// MACRO tile of MT sub-tiles (each 8 wide x 16 tall = 128 output pixels = one UMMA M=128 accumulator) times NT output
+// channels.  GEMM view per sub-tile: M = 128 pixels, N = NT, K = 9 taps x Cin, walked in 32-channel chunks.
 //
-//  * A operand (pixels x channels).  The fp32 NHWC halo tile (18 x 10 pixels) of one 64-channel chunk is loaded ONCE
-//    by the producer warps with coalesced 128-bit loads, split on the fly into bf16 (hi, lo) planes and written to
-//    shared memory in the UMMA K-major SWIZZLE_128B layout (one pixel = one 128-byte row).  The 9 taps are then just
-//    9 shifted VIEWS of that tile: the smem descriptor's start address moves by (dy*10+dx) rows and its stride-byte-
-//    offset (distance between 8-row groups = one image row of the tile) is the halo pitch, 1280 B.  The swizzle is a
-//    function of the absolute smem address (Swizzle<3,4,3> o smem_ptr), so shifted views stay consistent.  Zero
-//    padding of the convolution and of ragged tiles is written as zeros by the producer.
+//  * A operand (pixels x channels).  The fp32 NHWC halo tile of the whole macro tile (e.g. 18 x 34 pixels for 2x2
+//    sub-tiles) of one 32-channel chunk is loaded ONCE by the producer warps with coalesced 128-bit loads, split on the
+//    fly into bf16 (hi, lo) planes and written to shared memory in the UMMA K-major SWIZZLE_64B layout (one pixel = one
+//    64-byte row).  Every (sub-tile, tap) operand is then just a shifted VIEW of that tile: the smem descriptor's start
+//    address moves by ((sy*16+dy)*pitch + sx*8+dx) rows and its stride-byte-offset (distance between 8-row groups =
+//    one image row of the tile) is the halo pitch.  The swizzle is a function of the absolute smem address
+//    (Swizzle<2,4,3> o smem_ptr), so shifted views stay consistent.  Conv zero padding / ragged edges are written as
+//    zeros by the producer; nearest-2x upsampling of the input (RRDBNet_arch.py:105) is folded into its index math.
 //  * B operand (weights), pre-packed at load time as [cout tile][chunk][tap] images of the exact smem layout
-//    ([W_hi ; W_lo] rows of 128 B, swizzled), streamed through a 4-slot ring with cp.async.bulk (TMA bulk copy,
-//    SASS UBLKCP) completing on mbarriers.
+//    ([W_hi ; W_lo] rows of 64 B, swizzled), streamed through a 4-slot ring with cp.async.bulk (TMA bulk copy, SASS
+//    UBLKCP) completing on mbarriers; one weight slot serves all MT sub-tiles of the macro tile.
 //  * fp32-accurate arithmetic on bf16 tensor cores (split-bf16 x3):
 //        x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi      (dropped term ~2^-16 relative)
 //    issued as TWO tcgen05.mma per K=16 step:  A_hi x [W_hi;W_lo] (N = 2*NT, accumulator columns [0,2NT)) and
 //    A_lo x W_hi (N = NT, accumulating into columns [0,NT)); the epilogue adds the two column halves.  The fast mode
 //    issues only A_hi x W_hi.
-//  * Accumulators live in TMEM; one elected thread issues the MMAs; tcgen05.commit arrives on the mbarriers that
-//    recycle the A / W slots and that release the epilogue.  Epilogue: tcgen05.ld 32x32b -> bias, pre-activation add,
-//    activation, scaled residuals -> fp32 NHWC channel-slice store (same fused epilogue as the fp32 kernel).
+//  * Accumulators live in TMEM (MT x 2NT columns per stage, double-buffered when 2 stages fit in 512 columns so the
+//    epilogue of tile i overlaps the MMAs of tile i+1); one elected thread issues the MMAs; tcgen05.commit arrives on
+//    the mbarriers that recycle the A / W slots and release the epilogue.  Epilogue: tcgen05.ld 32x32b -> bias,
+//    pre-activation add, activation, scaled residuals -> fp32 NHWC channel-slice store.
 //
-// Warp roles (192 threads): warps 0-3 = A producers, then epilogue (TMEM lane quarter = warp id); warp 4 = TMEM
-// allocator + MMA issuer; warp 5 = weight TMA producer.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMEM allocator + MMA issuer, warp 5 weight TMA
+// producer, warps 6-13 A producers.
 #include "ops.cuh"
 #include <vector>
 #include <cstring>
@@ -34,23 +38,30 @@ namespace bfsr {
 thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
 
 namespace tc {
-constexpr int TW = 8, TH = 16, PITCH = 10, HROWS = TH + 2, HPIX = HROWS * PITCH;   // 180 halo pixels
-constexpr int KC = 64;                       // channels per chunk = one 128-byte bf16 row
-constexpr int A_PLANE = 23552;               // >= HPIX*128, multiple of 1024
-constexpr int A_SLOT = 2 * A_PLANE;
+constexpr int KC = 32;                       // channels per chunk = one 64-byte bf16 row (SWIZZLE_64B)
+constexpr int ROWB = 64;                     // bytes per smem row
 constexpr int NA = 2, NW = 4;
-constexpr int W_SLOT_MAX = 2 * 64 * 128;     // [W_hi;W_lo] for NT = 64
-constexpr int SMEM_BYTES = NA * A_SLOT + NW * W_SLOT_MAX + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NPROD = 128;
+constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
+constexpr int NTHREADS = (6 + PROD_WARPS) * 32;
+constexpr int MAX_SMEM = 227 * 1024;
+constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
+constexpr int STG_PITCH = 36;                // floats per staged epilogue row (32 columns + pad, keeps float4 alignment)
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // one 32x32 block per epilogue warp
 }  // namespace tc
 
 struct TcArgs {
   View in, out, pre, res1, res2;
   const unsigned char* w; const float* bias;
-  int cin, cout, nt, n_chunks;
-  int H, W, in_mode, act;
+  int cin, cout, nt, n_chunks, n_ct;     // n_ct = cout tiles
+  int H, W, N, in_mode, act;
   float eps, alpha, beta1, beta2;
-  int tiles_x, fast, vec_in, vec_out;
+  int fast, vec_in, vec_out;
+  int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
+  int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
+  int a_plane, a_slot, w_slot;           // bytes
+  int nacc;                              // TMEM accumulator stages (1 or 2)
+  int tiles_x, tiles_y, total_tiles;     // macro tiles per image and total work tiles (incl. cout tiles, batch)
+  uint32_t tmem_cols;
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -75,7 +86,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("bfsr conv_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    if (clock64() - t0 > 8000000000LL) {
+      printf("bfsr conv_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -99,10 +113,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1, layout type 4)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
 __device__ __forceinline__ uint32_t make_idesc(int n) {
@@ -113,34 +127,57 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(TcArgs a) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+#ifdef BFSR_TC_TRACE
+#define TR_DECL(...) long long __VA_ARGS__
+#define TR_T(x) const long long x = clock64()
+#define TR_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define TR_DECL(...)
+#define TR_T(x)
+#define TR_ADD(acc, t0)
+#endif
+
+struct TileCoord { int n, ty0, tx0, ct; };
+__device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
+  TileCoord c;
+  c.ct = t % a.n_ct; t /= a.n_ct;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y; c.n = t / a.tiles_y;
+  c.ty0 = ty * 16 * a.sy; c.tx0 = tx * 8 * a.sx;
+  return c;
+}
+
+__global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_smem = base;                               // NA slots of [hi plane | lo plane]
-  const uint32_t w_smem = base + NA * A_SLOT;                 // NW slots
-  const uint32_t bars = w_smem + NW * W_SLOT_MAX;             // mbarriers (8 B each)
+  const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
+  const uint32_t w_smem = base + NA * a.a_slot;                   // NW slots
+  const uint32_t bars = w_smem + NW * a.w_slot;                   // mbarriers (8 B each)
   const uint32_t a_full = bars, a_empty = bars + 8 * NA, w_full = bars + 16 * NA, w_empty = w_full + 8 * NW;
-  const uint32_t acc_full = w_empty + 8 * NW, tmem_slot = acc_full + 8;
+  const uint32_t acc_full = w_empty + 8 * NW, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+  float* stage_all = reinterpret_cast<float*>(smem_gen + NA * a.a_slot + NW * a.w_slot + 256);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int ty0 = (tile / a.tiles_x) * TH, tx0 = (tile % a.tiles_x) * TW;
-  const int nt = a.nt, co_base = blockIdx.y * nt;
-  const int n = blockIdx.z;
-  const int w_rows = a.fast ? nt : 2 * nt;
-  const uint32_t w_bytes = (uint32_t)w_rows * 128u;
-  uint32_t ncols = 32; while ((int)ncols < (a.fast ? nt : 2 * nt)) ncols <<= 1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform role index
+  const int nt = a.nt;
+  const int acc_cols = a.mt * (a.fast ? nt : 2 * nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, NPROD); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ncols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -148,158 +185,281 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(TcArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-  if (warp < 4) {
+  if (warp >= 6) {
     // ===================== A producers: fp32 halo tile -> (hi, lo) bf16 planes, swizzled =====================
+    // Each thread owns up to MAXI (pixel, 8-channel) items of a chunk.  The global loads of chunk i+1 are issued
+    // into registers BEFORE waiting for its smem slot, so their latency hides behind the MMAs of chunk i-1.
+    const int ptid = tid - 6 * 32;
     const int inH = a.in_mode == IN_UP2 ? a.H >> 1 : a.H, inW = a.in_mode == IN_UP2 ? a.W >> 1 : a.W;
-    const long long img = (long long)n * inH * inW;
-    for (int c = 0; c < a.n_chunks; ++c) {
-      const int slot = c % NA;
-      mbar_wait(a_empty + 8 * slot, ((c / NA) & 1) ^ 1);
-      unsigned char* pl_hi = smem_gen + slot * A_SLOT;
-      constexpr int ITEMS = HPIX * 8;
-      constexpr int U = 4;
-      for (int it0 = tid; it0 < ITEMS; it0 += NPROD * U) {
-        float4 v[U][2];
+    const int items = a.hrows * a.pitch * 4;           // (pixel, 8-channel group) pairs per chunk
+    float4 v[MAXI][2];
+    auto load_chunk = [&](const TileCoord& tcd, int c) {
+      const long long img = (long long)tcd.n * inH * inW;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int it = it0 + u * NPROD;
-          v[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[u][1] = v[u][0];
-          if (it < ITEMS) {
-            const int q = it >> 3, j = it & 7;
-            const int yy = q / PITCH, xx = q - yy * PITCH;
-            const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-            const int cb = c * KC + j * 8;
-            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && cb < a.cin) {
-              const int sy = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx = a.in_mode == IN_UP2 ? gx >> 1 : gx;
-              const long long p = img + (long long)sy * inW + sx;
-              if (a.vec_in && cb + 8 <= a.cin) {
-                const float4* src = reinterpret_cast<const float4*>((const float*)a.in.p + p * a.in.cs + a.in.coff + cb);
-                v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1);
-              } else {
-                float t[8];
+      for (int u = 0; u < MAXI; ++u) {
+        const int it = ptid + u * NPROD;
+        v[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[u][1] = v[u][0];
+        if (it < items) {
+          const int q = it >> 2, j = it & 3;
+          const int yy = q / a.pitch, xx = q - yy * a.pitch;
+          const int gy = tcd.ty0 + yy - 1, gx = tcd.tx0 + xx - 1;
+          const int cb = c * KC + j * 8;
+          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && cb < a.cin) {
+            const int sy_ = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx_ = a.in_mode == IN_UP2 ? gx >> 1 : gx;
+            const long long p = img + (long long)sy_ * inW + sx_;
+            if (a.vec_in && cb + 8 <= a.cin) {
+              const float4* src = reinterpret_cast<const float4*>((const float*)a.in.p + p * a.in.cs + a.in.coff + cb);
+              v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1);
+            } else {
+              float tt[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) t[e] = cb + e < a.cin ? ld(a.in, p, cb + e) : 0.f;
-                v[u][0] = make_float4(t[0], t[1], t[2], t[3]); v[u][1] = make_float4(t[4], t[5], t[6], t[7]);
-              }
+              for (int e = 0; e < 8; ++e) tt[e] = cb + e < a.cin ? ld(a.in, p, cb + e) : 0.f;
+              v[u][0] = make_float4(tt[0], tt[1], tt[2], tt[3]); v[u][1] = make_float4(tt[4], tt[5], tt[6], tt[7]);
             }
           }
         }
+      }
+    };
+    auto store_chunk = [&](unsigned char* pl_hi) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int it = it0 + u * NPROD;
-          if (it < ITEMS) {
-            const int q = it >> 3, j = it & 7;
-            const float x[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-            float hi[8], lo[8];
+      for (int u = 0; u < MAXI; ++u) {
+        const int it = ptid + u * NPROD;
+        if (it < items) {
+          const int q = it >> 2, j = it & 3;
+          const float x[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+          float hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { hi[e] = __bfloat162float(__float2bfloat16_rn(x[e])); lo[e] = x[e] - hi[e]; }
-            const uint32_t off = (uint32_t)q * 128u + (uint32_t)((j ^ (q & 7)) << 4);
-            *reinterpret_cast<uint4*>(pl_hi + off) =
-                make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-            if (!a.fast)
-              *reinterpret_cast<uint4*>(pl_hi + A_PLANE + off) =
-                  make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-          }
+          for (int e = 0; e < 8; ++e) { hi[e] = __bfloat162float(__float2bfloat16_rn(x[e])); lo[e] = x[e] - hi[e]; }
+          const uint32_t off = (uint32_t)q * ROWB + (uint32_t)((j ^ ((q >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(pl_hi + off) =
+              make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+          if (!a.fast)
+            *reinterpret_cast<uint4*>(pl_hi + a.a_plane + off) =
+                make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
         }
       }
+    };
+    int a_it = 0, t = blockIdx.x, c = 0;
+    bool have = t < a.total_tiles;
+    TileCoord tcd = tile_coord(a, have ? t : 0);
+    TR_DECL(tr_wait = 0, tr_fill = 0); TR_T(tr_start);
+    if (have) load_chunk(tcd, 0);
+    while (have) {
+      const int slot = a_it % NA;
+      TR_T(tr0);
+      mbar_wait(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+      TR_ADD(tr_wait, tr0); TR_T(tr1);
+      store_chunk(smem_gen + slot * a.a_slot);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(a_full + 8 * slot);
+      ++a_it;
+      if (++c == a.n_chunks) { c = 0; t += gridDim.x; have = t < a.total_tiles; if (have) tcd = tile_coord(a, t); }
+      if (have) load_chunk(tcd, c);
+      TR_ADD(tr_fill, tr1);
     }
-    // ===================== epilogue: TMEM -> registers -> fused epilogue -> global =====================
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = warp * 32 + lane;                 // accumulator row = TMEM lane
-    const int gy = ty0 + (row >> 3), gx = tx0 + (row & 7);
-    const bool valid = gy < a.H && gx < a.W;
-    const long long p = ((long long)n * a.H + gy) * a.W + gx;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int n0 = 0; n0 < nt; n0 += 16) {
-      float acc[16], acc2[16];
-      tmem_ld16(t_row + n0, acc);
-      if (!a.fast) tmem_ld16(t_row + nt + n0, acc2);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!a.fast) {
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && ptid == 0) printf("[tc trace] producer: total %lld wait_a_empty %lld fill %lld (chunks %d)\n", clock64() - tr_start, tr_wait, tr_fill, a_it);
+#endif
+  } else if (warp < 4) {
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> coalesced stores ============
+    float* stg = stage_all + warp * 32 * STG_PITCH;   // this warp's 32 x 32 staging block
+    const int sub_cols = a.fast ? nt : 2 * nt;
+    const bool vpre = a.pre.p && a.pre.fmt == F32 && a.pre.cs % 4 == 0 && a.pre.coff % 4 == 0 && ((uintptr_t)a.pre.p % 16) == 0;
+    const bool vr1 = a.res1.p && a.res1.fmt == F32 && a.res1.cs % 4 == 0 && a.res1.coff % 4 == 0 && ((uintptr_t)a.res1.p % 16) == 0;
+    const bool vr2 = a.res2.p && a.res2.fmt == F32 && a.res2.cs % 4 == 0 && a.res2.coff % 4 == 0 && ((uintptr_t)a.res2.p % 16) == 0;
+    int t_it = 0;
+    TR_DECL(tr_wait = 0, tr_work = 0); TR_T(tr_start);
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
+      const TileCoord tcd = tile_coord(a, t);
+      const int as = t_it % a.nacc;
+      TR_T(tr0);
+      mbar_wait(acc_full + 8 * as, (t_it / a.nacc) & 1);
+      TR_ADD(tr_wait, tr0); TR_T(tr1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int co_base = tcd.ct * nt;
+      for (int sub = 0; sub < a.mt; ++sub) {
+        const int sy0 = tcd.ty0 + (sub / a.sx) * 16, sx0 = tcd.tx0 + (sub % a.sx) * 8;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols + sub * sub_cols;
+        for (int n0 = 0; n0 < nt; n0 += 32) {
+          if (co_base + n0 >= a.cout) break;             // warp-uniform
+          const int ncol = nt - n0 < 32 ? 16 : 32;
+          float acc[32];
+          tmem_ld16(t_row + n0, acc);
+          if (ncol == 32) tmem_ld16(t_row + n0 + 16, acc + 16);
+          if (!a.fast) {
+            float acc2[32];
+            tmem_ld16(t_row + nt + n0, acc2);
+            if (ncol == 32) tmem_ld16(t_row + nt + n0 + 16, acc2 + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
-      }
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int co = co_base + n0 + i;
-          if (co < a.cout) {
-            float v = acc[i] + a.bias[co];
-            if (a.pre.p) v += ld(a.pre, p, co);
-            if (a.act == ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
-            else if (a.act == ACT_RELU) v = fmaxf(v, 0.f);
-            else if (a.act == ACT_CROSS_SIGMOID) { if (co & 1) v = 1.f / (1.f + expf(-(v + 2.f))) + a.eps; }
-            v *= a.alpha;
-            if (a.res1.p) v = fmaf(a.beta1, ld(a.res1, p, co), v);
-            if (a.res2.p) v = fmaf(a.beta2, ld(a.res2, p, co), v);
-            acc[i] = v;
+            for (int i = 0; i < 32; ++i) acc[i] += acc2[i];
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
-        }
-        const int co = co_base + n0;
-        if (a.vec_out && co + 16 <= a.cout) {
-          float4* dst = reinterpret_cast<float4*>((float*)a.out.p + p * a.out.cs + a.out.coff + co);
+          // phase A: accumulator row (one pixel per lane) -> staging row
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-        } else {
+          for (int k = 0; k < 8; ++k)
+            if (4 * k < ncol)
+              *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * k) = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+          __syncwarp();
+          // phase B: lanes sweep channels first, so every global access covers whole 64/128-byte pixel runs
+          const int q4 = ncol >> 2, ppi = 32 / q4;
+          const int c4 = (lane % q4) * 4, rsub = lane / q4;
+          const int co = co_base + n0 + c4;              // this lane's 4 output channels (same for every pixel it touches)
+          const bool cok = co < a.cout, full = co + 4 <= a.cout;
+          float bb[4] = {0.f, 0.f, 0.f, 0.f};
+          if (cok) { const float4 b4 = *reinterpret_cast<const float4*>(a.bias + co); bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w; }
+#pragma unroll 1
+          for (int i = 0; i < q4; ++i) {
+            {
+              const int r = i * ppi + rsub;
+              const int idx = warp * 32 + r;
+              const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
+              if (gy < a.H && gx < a.W && cok) {
+                const float4 s4 = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
+                const long long p = ((long long)tcd.n * a.H + gy) * a.W + gx;
+                float o[4] = {s4.x, s4.y, s4.z, s4.w};
+                float pr[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f};
+                if (a.pre.p) {
+                  if (vpre && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.pre.p + p * a.pre.cs + a.pre.coff + co); pr[0] = t4.x; pr[1] = t4.y; pr[2] = t4.z; pr[3] = t4.w; }
+                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) pr[e] = ld(a.pre, p, co + e); }
+                }
+                if (a.res1.p) {
+                  if (vr1 && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.res1.p + p * a.res1.cs + a.res1.coff + co); r1[0] = t4.x; r1[1] = t4.y; r1[2] = t4.z; r1[3] = t4.w; }
+                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) r1[e] = ld(a.res1, p, co + e); }
+                }
+                if (a.res2.p) {
+                  if (vr2 && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.res2.p + p * a.res2.cs + a.res2.coff + co); r2[0] = t4.x; r2[1] = t4.y; r2[2] = t4.z; r2[3] = t4.w; }
+                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) r2[e] = ld(a.res2, p, co + e); }
+                }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (co + i < a.cout) st(a.out, p, co + i, acc[i]);
+                for (int e = 0; e < 4; ++e) {
+                  float vv = o[e] + bb[e] + pr[e];
+                  if (a.act == ACT_LRELU) vv = vv > 0.f ? vv : 0.2f * vv;
+                  else if (a.act == ACT_RELU) vv = fmaxf(vv, 0.f);
+                  else if (a.act == ACT_CROSS_SIGMOID) { if ((co + e) & 1) vv = 1.f / (1.f + expf(-(vv + 2.f))) + a.eps; }
+                  vv *= a.alpha;
+                  vv = fmaf(a.beta1, r1[e], vv);
+                  vv = fmaf(a.beta2, r2[e], vv);
+                  o[e] = vv;
+                }
+                if (a.vec_out && full)
+                  *reinterpret_cast<float4*>((float*)a.out.p + p * a.out.cs + a.out.coff + co) = make_float4(o[0], o[1], o[2], o[3]);
+                else
+                  for (int e = 0; e < 4; ++e) if (co + e < a.cout) st(a.out, p, co + e, o[e]);
+              }
+            }
+          }
+          __syncwarp();
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(acc_empty + 8 * as);                 // 128 arrivals free the accumulator stage
+      TR_ADD(tr_work, tr1);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
+#endif
   } else if (warp == 4) {
-    // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0) {
-      const uint32_t idesc_wide = make_idesc(a.fast ? nt : 2 * nt), idesc_nt = make_idesc(nt);
-      int wi = 0;
-      uint32_t first = 1;
-      for (int c = 0; c < a.n_chunks; ++c) {
-        const int slot = c % NA;
-        mbar_wait(a_full + 8 * slot, (c / NA) & 1);
-        const uint32_t a_hi = a_smem + slot * A_SLOT, a_lo = a_hi + A_PLANE;
-        int nk = (a.cin - c * KC + 15) >> 4; nk = nk > 4 ? 4 : nk;
-        for (int t = 0; t < 9; ++t, ++wi) {
-          const int ws = wi % NW;
-          mbar_wait(w_full + 8 * ws, (wi / NW) & 1);
+    // ===================== MMA issuer: whole warp walks the (uniform) loop, one elected lane issues =====================
+    const uint32_t idesc_wide = make_idesc(a.fast ? nt : 2 * nt), idesc_nt = make_idesc(nt);
+    const uint32_t sbo = (uint32_t)a.pitch * ROWB;
+    const int sub_cols = a.fast ? nt : 2 * nt;
+    // constant descriptor fields (LBO=1, SBO, version 1, SWIZZLE_64B); the start address is added per operand
+    const uint64_t desc_a_hi = make_desc(0, sbo), desc_b_hi = make_desc(0, 8 * ROWB);
+    uint32_t sub_off[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) sub_off[sub] = (uint32_t)((sub / a.sx) * 16 * a.pitch + (sub % a.sx) * 8) * (ROWB >> 4);
+    int a_it = 0, w_it = 0, t_it = 0;
+    TR_DECL(tr_acc = 0, tr_a = 0, tr_w = 0, tr_issue = 0); TR_T(tr_start);
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
+      const int as = t_it % a.nacc;
+      TR_T(tr0);
+      mbar_wait(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
+      TR_ADD(tr_acc, tr0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_base = tmem_base + as * acc_cols;
+      for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
+        const int slot = a_it % NA;
+        TR_T(tr1);
+        mbar_wait(a_full + 8 * slot, (a_it / NA) & 1);
+        TR_ADD(tr_a, tr1);
+        const uint32_t a_hi = a_smem + slot * a.a_slot, a_lo = a_hi + a.a_plane;
+        const uint64_t a_hi_d = desc_a_hi | (uint64_t)((a_hi & 0x3FFFF) >> 4), a_lo_d = desc_a_hi | (uint64_t)((a_lo & 0x3FFFF) >> 4);
+        int nk = (a.cin - c * KC + 15) >> 4; nk = nk > 2 ? 2 : nk;
+        for (int tap = 0; tap < 9; ++tap, ++w_it) {
+          const int ws = w_it % NW;
+          TR_T(tr2);
+          mbar_wait(w_full + 8 * ws, (w_it / NW) & 1);
+          TR_ADD(tr_w, tr2); TR_T(tr3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t shift = (uint32_t)((t / 3) * PITCH + (t % 3)) * 128u;
-          const uint32_t wb = w_smem + ws * W_SLOT_MAX;
-          for (int kk = 0; kk < nk; ++kk) {
-            const uint64_t bd = make_desc(wb + kk * 32, 1024);
-            umma_f16(tmem_base, make_desc(a_hi + shift + kk * 32, PITCH * 128), bd, idesc_wide, first ? 0u : 1u);
-            first = 0;
-            if (!a.fast) umma_f16(tmem_base, make_desc(a_lo + shift + kk * 32, PITCH * 128), bd, idesc_nt, 1u);
+          const uint32_t wb = w_smem + ws * a.w_slot;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          // One elected lane issues the whole tap.  Descriptors differ only in the 14-bit start-address field, so each
+          // operand is the chunk/slot base descriptor plus a small precomputed offset (uniform-datapath adds).
+          const uint32_t tap_off = (uint32_t)(dy * a.pitch + dx) * (ROWB >> 4);
+          const uint64_t bd0 = desc_b_hi | (uint64_t)(((wb & 0x3FFFF) >> 4));
+          const uint32_t accf0 = (c | tap) ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+              if (sub < a.mt) {
+                const uint32_t d = d_base + sub * sub_cols;
+                const uint64_t ah = a_hi_d + tap_off + sub_off[sub], al = a_lo_d + tap_off + sub_off[sub];
+                umma_f16(d, ah, bd0, idesc_wide, accf0);
+                if (!a.fast) umma_f16(d, al, bd0, idesc_nt, 1u);
+                if (nk > 1) {
+                  umma_f16(d, ah + 2, bd0 + 2, idesc_wide, 1u);
+                  if (!a.fast) umma_f16(d, al + 2, bd0 + 2, idesc_nt, 1u);
+                }
+              }
+            }
+            umma_commit(w_empty + 8 * ws);      // weight slot reusable once these MMAs retire
           }
-          umma_commit(w_empty + 8 * ws);      // weight slot reusable once these MMAs retire
+          __syncwarp();
+          TR_ADD(tr_issue, tr3);
         }
-        umma_commit(a_empty + 8 * slot);      // A slot reusable
+        if (elect_one()) umma_commit(a_empty + 8 * slot);      // A slot reusable
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full + 8 * as);
+      __syncwarp();
     }
-    __syncwarp();
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0) printf("[tc trace] mma: total %lld wait_acc_empty %lld wait_a_full %lld wait_w_full %lld issue %lld (taps %d)\n", clock64() - tr_start, tr_acc, tr_a, tr_w, tr_issue, w_it);
+#endif
   } else {
     // ===================== weight producer: cp.async.bulk of pre-swizzled [W_hi;W_lo] images =====================
-    if (lane == 0) {
-      const size_t tap_stride = (size_t)2 * nt * 128;    // packed image always holds both planes
-      const unsigned char* wsrc = a.w + (size_t)blockIdx.y * a.n_chunks * 9 * tap_stride;
+    const size_t tap_stride = (size_t)2 * nt * ROWB;    // packed image always holds both planes
+    const uint32_t w_bytes = (uint32_t)(a.fast ? nt : 2 * nt) * ROWB;
+    int w_it = 0;
+    TR_DECL(tr_wait = 0); TR_T(tr_start);
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      const int ct = t % a.n_ct;
+      const unsigned char* wsrc = a.w + (size_t)ct * a.n_chunks * 9 * tap_stride;
       const int total = a.n_chunks * 9;
-      for (int wi = 0; wi < total; ++wi) {
-        const int ws = wi % NW;
-        mbar_wait(w_empty + 8 * ws, ((wi / NW) & 1) ^ 1);
-        mbar_expect_tx(w_full + 8 * ws, w_bytes);
-        bulk_g2s(w_smem + ws * W_SLOT_MAX, wsrc + (size_t)wi * tap_stride, w_bytes, w_full + 8 * ws);
+      for (int wi = 0; wi < total; ++wi, ++w_it) {
+        const int ws = w_it % NW;
+        TR_T(tr0);
+        mbar_wait(w_empty + 8 * ws, ((w_it / NW) & 1) ^ 1);
+        TR_ADD(tr_wait, tr0);
+        if (elect_one()) {
+          mbar_expect_tx(w_full + 8 * ws, w_bytes);
+          bulk_g2s(w_smem + ws * a.w_slot, wsrc + (size_t)wi * tap_stride, w_bytes, w_full + 8 * ws);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0) printf("[tc trace] wprod: total %lld wait_w_empty %lld (taps %d)\n", clock64() - tr_start, tr_wait, w_it);
+#endif
   }
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }
 
@@ -312,18 +472,23 @@ static inline unsigned short f2bf(float x) {   // round-to-nearest-even
 }
 static inline float bf2f(unsigned short b) { uint32_t u = (uint32_t)b << 16; float x; memcpy(&x, &u, 4); return x; }
 
+static int pick_nt(int cout) {
+  const int r = (cout + 15) / 16 * 16;
+  return r > 128 ? 128 : r;
+}
+
 // h: host fp32 packed [tap][cin_pad][cout_pad] (the fp32 kernel's layout)
 void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
   using namespace tc;
   if (c.ks != 3 || c.cin < 32) return;
-  const int nt = c.cout > 48 ? 64 : (c.cout + 15) / 16 * 16;
+  const int nt = pick_nt(c.cout);
   const int n_tiles = (c.cout + nt - 1) / nt, n_chunks = (c.cin + KC - 1) / KC;
-  const size_t tap_bytes = (size_t)2 * nt * 128;
-  std::vector<unsigned short> img((size_t)n_tiles * n_chunks * 9 * tap_bytes / 2, 0);
+  const size_t tap_elems = (size_t)2 * nt * (ROWB / 2);
+  std::vector<unsigned short> img((size_t)n_tiles * n_chunks * 9 * tap_elems, 0);
   for (int t = 0; t < n_tiles; ++t)
     for (int ch = 0; ch < n_chunks; ++ch)
       for (int tap = 0; tap < 9; ++tap) {
-        unsigned short* dst = img.data() + (((size_t)t * n_chunks + ch) * 9 + tap) * tap_bytes / 2;
+        unsigned short* dst = img.data() + (((size_t)t * n_chunks + ch) * 9 + tap) * tap_elems;
         for (int r = 0; r < nt; ++r) {
           const int co = t * nt + r;
           for (int k = 0; k < KC; ++k) {
@@ -332,9 +497,9 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
             if (co < c.cout && ci < c.cin) w = h[((size_t)tap * c.cin_pad + ci) * c.cout_pad + co];
             const unsigned short hi = f2bf(w), lo = f2bf(w - bf2f(hi));
             const int j = k >> 3, e = k & 7;
-            dst[(size_t)r * 64 + ((j ^ (r & 7)) << 3) + e] = hi;
+            dst[(size_t)r * 32 + ((j ^ ((r >> 1) & 3)) << 3) + e] = hi;
             const int r2 = nt + r;
-            dst[(size_t)r2 * 64 + ((j ^ (r2 & 7)) << 3) + e] = lo;
+            dst[(size_t)r2 * 32 + ((j ^ ((r2 >> 1) & 3)) << 3) + e] = lo;
           }
         }
       }
@@ -344,8 +509,11 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
 }
 
 bool conv_tc_eligible(const ConvW& w, const View& in, const View& out) {
-  return w.w_tc != nullptr && g_conv_mode != 2 && in.fmt == F32 && out.npix() >= 128;
+  (void)out;
+  return w.w_tc != nullptr && g_conv_mode != 2 && in.fmt == F32;   // batch-independent, so results do not depend on chunking
 }
+
+static int g_num_sms = 0;
 
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
   using namespace tc;
@@ -353,22 +521,47 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
   BFSR_CHECK(in.C == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
   if (in_mode == IN_UP2) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
   else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv_tc: spatial mismatch");
+  if (out.npix() == 0) return;
   TcArgs a;
   a.in = in; a.out = out;
   a.pre = epi.pre ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
   a.w = (const unsigned char*)w.w_tc; a.bias = w.bias;
   a.cin = w.cin; a.cout = w.cout; a.nt = w.tc_npad; a.n_chunks = w.tc_kchunks;
-  a.H = out.H; a.W = out.W; a.in_mode = in_mode; a.act = epi.act;
+  a.n_ct = cdiv(w.cout, w.tc_npad);
+  a.H = out.H; a.W = out.W; a.N = out.N; a.in_mode = in_mode; a.act = epi.act;
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
-  a.tiles_x = cdiv(out.W, TW);
   a.fast = g_conv_mode == 1;
   a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
-  if (out.npix() == 0) return;
-  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  dim3 grid(a.tiles_x * cdiv(out.H, TH), cdiv(w.cout, w.tc_npad), out.N);
+  // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
+  const int sub_cols = a.fast ? a.nt : 2 * a.nt;
+  int mt = 512 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);
+  a.sx = 1; a.sy = 1;
+  if (mt == 4) {
+    if (out.W > 8 && out.H > 16) { a.sx = 2; a.sy = 2; }
+    else if (out.H > 16) { a.sy = 2; }
+    else if (out.W > 8) { a.sx = 2; }
+  } else if (mt == 2) {
+    if (out.H > 16) a.sy = 2; else if (out.W > 8) a.sx = 2;
+  }
+  a.mt = a.sx * a.sy;
+  a.pitch = 8 * a.sx + 2; a.hrows = 16 * a.sy + 2;
+  a.a_plane = (a.pitch * a.hrows * ROWB + 1023) / 1024 * 1024;
+  a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
+  a.w_slot = 2 * a.nt * ROWB;
+  a.nacc = 2 * a.mt * sub_cols <= 512 ? 2 : 1;
+  uint32_t cols = 32; while ((int)cols < a.nacc * a.mt * sub_cols) cols <<= 1;
+  a.tmem_cols = cols;
+  a.tiles_x = cdiv(out.W, 8 * a.sx); a.tiles_y = cdiv(out.H, 16 * a.sy);
+  a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct;
+  const int smem = NA * a.a_slot + NW * a.w_slot + 1024 + 256 + STG_BYTES;
+  BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
+  BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
+  if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+  const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * 9 * w.cout, s);
-  conv_tc_kernel<<<grid, 192, SMEM_BYTES, s>>>(a);
+  conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
   count_launch();
 }
 
