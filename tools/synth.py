@@ -292,3 +292,112 @@ def img(B: int, h: int, w: int, seed: int) -> torch.Tensor:
     x = torch.nn.functional.interpolate(base, size=(h, w), mode="bicubic", align_corners=False)
     x = x.clamp(0, 1) + 0.02 * torch.randn(B, 3, h, w, generator=g)
     return x.clamp(0, 1).contiguous()
+
+
+# --------------------------------------------------------------------------
+# LINF-LP (LINF-LP/models/linf.py:221-242, edsr.py:107-132, rrdb.py:79-103, flow.py:12-27, unet.py:105-142)
+# --------------------------------------------------------------------------
+
+
+def linf_param_shapes(encoder="edsr-baseline", hidden=256, flow_layers=10, ps=3, nb=23):
+    s = OrderedDict()
+    D = 3 * ps * ps
+    if encoder == "edsr-baseline":
+        for n in ("sub_mean", "add_mean"):
+            s[f"encoder.{n}.weight"] = (3, 3, 1, 1)
+            s[f"encoder.{n}.bias"] = (3,)
+        s["encoder.head.0.weight"] = (64, 3, 3, 3)
+        s["encoder.head.0.bias"] = (64,)
+        for i in range(16):
+            for j in (0, 2):
+                s[f"encoder.body.{i}.body.{j}.weight"] = (64, 64, 3, 3)
+                s[f"encoder.body.{i}.body.{j}.bias"] = (64,)
+        s["encoder.body.16.weight"] = (64, 64, 3, 3)
+        s["encoder.body.16.bias"] = (64,)
+    else:
+        s["encoder.conv_first.weight"] = (64, 3, 3, 3)
+        s["encoder.conv_first.bias"] = (64,)
+        for i in range(nb):
+            for r in (1, 2, 3):
+                for c in range(1, 6):
+                    p = f"encoder.RRDB_trunk.{i}.RDB{r}.conv{c}"
+                    s[p + ".weight"] = (32 if c < 5 else 64, 64 + (c - 1) * 32, 3, 3)
+                    s[p + ".bias"] = (32 if c < 5 else 64,)
+        for n in ("trunk_conv", "upconv1", "upconv2", "HRconv"):
+            s[f"encoder.{n}.weight"] = (64, 64, 3, 3)
+            s[f"encoder.{n}.bias"] = (64,)
+        s["encoder.conv_last.weight"] = (3, 64, 3, 3)
+        s["encoder.conv_last.bias"] = (3,)
+    for n in ("coef", "freq"):
+        s[f"{n}.weight"] = (hidden, 64, 3, 3)
+        s[f"{n}.bias"] = (hidden,)
+    s["phase.weight"] = (hidden // 2, 2)
+    dims = [(hidden * 4, hidden), (hidden, hidden), (hidden, hidden), (hidden, flow_layers * D * 2)]
+    for k, (a, b) in zip((0, 2, 4, 6), dims):
+        s[f"layers.{k}.weight"] = (b, a, 1, 1)
+        s[f"layers.{k}.bias"] = (b,)
+    for i in range(flow_layers):
+        s[f"imnet.linears.{i}.bias"] = (D,)
+        s[f"imnet.linears.{i}._weight"] = (D, D)
+    s["imnet.last.bias"] = (D,)
+    s["imnet.last._weight"] = (D, D)
+    return s
+
+
+def synth_linf_state_dict(shapes, seed=5):
+    rs = np.random.RandomState(seed)
+    sd = OrderedDict()
+    for k in sorted(shapes):
+        shp = shapes[k]
+        if "_mean." in k:
+            v = np.eye(3).reshape(3, 3, 1, 1) if k.endswith("weight") else np.zeros(3)
+        elif k.endswith("._weight"):
+            v = _orthogonal(rs, shp[0]) + 0.03 * rs.randn(*shp)
+        elif len(shp) == 4:
+            fan_in = shp[1] * shp[2] * shp[3]
+            std = math.sqrt(1.0 / fan_in)
+            if ".RDB" in k:
+                std = math.sqrt(2.0 / fan_in) * 0.03
+            if ".body." in k and k.endswith(".body.2.weight"):
+                std *= 0.3       # keep the 16 residual adds of EDSR O(1)
+            if k.startswith("layers.6"):
+                std *= 0.5
+            v = rs.randn(*shp) * std
+        elif k == "phase.weight":
+            v = rs.randn(*shp) * 0.5
+        else:
+            v = rs.randn(*shp) * 0.02
+        sd[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+    return sd
+
+
+def unet_linf_param_shapes(in_chans=27, depth=3, dim=64):
+    s = OrderedDict()
+    gc = dim // 2
+
+    def dense(p, nf):
+        for c in range(1, 6):
+            s[f"{p}.conv{c}.weight"] = (gc, nf + (c - 1) * gc, 3, 3)
+            s[f"{p}.conv{c}.bias"] = (gc,)
+
+    def dconv(p, cin, cout, mid=None):
+        mid = mid or cout
+        for j, (a, b) in zip((0, 3), ((cin, mid), (mid, cout))):
+            s[f"{p}.double_conv.{j}.weight"] = (b, a, 3, 3)
+            for n, shp in (("weight", (b,)), ("bias", (b,)), ("running_mean", (b,)), ("running_var", (b,)),
+                           ("num_batches_tracked", ())):
+                s[f"{p}.double_conv.{j + 1}.{n}"] = shp
+
+    dense("input_proj", in_chans)
+    s["lr_proj.0.weight"] = (in_chans, 3, 3, 3)
+    s["lr_proj.0.bias"] = (in_chans,)
+    dense("lr_proj.2", in_chans)
+    for i in range(depth):
+        dconv(f"down_layers.{i}.maxpool_conv.1", dim * 2 ** i, dim * 2 ** (i + 1) // (2 if i == depth - 1 else 1))
+    for i in range(depth):
+        cin = dim * 2 ** (depth - i)
+        dconv(f"up_layers.{i}.conv", cin, dim * 2 ** (depth - i - 1) // (2 if i < depth - 1 else 1), cin // 2)
+    dconv("inc", dim, dim)
+    s["outc.conv.weight"] = (in_chans, dim, 1, 1)
+    s["outc.conv.bias"] = (in_chans,)
+    return s
