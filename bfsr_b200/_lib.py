@@ -35,6 +35,11 @@ class UNetDesc(C.Structure):
                 ("precision", C.c_int32)]
 
 
+class LINFDesc(C.Structure):
+    _fields_ = [("encoder", C.c_int32), ("nb", C.c_int32), ("hidden", C.c_int32), ("flow_layers", C.c_int32),
+                ("patch_size", C.c_int32), ("tile_chunk", C.c_int32), ("precision", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/bfsr_b200.h declares: (restype, argtypes)
@@ -58,6 +63,13 @@ SYMBOLS = {
     "bfsr_unet_create": (C.c_int, [C.POINTER(_P), C.POINTER(UNetDesc), C.POINTER(Tensor), _I, _I]),
     "bfsr_unet_destroy": (None, [_P]),
     "bfsr_unet_forward_srflow": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_P), _P]),
+    "bfsr_unet_forward_linf": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "bfsr_linf_create": (C.c_int, [C.POINTER(_P), C.POINTER(LINFDesc), C.POINTER(Tensor), _I, _I]),
+    "bfsr_linf_destroy": (None, [_P]),
+    "bfsr_linf_gen_feat": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "bfsr_linf_query": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "bfsr_linf_lp_sr": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "bfsr_linf_lp_sr_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "bfsr_op_conv2d": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "bfsr_op_squeeze2d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
 }

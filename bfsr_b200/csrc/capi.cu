@@ -11,6 +11,13 @@ void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode, const float* lr, con
                 const float* const* lat_in, float* sr, int B, int h, int w, cudaStream_t s);
 void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n);
 std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s);
+View run_unet_linf(bfsr_unet* u, Arena& A, const View& x, const float* lr_nchw, int h, int w, cudaStream_t s);
+void linf_build(bfsr_linf* e, const bfsr_tensor_t* weights, int n);
+void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* feat_out, cudaStream_t s);
+void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh,
+                int qw, int mode, const float* zin, float* out, cudaStream_t s);
+void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, int w, const float* coord, const float* cell,
+                const float* gt, int qh, int qw, int OH, int OW, float* pred, cudaStream_t s);
 }
 
 static thread_local std::string g_err;
@@ -140,6 +147,106 @@ int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, co
     if (pass == 0) { A.plan = false; if (A.peak + (1 << 20) > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(A.peak + (1 << 20)); } }
   }
   CUDA_OK(cudaGetLastError());
+  API_END
+}
+
+int bfsr_unet_forward_linf(bfsr_unet_t* h, const float* z_dev, const float* inp_dev, int32_t B, int32_t qh, int32_t qw,
+                           int32_t lr_h, int32_t lr_w, float* out_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && (B == 0 || (z_dev && inp_dev && out_dev)), "null argument");
+  BFSR_CHECK(h->d.variant == 1, "not a LINF-LP prior");
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena& A = h->arena;
+  g_conv_mode = h->d.precision;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
+    View x = make_view(A, B, qh, qw, h->d.in_chans);
+    if (!A.plan) nchw_to_nhwc(z_dev, x, s);
+    View o = run_unet_linf(h, A, x, inp_dev, lr_h, lr_w, s);
+    if (!A.plan) nhwc_to_nchw(o, out_dev, s);
+    if (pass == 0) { A.plan = false; if (A.peak + (1 << 20) > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(A.peak + (1 << 20)); } }
+  }
+  CUDA_OK(cudaGetLastError());
+  API_END
+}
+
+// ------------------------------------------------------------------ LINF
+int bfsr_linf_create(bfsr_linf_t** out, const bfsr_linf_desc_t* desc, const bfsr_tensor_t* weights, int32_t n_weights,
+                     int32_t device) {
+  API_BEGIN
+  BFSR_CHECK(out && desc && weights, "null argument");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  BFSR_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<bfsr_linf> e(new bfsr_linf());
+  e->d = *desc; e->device = device;
+  linf_build(e.get(), weights, n_weights);
+  *out = e.release();
+  API_END
+}
+void bfsr_linf_destroy(bfsr_linf_t* h) { if (h) { cudaSetDevice(h->device); delete h; } }
+
+int bfsr_linf_gen_feat(bfsr_linf_t* h, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w, float* feat_dev,
+                       void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && (B == 0 || (inp_dev && feat_dev)), "null argument");
+  BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0, "bad input shape");
+  g_conv_mode = h->d.precision;
+  linf_gen_feat(h, inp_dev, B, lr_h, lr_w, feat_dev, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_linf_query(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr_h, int32_t lr_w, const float* coord_dev,
+                    const float* cell_dev, int32_t qh, int32_t qw, int32_t mode, const float* zin_dev, float* out_dev,
+                    void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && (B == 0 || (feat_dev && coord_dev && cell_dev && zin_dev && out_dev)), "null argument");
+  BFSR_CHECK(mode == 0 || mode == 1, "mode must be 0 (log_p) or 1 (rgb)");
+  BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0 && qh > 0 && qw > 0, "bad shape");
+  g_conv_mode = h->d.precision;
+  linf_query(h, feat_dev, B, lr_h, lr_w, coord_dev, cell_dev, qh, qw, mode, zin_dev, out_dev, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_linf_lp_sr(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w,
+                    const float* coord_dev, const float* cell_dev, const float* gt_lr_up_dev, int32_t qh, int32_t qw,
+                    int32_t out_h, int32_t out_w, float* pred_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && prior && (B == 0 || (inp_dev && coord_dev && cell_dev && gt_lr_up_dev && pred_dev)), "null argument");
+  BFSR_CHECK(prior->device == h->device, "prior and model live on different devices");
+  BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0 && qh > 0 && qw > 0, "bad shape");
+  g_conv_mode = h->d.precision;
+  linf_lp_sr(h, prior, inp_dev, B, lr_h, lr_w, coord_dev, cell_dev, gt_lr_up_dev, qh, qw, out_h, out_w, pred_dev,
+             (cudaStream_t)stream);
+  API_END
+}
+int bfsr_linf_lp_sr_host(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_host, int32_t B, int32_t lr_h, int32_t lr_w,
+                         const float* coord_host, const float* cell_host, const float* gt_lr_up_host, int32_t qh,
+                         int32_t qw, int32_t out_h, int32_t out_w, float* pred_host, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && prior && (B == 0 || (inp_host && coord_host && cell_host && gt_lr_up_host && pred_host)), "null argument");
+  BFSR_CHECK(prior->device == h->device, "prior and model live on different devices");
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = 3 * h->d.patch_size * h->d.patch_size;
+  const size_t n_inp = (size_t)B * 3 * lr_h * lr_w, n_coord = (size_t)B * qh * qw * 2, n_cell = (size_t)B * 2,
+               n_gt = (size_t)B * D * qh * qw, n_out = (size_t)B * 3 * out_h * out_w;
+  const size_t total = (n_inp + n_coord + n_cell + n_gt + n_out + 64) * 4;
+  if (total > h->stage_in_sz) { if (h->stage_in) cudaFree(h->stage_in); h->stage_in = nullptr; h->stage_in_sz = 0;
+                                CUDA_OK(cudaMalloc((void**)&h->stage_in, total)); h->stage_in_sz = total; }
+  auto al = [](size_t n) { return (n + 15) / 16 * 16; };
+  float* d_inp = h->stage_in; float* d_coord = d_inp + al(n_inp); float* d_cell = d_coord + al(n_coord);
+  float* d_gt = d_cell + al(n_cell); float* d_out = d_gt + al(n_gt);
+  CUDA_OK(cudaMemcpyAsync(d_inp, inp_host, n_inp * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(d_coord, coord_host, n_coord * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(d_cell, cell_host, n_cell * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(d_gt, gt_lr_up_host, n_gt * 4, cudaMemcpyHostToDevice, s));
+  g_conv_mode = h->d.precision;
+  linf_lp_sr(h, prior, d_inp, B, lr_h, lr_w, d_coord, d_cell, d_gt, qh, qw, out_h, out_w, d_out, s);
+  CUDA_OK(cudaMemcpyAsync(pred_host, d_out, n_out * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
   API_END
 }
 

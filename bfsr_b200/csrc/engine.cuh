@@ -55,11 +55,20 @@ struct RRDBW {
 struct UNetBranchW {
   int nf = 0, nf_pad = 0, gc = 64;
   ConvW dense[5];
+  ConvW lr_dense[5];          // LINF variant: lr_proj.2
+  float* lr_w = nullptr; float* lr_b = nullptr;   // LINF variant: lr_proj.0 (3 -> in_chans, stride 3), raw OIHW
   ConvW inc[2];
   std::vector<ConvW> down;   // 2 per level
   std::vector<ConvW> up;     // 2 per level
   ConvW outc;
 };
+
+std::vector<double> invert_f64(const float* W, int n);   // fp64 Gauss-Jordan inverse (srflow_engine.cu)
+float* to_device(const std::vector<float>& v);
+// UNet pieces shared by both prior variants (unet_engine.cu)
+void pack_dense5(const Weights& W, const std::string& p, int nf, int gc, int out_dim, ConvW* out5, int* nf_pad_out);
+View run_dense5(const ConvW* dense, int nf, int nf_pad, int gc, Arena& A, const View& x, cudaStream_t s);
+View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const View& x, cudaStream_t s);
 
 }  // namespace bfsr
 
@@ -69,6 +78,20 @@ struct bfsr_unet {
   std::vector<bfsr::UNetBranchW> br;
   bfsr::Arena arena;          // used only by the standalone forward entry point
   ~bfsr_unet();
+};
+
+struct bfsr_linf {
+  bfsr_linf_desc_t d;
+  int device = 0;
+  bfsr::ConvW head;                     // EDSR head / RRDB conv_first (3 -> 64)
+  std::vector<bfsr::ConvW> body;        // EDSR: 2*16 + 1 ; RRDB: nb*15 + trunk_conv
+  bfsr::ConvW cf;                       // coef | freq (64 -> 2*hidden)
+  bfsr::ConvW mlp[4];                   // 1x1: 4*hidden -> hidden -> hidden -> hidden -> 2*D*flow_layers
+  float* phase = nullptr;               // (hidden/2, 2)
+  float* Mf = nullptr; float* Mi = nullptr; float* fbias = nullptr;   // flow: W_i, W_i^-1, b_i  (index flow_layers = last)
+  bfsr::Arena arena;
+  float* stage_in = nullptr; size_t stage_in_sz = 0;
+  ~bfsr_linf();
 };
 
 struct bfsr_srflow {

@@ -1,0 +1,229 @@
+// LINF-LP inference engine ('linf-patch' with an EDSR-baseline or RRDB encoder, LINF-LP/models/linf.py:218-428).
+//
+// Path of LINF-LP/test.py:143-171: encoder -> [coef|freq] conv -> per-query local Fourier features -> 1x1-conv MLP ->
+// per-query affine parameters -> flow forward on the LR residual patches (latent) -> UNet prior -> flow inverse ->
+// fold + crop + bilinear(LR).  Relative to the reference graph: the encoder, the coef/freq convs and the MLP run ONCE and
+// their result (affine_info) is shared by the log_p and rgb passes (the reference recomputes all of it in the second
+// pass and the coef/freq convs per 256-row chunk, test.py:22-32,40-45); NaiveLinear inverses are precomputed in fp64
+// (flow.py:110-122 solves per call); F.fold, the crop and the bilinear residual are fused into the flow-inverse kernel.
+#include "engine.cuh"
+#include <cmath>
+#include <cstring>
+
+using namespace bfsr;
+
+bfsr_linf::~bfsr_linf() {
+  free_conv(head);
+  for (auto& c : body) free_conv(c);
+  free_conv(cf);
+  for (auto& c : mlp) free_conv(c);
+  if (phase) cudaFree(phase);
+  if (Mf) cudaFree(Mf);
+  if (Mi) cudaFree(Mi);
+  if (fbias) cudaFree(fbias);
+  if (stage_in) cudaFree(stage_in);
+}
+
+namespace bfsr {
+
+View run_unet_linf(bfsr_unet* u, Arena& A, const View& x, const float* lr_nchw, int h, int w, cudaStream_t s);
+
+static ConvW pack_plain(const Weights& W, const std::string& p, int cout, int cin, int ks) {
+  return pack_conv(W.data(p + ".weight", {cout, cin, ks, ks}), cout, cin, ks, W.data(p + ".bias", {cout}), nullptr, {});
+}
+
+void linf_build(bfsr_linf* e, const bfsr_tensor_t* weights, int n) {
+  Weights W(weights, n);
+  const auto& d = e->d;
+  BFSR_CHECK(d.patch_size == 3, "linf-patch: only patch_size 3 is built (the shipped checkpoints)");
+  BFSR_CHECK(d.hidden > 0 && d.hidden % 8 == 0 && d.flow_layers > 0, "bad LINF descriptor");
+  const int hid = d.hidden, D = 3 * d.patch_size * d.patch_size;
+  if (d.encoder == 0) {   // EDSR-baseline, no_upsampling (edsr.py:107-146)
+    e->head = pack_plain(W, "encoder.head.0", 64, 3, 3);
+    for (int i = 0; i < d.nb; ++i) {
+      e->body.push_back(pack_plain(W, "encoder.body." + std::to_string(i) + ".body.0", 64, 64, 3));
+      e->body.push_back(pack_plain(W, "encoder.body." + std::to_string(i) + ".body.2", 64, 64, 3));
+    }
+    e->body.push_back(pack_plain(W, "encoder.body." + std::to_string(d.nb), 64, 64, 3));
+  } else {                // RRDB, no_upsampling (rrdb.py:79-116)
+    e->head = pack_plain(W, "encoder.conv_first", 64, 3, 3);
+    for (int i = 0; i < d.nb; ++i)
+      for (int r = 1; r <= 3; ++r)
+        for (int c = 1; c <= 5; ++c)
+          e->body.push_back(pack_plain(W, "encoder.RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r) + ".conv" +
+                                       std::to_string(c), c < 5 ? 32 : 64, 64 + (c - 1) * 32, 3));
+    e->body.push_back(pack_plain(W, "encoder.trunk_conv", 64, 64, 3));
+  }
+  {   // coef | freq as one conv (linf.py:228-229)
+    const float* wc = W.data("coef.weight", {hid, 64, 3, 3}); const float* bc = W.data("coef.bias", {hid});
+    const float* wf = W.data("freq.weight", {hid, 64, 3, 3}); const float* bf = W.data("freq.bias", {hid});
+    std::vector<float> w((size_t)2 * hid * 64 * 9), b(2 * hid);
+    memcpy(w.data(), wc, (size_t)hid * 64 * 9 * 4); memcpy(w.data() + (size_t)hid * 64 * 9, wf, (size_t)hid * 64 * 9 * 4);
+    memcpy(b.data(), bc, hid * 4); memcpy(b.data() + hid, bf, hid * 4);
+    e->cf = pack_conv(w.data(), 2 * hid, 64, 3, b.data(), nullptr, {});
+  }
+  const int dims[5] = {4 * hid, hid, hid, hid, 2 * D * d.flow_layers};
+  for (int i = 0; i < 4; ++i) e->mlp[i] = pack_plain(W, "layers." + std::to_string(2 * i), dims[i + 1], dims[i], 1);
+  const float* ph = W.data("phase.weight", {hid / 2, 2});
+  e->phase = to_device(std::vector<float>(ph, ph + hid));
+  const int nl = d.flow_layers;
+  std::vector<float> Mf((size_t)(nl + 1) * D * D), Mi((size_t)(nl + 1) * D * D), fb((size_t)(nl + 1) * D);
+  for (int i = 0; i <= nl; ++i) {
+    const std::string p = i < nl ? "imnet.linears." + std::to_string(i) : std::string("imnet.last");
+    const float* w = W.data(p + "._weight", {D, D}); const float* b = W.data(p + ".bias", {D});
+    memcpy(&Mf[(size_t)i * D * D], w, (size_t)D * D * 4);
+    std::vector<double> inv = invert_f64(w, D);
+    for (int k = 0; k < D * D; ++k) Mi[(size_t)i * D * D + k] = (float)inv[k];
+    memcpy(&fb[(size_t)i * D], b, D * 4);
+  }
+  e->Mf = to_device(Mf); e->Mi = to_device(Mi); e->fbias = to_device(fb);
+}
+
+#define K_(...) do { if (!A.plan) { __VA_ARGS__; } } while (0)
+
+// model("gen_feat", inp): x NHWC (B,h,w,3) -> feat NHWC (B,h,w,64)
+static View run_linf_encoder(bfsr_linf* e, Arena& A, const View& x, cudaStream_t s) {
+  const int B = x.N, h = x.H, w = x.W;
+  View feat = make_view(A, B, h, w, 64);
+  const size_t mark = A.off;
+  if (e->d.encoder == 0) {
+    View head = make_view(A, B, h, w, 64), res = make_view(A, B, h, w, 64), t = make_view(A, B, h, w, 64);
+    K_(conv2d(e->head, x, head, ConvEpi(), IN_DIRECT, s));
+    ConvEpi relu; relu.act = ACT_RELU;
+    View cur = head;
+    for (int i = 0; i < e->d.nb; ++i) {   // ResBlock: conv-ReLU-conv, res_scale 1, += x (edsr.py:45-49)
+      K_(conv2d(e->body[2 * i], cur, t, relu, IN_DIRECT, s));
+      ConvEpi ep; ep.res1 = &cur; ep.beta1 = 1.f;
+      K_(conv2d(e->body[2 * i + 1], t, res, ep, IN_DIRECT, s));   // res may alias cur: each element is read then written by one thread
+      cur = res;
+    }
+    ConvEpi ep; ep.res1 = &head; ep.beta1 = 1.f;                  // res += x (edsr.py:138-139)
+    K_(conv2d(e->body[2 * e->d.nb], cur, feat, ep, IN_DIRECT, s));
+  } else {
+    const int nf = 64, gc = 32;
+    View first = make_view(A, B, h, w, nf);
+    View D[3];
+    for (int i = 0; i < 3; ++i) D[i] = make_view(A, B, h, w, nf + 4 * gc);
+    ConvEpi lrelu; lrelu.act = ACT_LRELU;
+    K_(conv2d(e->head, x, first, ConvEpi(), IN_DIRECT, s));
+    K_(resample(first, D[0].slice(0, nf), RS_COPY, s));
+    for (int i = 0; i < e->d.nb; ++i)
+      for (int rb = 0; rb < 3; ++rb) {
+        View& cur = D[rb]; View& nxt = D[(rb + 1) % 3];
+        const ConvW* cw = &e->body[(size_t)(i * 3 + rb) * 5];
+        for (int c = 0; c < 4; ++c)
+          K_(conv2d(cw[c], cur.slice(0, nf + c * gc), cur.slice(nf + c * gc, gc), lrelu, IN_DIRECT, s));
+        ConvEpi ep;
+        View x_rdb = cur.slice(0, nf), x_rrdb = D[0].slice(0, nf);
+        if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &x_rdb; ep.beta1 = 1.f; }
+        else { ep.alpha = 0.04f; ep.res1 = &x_rdb; ep.beta1 = 0.2f; ep.res2 = &x_rrdb; ep.beta2 = 1.f; }
+        K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), nxt.slice(0, nf), ep, IN_DIRECT, s));
+      }
+    ConvEpi ep; ep.res1 = &first; ep.beta1 = 1.f;                 // fea = conv_first(x) + trunk (rrdb.py:106-108)
+    K_(conv2d(e->body.back(), D[0].slice(0, nf), feat, ep, IN_DIRECT, s));
+  }
+  A.off = mark;
+  return feat;
+}
+
+// coef/freq -> local Fourier features -> MLP -> affine_info NHWC (B,qh,qw,2*D*L)
+static View run_affine_info(bfsr_linf* e, Arena& A, const View& feat, const float* coord, const float* cell, int qh, int qw,
+                            cudaStream_t s) {
+  const int B = feat.N, hid = e->d.hidden;
+  View aff = make_view(A, B, qh, qw, e->mlp[3].cout);
+  const size_t mark = A.off;
+  View cfm = make_view(A, B, feat.H, feat.W, 2 * hid);
+  K_(conv2d(e->cf, feat, cfm, ConvEpi(), IN_DIRECT, s));
+  View f = make_view(A, B, qh, qw, 4 * hid);
+  K_(linf_features(cfm, coord, cell, e->phase, f, qh, qw, s));
+  ConvEpi relu; relu.act = ACT_RELU;
+  View a1 = make_view(A, B, qh, qw, hid), a2 = make_view(A, B, qh, qw, hid);
+  K_(conv2d(e->mlp[0], f, a1, relu, IN_DIRECT, s));
+  K_(conv2d(e->mlp[1], a1, a2, relu, IN_DIRECT, s));
+  K_(conv2d(e->mlp[2], a2, a1, relu, IN_DIRECT, s));
+  K_(conv2d(e->mlp[3], a1, aff, ConvEpi(), IN_DIRECT, s));
+  A.off = mark;
+  return aff;
+}
+
+static void ensure(Arena& A, cudaStream_t s) {
+  const size_t need = A.peak + (1 << 20);
+  if (need > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(need); }
+}
+
+void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* feat_out, cudaStream_t s) {
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  Arena& A = e->arena;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
+    View x = make_view(A, B, h, w, 3);
+    K_(nchw_to_nhwc(inp, x, s));
+    View feat = run_linf_encoder(e, A, x, s);
+    K_(nhwc_to_nchw(feat, feat_out, s));
+    if (pass == 0) { A.plan = false; ensure(A, s); }
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh,
+                int qw, int mode, const float* zin, float* out, cudaStream_t s) {
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  Arena& A = e->arena;
+  const int ps = e->d.patch_size;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
+    View feat = make_view(A, B, h, w, 64);
+    K_(nchw_to_nhwc(feat_nchw, feat, s));
+    View aff = run_affine_info(e, A, feat, coord, cell, qh, qw, s);
+    if (mode == 0) K_(linf_flow(false, e->Mf, e->fbias, e->d.flow_layers, aff, zin, B, qh, qw, out, 0, 0, nullptr, 0, 0, ps, s));
+    else K_(linf_flow(true, e->Mi, e->fbias, e->d.flow_layers, aff, zin, B, qh, qw, out, qh * ps, qw * ps, nullptr, 0, 0, ps, s));
+    if (pass == 0) { A.plan = false; ensure(A, s); }
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+// whole LP path for one chunk of images (all pointers already offset to the chunk)
+static void linf_lp_chunk(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, int w, const float* coord,
+                          const float* cell, const float* gt, int qh, int qw, int OH, int OW, float* pred, cudaStream_t s) {
+  Arena& A = e->arena;
+  A.reset();
+  const int ps = e->d.patch_size, D = 3 * ps * ps;
+  View x = make_view(A, B, h, w, 3);
+  K_(nchw_to_nhwc(inp, x, s));
+  View feat = run_linf_encoder(e, A, x, s);
+  View aff = run_affine_info(e, A, feat, coord, cell, qh, qw, s);
+  float* z_lr = (float*)A.alloc((size_t)B * D * qh * qw * 4);          // NCHW, as the reference hands it to the prior
+  K_(linf_flow(false, e->Mf, e->fbias, e->d.flow_layers, aff, gt, B, qh, qw, z_lr, 0, 0, nullptr, 0, 0, ps, s));
+  View zl = make_view(A, B, qh, qw, D);
+  K_(nchw_to_nhwc(z_lr, zl, s));
+  View learned = run_unet_linf(prior, A, zl, inp, h, w, s);
+  float* z_learned = (float*)A.alloc((size_t)B * D * qh * qw * 4);
+  K_(nhwc_to_nchw(learned, z_learned, s));
+  K_(linf_flow(true, e->Mi, e->fbias, e->d.flow_layers, aff, z_learned, B, qh, qw, pred, OH, OW, inp, h, w, ps, s));
+}
+
+void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, int w, const float* coord, const float* cell,
+                const float* gt, int qh, int qw, int OH, int OW, float* pred, cudaStream_t s) {
+  BFSR_CHECK(prior && prior->d.variant == 1, "linf lp_sr needs a LINF-LP prior handle");
+  BFSR_CHECK(prior->d.in_chans == 3 * e->d.patch_size * e->d.patch_size, "prior in_chans does not match the patch size");
+  BFSR_CHECK(OH <= qh * e->d.patch_size && OW <= qw * e->d.patch_size && OH > 0 && OW > 0, "output size exceeds the query grid");
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  const int chunk = e->d.tile_chunk > 0 ? e->d.tile_chunk : 64;
+  Arena& A = e->arena;
+  A.plan = true; A.peak = 0;
+  linf_lp_chunk(e, prior, nullptr, B < chunk ? B : chunk, h, w, nullptr, nullptr, nullptr, qh, qw, OH, OW, nullptr, s);
+  A.plan = false;
+  ensure(A, s);
+  const int D = 3 * e->d.patch_size * e->d.patch_size;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    linf_lp_chunk(e, prior, inp + (size_t)b0 * 3 * h * w, nb, h, w, coord + (size_t)b0 * qh * qw * 2, cell + (size_t)b0 * 2,
+                  gt + (size_t)b0 * D * qh * qw, qh, qw, OH, OW, pred + (size_t)b0 * 3 * OH * OW, s);
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace bfsr

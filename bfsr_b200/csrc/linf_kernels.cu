@@ -1,0 +1,258 @@
+// LINF-LP query-side kernels: local Fourier features, the 27-dim conditional flow (both directions, fold + residual
+// fused into the inverse), the stride-3 LR embedding conv and a general bilinear resize.
+//
+// Reference: LINF-LP/models/linf.py:248-407 (~60 ATen kernels per query chunk, 4 grid_sample gathers, an LU solve per
+// flow layer per call, flow.py:110-122) — here W^-1 of every NaiveLinear is precomputed in fp64 at load time.
+#include "ops.cuh"
+
+namespace bfsr {
+
+// ------------------------------------------------------------------ local Fourier features (linf.py:251-309)
+struct FeatArgs {
+  View cf;              // (B,h,w,2*hid): [coef | freq]
+  const float* coord;   // (B,qh,qw,2) (row, col) in [-1,1]
+  const float* cell;    // (B,2)
+  const float* phase;   // (hid/2, 2)
+  View out;             // (B,qh,qw,4*hid)
+  int h, w, qh, qw, hid;
+  float shift_y[2], shift_x[2];   // fp32(v*r + 1e-6) for v = -1, +1
+  float lo, hi;                   // clamp bounds fp32(-1+1e-6), fp32(1-1e-6)
+  float two_ry, v0_ry, two_rx, v0_rx;   // make_coord: c_k = fp32(2r)*k + fp32(-1+r)   (utils.py:105-120)
+};
+
+// grid_sample(mode='nearest', align_corners=False) source index: clamp(rne(((c+1)*n-1)/2), 0, n-1)
+__device__ __forceinline__ int nearest_index(float c, int n) {
+  const float x = __fdiv_rn(__fadd_rn(__fmul_rn(__fadd_rn(c, 1.f), (float)n), -1.f), 2.f);
+  int i = (int)nearbyintf(x);
+  return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+}
+
+__global__ void __launch_bounds__(128) linf_features_kernel(FeatArgs a) {
+  const long long q = blockIdx.x;
+  const int half = a.hid / 2;                      // 128
+  const int qx = (int)(q % a.qw); const long long t = q / a.qw; const int qy = (int)(t % a.qh); const int b = (int)(t / a.qh);
+  const float cy = a.coord[q * 2 + 0], cx = a.coord[q * 2 + 1];
+  const float cell_y = __fmul_rn(a.cell[b * 2 + 0], (float)a.h), cell_x = __fmul_rn(a.cell[b * 2 + 1], (float)a.w);
+  float rel_y[4], rel_x[4], area[4]; long long src[4];
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) {
+    const int vx = nb >> 1, vy = nb & 1;           // vx outer (dim 0 = rows), vy inner (linf.py:271-272)
+    float sy = __fadd_rn(cy, a.shift_y[vx]), sx = __fadd_rn(cx, a.shift_x[vy]);
+    sy = fminf(fmaxf(sy, a.lo), a.hi); sx = fminf(fmaxf(sx, a.lo), a.hi);
+    const int iy = nearest_index(sy, a.h), ix = nearest_index(sx, a.w);
+    const float qcy = __fadd_rn(__fmul_rn(a.two_ry, (float)iy), a.v0_ry), qcx = __fadd_rn(__fmul_rn(a.two_rx, (float)ix), a.v0_rx);
+    rel_y[nb] = __fmul_rn(__fadd_rn(cy, -qcy), (float)a.h);
+    rel_x[nb] = __fmul_rn(__fadd_rn(cx, -qcx), (float)a.w);
+    area[nb] = __fadd_rn(fabsf(__fmul_rn(rel_y[nb], rel_x[nb])), 1e-9f);
+    src[nb] = ((long long)b * a.h + iy) * a.w + ix;
+  }
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+  (void)qy; (void)qx;
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const float ph = fmaf(cell_x, a.phase[k * 2 + 1], __fmul_rn(cell_y, a.phase[k * 2 + 0]));
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const float wgt = __fdiv_rn(area[3 - nb], tot);          // diagonal swap (linf.py:305-306)
+      const float fy = ld(a.cf, src[nb], a.hid + k), fx = ld(a.cf, src[nb], a.hid + half + k);
+      const float f = __fadd_rn(__fadd_rn(__fmul_rn(fy, rel_y[nb]), __fmul_rn(fx, rel_x[nb])), ph);
+      const float ang = __fmul_rn(3.14159265358979323846f, f);
+      float sn, cs;
+      sincosf(ang, &sn, &cs);
+      const float c0 = ld(a.cf, src[nb], k), c1 = ld(a.cf, src[nb], half + k);
+      st(a.out, q, nb * a.hid + k, __fmul_rn(__fmul_rn(wgt, c0), cs));
+      st(a.out, q, nb * a.hid + half + k, __fmul_rn(__fmul_rn(wgt, c1), sn));
+    }
+  }
+}
+
+void linf_features(const View& cf, const float* coord, const float* cell, const float* phase, const View& out, int qh, int qw,
+                   cudaStream_t s) {
+  FeatArgs a;
+  a.cf = cf; a.coord = coord; a.cell = cell; a.phase = phase; a.out = out;
+  a.h = cf.H; a.w = cf.W; a.qh = qh; a.qw = qw; a.hid = cf.C / 2;
+  BFSR_CHECK(out.C == 4 * a.hid && out.N == cf.N && out.H == qh && out.W == qw, "linf_features: output shape");
+  const double ry = 2.0 / a.h / 2.0, rx = 2.0 / a.w / 2.0;
+  for (int v = 0; v < 2; ++v) { a.shift_y[v] = (float)((v ? 1 : -1) * ry + 1e-6); a.shift_x[v] = (float)((v ? 1 : -1) * rx + 1e-6); }
+  a.lo = (float)(-1 + 1e-6); a.hi = (float)(1 - 1e-6);
+  a.two_ry = (float)(2 * (1.0 / a.h)); a.v0_ry = (float)(-1 + 1.0 / a.h);
+  a.two_rx = (float)(2 * (1.0 / a.w)); a.v0_rx = (float)(-1 + 1.0 / a.w);
+  const long long nq = (long long)cf.N * qh * qw;
+  if (!nq) return;
+  linf_features_kernel<<<(unsigned)nq, 128, 0, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ conditional flow on D-vectors (flow.py:29-63)
+constexpr int FD = 27;
+struct FlowArgs {
+  const float* M;      // [n_layers+1][D][D]: forward W_i, inverse W_i^-1 ; index n_layers = `last`
+  const float* bias;   // [n_layers+1][D]
+  View aff;            // (B,qh,qw, 2*D*n_layers)
+  const float* zin;    // NCHW (B,D,qh,qw)
+  float* out;          // forward: NCHW (B,D,qh,qw); inverse: NCHW (B,3,OH,OW)
+  const float* inp;    // inverse + residual: NCHW (B,3,h,w) LR input (added through bilinear resize), or null
+  int n_layers, qh, qw, OH, OW, h, w, ps;
+  long long nq;
+};
+
+template <bool INV>
+__global__ void __launch_bounds__(128) linf_flow_kernel(FlowArgs a) {
+  extern __shared__ float sm[];
+  const int nm = (a.n_layers + 1) * FD * FD;
+  float* Ms = sm; float* bs = sm + nm;
+  for (int e = threadIdx.x; e < nm; e += blockDim.x) Ms[e] = a.M[e];
+  for (int e = threadIdx.x; e < (a.n_layers + 1) * FD; e += blockDim.x) bs[e] = a.bias[e];
+  __syncthreads();
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.nq) return;
+  const int qx = (int)(q % a.qw); const long long t = q / a.qw; const int qy = (int)(t % a.qh); const long long b = t / a.qh;
+  const long long plane = (long long)a.qh * a.qw;
+  float x[FD], y[FD];
+#pragma unroll
+  for (int c = 0; c < FD; ++c) x[c] = a.zin[(b * FD + c) * plane + (long long)qy * a.qw + qx];
+  const float* af = (const float*)a.aff.p + q * a.aff.cs + a.aff.coff;
+  if (!INV) {
+    for (int i = 0; i < a.n_layers; ++i) {
+      const float* W = Ms + i * FD * FD;
+#pragma unroll
+      for (int o = 0; o < FD; ++o) {
+        float acc = bs[i * FD + o];
+#pragma unroll
+        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        y[o] = acc;
+      }
+#pragma unroll
+      for (int c = 0; c < FD; ++c) {
+        const float scale = 1.f / (1.f + expf(-(af[i * 2 * FD + c] + 2.f))) + 1e-4f;
+        x[c] = fmaf(y[c], scale, af[i * 2 * FD + FD + c]);
+      }
+    }
+    const float* W = Ms + a.n_layers * FD * FD;
+#pragma unroll
+    for (int o = 0; o < FD; ++o) {
+      float acc = bs[a.n_layers * FD + o];
+#pragma unroll
+      for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+      a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = acc;
+    }
+  } else {
+    {   // last^-1
+      const float* W = Ms + a.n_layers * FD * FD;
+#pragma unroll
+      for (int c = 0; c < FD; ++c) x[c] -= bs[a.n_layers * FD + c];
+#pragma unroll
+      for (int o = 0; o < FD; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        y[o] = acc;
+      }
+    }
+    for (int i = a.n_layers - 1; i >= 0; --i) {
+      const float* W = Ms + i * FD * FD;
+#pragma unroll
+      for (int c = 0; c < FD; ++c) {
+        const float scale = 1.f / (1.f + expf(-(af[i * 2 * FD + c] + 2.f))) + 1e-4f;
+        x[c] = (y[c] - af[i * 2 * FD + FD + c]) / scale - bs[i * FD + c];
+      }
+#pragma unroll
+      for (int o = 0; o < FD; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        y[o] = acc;
+      }
+    }
+    // fold 3x3 patches (== pixel_shuffle(3), linf.py:401-406), crop to (OH,OW), add bilinear(inp) (test.py:168-171)
+    const int ps = a.ps;
+    for (int c = 0; c < 3; ++c)
+      for (int ky = 0; ky < ps; ++ky)
+        for (int kx = 0; kx < ps; ++kx) {
+          const int oy = qy * ps + ky, ox = qx * ps + kx;
+          if (oy >= a.OH || ox >= a.OW) continue;
+          float v = y[c * ps * ps + ky * ps + kx];
+          if (a.inp) {
+            const float sh = (float)a.h / (float)a.OH, sw = (float)a.w / (float)a.OW;
+            float fy = sh * (oy + 0.5f) - 0.5f, fx = sw * (ox + 0.5f) - 0.5f;
+            fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = y0 + (y0 < a.h - 1 ? 1 : 0), x1 = x0 + (x0 < a.w - 1 ? 1 : 0);
+            const float ly = fy - y0, lx = fx - x0;
+            const float* sp = a.inp + (b * 3 + c) * (long long)a.h * a.w;
+            v += (1.f - ly) * ((1.f - lx) * sp[y0 * a.w + x0] + lx * sp[y0 * a.w + x1]) +
+                 ly * ((1.f - lx) * sp[y1 * a.w + x0] + lx * sp[y1 * a.w + x1]);
+          }
+          a.out[((b * 3 + c) * a.OH + oy) * (long long)a.OW + ox] = v;
+        }
+  }
+}
+
+void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, const View& aff, const float* zin, int B,
+               int qh, int qw, float* out, int OH, int OW, const float* inp, int h, int w, int ps, cudaStream_t s) {
+  BFSR_CHECK(3 * ps * ps == FD, "linf_flow: only patch_size 3 (D = 27) is built");
+  BFSR_CHECK(aff.fmt == F32 && aff.C == 2 * FD * n_layers, "linf_flow: affine_info shape");
+  FlowArgs a;
+  a.M = M; a.bias = bias; a.aff = aff; a.zin = zin; a.out = out; a.inp = inp;
+  a.n_layers = n_layers; a.qh = qh; a.qw = qw; a.OH = OH; a.OW = OW; a.h = h; a.w = w; a.ps = ps;
+  a.nq = (long long)B * qh * qw;
+  if (!a.nq) return;
+  const size_t smem = (size_t)(n_layers + 1) * (FD * FD + FD) * 4;
+  const int grid = cdiv(a.nq, 128);
+  if (inverse) linf_flow_kernel<true><<<grid, 128, smem, s>>>(a);
+  else linf_flow_kernel<false><<<grid, 128, smem, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ stride-3 3x3 conv, pad 1 (unet.py lr_proj.0) + LeakyReLU
+__global__ void conv3x3_s3_kernel(const float* x, int B, int Cin, int h, int w, const float* wgt, const float* bias, View out,
+                                  long long n) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int co = (int)(e % out.C); const long long pix = e / out.C;
+  const int ox = (int)(pix % out.W); const long long t = pix / out.W; const int oy = (int)(t % out.H); const long long b = t / out.H;
+  float acc = bias[co];
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = oy * 3 - 1 + ky, ix = ox * 3 - 1 + kx;
+        if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+        acc = fmaf(x[((b * Cin + ci) * h + iy) * (long long)w + ix], wgt[((co * Cin + ci) * 3 + ky) * 3 + kx], acc);
+      }
+  st(out, pix, co, acc > 0.f ? acc : 0.2f * acc);
+}
+void conv3x3_s3_lrelu(const float* x_nchw, int B, int Cin, int h, int w, const float* w_oihw_dev, const float* bias_dev,
+                      const View& out, cudaStream_t s) {
+  BFSR_CHECK(out.H == (h + 2 - 3) / 3 + 1 && out.W == (w + 2 - 3) / 3 + 1 && out.N == B, "conv3x3_s3: output shape");
+  const long long n = out.npix() * out.C;
+  if (!n) return;
+  conv3x3_s3_kernel<<<cdiv(n, 128), 128, 0, s>>>(x_nchw, B, Cin, h, w, w_oihw_dev, bias_dev, out, n);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ F.interpolate(size=..., bilinear, align_corners=False) NHWC
+__global__ void bilinear_resize_kernel(View src, View dst, long long n) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int C = dst.C;
+  const long long pix = e / C; const int c = (int)(e % C);
+  const int x = (int)(pix % dst.W); const long long t = pix / dst.W; const int y = (int)(t % dst.H); const long long b = t / dst.H;
+  const float sh = (float)src.H / (float)dst.H, sw = (float)src.W / (float)dst.W;
+  float fy = sh * (y + 0.5f) - 0.5f, fx = sw * (x + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < src.H - 1 ? 1 : 0), x1 = x0 + (x0 < src.W - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const long long sb = b * src.H * src.W;
+  const float a00 = ld(src, sb + (long long)y0 * src.W + x0, c), a01 = ld(src, sb + (long long)y0 * src.W + x1, c);
+  const float a10 = ld(src, sb + (long long)y1 * src.W + x0, c), a11 = ld(src, sb + (long long)y1 * src.W + x1, c);
+  st(dst, pix, c, (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11));
+}
+void bilinear_resize(const View& src, const View& dst, cudaStream_t s) {
+  BFSR_CHECK(src.C == dst.C && src.N == dst.N, "bilinear_resize: channel/batch mismatch");
+  const long long n = dst.npix() * dst.C;
+  if (!n) return;
+  bilinear_resize_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n);
+  count_launch();
+}
+
+}  // namespace bfsr

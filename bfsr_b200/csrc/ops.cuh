@@ -79,4 +79,16 @@ void normalise_latent(const View& e, const View& out, cudaStream_t s);
 void squeeze_copy(const View& src, const View& dst, cudaStream_t s);
 void unsqueeze_copy(const View& src, const View& dst, cudaStream_t s);
 
+// ------------------------------------------------------------------ LINF query side (linf_kernels.cu)
+// local Fourier features of every query: cf = [coef | freq] maps (B,h,w,2*hid) -> out (B,qh,qw,4*hid)   (linf.py:251-309)
+void linf_features(const View& cf, const float* coord, const float* cell, const float* phase, const View& out, int qh, int qw,
+                   cudaStream_t s);
+// 27-dim conditional flow; forward: zin (B,27,qh,qw) NCHW -> out same shape; inverse: -> out (B,3,OH,OW) NCHW with the
+// 3x3 fold, crop to (OH,OW) and optional `+ bilinear(inp)` fused   (flow.py:44-63, linf.py:401-406, test.py:168-171)
+void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, const View& aff, const float* zin, int B,
+               int qh, int qw, float* out, int OH, int OW, const float* inp, int h, int w, int ps, cudaStream_t s);
+void conv3x3_s3_lrelu(const float* x_nchw, int B, int Cin, int h, int w, const float* w_oihw_dev, const float* bias_dev,
+                      const View& out, cudaStream_t s);
+void bilinear_resize(const View& src, const View& dst, cudaStream_t s);
+
 }  // namespace bfsr

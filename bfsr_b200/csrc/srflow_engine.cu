@@ -38,7 +38,7 @@ bfsr_srflow::~bfsr_srflow() {
 
 namespace bfsr {
 
-static float* to_device(const std::vector<float>& v) {
+float* to_device(const std::vector<float>& v) {
   float* d = nullptr;
   CUDA_OK(cudaMalloc((void**)&d, v.size() * 4));
   CUDA_OK(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
@@ -46,7 +46,7 @@ static float* to_device(const std::vector<float>& v) {
 }
 
 // fp64 Gauss-Jordan inverse with partial pivoting (stands in for torch.inverse(W.double()), Permutations.py:41)
-static std::vector<double> invert(const float* W, int n) {
+std::vector<double> invert_f64(const float* W, int n) {
   std::vector<double> a((size_t)n * 2 * n, 0.0);
   for (int i = 0; i < n; ++i) { for (int j = 0; j < n; ++j) a[(size_t)i * 2 * n + j] = W[i * n + j]; a[(size_t)i * 2 * n + n + i] = 1.0; }
   for (int c = 0; c < n; ++c) {
@@ -81,7 +81,7 @@ static StepW pack_step(const Weights& W, const std::string& p, int C, bool coupl
     }
     cf[o] = (float)acc;
   }
-  std::vector<double> inv = invert(w, C);
+  std::vector<double> inv = invert_f64(w, C);
   for (int o = 0; o < C; ++o) {
     const double e = std::exp(-(double)l[o]);
     for (int i = 0; i < C; ++i) Mi[(size_t)o * C + i] = (float)(inv[(size_t)o * C + i] * e);

@@ -12,6 +12,9 @@ using namespace bfsr;
 bfsr_unet::~bfsr_unet() {
   for (auto& b : br) {
     for (auto& c : b.dense) free_conv(c);
+    for (auto& c : b.lr_dense) free_conv(c);
+    if (b.lr_w) cudaFree(b.lr_w);
+    if (b.lr_b) cudaFree(b.lr_b);
     for (auto& c : b.inc) free_conv(c);
     for (auto& c : b.down) free_conv(c);
     for (auto& c : b.up) free_conv(c);
@@ -59,9 +62,32 @@ void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n) {
   Weights W(weights, n);
   const auto& d = u->d;
   BFSR_CHECK(d.bilinear == 1, "UNet: only bilinear=True is supported (the shipped priors, SURVEY.md §5)");
-  BFSR_CHECK(d.variant == 0, "UNet variant %d not built yet", d.variant);
-  BFSR_CHECK(d.n_latents >= 1 && d.n_latents <= 4, "UNet: bad latent count");
   const int dim = d.dim, depth = d.depth;
+  if (d.variant == 1) {   // LINF-LP UNet (LINF-LP/models/unet.py:105-142)
+    UNetBranchW B; B.nf = d.in_chans; B.gc = dim / 2;
+    pack_dense5(W, "input_proj", B.nf, dim / 2, dim / 2, B.dense, &B.nf_pad);
+    int pad2 = 0;
+    pack_dense5(W, "lr_proj.2", B.nf, dim / 2, dim / 2, B.lr_dense, &pad2);
+    const float* lw = W.data("lr_proj.0.weight", {B.nf, 3, 3, 3});
+    const float* lb = W.data("lr_proj.0.bias", {B.nf});
+    B.lr_w = to_device(std::vector<float>(lw, lw + (size_t)B.nf * 27));
+    B.lr_b = to_device(std::vector<float>(lb, lb + B.nf));
+    pack_double_conv(W, "inc", dim, dim, dim, B.inc);
+    B.down.resize(2 * depth); B.up.resize(2 * depth);
+    for (int i = 0; i < depth; ++i) {
+      const int cin = dim << i, cout = (dim << (i + 1)) / (i == depth - 1 ? 2 : 1);
+      pack_double_conv(W, "down_layers." + std::to_string(i) + ".maxpool_conv.1", cin, cout, cout, &B.down[2 * i]);
+    }
+    for (int i = 0; i < depth; ++i) {
+      const int cin = dim << (depth - i), cout = (dim << (depth - i - 1)) / (i < depth - 1 ? 2 : 1);
+      pack_double_conv(W, "up_layers." + std::to_string(i) + ".conv", cin, cin / 2, cout, &B.up[2 * i]);
+    }
+    B.outc = pack_conv(W.data("outc.conv.weight", {B.nf, dim, 1, 1}), B.nf, dim, 1, W.data("outc.conv.bias", {B.nf}), nullptr, {});
+    u->br.push_back(B);
+    return;
+  }
+  BFSR_CHECK(d.variant == 0, "UNet variant %d unknown", d.variant);
+  BFSR_CHECK(d.n_latents >= 1 && d.n_latents <= 4, "UNet: bad latent count");
   for (int b = 0; b < d.n_latents; ++b) {
     UNetBranchW B; B.nf = d.latent_ch[b]; B.gc = dim;
     const std::string sb = std::to_string(b);
@@ -137,6 +163,24 @@ View run_dense5(const ConvW* dense, int nf, int nf_pad, int gc, Arena& A, const 
   K_(conv2d(dense[4], D, o, ConvEpi(), IN_DIRECT, s));
   (void)nf;
   return o;
+}
+
+// LINF-LP UNet.forward(x, lr) (LINF-LP/models/unet.py:144-167): x NHWC (B,qh,qw,in_chans), lr NCHW device (B,3,h,w)
+View run_unet_linf(bfsr_unet* u, Arena& A, const View& x, const float* lr_nchw, int h, int w, cudaStream_t s) {
+  BFSR_CHECK(u->d.variant == 1, "not a LINF-LP prior");
+  const UNetBranchW& B = u->br[0];
+  BFSR_CHECK(x.C == B.nf, "prior: latent has %d channels, expected %d", x.C, B.nf);
+  const int dim = u->d.dim, half = dim / 2;
+  View cat = make_view(A, x.N, x.H, x.W, dim);
+  View xa = run_dense5(B.dense, B.nf, B.nf_pad, B.gc, A, x, s);
+  K_(resample(xa, cat.slice(0, half), RS_COPY, s));
+  const int eh = (h + 2 - 3) / 3 + 1, ew = (w + 2 - 3) / 3 + 1;
+  View e0 = make_view(A, x.N, eh, ew, B.nf);
+  K_(conv3x3_s3_lrelu(lr_nchw, x.N, 3, h, w, B.lr_w, B.lr_b, e0, s));
+  View e1 = run_dense5(B.lr_dense, B.nf, B.nf_pad, B.gc, A, e0, s);
+  if (eh == x.H && ew == x.W) K_(resample(e1, cat.slice(half, half), RS_COPY, s));
+  else K_(bilinear_resize(e1, cat.slice(half, half), s));
+  return run_unet_body(B, u->d.depth, dim, A, cat, s);
 }
 
 std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s) {

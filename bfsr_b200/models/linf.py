@@ -1,0 +1,277 @@
+"""LINF engine ('linf-patch') and LINF-LP prior on the B200 engine.
+
+Mirrors LINF-LP/models/linf.py:218-428: `model(op, inp=, feat=, coord=, cell=, gt=, temperature=, zmap=)` with
+`op in {"gen_feat", "query_log_p", "query_rgb", "log_p", "rgb"}`, attribute `patch_size`, and the state_dict keys of the
+shipped `edsr-baseline-linf.pth` / `rrdb-linf.pth`, so `models.make(torch.load(path)['model'], load_sd=True)` works
+unchanged (LINF-LP/test.py:276-281).  `batched_predict` / `batched_predict_log_p` restate LINF-LP/test.py:20-47 on top of
+that surface; `lp_sr` is the fused path of test.py:143-171.  All arithmetic runs in libbfsr_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from .. import _lib, param_tree
+from .models import register
+from .unet import _PriorBase, _body_shapes, _dconv_shapes, _dense_shapes
+
+
+def _encoder_shapes(s, name, args):
+    if name == "edsr-baseline":
+        if not args.get("no_upsampling", True):
+            raise NotImplementedError("edsr-baseline with upsampling tail (LINF uses no_upsampling=True)")
+        nb = args.get("n_resblocks", 16)
+        for n in ("sub_mean", "add_mean"):      # present in the checkpoint, unused by forward (edsr.py:134-146)
+            s[f"encoder.{n}.weight"] = (3, 3, 1, 1)
+            s[f"encoder.{n}.bias"] = (3,)
+        s["encoder.head.0.weight"] = (64, 3, 3, 3)
+        s["encoder.head.0.bias"] = (64,)
+        for i in range(nb):
+            for j in (0, 2):
+                s[f"encoder.body.{i}.body.{j}.weight"] = (64, 64, 3, 3)
+                s[f"encoder.body.{i}.body.{j}.bias"] = (64,)
+        s[f"encoder.body.{nb}.weight"] = (64, 64, 3, 3)
+        s[f"encoder.body.{nb}.bias"] = (64,)
+        return 0, nb
+    if name == "rrdb":
+        nb = args.get("nb", 23)
+        s["encoder.conv_first.weight"] = (64, 3, 3, 3)
+        s["encoder.conv_first.bias"] = (64,)
+        for i in range(nb):
+            for r in (1, 2, 3):
+                for c in range(1, 6):
+                    p = f"encoder.RRDB_trunk.{i}.RDB{r}.conv{c}"
+                    s[p + ".weight"] = (32 if c < 5 else 64, 64 + (c - 1) * 32, 3, 3)
+                    s[p + ".bias"] = (32 if c < 5 else 64,)
+        for n in ("trunk_conv", "upconv1", "upconv2", "HRconv"):
+            s[f"encoder.{n}.weight"] = (64, 64, 3, 3)
+            s[f"encoder.{n}.bias"] = (64,)
+        s["encoder.conv_last.weight"] = (3, 64, 3, 3)
+        s["encoder.conv_last.bias"] = (3,)
+        return 1, nb
+    raise NotImplementedError(f"LINF encoder {name!r}: only 'edsr-baseline' and 'rrdb' ship checkpoints (SURVEY.md §2.1)")
+
+
+@register('linf-patch')
+class LINFEngine(nn.Module):
+    """`LINFPatch(encoder_spec, imnet_spec, flow_layers=10, num_layer=3, hidden_dim=256, patch_size=3)`."""
+
+    def __init__(self, encoder_spec, imnet_spec=None, flow_layers=10, num_layer=3, hidden_dim=256, patch_size=3,
+                 device=None, precision=0, tile_chunk=0):
+        super().__init__()
+        if num_layer != 3:
+            raise NotImplementedError("num_layer != 3 (shipped checkpoints use 3)")
+        if patch_size != 3:
+            raise NotImplementedError("patch_size != 3 (shipped checkpoints use 3)")
+        self.patch_size, self.flow_layers, self.hidden_dim = patch_size, flow_layers, hidden_dim
+        self.precision, self.tile_chunk = int(precision), int(tile_chunk)
+        D = 3 * patch_size * patch_size
+        s = OrderedDict()
+        self._enc_kind, self._nb = _encoder_shapes(s, encoder_spec["name"], dict(encoder_spec.get("args") or {}))
+        for n in ("coef", "freq"):
+            s[f"{n}.weight"] = (hidden_dim, 64, 3, 3)
+            s[f"{n}.bias"] = (hidden_dim,)
+        s["phase.weight"] = (hidden_dim // 2, 2)
+        dims = [hidden_dim * 4, hidden_dim, hidden_dim, hidden_dim, flow_layers * D * 2]
+        for i in range(4):
+            s[f"layers.{2 * i}.weight"] = (dims[i + 1], dims[i], 1, 1)
+            s[f"layers.{2 * i}.bias"] = (dims[i + 1],)
+        for i in range(flow_layers):
+            s[f"imnet.linears.{i}.bias"] = (D,)
+            s[f"imnet.linears.{i}._weight"] = (D, D)
+        s["imnet.last.bias"] = (D,)
+        s["imnet.last._weight"] = (D, D)
+        param_tree.build(self, s)
+        self._device = torch.device(device) if device is not None else None
+        self._handle = None
+
+    # ---- plumbing ----------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._destroy()
+        return r
+
+    def cuda(self, device=None):
+        """`.cuda()` (LINF-LP/test.py:278): weights are packed on the device lazily; parameters stay on the host."""
+        if device is not None:
+            self._device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        return self
+
+    def device(self):
+        if self._device is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return self._device
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.lib().bfsr_linf_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def handle(self):
+        if self._handle is None:
+            if not torch.cuda.is_available():
+                raise _lib.BfsrError("bfsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            d = _lib.LINFDesc()
+            d.encoder, d.nb, d.hidden, d.flow_layers = self._enc_kind, self._nb, self.hidden_dim, self.flow_layers
+            d.patch_size, d.tile_chunk, d.precision = self.patch_size, self.tile_chunk, self.precision
+            table, keep = _lib.tensor_table(self.state_dict())
+            h = C.c_void_p()
+            _lib.check(_lib.lib().bfsr_linf_create(C.byref(h), C.byref(d), table, len(table), self.device().index or 0))
+            del keep
+            self._handle = h
+        return self._handle
+
+    def _prep(self, t):
+        return t.detach().to(self.device(), torch.float32).contiguous()
+
+    # ---- LINFPatch operators (linf.py:244-428) --------------------------------------------
+    def gen_feat(self, inp):
+        x = self._prep(inp)
+        B, _, h, w = x.shape
+        feat = torch.empty((B, 64, h, w), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().bfsr_linf_gen_feat(self.handle(), x.data_ptr(), B, h, w, feat.data_ptr(),
+                                                     _lib.stream_ptr(x.device)))
+        return feat
+
+    def _query(self, feat, coord, cell, zin, mode):
+        feat, coord, cell, zin = self._prep(feat), self._prep(coord), self._prep(cell), self._prep(zin)
+        B, _, h, w = feat.shape
+        _, qh, qw, _ = coord.shape
+        D = 3 * self.patch_size ** 2
+        assert tuple(zin.shape) == (B, D, qh, qw), (tuple(zin.shape), (B, D, qh, qw))
+        shape = (B, D, qh, qw) if mode == 0 else (B, 3, qh * self.patch_size, qw * self.patch_size)
+        out = torch.empty(shape, device=feat.device, dtype=torch.float32)
+        with torch.cuda.device(feat.device):
+            _lib.check(_lib.lib().bfsr_linf_query(self.handle(), feat.data_ptr(), B, h, w, coord.data_ptr(), cell.data_ptr(),
+                                                  qh, qw, mode, zin.data_ptr(), out.data_ptr(), _lib.stream_ptr(feat.device)))
+        return out
+
+    def query_log_p(self, inp, feat, coord, cell, gt):
+        """-> (log_p, z); log_p is dead on the inference path (test.py:43 discards it) and returned as NaN."""
+        z = self._query(feat, coord, cell, gt, 0)
+        return torch.full((z.shape[0] * z.shape[2] * z.shape[3],), float("nan"), device=z.device), z
+
+    def query_rgb(self, inp, feat, coord, cell, temperature=0, zmap=None):
+        if zmap is None:   # sampling mode (linf.py:398): z ~ N(0, temperature^2)
+            B, qh, qw, _ = coord.shape
+            zmap = torch.randn((B, 3 * self.patch_size ** 2, qh, qw), device=self.device()) * temperature
+        return self._query(feat, coord, cell, zmap, 1)
+
+    def log_p(self, inp, coord, cell, gt):
+        return self.query_log_p(inp, self.gen_feat(inp), coord, cell, gt)
+
+    def rgb(self, inp, coord, cell, temperature=0, zmap=None):
+        return self.query_rgb(inp, self.gen_feat(inp), coord, cell, temperature, zmap)
+
+    def forward(self, op, inp=None, feat=None, coord=None, cell=None, gt=None, temperature=0, zmap=None):
+        if op == "query_log_p":
+            return self.query_log_p(inp, feat, coord, cell, gt)
+        if op == "query_rgb":
+            return self.query_rgb(inp, feat, coord, cell, temperature, zmap)
+        if op == "log_p":
+            return self.log_p(inp, coord, cell, gt)
+        if op == "rgb":
+            return self.rgb(inp, coord, cell, temperature, zmap)
+        if op == "gen_feat":
+            return self.gen_feat(inp)
+        raise ValueError(f"unknown op {op!r}")
+
+    # ---- fused LP path (test.py:143-171) -------------------------------------------------
+    def lp_sr(self, inp, coord, cell, gt_lr_up, prior, out_hw):
+        inp, coord, cell, gt = self._prep(inp), self._prep(coord), self._prep(cell), self._prep(gt_lr_up)
+        B, _, h, w = inp.shape
+        _, qh, qw, _ = coord.shape
+        pred = torch.empty((B, 3, out_hw[0], out_hw[1]), device=inp.device, dtype=torch.float32)
+        with torch.cuda.device(inp.device):
+            _lib.check(_lib.lib().bfsr_linf_lp_sr(self.handle(), prior.handle(self.device()), inp.data_ptr(), B, h, w,
+                                                  coord.data_ptr(), cell.data_ptr(), gt.data_ptr(), qh, qw, out_hw[0], out_hw[1],
+                                                  pred.data_ptr(), _lib.stream_ptr(inp.device)))
+        return pred
+
+    def lp_sr_host(self, inp, coord, cell, gt_lr_up, prior, out_hw, out=None):
+        for t in (inp, coord, cell, gt_lr_up):
+            assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        B, _, h, w = inp.shape
+        _, qh, qw, _ = coord.shape
+        if out is None:
+            out = torch.empty((B, 3, out_hw[0], out_hw[1]), dtype=torch.float32, pin_memory=True)
+        dev = self.device()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().bfsr_linf_lp_sr_host(self.handle(), prior.handle(dev), inp.data_ptr(), B, h, w, coord.data_ptr(),
+                                                       cell.data_ptr(), gt_lr_up.data_ptr(), qh, qw, out_hw[0], out_hw[1],
+                                                       out.data_ptr(), _lib.stream_ptr(dev)))
+        return out
+
+
+class LINFPriorEngine(_PriorBase):
+    """LINF-LP UNet(in_chans, depth, dim, bilinear) — LINF-LP/models/unet.py:105-172."""
+
+    def __init__(self, in_chans=27, depth=3, dim=64, bilinear=True, cell_input=False):
+        super().__init__()
+        assert bilinear, "only bilinear=True priors are shipped/supported"
+        self.in_chans, self.depth, self.dim, self.bilinear = in_chans, depth, dim, bilinear
+        s, bufs = OrderedDict(), []
+        _dense_shapes(s, "input_proj", in_chans, dim // 2, dim // 2)
+        s["lr_proj.0.weight"] = (in_chans, 3, 3, 3)
+        s["lr_proj.0.bias"] = (in_chans,)
+        _dense_shapes(s, "lr_proj.2", in_chans, dim // 2, dim // 2)
+        _body_shapes(s, bufs, depth, dim, "")
+        _dconv_shapes(s, bufs, "inc", dim, dim)
+        s["outc.conv.weight"] = (in_chans, dim, 1, 1)
+        s["outc.conv.bias"] = (in_chans,)
+        param_tree.build(self, s, bufs)
+
+    def _desc(self):
+        d = _lib.UNetDesc()
+        d.variant, d.depth, d.dim, d.bilinear, d.in_chans = 1, self.depth, self.dim, int(self.bilinear), self.in_chans
+        return d
+
+    def forward(self, x, lr):
+        """prior_model(z_lr, inp) (LINF-LP/test.py:147)."""
+        dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = x.detach().to(dev, torch.float32).contiguous()
+        lr = lr.detach().to(dev, torch.float32).contiguous()
+        B, Cc, qh, qw = x.shape
+        assert Cc == self.in_chans and lr.shape[0] == B and lr.shape[1] == 3
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().bfsr_unet_forward_linf(self.handle(dev), x.data_ptr(), lr.data_ptr(), B, qh, qw,
+                                                         lr.shape[2], lr.shape[3], out.data_ptr(), _lib.stream_ptr(dev)))
+        return out
+
+
+# ---- LINF-LP/test.py:20-47 -------------------------------------------------------------------
+def batched_predict(model, inp, coord, cell, temperature, zmap=None):
+    with torch.no_grad():
+        feat = model("gen_feat", inp=inp)
+        _, h, w, _ = coord.shape
+        row, preds = 0, []
+        while row < h:
+            z = None if zmap is None else zmap[:, :, row:row + 256, :]
+            preds.append(model("query_rgb", inp=inp, feat=feat, coord=coord[:, row:row + 256, :, :], cell=cell,
+                               temperature=temperature, zmap=z))
+            row += 256
+        return torch.cat(preds, dim=2)
+
+
+def batched_predict_log_p(model, inp, coord, cell, gt):
+    with torch.no_grad():
+        feat = model("gen_feat", inp=inp)
+        _, h, w, _ = coord.shape
+        row, preds = 0, []
+        while row < h:
+            _, z = model("query_log_p", inp=inp, feat=feat, coord=coord[:, row:row + 256, :, :], cell=cell,
+                         gt=gt[:, :, row:row + 256, :])
+            preds.append(z)
+            row += 256
+        return torch.cat(preds, dim=2)

@@ -110,6 +110,45 @@ void bfsr_unet_destroy(bfsr_unet_t* h);
 int bfsr_unet_forward_srflow(bfsr_unet_t* h, const float* const* latents_dev, const int32_t* H, const int32_t* W,
                              int32_t B, float* const* out_dev, void* stream);
 
+/* variant 1: prior_model(z, inp) (LINF-LP/test.py:147): z (B,in_chans,qh,qw), inp (B,3,h,w) -> (B,in_chans,qh,qw) */
+int bfsr_unet_forward_linf(bfsr_unet_t* h, const float* z_dev, const float* inp_dev, int32_t B, int32_t qh, int32_t qw,
+                           int32_t lr_h, int32_t lr_w, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ LINF ('linf-patch', LINF-LP/models/linf.py:218-428)
+ * Stands behind model(op, ...) as called by batched_predict / batched_predict_log_p (LINF-LP/test.py:20-47). */
+typedef struct {
+  int32_t encoder;          /* 0 = 'edsr-baseline' (edsr.py), 1 = 'rrdb' (rrdb.py) */
+  int32_t nb;               /* rrdb: number of RRDB blocks (23) ; edsr-baseline: number of ResBlocks (16) */
+  int32_t hidden;           /* hidden_dim (256) */
+  int32_t flow_layers;      /* 10 */
+  int32_t patch_size;       /* 3 */
+  int32_t tile_chunk;       /* images per pass through the workspace (0 = default) */
+  int32_t precision;        /* as bfsr_srflow_desc_t.precision */
+} bfsr_linf_desc_t;
+typedef struct bfsr_linf bfsr_linf_t;
+
+int bfsr_linf_create(bfsr_linf_t** out, const bfsr_linf_desc_t* desc, const bfsr_tensor_t* weights, int32_t n_weights,
+                     int32_t device);
+void bfsr_linf_destroy(bfsr_linf_t* h);
+/* model("gen_feat", inp): inp (B,3,h,w) in [-1,1] -> feat (B,64,h,w)   (linf.py:244-246) */
+int bfsr_linf_gen_feat(bfsr_linf_t* h, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w, float* feat_dev,
+                       void* stream);
+/* model("query_log_p", feat, coord, cell, gt) -> z (B,27,qh,qw)  [mode 0]   (linf.py:248-322)
+ * model("query_rgb", feat, coord, cell, zmap) -> (B,3,3qh,3qw)   [mode 1]   (linf.py:324-407)
+ * coord: (B,qh,qw,2) (row,col) in [-1,1]; cell: (B,2); zin: gt or zmap (B,27,qh,qw). */
+int bfsr_linf_query(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr_h, int32_t lr_w, const float* coord_dev,
+                    const float* cell_dev, int32_t qh, int32_t qw, int32_t mode, const float* zin_dev, float* out_dev,
+                    void* stream);
+/* The whole LP path of LINF-LP/test.py:143-171 (--patch, eval_bsize set) in one call: encoder and per-query affine
+ * parameters computed once and shared by the log_p and rgb passes; returns pred cropped to (out_h,out_w) + bilinear(inp). */
+int bfsr_linf_lp_sr(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w,
+                    const float* coord_dev, const float* cell_dev, const float* gt_lr_up_dev, int32_t qh, int32_t qw,
+                    int32_t out_h, int32_t out_w, float* pred_dev, void* stream);
+/* Same with host buffers (H2D of inp/coord/cell/gt_lr_up, compute, D2H of pred, synchronises the stream). */
+int bfsr_linf_lp_sr_host(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_host, int32_t B, int32_t lr_h, int32_t lr_w,
+                         const float* coord_host, const float* cell_host, const float* gt_lr_up_host, int32_t qh,
+                         int32_t qw, int32_t out_h, int32_t out_w, float* pred_host, void* stream);
+
 /* ------------------------------------------------------------------ single operators (parity tests, P1 in SURVEY.md §8c)
  * fp32 NCHW in / out on the device; weights in the reference's per-module layout (host). */
 /* nn.Conv2d(ks in {1,3}, stride 1, 'same') + bias + activation (0 none, 1 LeakyReLU(0.2), 2 ReLU);

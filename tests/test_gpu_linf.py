@@ -1,0 +1,64 @@
+"""GPU parity tests of the LINF-LP path (C ABI -> sm_100a kernels) vs the golden fixtures recorded from the unmodified
+reference: real shipped checkpoints when exported next to the fixtures, synthetic weights always."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.test_oracle_linf import CASES, load_case
+from tests.util import max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _engines(enc, sd, psd, precision=0):
+    from bfsr_b200 import models
+    spec = {"name": "linf-patch", "args": {"encoder_spec": {"name": enc, "args": {"no_upsampling": True}},
+                                           "imnet_spec": {"name": "flow", "args": {"name": "flow"}}, "flow_layers": 10,
+                                           "num_layer": 3, "hidden_dim": 256, "patch_size": 3}, "sd": sd}
+    model = models.make(spec, args={"precision": precision}, load_sd=True).cuda()
+    prior = models.make({"name": "unet", "args": {"in_chans": 27, "depth": 3, "dim": 64, "cell_input": False, "bilinear": True},
+                         "sd": psd}, load_sd=True).cuda()
+    return model, prior
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_linf_lp_path_vs_reference(name):
+    """LINF-LP/test.py:143-171 through the reference-shaped surface (batched_predict*) and through the fused lp_sr call."""
+    from bfsr_b200 import models
+    g, enc, sd, psd, inp, coord, cell, gt, hw = load_case(name)
+    model, prior = _engines(enc, sd, psd)
+    assert model.patch_size == 3
+    z_lr = models.batched_predict_log_p(model, inp, coord, cell, gt)
+    assert rel_l2(g["z_lr"], z_lr) < 1e-4
+    z_learned = prior(torch.from_numpy(g["z_lr"]), inp)
+    assert rel_l2(g["z_learned"], z_learned) < 1e-4
+    pred = models.batched_predict(model, inp, coord, cell, 0, torch.from_numpy(g["z_learned"]))
+    pred = pred[..., :hw[0], :hw[1]].cpu()
+    pred = pred + F.interpolate(inp, pred.shape[-2:], mode="bilinear", align_corners=False)
+    assert rel_l2(g["pred"], pred) < 1e-4
+    assert max_abs(g["pred"], pred) < 1e-3
+    fused = model.lp_sr(inp, coord, cell, gt, prior, hw)
+    assert rel_l2(g["pred"], fused) < 1e-4 and max_abs(g["pred"], fused) < 1e-3
+    host = model.lp_sr_host(inp.contiguous(), coord.contiguous(), cell.contiguous(), gt.contiguous(), prior, hw)
+    assert torch.equal(host, fused.cpu())
+
+
+def test_linf_flow_invertibility_and_fold():
+    """P2: query_rgb(zmap = query_log_p(gt)) reproduces gt through the fold (pixel_shuffle(3)) index map."""
+    g, enc, sd, psd, inp, coord, cell, gt, hw = load_case("linf_edsr_synth_x4")
+    model, _ = _engines(enc, sd, psd)
+    feat = model("gen_feat", inp=inp)
+    _, z = model("query_log_p", inp=inp, feat=feat, coord=coord, cell=cell, gt=gt)
+    rgb = model("query_rgb", inp=inp, feat=feat, coord=coord, cell=cell, zmap=z)
+    assert max_abs(gt, F.pixel_unshuffle(rgb.cpu(), 3)) < 5e-5
+
+
+def test_linf_rejects_bad_prior():
+    from bfsr_b200 import BfsrError, models
+    g, enc, sd, psd, inp, coord, cell, gt, hw = load_case("linf_edsr_synth_x4")
+    model, prior = _engines(enc, sd, psd)
+    srflow_prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}})
+    with pytest.raises(BfsrError):
+        model.lp_sr(inp, coord, cell, gt, srflow_prior, hw)
