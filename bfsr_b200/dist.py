@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: the hot path shards by independent LR tiles, one process per GPU, no data-path collective.
+
+The reference's only parallelism is `nn.DataParallel` (SRFlow_model.py:53), which re-broadcasts the weights on every
+forward; here every rank holds its own packed weights and processes a contiguous slice of the batch.  The optional final
+gather of the SR tiles is the single collective (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous, balanced slice [lo, hi) of n independent tiles for `rank` (first n % world ranks get one extra)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_tiles(local: torch.Tensor, n_total: int, group=None, dst=None):
+    """Reassemble the per-rank slices (dim 0) of a sharded batch.  dst=None -> every rank gets the full batch
+    (all_gather); dst=r -> only rank r does (gather); other ranks get None.  Ragged slices are padded to the largest."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_total, world, r) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    buf = local
+    if local.shape[0] < mx:
+        pad = torch.zeros((mx - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        buf = torch.cat([local, pad], 0)
+    buf = buf.contiguous()
+    if dst is None:
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf, group=group)
+    else:
+        outs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, outs, dst=dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(outs, sizes)], 0)
