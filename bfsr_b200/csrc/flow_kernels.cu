@@ -68,44 +68,131 @@ __global__ void __launch_bounds__(256) flowstep_kernel(StepArgs a) {
   }
   __syncthreads();
 
-  // ---- phase 2: channel mix, 4 outputs per thread
-  for (int e = tid; e < P * C4; e += 256) {
-    const int p = e / C4, g = e % C4;
-    const long long pix = p0 + p;
-    if (pix >= a.npix) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* zr = zs + p * ZP;
+  // ---- phase 2: channel mix, register tile of 4 pixels x 4 output channels per thread (5 LDS per 16 FMA)
+  const int PQ = P >> 2;
+  for (int e = tid; e < PQ * C4; e += 256) {
+    const int pq = e / C4, g = e % C4;
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* zr = zs + (pq * 4) * ZP;
     const float* mr = Mt + 4 * g;
 #pragma unroll 4
     for (int ci = 0; ci < C; ++ci) {
-      const float zv = zr[ci];
       const float4 m = *reinterpret_cast<const float4*>(mr + ci * C);
-      acc.x = fmaf(m.x, zv, acc.x); acc.y = fmaf(m.y, zv, acc.y);
-      acc.z = fmaf(m.z, zv, acc.z); acc.w = fmaf(m.w, zv, acc.w);
-    }
-    float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = 4 * g + j;
-      if (INV) o[j] -= a.cvec[c];
-      else {
-        o[j] += a.cvec[c];
-        if (a.has_hF) { const float shiftF = ld(a.hF, pix, 2 * c), scaleF = ld(a.hF, pix, 2 * c + 1); o[j] = (o[j] + shiftF) * scaleF; }
+      for (int k = 0; k < 4; ++k) {
+        const float zv = zr[k * ZP + ci];
+        acc[k].x = fmaf(m.x, zv, acc[k].x); acc[k].y = fmaf(m.y, zv, acc[k].y);
+        acc[k].z = fmaf(m.z, zv, acc[k].z); acc[k].w = fmaf(m.w, zv, acc[k].w);
       }
     }
-    if (a.unsqueeze_out) {
-      const int jx = (int)(pix % a.W); const long long t = pix / a.W; const int iy = (int)(t % a.H); const long long b = t / a.H;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pix = p0 + pq * 4 + k;
+      if (pix >= a.npix) continue;
+      float o[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int fh = j >> 1, fw = j & 1;
-        const long long dp = (b * (2 * a.H) + (2 * iy + fh)) * (2 * a.W) + (2 * jx + fw);
-        st(a.zout, dp, g, o[j]);
+        const int c = 4 * g + j;
+        if (INV) o[j] -= a.cvec[c];
+        else {
+          o[j] += a.cvec[c];
+          if (a.has_hF) { const float shiftF = ld(a.hF, pix, 2 * c), scaleF = ld(a.hF, pix, 2 * c + 1); o[j] = (o[j] + shiftF) * scaleF; }
+        }
       }
-    } else {
+      if (a.unsqueeze_out) {
+        const int jx = (int)(pix % a.W); const long long t = pix / a.W; const int iy = (int)(t % a.H); const long long b = t / a.H;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) st(a.zout, pix, 4 * g + j, o[j]);
+        for (int j = 0; j < 4; ++j) {
+          const int fh = j >> 1, fw = j & 1;
+          const long long dp = (b * (2 * a.H) + (2 * iy + fh)) * (2 * a.W) + (2 * jx + fw);
+          st(a.zout, dp, g, o[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st(a.zout, pix, 4 * g + j, o[j]);
+      }
     }
   }
+}
+
+// ---- small-C variant (C = 12, 24): one pixel per thread, the whole step in registers.  Per pixel the thread streams
+// z (C), h (C) and hF (2C) with 128-bit loads (consecutive lanes read consecutive pixels, so the warp's loads tile a
+// contiguous span), the C x C mix reads the matrix from shared memory as broadcast float4s, and the result leaves with
+// 128-bit stores.  Squeeze2d / Unsqueeze2d are index maps on the load / store side.
+template <int C, bool INV>
+__global__ void __launch_bounds__(128) flowstep_px_kernel(StepArgs a) {
+  __shared__ __align__(16) float Ms[C * C];
+  __shared__ float cs[C];
+  for (int e = threadIdx.x; e < C * C; e += blockDim.x) Ms[e] = a.M[e];
+  for (int e = threadIdx.x; e < C; e += blockDim.x) cs[e] = a.cvec[e];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= a.npix) return;
+  float z[C];
+  const int jx = (int)(pix % a.W); const long long t = pix / a.W; const int iy = (int)(t % a.H); const long long b = t / a.H;
+  if (a.squeeze_in) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const long long sp = (b * (2 * a.H) + (2 * iy + (f >> 1))) * (2 * a.W) + (2 * jx + (f & 1));
+      const float* src = (const float*)a.zin.p + sp * a.zin.cs + a.zin.coff;
+#pragma unroll
+      for (int cc = 0; cc < C / 4; ++cc) z[4 * cc + f] = src[cc];
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>((const float*)a.zin.p + pix * a.zin.cs + a.zin.coff);
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) { const float4 v = src[k]; z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+  }
+  if (a.has_h) {   // self-conditional coupling on the second half: (shift, scale) pairs
+    const float4* hp = reinterpret_cast<const float4*>((const float*)a.h.p + pix * a.h.cs + a.h.coff);
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) {
+      const float4 v = hp[k];           // pairs for channels C/2 + 2k, C/2 + 2k + 1
+      const int c0 = C / 2 + 2 * k;
+      if (INV) { z[c0] = z[c0] / v.y - v.x; z[c0 + 1] = z[c0 + 1] / v.w - v.z; }
+      else { z[c0] = (z[c0] + v.x) * v.y; z[c0 + 1] = (z[c0 + 1] + v.z) * v.w; }
+    }
+  }
+  const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
+  if (INV && a.has_hF) {
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) { const float4 v = fp[k]; z[2 * k] = z[2 * k] / v.y - v.x; z[2 * k + 1] = z[2 * k + 1] / v.w - v.z; }
+  }
+  float o[C];
+#pragma unroll
+  for (int co = 0; co < C; ++co) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) {
+      const float4 m = *reinterpret_cast<const float4*>(&Ms[co * C + 4 * k]);
+      acc = fmaf(m.x, z[4 * k], acc); acc = fmaf(m.y, z[4 * k + 1], acc);
+      acc = fmaf(m.z, z[4 * k + 2], acc); acc = fmaf(m.w, z[4 * k + 3], acc);
+    }
+    o[co] = INV ? acc - cs[co] : acc + cs[co];
+  }
+  if (!INV && a.has_hF) {
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) { const float4 v = fp[k]; o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
+  }
+  if (a.unsqueeze_out) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const long long dp = (b * (2 * a.H) + (2 * iy + (f >> 1))) * (2 * a.W) + (2 * jx + (f & 1));
+      float* dst = (float*)a.zout.p + dp * a.zout.cs + a.zout.coff;
+#pragma unroll
+      for (int cc = 0; cc < C / 4; ++cc) dst[cc] = o[4 * cc + f];
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>((float*)a.zout.p + pix * a.zout.cs + a.zout.coff);
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  }
+}
+
+static bool vec4_ok(const View& v) {
+  return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0;
 }
 
 static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, const View* h, const View* hF,
@@ -129,12 +216,22 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   a.has_h = h != nullptr; a.has_hF = hF != nullptr;
   a.M = inv ? w.Mi : w.Mf; a.cvec = inv ? w.ci : w.cf;
   a.squeeze_in = sq_in; a.unsqueeze_out = unsq_out;
-  a.pix_per_block = w.C <= 24 ? 256 : (w.C <= 96 ? 64 : 32);
+  a.pix_per_block = w.C <= 24 ? 256 : (w.C <= 96 ? 128 : 32);
   if (a.npix == 0) return;
   const size_t smem = ((size_t)w.C * w.C + (size_t)a.pix_per_block * (w.C + 1)) * 4;
   const int grid = cdiv(a.npix, a.pix_per_block);
   // algorithmic HBM bytes: z in + z out (+ h: C, + hF: 2C) fp32 per level-pixel
   ProfScope prof(PK_FLOWSTEP, 4.0 * (double)a.npix * w.C * (2 + (h ? 1 : 0) + (hF ? 2 : 0)), s);
+  // small-C fast path (levels 1 and 2 of the shipped topology)
+  const bool px_ok = (w.C == 12 || w.C == 24) && zin.fmt == F32 && zout.fmt == F32 && (sq_in || vec4_ok(zin)) &&
+                     (unsq_out || vec4_ok(zout)) && (!h || vec4_ok(*h)) && (!hF || vec4_ok(*hF));
+  if (px_ok) {
+    const int g = cdiv(a.npix, 128);
+    if (w.C == 12) { if (inv) flowstep_px_kernel<12, true><<<g, 128, 0, s>>>(a); else flowstep_px_kernel<12, false><<<g, 128, 0, s>>>(a); }
+    else { if (inv) flowstep_px_kernel<24, true><<<g, 128, 0, s>>>(a); else flowstep_px_kernel<24, false><<<g, 128, 0, s>>>(a); }
+    count_launch();
+    return;
+  }
   if (inv) {
     CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     flowstep_kernel<true><<<grid, 256, smem, s>>>(a);

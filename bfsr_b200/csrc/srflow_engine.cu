@@ -471,17 +471,22 @@ void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode_i, const float* lr, c
   }
   if (B == 0) return;
   CUDA_OK(cudaSetDevice(e->device));
-  const int chunk = e->d.tile_chunk > 0 ? e->d.tile_chunk : 8;
+  // tiles per pass through the workspace: 32 by default, halved until the planned workspace fits 64 GB
+  int chunk = e->d.tile_chunk > 0 ? e->d.tile_chunk : 32;
   const int S = e->d.scale;
   const int nl = (int)e->latent_C.size();
-  // plan pass: measure the workspace of the largest chunk
   {
     Arena& A = e->arena;
     const size_t peak0 = A.peak;
-    A.plan = true; A.peak = 0;
-    run_chunk(e, prior, mode, nullptr, nullptr, nullptr, nullptr, nullptr, B < chunk ? B : chunk, h, w, s);
-    A.plan = false;
-    const size_t need = A.peak + (1 << 20);
+    size_t need = 0;
+    for (;;) {
+      A.plan = true; A.peak = 0;
+      run_chunk(e, prior, mode, nullptr, nullptr, nullptr, nullptr, nullptr, B < chunk ? B : chunk, h, w, s);
+      A.plan = false;
+      need = A.peak + (1 << 20);
+      if (e->d.tile_chunk > 0 || chunk == 1 || need <= ((size_t)64 << 30)) break;
+      chunk = (chunk + 1) / 2;
+    }
     A.peak = peak0 > need ? peak0 : need;
     if (need > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(need); }
   }
