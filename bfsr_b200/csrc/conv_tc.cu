@@ -32,6 +32,7 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 namespace bfsr {
 
@@ -56,6 +57,7 @@ struct TcArgs {
   int H, W, N, in_mode, act;
   float eps, alpha, beta1, beta2;
   int fast, vec_in, vec_out;
+  int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
   int a_plane, a_slot, w_slot;           // bytes
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         if (it < items) {
           const int q = it >> 2, j = it & 3;
           const int yy = q / a.pitch, xx = q - yy * a.pitch;
-          const int gy = tcd.ty0 + yy - 1, gx = tcd.tx0 + xx - 1;
+          const int gy = tcd.ty0 + yy - a.halo, gx = tcd.tx0 + xx - a.halo;
           const int cb = c * KC + j * 8;
           if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && cb < a.cin) {
             const int sy_ = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx_ = a.in_mode == IN_UP2 ? gx >> 1 : gx;
@@ -389,14 +391,14 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         const uint32_t a_hi = a_smem + slot * a.a_slot, a_lo = a_hi + a.a_plane;
         const uint64_t a_hi_d = desc_a_hi | (uint64_t)((a_hi & 0x3FFFF) >> 4), a_lo_d = desc_a_hi | (uint64_t)((a_lo & 0x3FFFF) >> 4);
         int nk = (a.cin - c * KC + 15) >> 4; nk = nk > 2 ? 2 : nk;
-        for (int tap = 0; tap < 9; ++tap, ++w_it) {
+        for (int tap = 0; tap < a.ntaps; ++tap, ++w_it) {
           const int ws = w_it % NW;
           TR_T(tr2);
           mbar_wait(w_full + 8 * ws, (w_it / NW) & 1);
           TR_ADD(tr_w, tr2); TR_T(tr3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t wb = w_smem + ws * a.w_slot;
-          const int dy = tap / 3, dx = tap - dy * 3;
+          const int dy = tap / a.ks, dx = tap - dy * a.ks;
           // One elected lane issues the whole tap.  Descriptors differ only in the 14-bit start-address field, so each
           // operand is the chunk/slot base descriptor plus a small precomputed offset (uniform-datapath adds).
           const uint32_t tap_off = (uint32_t)(dy * a.pitch + dx) * (ROWB >> 4);
@@ -438,8 +440,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     TR_DECL(tr_wait = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       const int ct = t % a.n_ct;
-      const unsigned char* wsrc = a.w + (size_t)ct * a.n_chunks * 9 * tap_stride;
-      const int total = a.n_chunks * 9;
+      const unsigned char* wsrc = a.w + (size_t)ct * a.n_chunks * a.ntaps * tap_stride;
+      const int total = a.n_chunks * a.ntaps;
       for (int wi = 0; wi < total; ++wi, ++w_it) {
         const int ws = w_it % NW;
         TR_T(tr0);
@@ -480,15 +482,17 @@ static int pick_nt(int cout) {
 // h: host fp32 packed [tap][cin_pad][cout_pad] (the fp32 kernel's layout)
 void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
   using namespace tc;
-  if (c.ks != 3 || c.cin < 32) return;
+  static const int min_cin = getenv("BFSR_TC_MIN_CIN") ? atoi(getenv("BFSR_TC_MIN_CIN")) : 32;
+  if (c.cin < min_cin) return;
+  const int taps = c.ks * c.ks;
   const int nt = pick_nt(c.cout);
   const int n_tiles = (c.cout + nt - 1) / nt, n_chunks = (c.cin + KC - 1) / KC;
   const size_t tap_elems = (size_t)2 * nt * (ROWB / 2);
-  std::vector<unsigned short> img((size_t)n_tiles * n_chunks * 9 * tap_elems, 0);
+  std::vector<unsigned short> img((size_t)n_tiles * n_chunks * taps * tap_elems, 0);
   for (int t = 0; t < n_tiles; ++t)
     for (int ch = 0; ch < n_chunks; ++ch)
-      for (int tap = 0; tap < 9; ++tap) {
-        unsigned short* dst = img.data() + (((size_t)t * n_chunks + ch) * 9 + tap) * tap_elems;
+      for (int tap = 0; tap < taps; ++tap) {
+        unsigned short* dst = img.data() + (((size_t)t * n_chunks + ch) * taps + tap) * tap_elems;
         for (int r = 0; r < nt; ++r) {
           const int co = t * nt + r;
           for (int k = 0; k < KC; ++k) {
@@ -545,7 +549,8 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
     if (out.H > 16) a.sy = 2; else if (out.W > 8) a.sx = 2;
   }
   a.mt = a.sx * a.sy;
-  a.pitch = 8 * a.sx + 2; a.hrows = 16 * a.sy + 2;
+  a.ks = w.ks; a.ntaps = w.ks * w.ks; a.halo = w.ks / 2;
+  a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
   a.a_plane = (a.pitch * a.hrows * ROWB + 1023) / 1024 * 1024;
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
   a.w_slot = 2 * a.nt * ROWB;
@@ -560,7 +565,7 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
-  ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * 9 * w.cout, s);
+  ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
   count_launch();
 }

@@ -16,6 +16,7 @@
 #include "engine.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 using namespace bfsr;
 
@@ -297,7 +298,9 @@ static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& t
   const int Hd = r.e->d.hidden;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
-  K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  static const bool tc_z = getenv("BFSR_TC_Z") && atoi(getenv("BFSR_TC_Z"));
+  if (tc_z) K_(conv2d(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  else K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
   ConvEpi relu; relu.act = ACT_RELU;
   K_(conv2d(l.cp.fA2, t1, t2, relu, IN_DIRECT, r.s));
   ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;

@@ -160,3 +160,18 @@ def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
                                       y.data_ptr(), None))
     err = rel_l2(ref, y)
     assert err < (2e-5 if impl == 1 else 1e-2), err
+
+
+@pytest.mark.parametrize("cin,cout,H,W,act", [(64, 64, 20, 24, 2), (256, 27, 9, 9, 0), (1024, 256, 33, 5, 2), (96, 540, 8, 8, 0)])
+def test_conv1x1_tcgen05(lib, cin, cout, H, W, act):
+    """1x1 convs (coupling hidden layers, LINF MLP) on the tcgen05 kernel (single tap, no halo), split-bf16 x3."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double())
+    ref = {0: lambda t: t, 2: F.relu}[act](ref)
+    y = torch.empty(2, cout, H, W, device="cuda")
+    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 1, act, 1,
+                                      y.data_ptr(), None))
+    assert rel_l2(ref, y) < 2e-5
