@@ -177,6 +177,82 @@ static void launch(const ConvArgs& a, int N, cudaStream_t s) {
   count_launch();
 }
 
+// ---- small-Cin variant (Cin <= 16, Cout == 64): the z-dependent first conv of every coupling (Cin = C/2 = 6, 12), the
+// RGB head convs and the stems of the priors.  These are HBM-bound (K <= 144): a warp owns 8 consecutive pixels x all 64
+// output channels (2 per lane), so the pre-activation rows it adds and the rows it stores are whole 256-byte runs;
+// inputs are broadcast shared-memory reads, weights conflict-free 64-bit reads.
+template <int CINP>
+__global__ void __launch_bounds__(256) conv3x3_small_kernel(ConvArgs a) {
+  constexpr int T = 16;                       // 16 x 16 output pixels per CTA, 4 passes of 8 warps x 8 pixels
+  constexpr int PITCH = 20;
+  extern __shared__ __align__(16) float smem_small[];
+  float* w_s = smem_small;                    // [9][CINP][64]
+  float* in_s = smem_small + 9 * CINP * 64;   // [CINP][18][PITCH]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / a.tiles_x) * T, tx0 = (tile % a.tiles_x) * T;
+  const int n = blockIdx.z;
+  const long long img = (long long)n * a.H * a.W;
+  for (int e = tid; e < 9 * CINP * 16; e += 256) {
+    const int c4 = e & 15, ci = (e >> 4) % CINP, tap = (e >> 4) / CINP;
+    const float4 v = ci < a.cin_pad ? *reinterpret_cast<const float4*>(a.w + ((long long)tap * a.cin_pad + ci) * a.cout_pad + c4 * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(&w_s[(tap * CINP + ci) * 64 + c4 * 4]) = v;
+  }
+  for (int e = tid; e < 18 * 18 * CINP; e += 256) {
+    const int ci = e % CINP, pix = e / CINP;
+    const int yy = pix / 18, xx = pix % 18;
+    const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+    float v = 0.f;
+    if (ci < a.cin && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = ld(a.in, img + (long long)gy * a.W + gx, ci);
+    in_s[(ci * 18 + yy) * PITCH + xx] = v;
+  }
+  __syncthreads();
+  const float2 b2 = *reinterpret_cast<const float2*>(a.bias + 2 * lane);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = pass * 4 + (warp >> 1), x0 = (warp & 1) * 8;
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 2
+    for (int ci = 0; ci < CINP; ++ci) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        float v[12];
+        const float* rp = &in_s[(ci * 18 + row + dy) * PITCH + x0];
+        *reinterpret_cast<float4*>(&v[0]) = *reinterpret_cast<const float4*>(rp);
+        *reinterpret_cast<float4*>(&v[4]) = *reinterpret_cast<const float4*>(rp + 4);
+        *reinterpret_cast<float2*>(&v[8]) = *reinterpret_cast<const float2*>(rp + 8);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float2 w2 = *reinterpret_cast<const float2*>(&w_s[((dy * 3 + dx) * CINP + ci) * 64 + 2 * lane]);
+#pragma unroll
+          for (int px = 0; px < 8; ++px) { acc[px][0] = fmaf(v[px + dx], w2.x, acc[px][0]); acc[px][1] = fmaf(v[px + dx], w2.y, acc[px][1]); }
+        }
+      }
+    }
+    const int gy = ty0 + row;
+    if (gy >= a.H) continue;
+#pragma unroll
+    for (int px = 0; px < 8; ++px) {
+      const int gx = tx0 + x0 + px;
+      if (gx >= a.W) break;
+      const long long p = img + (long long)gy * a.W + gx;
+      float o0 = acc[px][0] + b2.x, o1 = acc[px][1] + b2.y;
+      if (a.pre.p) { const float2 t = *reinterpret_cast<const float2*>((const float*)a.pre.p + p * a.pre.cs + a.pre.coff + 2 * lane); o0 += t.x; o1 += t.y; }
+      if (a.act == ACT_LRELU) { o0 = o0 > 0.f ? o0 : 0.2f * o0; o1 = o1 > 0.f ? o1 : 0.2f * o1; }
+      else if (a.act == ACT_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+      *reinterpret_cast<float2*>((float*)a.out.p + p * a.out.cs + a.out.coff + 2 * lane) = make_float2(o0 * a.alpha, o1 * a.alpha);
+    }
+  }
+}
+
+static bool small_ok(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode) {
+  auto v2 = [](const View& v) { return v.fmt == F32 && v.cs % 2 == 0 && v.coff % 2 == 0 && ((uintptr_t)v.p % 8) == 0; };
+  return w.ks == 3 && w.cin <= 16 && w.cout == 64 && in_mode == IN_DIRECT && !epi.res1 && !epi.res2 &&
+         epi.act != ACT_CROSS_SIGMOID && in.fmt == F32 && v2(out) && (!epi.pre || v2(*epi.pre));
+}
+
 void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
   BFSR_CHECK(in.C == w.cin, "conv: input view has %d channels, weights expect %d", in.C, w.cin);
   BFSR_CHECK(out.C == w.cout, "conv: output view has %d channels, weights produce %d", out.C, w.cout);
@@ -197,6 +273,20 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
   a.tiles_x = 0;
   if (out.npix() == 0) return;
   ProfScope prof(PK_CONV_FP32, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
+  if (small_ok(w, in, out, epi, in_mode)) {
+    a.tiles_x = cdiv(a.W, 16);
+    dim3 grid(a.tiles_x * cdiv(a.H, 16), 1, out.N);
+    if (w.cin <= 8) {
+      const size_t smem = (size_t)(9 * 8 * 64 + 8 * 18 * 20) * 4;
+      conv3x3_small_kernel<8><<<grid, 256, smem, s>>>(a);
+    } else {
+      const size_t smem = (size_t)(9 * 16 * 64 + 16 * 18 * 20) * 4;
+      CUDA_OK(cudaFuncSetAttribute(conv3x3_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3x3_small_kernel<16><<<grid, 256, smem, s>>>(a);
+    }
+    count_launch();
+    return;
+  }
 #define L(KS, T) launch<KS, T>(a, out.N, s)
   if (w.ks == 3) { if (w.co_tile == 64) L(3, 64); else if (w.co_tile == 32) L(3, 32); else L(3, 16); }
   else           { if (w.co_tile == 64) L(1, 64); else if (w.co_tile == 32) L(1, 32); else L(1, 16); }

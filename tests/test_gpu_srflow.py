@@ -48,7 +48,7 @@ def test_squeeze_bit_exact(lib, shape):
 
 
 @pytest.mark.parametrize("cin,cout,ks,H,W,act", [
-    (3, 64, 3, 17, 23, 0), (64, 32, 3, 16, 16, 1), (70, 64, 3, 9, 31, 1), (6, 12, 3, 20, 12, 0),
+    (3, 64, 3, 17, 23, 0), (6, 64, 3, 33, 40, 2), (12, 64, 3, 16, 16, 1), (16, 64, 3, 5, 50, 0), (64, 32, 3, 16, 16, 1), (70, 64, 3, 9, 31, 1), (6, 12, 3, 20, 12, 0),
     (64, 64, 1, 13, 7, 2), (192, 64, 3, 32, 32, 0), (320, 128, 3, 8, 24, 2), (64, 48, 3, 40, 40, 0),
     (96, 27, 1, 5, 5, 0)])
 def test_conv2d_fp32(lib, cin, cout, ks, H, W, act):
