@@ -281,6 +281,44 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
   API_END
 }
 
+int bfsr_op_conv2d_up2(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
+                       const float* bias_host, int32_t Cout, int32_t impl, float* y_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(x_dev && w_host && y_dev, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvW cw = pack_conv(w_host, Cout, Cin, 3, bias_host, nullptr, {});
+  ConvW pw;
+  float *xn = nullptr, *yn = nullptr;
+  const size_t npix = (size_t)B * H * W;
+  const int saved = g_conv_mode;
+  try {
+    CUDA_OK(cudaMalloc((void**)&xn, (npix * Cin + 4) * 4));
+    CUDA_OK(cudaMalloc((void**)&yn, (npix * 4 * Cout + 4) * 4));
+    View x; x.p = xn; x.N = B; x.H = H; x.W = W; x.C = Cin; x.cs = Cin;
+    View y; y.p = yn; y.N = B; y.H = 2 * H; y.W = 2 * W; y.C = Cout; y.cs = Cout;
+    nchw_to_nhwc(x_dev, x, s);
+    if (impl == 0) conv2d_fp32(cw, x, y, ConvEpi(), IN_UP2, s);
+    else if (impl == 1) { g_conv_mode = 0; conv2d_tc(cw, x, y, ConvEpi(), IN_UP2, s); }
+    else {
+      g_conv_mode = 0;
+      pw = pack_conv_tc_phase(w_host, Cout, Cin, 0, Cin, nullptr);
+      // bias first (as the engine does with the hi-res part of the conditioning tensor), then accumulate the phases
+      CUDA_OK(cudaMemsetAsync(yn, 0, npix * 4 * Cout * 4, s));
+      ConvEpi ep; ep.pre = &y;
+      std::vector<float> hb(Cout, 0.f);
+      if (bias_host) for (int i = 0; i < Cout; ++i) hb[i] = bias_host[i];
+      CUDA_OK(cudaMemcpyAsync(pw.bias, hb.data(), Cout * 4, cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      conv2d_tc_up2_phase(pw, x, y, ep, s);
+    }
+    g_conv_mode = saved;
+    nhwc_to_nchw(y, y_dev, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { g_conv_mode = saved; cudaFree(xn); cudaFree(yn); free_conv(cw); free_conv(pw); throw; }
+  cudaFree(xn); cudaFree(yn); free_conv(cw); free_conv(pw);
+  API_END
+}
+
 int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
                       void* stream) {
   API_BEGIN

@@ -58,6 +58,7 @@ struct TcArgs {
   float eps, alpha, beta1, beta2;
   int fast, vec_in, vec_out;
   int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
+  int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
   int a_plane, a_slot, w_slot;           // bytes
@@ -145,10 +146,12 @@ __device__ __forceinline__ bool elect_one() {
 #define TR_ADD(acc, t0)
 #endif
 
-struct TileCoord { int n, ty0, tx0, ct; };
+struct TileCoord { int n, ty0, tx0, ct, ph; };
 __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
   TileCoord c;
   c.ct = t % a.n_ct; t /= a.n_ct;
+  c.ph = 0;
+  if (a.phase) { c.ph = t & 3; t >>= 2; }
   const int tx = t % a.tiles_x; t /= a.tiles_x;
   const int ty = t % a.tiles_y; c.n = t / a.tiles_y;
   c.ty0 = ty * 16 * a.sy; c.tx0 = tx * 8 * a.sx;
@@ -321,7 +324,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
               const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
               if (gy < a.H && gx < a.W && cok) {
                 const float4 s4 = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
-                const long long p = ((long long)tcd.n * a.H + gy) * a.W + gx;
+                const long long p = a.phase ? ((long long)tcd.n * 2 * a.H + 2 * gy + (tcd.ph >> 1)) * (2 * a.W) + 2 * gx + (tcd.ph & 1)
+                                            : ((long long)tcd.n * a.H + gy) * a.W + gx;
                 float o[4] = {s4.x, s4.y, s4.z, s4.w};
                 float pr[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f};
                 if (a.pre.p) {
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     TR_DECL(tr_acc = 0, tr_a = 0, tr_w = 0, tr_issue = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
       const int as = t_it % a.nacc;
+      const int ph = a.phase ? (t / a.n_ct) & 3 : 0;
       TR_T(tr0);
       mbar_wait(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
       TR_ADD(tr_acc, tr0);
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           TR_ADD(tr_w, tr2); TR_T(tr3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t wb = w_smem + ws * a.w_slot;
-          const int dy = tap / a.ks, dx = tap - dy * a.ks;
+          const int dy = a.phase ? (ph >> 1) + (tap >> 1) : tap / a.ks, dx = a.phase ? (ph & 1) + (tap & 1) : tap - (tap / a.ks) * a.ks;
           // One elected lane issues the whole tap.  Descriptors differ only in the 14-bit start-address field, so each
           // operand is the chunk/slot base descriptor plus a small precomputed offset (uniform-datapath adds).
           const uint32_t tap_off = (uint32_t)(dy * a.pitch + dx) * (ROWB >> 4);
@@ -440,7 +445,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     TR_DECL(tr_wait = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       const int ct = t % a.n_ct;
-      const unsigned char* wsrc = a.w + (size_t)ct * a.n_chunks * a.ntaps * tap_stride;
+      const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
+      const unsigned char* wsrc = a.w + (size_t)wsel * a.n_chunks * a.ntaps * tap_stride;
       const int total = a.n_chunks * a.ntaps;
       for (int wi = 0; wi < total; ++wi, ++w_it) {
         const int ws = w_it % NW;
@@ -519,22 +525,27 @@ bool conv_tc_eligible(const ConvW& w, const View& in, const View& out) {
 
 static int g_num_sms = 0;
 
-void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
+// phase = false: out (N,H,W) = conv_ks(in) (+ optional nearest-2x folded into the loader).
+// phase = true : out (N,2H,2W) (+)= conv3x3(nearest2x(in)) evaluated on the LOW-RES grid as four 2x2 phase convs with
+//                pre-summed weights (exact in real arithmetic, 16/36 of the MACs); `in` is the low-res tensor.
+static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, bool phase, cudaStream_t s) {
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
-  if (in_mode == IN_UP2) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
+  if (in_mode == IN_UP2 || phase) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
   else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv_tc: spatial mismatch");
   if (out.npix() == 0) return;
+  const int gH = phase ? in.H : out.H, gW = phase ? in.W : out.W;      // grid the GEMM rows live on
   TcArgs a;
   a.in = in; a.out = out;
   a.pre = epi.pre ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
   a.w = (const unsigned char*)w.w_tc; a.bias = w.bias;
   a.cin = w.cin; a.cout = w.cout; a.nt = w.tc_npad; a.n_chunks = w.tc_kchunks;
   a.n_ct = cdiv(w.cout, w.tc_npad);
-  a.H = out.H; a.W = out.W; a.N = out.N; a.in_mode = in_mode; a.act = epi.act;
+  a.H = gH; a.W = gW; a.N = out.N; a.in_mode = phase ? (int)IN_DIRECT : in_mode; a.act = epi.act;
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
   a.fast = g_conv_mode == 1;
+  a.phase = phase ? 1 : 0;
   a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
@@ -542,14 +553,14 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
   int mt = 512 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);
   a.sx = 1; a.sy = 1;
   if (mt == 4) {
-    if (out.W > 8 && out.H > 16) { a.sx = 2; a.sy = 2; }
-    else if (out.H > 16) { a.sy = 2; }
-    else if (out.W > 8) { a.sx = 2; }
+    if (gW > 8 && gH > 16) { a.sx = 2; a.sy = 2; }
+    else if (gH > 16) { a.sy = 2; }
+    else if (gW > 8) { a.sx = 2; }
   } else if (mt == 2) {
-    if (out.H > 16) a.sy = 2; else if (out.W > 8) a.sx = 2;
+    if (gH > 16) a.sy = 2; else if (gW > 8) a.sx = 2;
   }
   a.mt = a.sx * a.sy;
-  a.ks = w.ks; a.ntaps = w.ks * w.ks; a.halo = w.ks / 2;
+  a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
   a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
   a.a_plane = (a.pitch * a.hrows * ROWB + 1023) / 1024 * 1024;
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
@@ -557,17 +568,78 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
   a.nacc = 2 * a.mt * sub_cols <= 512 ? 2 : 1;
   uint32_t cols = 32; while ((int)cols < a.nacc * a.mt * sub_cols) cols <<= 1;
   a.tmem_cols = cols;
-  a.tiles_x = cdiv(out.W, 8 * a.sx); a.tiles_y = cdiv(out.H, 16 * a.sy);
-  a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct;
+  a.tiles_x = cdiv(gW, 8 * a.sx); a.tiles_y = cdiv(gH, 16 * a.sy);
+  a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
   const int smem = NA * a.a_slot + NW * a.w_slot + 1024 + 256 + STG_BYTES;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
   BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
   count_launch();
+}
+
+void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
+  BFSR_CHECK(!w.tc_phase, "conv_tc: phase-packed weights need conv2d_tc_up2_phase");
+  launch_tc(w, in, out, epi, in_mode, false, s);
+}
+void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s) {
+  BFSR_CHECK(w.tc_phase, "conv_tc: weights are not phase-packed");
+  launch_tc(w, in_lowres, out, epi, IN_DIRECT, true, s);
+}
+
+// Phase packing of a 3x3 conv applied to nearest2x(x) (SRFlowNet_arch.py:136 feeds such tensors to every level-1 coupling):
+//   out(2y+fy, 2x+fx) = sum_{a,b in {0,1}} W'[fy,fx,a,b] . x(y+fy-1+a, x+fx-1+b),
+//   W'[f=0]: a=0 <- {d=0}, a=1 <- {d=1,2};   W'[f=1]: a=0 <- {d=0,1}, a=1 <- {d=2}   (same rule along x).
+// w_oihw: [cout][cin_src][3][3]; uses source channels [c0, c0+cn); out_scale multiplies per output channel.
+ConvW pack_conv_tc_phase(const float* w_oihw, int cout, int cin_src, int c0, int cn, const float* out_scale) {
+  using namespace tc;
+  ConvW c;
+  c.ks = 3; c.cin = cn; c.cout = cout; c.cin_pad = cn; c.co_tile = 64; c.cout_pad = (cout + 63) / 64 * 64;
+  c.tc_phase = 1;
+  const int nt = pick_nt(cout);
+  const int n_tiles = (cout + nt - 1) / nt, n_chunks = (cn + KC - 1) / KC;
+  const size_t tap_elems = (size_t)2 * nt * (ROWB / 2);
+  std::vector<unsigned short> img((size_t)n_tiles * 4 * n_chunks * 4 * tap_elems, 0);
+  auto members = [](int f, int a, int* d) {   // taps of the 3-tap filter that land on low-res offset a for phase f
+    if (f == 0) { if (a == 0) { d[0] = 0; return 1; } d[0] = 1; d[1] = 2; return 2; }
+    if (a == 0) { d[0] = 0; d[1] = 1; return 2; } d[0] = 2; return 1;
+  };
+  for (int t = 0; t < n_tiles; ++t)
+    for (int ph = 0; ph < 4; ++ph)
+      for (int ch = 0; ch < n_chunks; ++ch)
+        for (int tap = 0; tap < 4; ++tap) {
+          unsigned short* dst = img.data() + ((((size_t)t * 4 + ph) * n_chunks + ch) * 4 + tap) * tap_elems;
+          int dys[2], dxs[2];
+          const int ny = members(ph >> 1, tap >> 1, dys), nx = members(ph & 1, tap & 1, dxs);
+          for (int r = 0; r < nt; ++r) {
+            const int co = t * nt + r;
+            for (int k = 0; k < KC; ++k) {
+              const int ci = ch * KC + k;
+              double acc = 0.0;
+              if (co < cout && ci < cn)
+                for (int iy = 0; iy < ny; ++iy)
+                  for (int ix = 0; ix < nx; ++ix)
+                    acc += (double)w_oihw[(((size_t)co * cin_src + c0 + ci) * 3 + dys[iy]) * 3 + dxs[ix]];
+              const float w = (float)(acc * (out_scale && co < cout ? (double)out_scale[co] : 1.0));
+              const unsigned short hi = f2bf(w), lo = f2bf(w - bf2f(hi));
+              const int j = k >> 3, e = k & 7;
+              dst[(size_t)r * 32 + ((j ^ ((r >> 1) & 3)) << 3) + e] = hi;
+              const int r2 = nt + r;
+              dst[(size_t)r2 * 32 + ((j ^ ((r2 >> 1) & 3)) << 3) + e] = lo;
+            }
+          }
+        }
+  CUDA_OK(cudaMalloc(&c.w_tc, img.size() * 2));
+  CUDA_OK(cudaMemcpy(c.w_tc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> zb(c.cout_pad + 128, 0.f);
+  CUDA_OK(cudaMalloc((void**)&c.bias, zb.size() * 4));
+  CUDA_OK(cudaMemcpy(c.bias, zb.data(), zb.size() * 4, cudaMemcpyHostToDevice));
+  c.tc_kchunks = n_chunks; c.tc_npad = nt;
+  return c;
 }
 
 }  // namespace bfsr

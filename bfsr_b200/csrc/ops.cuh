@@ -17,7 +17,7 @@ struct ConvW {
   float* bias = nullptr;   // [cout_pad] (zeros if the conv has none)
   // split-bf16 packing for the tcgen05 path (built lazily by conv_tc.cu)
   void* w_tc = nullptr;
-  int tc_kchunks = 0, tc_npad = 0;
+  int tc_kchunks = 0, tc_npad = 0, tc_phase = 0;
 };
 
 struct ConvEpi {
@@ -38,6 +38,9 @@ extern thread_local int g_conv_mode;
 void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed);
 bool conv_tc_eligible(const ConvW& w, const View& in, const View& out);
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
+// 3x3 conv over nearest2x(in_lowres) as four 2x2 phase convs on the low-res grid (16/36 of the MACs); out is (N,2H,2W)
+ConvW pack_conv_tc_phase(const float* w_oihw, int cout, int cin_src, int c0, int cn, const float* out_scale);
+void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s);
 
 // Host-side packing: src is OIHW fp32 [cout][cin_src][ks][ks]; `out_scale` (optional) multiplies the weights per
 // output channel, `bias` is the FINAL bias (already scaled); the input-channel gather map makes packed input channel

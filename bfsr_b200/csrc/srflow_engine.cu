@@ -32,7 +32,10 @@ bfsr_srflow::~bfsr_srflow() {
     free_conv(l.cp.fF2); free_conv(l.cp.fF4); free_conv(l.cp.fA0z); free_conv(l.cp.fA2); free_conv(l.cp.fA4);
     free_conv(l.split_conv);
   }
-  for (auto& l : levels) { free_conv(l.fF0_all); free_conv(l.fA0ft_all); }
+  for (auto& l : levels) {
+    free_conv(l.fF0_all); free_conv(l.fA0ft_all);
+    free_conv(l.fF0_hi); free_conv(l.fA0ft_hi); free_conv(l.fF0_ph); free_conv(l.fA0ft_ph);
+  }
   if (stage_in) cudaFree(stage_in);
   if (stage_out) cudaFree(stage_out);
 }
@@ -184,6 +187,18 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
     }
     lv.fF0_all = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), {});
     lv.fA0ft_all = pack_conv(wA.data(), d.K * Hd, 320, 3, bA.data(), sA.data(), {});
+    // Two-pass phase evaluation (3x3 on the 64 hi-res channels, then four 2x2 phase convs accumulating on top).  Measured
+    // on B200: 44 % fewer MACs but a second exposed epilogue over the 1024-channel output -> slower (592 vs 499 ms/step),
+    // so it is opt-in until the single-pass variant (parity planes of the hi-res part) exists.
+    static const bool use_phase = getenv("BFSR_PHASE") && atoi(getenv("BFSR_PHASE"));
+    if (use_phase && level == log2s - 1) {   // conditioning = [upconv output | nearest2x(taps of the LR-resolution level)]
+      std::vector<int> hi_map(nf); for (int i = 0; i < nf; ++i) hi_map[i] = i;
+      lv.has_phase = true;
+      lv.fF0_hi = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), hi_map);
+      lv.fA0ft_hi = pack_conv(wA.data(), d.K * Hd, 320, 3, bA.data(), sA.data(), hi_map);
+      lv.fF0_ph = pack_conv_tc_phase(wF.data(), d.K * Hd, 320, nf, 320 - nf, sF.data());
+      lv.fA0ft_ph = pack_conv_tc_phase(wA.data(), d.K * Hd, 320, nf, 320 - nf, sA.data());
+    }
     if (d.split_enable && level < d.L - 1) {
       LayerW l; l.kind = 3; l.C = C; l.level = level;
       const int cons = (int)std::lround(C * 0.5), pass = C - cons;
@@ -252,7 +267,8 @@ static void run_encoder(Run& r, const View& x) {
   // finer levels: fea_up2 = lrelu(upconv1(nearest2x(last_lr_fea))) etc. (post-activation: in-place LeakyReLU aliasing)
   for (int lv = lv0 - 1, u = 0; lv >= 1; --lv, ++u) {
     K_(conv2d(e->rrdb.upconv[u], r.ft[lv + 1].slice(0, nf), r.ft[lv].slice(0, nf), lrelu, IN_UP2, r.s));
-    K_(resample(r.ft[lv + 1].slice(nf, e->n_cond - nf), r.ft[lv].slice(nf, e->n_cond - nf), RS_NEAREST_UP2, r.s));
+    if (!(e->levels[lv].has_phase && g_conv_mode != 2))   // the phase path reads the low-res taps directly
+      K_(resample(r.ft[lv + 1].slice(nf, e->n_cond - nf), r.ft[lv].slice(nf, e->n_cond - nf), RS_NEAREST_UP2, r.s));
   }
   // coarser level: fea_up0 = bilinear x0.5 (== 2x2 mean), taps nearest x0.5
   for (int lv = lv0 + 1; lv <= L; ++lv) {
@@ -282,8 +298,19 @@ static void run_ft_convs(Run& r) {
     View t = make_view(r.A, r.B, H, W, Hd);
     ConvEpi relu; relu.act = ACT_RELU;
     ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
-    K_(conv2d(L.fF0_all, r.ft[lv], bufF, relu, IN_DIRECT, r.s));
-    K_(conv2d(L.fA0ft_all, r.ft[lv], r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));
+    if (L.has_phase && g_conv_mode != 2) {
+      const int nf = d.nf;
+      View taps = r.ft[lv + 1].slice(nf, e->n_cond - nf);
+      ConvEpi acc_relu; acc_relu.act = ACT_RELU; acc_relu.pre = &bufF;
+      ConvEpi acc; acc.pre = &r.bufA[lv];
+      K_(conv2d(L.fF0_hi, r.ft[lv].slice(0, nf), bufF, ConvEpi(), IN_DIRECT, r.s));
+      K_(conv2d_tc_up2_phase(L.fF0_ph, taps, bufF, acc_relu, r.s));
+      K_(conv2d(L.fA0ft_hi, r.ft[lv].slice(0, nf), r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));
+      K_(conv2d_tc_up2_phase(L.fA0ft_ph, taps, r.bufA[lv], acc, r.s));
+    } else {
+      K_(conv2d(L.fF0_all, r.ft[lv], bufF, relu, IN_DIRECT, r.s));
+      K_(conv2d(L.fA0ft_all, r.ft[lv], r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));
+    }
     for (const LayerW& l : e->layers) {
       if (l.kind != 2 || l.level != lv) continue;
       K_(conv2d(l.cp.fF2, bufF.slice(l.k_in_level * Hd, Hd), t, relu, IN_DIRECT, r.s));

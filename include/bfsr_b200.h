@@ -156,6 +156,11 @@ int bfsr_linf_lp_sr_host(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_ho
 int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                    const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
                    void* stream);
+/* conv3x3(F.interpolate(x, scale_factor=2, mode='nearest')) + bias (RRDBNet_arch.py:105; the conditioning path of
+ * SRFlowNet_arch.py:136): y is (B,Cout,2H,2W).  impl: 0 = fp32 kernel, upsample folded into the loader; 1 = tcgen05,
+ * folded loader; 2 = tcgen05, four 2x2 phase convs on the low-res grid with pre-summed weights (16/36 of the MACs). */
+int bfsr_op_conv2d_up2(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
+                       const float* bias_host, int32_t Cout, int32_t impl, float* y_dev, void* stream);
 /* flow.squeeze2d / unsqueeze2d (flow.py:122-152) */
 int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
                       void* stream);

@@ -175,3 +175,18 @@ def test_conv1x1_tcgen05(lib, cin, cout, H, W, act):
     lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 1, act, 1,
                                       y.data_ptr(), None))
     assert rel_l2(ref, y) < 2e-5
+
+
+@pytest.mark.parametrize("impl,tol", [(0, 2e-6), (1, 2e-5), (2, 2e-5)])
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 12, 10), (256, 128, 17, 9), (96, 48, 8, 24)])
+def test_conv_over_nearest_up2(lib, cin, cout, H, W, impl, tol):
+    """conv3x3(nearest2x(x)): folded loader (fp32 / tcgen05) and the four-phase 2x2 evaluation all equal the reference op."""
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(F.interpolate(x.double(), scale_factor=2, mode="nearest"), w.double(), b.double(), padding=1)
+    y = torch.empty(2, cout, 2 * H, 2 * W, device="cuda")
+    lib.check(lib.lib().bfsr_op_conv2d_up2(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, impl,
+                                          y.data_ptr(), None))
+    assert rel_l2(ref, y) < tol
