@@ -348,7 +348,7 @@ namespace bfsr {
 // conv dispatcher: the tcgen05 implicit-GEMM path takes the shapes it supports, everything else runs on the
 // fp32 CUDA-core kernel.
 void conv2d(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
-  if (conv_tc_eligible(w, in, out)) conv2d_tc(w, in, out, epi, in_mode, s);
+  if (conv_tc_eligible(w, in, out, epi)) conv2d_tc(w, in, out, epi, in_mode, s);
   else conv2d_fp32(w, in, out, epi, in_mode, s);
 }
 }  // namespace bfsr

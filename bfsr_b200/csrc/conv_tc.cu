@@ -41,7 +41,7 @@ thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 
 namespace tc {
 constexpr int KC = 32;                       // channels per chunk = one 64-byte bf16 row (SWIZZLE_64B)
 constexpr int ROWB = 64;                     // bytes per smem row
-constexpr int NA = 2, NW = 4;
+constexpr int NA = 2, NW_MAX = 4;
 constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
 constexpr int NTHREADS = (6 + PROD_WARPS) * 32;
 constexpr int MAX_SMEM = 227 * 1024;
@@ -61,7 +61,8 @@ struct TcArgs {
   int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
-  int a_plane, a_slot, w_slot;           // bytes
+  int a_plane, a_slot, w_slot;           // bytes (w_slot = one tap image)
+  int tps, nw, w_stage;                  // taps per weight stage, number of stages, bytes per stage
   int nacc;                              // TMEM accumulator stages (1 or 2)
   int tiles_x, tiles_y, total_tiles;     // macro tiles per image and total work tiles (incl. cout tiles, batch)
   uint32_t tmem_cols;
@@ -164,11 +165,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
   const uint32_t w_smem = base + NA * a.a_slot;                   // NW slots
-  const uint32_t bars = w_smem + NW * a.w_slot;                   // mbarriers (8 B each)
-  const uint32_t a_full = bars, a_empty = bars + 8 * NA, w_full = bars + 16 * NA, w_empty = w_full + 8 * NW;
-  const uint32_t acc_full = w_empty + 8 * NW, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
+  const uint32_t bars = w_smem + a.nw * a.w_stage;                // mbarriers (8 B each)
+  const uint32_t a_full = bars, a_empty = bars + 8 * NA, w_full = bars + 16 * NA, w_empty = w_full + 8 * NW_MAX;
+  const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  float* stage_all = reinterpret_cast<float*>(smem_gen + NA * a.a_slot + NW * a.w_slot + 256);
+  float* stage_all = reinterpret_cast<float*>(smem_gen + NA * a.a_slot + a.nw * a.w_stage + 256);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform role index
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, NPROD); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < NW; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
+    for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -214,14 +215,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && cb < a.cin) {
             const int sy_ = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx_ = a.in_mode == IN_UP2 ? gx >> 1 : gx;
             const long long p = img + (long long)sy_ * inW + sx_;
-            if (a.vec_in && cb + 8 <= a.cin) {
+            {   // eligibility guarantees 128-bit addressable views and Cin % 8 == 0
               const float4* src = reinterpret_cast<const float4*>((const float*)a.in.p + p * a.in.cs + a.in.coff + cb);
               v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1);
-            } else {
-              float tt[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) tt[e] = cb + e < a.cin ? ld(a.in, p, cb + e) : 0.f;
-              v[u][0] = make_float4(tt[0], tt[1], tt[2], tt[3]); v[u][1] = make_float4(tt[4], tt[5], tt[6], tt[7]);
             }
           }
         }
@@ -271,9 +267,6 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     // ===================== epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> coalesced stores ============
     float* stg = stage_all + warp * 32 * STG_PITCH;   // this warp's 32 x 32 staging block
     const int sub_cols = a.fast ? nt : 2 * nt;
-    const bool vpre = a.pre.p && a.pre.fmt == F32 && a.pre.cs % 4 == 0 && a.pre.coff % 4 == 0 && ((uintptr_t)a.pre.p % 16) == 0;
-    const bool vr1 = a.res1.p && a.res1.fmt == F32 && a.res1.cs % 4 == 0 && a.res1.coff % 4 == 0 && ((uintptr_t)a.res1.p % 16) == 0;
-    const bool vr2 = a.res2.p && a.res2.fmt == F32 && a.res2.cs % 4 == 0 && a.res2.coff % 4 == 0 && ((uintptr_t)a.res2.p % 16) == 0;
     int t_it = 0;
     TR_DECL(tr_wait = 0, tr_work = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
@@ -313,48 +306,38 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           const int q4 = ncol >> 2, ppi = 32 / q4;
           const int c4 = (lane % q4) * 4, rsub = lane / q4;
           const int co = co_base + n0 + c4;              // this lane's 4 output channels (same for every pixel it touches)
-          const bool cok = co < a.cout, full = co + 4 <= a.cout;
+          const bool cok = co < a.cout;                  // Cout % 4 == 0 (eligibility), so a live lane owns 4 valid channels
           float bb[4] = {0.f, 0.f, 0.f, 0.f};
           if (cok) { const float4 b4 = *reinterpret_cast<const float4*>(a.bias + co); bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w; }
-#pragma unroll 1
-          for (int i = 0; i < q4; ++i) {
-            {
+          if (cok) {
+            // lean path (every operand 128-bit addressable, block fully inside Cout): ~40 instructions per 4 outputs
+            const float slope = a.act == ACT_LRELU ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+            const float* prep = (const float*)a.pre.p + a.pre.coff + co;
+            const float* r1p = (const float*)a.res1.p + a.res1.coff + co;
+            const float* r2p = (const float*)a.res2.p + a.res2.coff + co;
+            float* outp = (float*)a.out.p + a.out.coff + co;
+#pragma unroll 2
+            for (int i = 0; i < q4; ++i) {
               const int r = i * ppi + rsub;
               const int idx = warp * 32 + r;
               const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
-              if (gy < a.H && gx < a.W && cok) {
-                const float4 s4 = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
+              if (gy < a.H && gx < a.W) {
                 const long long p = a.phase ? ((long long)tcd.n * 2 * a.H + 2 * gy + (tcd.ph >> 1)) * (2 * a.W) + 2 * gx + (tcd.ph & 1)
                                             : ((long long)tcd.n * a.H + gy) * a.W + gx;
-                float o[4] = {s4.x, s4.y, s4.z, s4.w};
-                float pr[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f};
-                if (a.pre.p) {
-                  if (vpre && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.pre.p + p * a.pre.cs + a.pre.coff + co); pr[0] = t4.x; pr[1] = t4.y; pr[2] = t4.z; pr[3] = t4.w; }
-                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) pr[e] = ld(a.pre, p, co + e); }
+                float4 o = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
+                o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
+                if (a.pre.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(prep + p * a.pre.cs)); o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+                if (a.act == ACT_CROSS_SIGMOID) {
+                  o.y = 1.f / (1.f + expf(-(o.y + 2.f))) + a.eps;      // co % 4 == 0: the odd channels are .y and .w
+                  o.w = 1.f / (1.f + expf(-(o.w + 2.f))) + a.eps;
+                } else {
+                  o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+                  o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
                 }
-                if (a.res1.p) {
-                  if (vr1 && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.res1.p + p * a.res1.cs + a.res1.coff + co); r1[0] = t4.x; r1[1] = t4.y; r1[2] = t4.z; r1[3] = t4.w; }
-                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) r1[e] = ld(a.res1, p, co + e); }
-                }
-                if (a.res2.p) {
-                  if (vr2 && full) { const float4 t4 = *reinterpret_cast<const float4*>((const float*)a.res2.p + p * a.res2.cs + a.res2.coff + co); r2[0] = t4.x; r2[1] = t4.y; r2[2] = t4.z; r2[3] = t4.w; }
-                  else { for (int e = 0; e < 4; ++e) if (co + e < a.cout) r2[e] = ld(a.res2, p, co + e); }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float vv = o[e] + bb[e] + pr[e];
-                  if (a.act == ACT_LRELU) vv = vv > 0.f ? vv : 0.2f * vv;
-                  else if (a.act == ACT_RELU) vv = fmaxf(vv, 0.f);
-                  else if (a.act == ACT_CROSS_SIGMOID) { if ((co + e) & 1) vv = 1.f / (1.f + expf(-(vv + 2.f))) + a.eps; }
-                  vv *= a.alpha;
-                  vv = fmaf(a.beta1, r1[e], vv);
-                  vv = fmaf(a.beta2, r2[e], vv);
-                  o[e] = vv;
-                }
-                if (a.vec_out && full)
-                  *reinterpret_cast<float4*>((float*)a.out.p + p * a.out.cs + a.out.coff + co) = make_float4(o[0], o[1], o[2], o[3]);
-                else
-                  for (int e = 0; e < 4; ++e) if (co + e < a.cout) st(a.out, p, co + e, o[e]);
+                o.x *= a.alpha; o.y *= a.alpha; o.z *= a.alpha; o.w *= a.alpha;
+                if (a.res1.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(r1p + p * a.res1.cs)); o.x = fmaf(a.beta1, t4.x, o.x); o.y = fmaf(a.beta1, t4.y, o.y); o.z = fmaf(a.beta1, t4.z, o.z); o.w = fmaf(a.beta1, t4.w, o.w); }
+                if (a.res2.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(r2p + p * a.res2.cs)); o.x = fmaf(a.beta2, t4.x, o.x); o.y = fmaf(a.beta2, t4.y, o.y); o.z = fmaf(a.beta2, t4.z, o.z); o.w = fmaf(a.beta2, t4.w, o.w); }
+                *reinterpret_cast<float4*>(outp + p * a.out.cs) = o;
               }
             }
           }
@@ -378,11 +361,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     uint32_t sub_off[4];
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) sub_off[sub] = (uint32_t)((sub / a.sx) * 16 * a.pitch + (sub % a.sx) * 8) * (ROWB >> 4);
+    const int kw = a.phase ? 2 : a.ks;                                   // taps per filter row
+    const uint32_t row_step = (uint32_t)(a.pitch - (kw - 1)) * (ROWB >> 4);   // from the last tap of a row to the first of the next
+    const int stages = a.ntaps / a.tps;
     int a_it = 0, w_it = 0, t_it = 0;
     TR_DECL(tr_acc = 0, tr_a = 0, tr_w = 0, tr_issue = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
       const int as = t_it % a.nacc;
       const int ph = a.phase ? (t / a.n_ct) & 3 : 0;
+      const uint32_t tap_base = a.phase ? (uint32_t)((ph >> 1) * a.pitch + (ph & 1)) * (ROWB >> 4) : 0u;
       TR_T(tr0);
       mbar_wait(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
       TR_ADD(tr_acc, tr0);
@@ -396,35 +383,39 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         const uint32_t a_hi = a_smem + slot * a.a_slot, a_lo = a_hi + a.a_plane;
         const uint64_t a_hi_d = desc_a_hi | (uint64_t)((a_hi & 0x3FFFF) >> 4), a_lo_d = desc_a_hi | (uint64_t)((a_lo & 0x3FFFF) >> 4);
         int nk = (a.cin - c * KC + 15) >> 4; nk = nk > 2 ? 2 : nk;
-        for (int tap = 0; tap < a.ntaps; ++tap, ++w_it) {
-          const int ws = w_it % NW;
+        // running tap geometry (no divisions on the issue path): kw taps per filter row, start offset of the phase
+        int tdx = 0;
+        uint32_t tap_off = tap_base;
+        for (int st = 0; st < stages; ++st, ++w_it) {
+          const int ws = w_it % a.nw;
           TR_T(tr2);
-          mbar_wait(w_full + 8 * ws, (w_it / NW) & 1);
+          mbar_wait(w_full + 8 * ws, (w_it / a.nw) & 1);
           TR_ADD(tr_w, tr2); TR_T(tr3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t wb = w_smem + ws * a.w_slot;
-          const int dy = a.phase ? (ph >> 1) + (tap >> 1) : tap / a.ks, dx = a.phase ? (ph & 1) + (tap & 1) : tap - (tap / a.ks) * a.ks;
-          // One elected lane issues the whole tap.  Descriptors differ only in the 14-bit start-address field, so each
-          // operand is the chunk/slot base descriptor plus a small precomputed offset (uniform-datapath adds).
-          const uint32_t tap_off = (uint32_t)(dy * a.pitch + dx) * (ROWB >> 4);
-          const uint64_t bd0 = desc_b_hi | (uint64_t)(((wb & 0x3FFFF) >> 4));
-          const uint32_t accf0 = (c | tap) ? 1u : 0u;
-          if (elect_one()) {
+          // One elected lane issues the whole stage.  Descriptors differ only in the 14-bit start-address field, so each
+          // operand is the chunk/slot base descriptor plus a small running offset (uniform-datapath adds).
+          uint64_t bd0 = desc_b_hi | (uint64_t)((((w_smem + ws * a.w_stage)) & 0x3FFFF) >> 4);
+          for (int tt = 0; tt < a.tps; ++tt) {             // uniform loop; one elected lane issues each tap
+            const uint32_t accf0 = (c | st | tt) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-              if (sub < a.mt) {
-                const uint32_t d = d_base + sub * sub_cols;
-                const uint64_t ah = a_hi_d + tap_off + sub_off[sub], al = a_lo_d + tap_off + sub_off[sub];
-                umma_f16(d, ah, bd0, idesc_wide, accf0);
-                if (!a.fast) umma_f16(d, al, bd0, idesc_nt, 1u);
-                if (nk > 1) {
-                  umma_f16(d, ah + 2, bd0 + 2, idesc_wide, 1u);
-                  if (!a.fast) umma_f16(d, al + 2, bd0 + 2, idesc_nt, 1u);
+              for (int sub = 0; sub < 4; ++sub) {
+                if (sub < a.mt) {
+                  const uint32_t d = d_base + sub * sub_cols;
+                  const uint64_t ah = a_hi_d + tap_off + sub_off[sub], al = a_lo_d + tap_off + sub_off[sub];
+                  umma_f16(d, ah, bd0, idesc_wide, accf0);
+                  if (!a.fast) umma_f16(d, al, bd0, idesc_nt, 1u);
+                  if (nk > 1) {
+                    umma_f16(d, ah + 2, bd0 + 2, idesc_wide, 1u);
+                    if (!a.fast) umma_f16(d, al + 2, bd0 + 2, idesc_nt, 1u);
+                  }
                 }
               }
             }
-            umma_commit(w_empty + 8 * ws);      // weight slot reusable once these MMAs retire
+            bd0 += (uint32_t)a.w_slot >> 4;
+            if (++tdx == kw) { tdx = 0; tap_off += row_step; } else tap_off += ROWB >> 4;
           }
+          if (elect_one()) umma_commit(w_empty + 8 * ws);      // weight stage reusable once these MMAs retire
           __syncwarp();
           TR_ADD(tr_issue, tr3);
         }
@@ -447,15 +438,18 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
       const int ct = t % a.n_ct;
       const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
       const unsigned char* wsrc = a.w + (size_t)wsel * a.n_chunks * a.ntaps * tap_stride;
-      const int total = a.n_chunks * a.ntaps;
+      const int total = a.n_chunks * (a.ntaps / a.tps);
       for (int wi = 0; wi < total; ++wi, ++w_it) {
-        const int ws = w_it % NW;
+        const int ws = w_it % a.nw;
         TR_T(tr0);
-        mbar_wait(w_empty + 8 * ws, ((w_it / NW) & 1) ^ 1);
+        mbar_wait(w_empty + 8 * ws, ((w_it / a.nw) & 1) ^ 1);
         TR_ADD(tr_wait, tr0);
         if (elect_one()) {
-          mbar_expect_tx(w_full + 8 * ws, w_bytes);
-          bulk_g2s(w_smem + ws * a.w_slot, wsrc + (size_t)wi * tap_stride, w_bytes, w_full + 8 * ws);
+          const uint32_t dst = w_smem + ws * a.w_stage;
+          const unsigned char* src = wsrc + (size_t)wi * a.tps * tap_stride;
+          mbar_expect_tx(w_full + 8 * ws, w_bytes * a.tps);
+          if (!a.fast) bulk_g2s(dst, src, w_bytes * a.tps, w_full + 8 * ws);        // taps are contiguous: one bulk copy
+          else for (int tt = 0; tt < a.tps; ++tt) bulk_g2s(dst + tt * a.w_slot, src + (size_t)tt * tap_stride, w_bytes, w_full + 8 * ws);
         }
         __syncwarp();
       }
@@ -518,9 +512,13 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
   c.tc_kchunks = n_chunks; c.tc_npad = nt;
 }
 
-bool conv_tc_eligible(const ConvW& w, const View& in, const View& out) {
-  (void)out;
-  return w.w_tc != nullptr && g_conv_mode != 2 && in.fmt == F32;   // batch-independent, so results do not depend on chunking
+static bool vec4(const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; }
+
+// Shapes the tensor-core kernel takes (everything else runs on the fp32 CUDA-core kernels).  Batch-independent, so results
+// do not depend on chunking.  The kernel has no scalar fallbacks (keeps its instruction footprint small).
+bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const ConvEpi& epi) {
+  return w.w_tc != nullptr && !w.tc_phase && g_conv_mode != 2 && w.cin % 8 == 0 && w.cout % 4 == 0 && vec4(in) && vec4(out) &&
+         (!epi.pre || vec4(*epi.pre)) && (!epi.res1 || vec4(*epi.res1)) && (!epi.res2 || vec4(*epi.res2));
 }
 
 static int g_num_sms = 0;
@@ -532,6 +530,9 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
+  BFSR_CHECK(w.cin % 8 == 0 && w.cout % 4 == 0 && vec4(in) && vec4(out) && (!epi.pre || vec4(*epi.pre)) &&
+             (!epi.res1 || vec4(*epi.res1)) && (!epi.res2 || vec4(*epi.res2)),
+             "conv_tc: operands must be fp32, 16-byte addressable, Cin %% 8 == 0 and Cout %% 4 == 0");
   if (in_mode == IN_UP2 || phase) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
   else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv_tc: spatial mismatch");
   if (out.npix() == 0) return;
@@ -570,7 +571,18 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.tmem_cols = cols;
   a.tiles_x = cdiv(gW, 8 * a.sx); a.tiles_y = cdiv(gH, 16 * a.sy);
   a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
-  const int smem = NA * a.a_slot + NW * a.w_slot + 1024 + 256 + STG_BYTES;
+  // weight stages: as many taps per stage as fit ~48 KB (fewer barrier round trips on the MMA issue path), 2-4 stages
+  a.tps = 1;
+  for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
+  a.w_stage = a.tps * a.w_slot;
+  const int fixed = NA * a.a_slot + 1024 + 256 + STG_BYTES;
+  a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
+  while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
+    int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
+    a.tps = next; a.w_stage = a.tps * a.w_slot; a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
+  }
+  BFSR_CHECK(a.nw >= 2, "conv_tc: no room for two weight stages");
+  const int smem = fixed + a.nw * a.w_stage;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
   BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }

@@ -36,7 +36,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
 // 2 = never use the tensor-core path (all convs on the fp32 CUDA-core kernel).
 extern thread_local int g_conv_mode;
 void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed);
-bool conv_tc_eligible(const ConvW& w, const View& in, const View& out);
+bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const ConvEpi& epi);
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
 // 3x3 conv over nearest2x(in_lowres) as four 2x2 phase convs on the low-res grid (16/36 of the MACs); out is (N,2H,2W)
 ConvW pack_conv_tc_phase(const float* w_oihw, int cout, int cin_src, int c0, int cn, const float* out_scale);

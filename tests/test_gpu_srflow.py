@@ -162,7 +162,7 @@ def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
     assert err < (2e-5 if impl == 1 else 1e-2), err
 
 
-@pytest.mark.parametrize("cin,cout,H,W,act", [(64, 64, 20, 24, 2), (256, 27, 9, 9, 0), (1024, 256, 33, 5, 2), (96, 540, 8, 8, 0)])
+@pytest.mark.parametrize("cin,cout,H,W,act", [(64, 64, 20, 24, 2), (256, 28, 9, 9, 0), (1024, 256, 33, 5, 2), (96, 540, 8, 8, 0)])
 def test_conv1x1_tcgen05(lib, cin, cout, H, W, act):
     """1x1 convs (coupling hidden layers, LINF MLP) on the tcgen05 kernel (single tap, no halo), split-bf16 x3."""
     g = torch.Generator().manual_seed(cin + cout)
