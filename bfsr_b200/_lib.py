@@ -50,6 +50,7 @@ SYMBOLS = {
     "bfsr_version": (C.c_char_p, []),
     "bfsr_launch_count": (C.c_int64, [C.c_int]),
     "bfsr_prof_enable": (C.c_int, [C.c_int]),
+    "bfsr_prof_dump": (C.c_int, [C.c_char_p, C.c_int]),
     "bfsr_prof_summary": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bfsr_srflow_create": (C.c_int, [C.POINTER(_P), C.POINTER(SRFlowDesc), C.POINTER(Tensor), _I, _I]),
     "bfsr_srflow_destroy": (None, [_P]),

@@ -103,6 +103,7 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 // When enabled, launchers bracket each launch with CUDA events on the launching stream; bfsr_prof_summary()
 // returns the summed device time and algorithmic work (flops for convs, bytes for flow steps) per class.
 enum ProfKind : int { PK_CONV_FP32 = 0, PK_CONV_TC = 1, PK_FLOWSTEP = 2, PK_OTHER = 3, PK_COUNT = 4 };
+extern thread_local char g_prof_tag[96];   // optional shape tag consumed by the next prof_begin (bfsr_prof_dump groups by it)
 void prof_begin(int kind, double work, cudaStream_t s);
 void prof_end(cudaStream_t s);
 struct ProfScope {

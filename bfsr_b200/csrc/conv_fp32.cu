@@ -272,6 +272,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   a.tiles_x = 0;
   if (out.npix() == 0) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "fp32 k%d %d->%d %dx%d", w.ks, w.cin, w.cout, out.H, out.W);
   ProfScope prof(PK_CONV_FP32, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   if (small_ok(w, in, out, epi, in_mode)) {
     a.tiles_x = cdiv(a.W, 16);

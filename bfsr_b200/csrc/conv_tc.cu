@@ -57,6 +57,7 @@ struct TcArgs {
   int H, W, N, in_mode, act;
   float eps, alpha, beta1, beta2;
   int fast, vec_in, vec_out;
+  int wide;                              // accurate mode with NT < 64: A_hi x [W_hi;W_lo] as one N = 2NT MMA (column halves summed by the epilogue)
   int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
   int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform role index
   const int nt = a.nt;
-  const int acc_cols = a.mt * (a.fast ? nt : 2 * nt);            // TMEM columns per accumulator stage
+  const int acc_cols = a.mt * (a.wide ? 2 * nt : nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, NPROD); mbar_init(a_empty + 8 * i, 1); }
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   } else if (warp < 4) {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> coalesced stores ============
     float* stg = stage_all + warp * 32 * STG_PITCH;   // this warp's 32 x 32 staging block
-    const int sub_cols = a.fast ? nt : 2 * nt;
+    const int sub_cols = a.wide ? 2 * nt : nt;
     int t_it = 0;
     TR_DECL(tr_wait = 0, tr_work = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           float acc[32];
           tmem_ld16(t_row + n0, acc);
           if (ncol == 32) tmem_ld16(t_row + n0 + 16, acc + 16);
-          if (!a.fast) {
+          if (a.wide) {
             float acc2[32];
             tmem_ld16(t_row + nt + n0, acc2);
             if (ncol == 32) tmem_ld16(t_row + nt + n0 + 16, acc2 + 16);
@@ -353,9 +354,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 #endif
   } else if (warp == 4) {
     // ===================== MMA issuer: whole warp walks the (uniform) loop, one elected lane issues =====================
-    const uint32_t idesc_wide = make_idesc(a.fast ? nt : 2 * nt), idesc_nt = make_idesc(nt);
+    const uint32_t idesc_wide = make_idesc(a.wide ? 2 * nt : nt), idesc_nt = make_idesc(nt);
+    const uint32_t lo_rows = (uint32_t)nt * (ROWB >> 4);               // descriptor offset of the W_lo rows inside a tap image
     const uint32_t sbo = (uint32_t)a.pitch * ROWB;
-    const int sub_cols = a.fast ? nt : 2 * nt;
+    const int sub_cols = a.wide ? 2 * nt : nt;
+    const bool merged = !a.fast && !a.wide;                             // three N = NT MMAs into the same accumulator columns
     // constant descriptor fields (LBO=1, SBO, version 1, SWIZZLE_64B); the start address is added per operand
     const uint64_t desc_a_hi = make_desc(0, sbo), desc_b_hi = make_desc(0, 8 * ROWB);
     uint32_t sub_off[4];
@@ -404,9 +407,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
                   const uint32_t d = d_base + sub * sub_cols;
                   const uint64_t ah = a_hi_d + tap_off + sub_off[sub], al = a_lo_d + tap_off + sub_off[sub];
                   umma_f16(d, ah, bd0, idesc_wide, accf0);
+                  if (merged) umma_f16(d, ah, bd0 + lo_rows, idesc_nt, 1u);
                   if (!a.fast) umma_f16(d, al, bd0, idesc_nt, 1u);
                   if (nk > 1) {
                     umma_f16(d, ah + 2, bd0 + 2, idesc_wide, 1u);
+                    if (merged) umma_f16(d, ah + 2, bd0 + lo_rows + 2, idesc_nt, 1u);
                     if (!a.fast) umma_f16(d, al + 2, bd0 + 2, idesc_nt, 1u);
                   }
                 }
@@ -550,8 +555,13 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
-  const int sub_cols = a.fast ? a.nt : 2 * a.nt;
-  int mt = 512 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);
+  // accurate mode: NT >= 64 issues the three products as separate N = NT MMAs into the same columns (half the TMEM, the
+  // epilogue reads each value once); NT < 64 keeps A_hi x [W_hi;W_lo] as one N = 2NT MMA (an N < 64 MMA is bound by the
+  // shared-memory read of A, so fewer, wider MMAs win there)
+  static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
+  a.wide = (!a.fast && (a.nt < 64 || force_wide)) ? 1 : 0;
+  const int sub_cols = a.wide ? 2 * a.nt : a.nt;
+  int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
   a.sx = 1; a.sy = 1;
   if (mt == 4) {
     if (gW > 8 && gH > 16) { a.sx = 2; a.sy = 2; }
@@ -589,6 +599,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
+  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", phase ? "-phase" : "", w.ks, w.cin, w.cout, out.H, out.W,
+           in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
   count_launch();

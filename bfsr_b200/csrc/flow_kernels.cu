@@ -221,6 +221,7 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   const size_t smem = ((size_t)w.C * w.C + (size_t)a.pix_per_block * (w.C + 1)) * 4;
   const int grid = cdiv(a.npix, a.pix_per_block);
   // algorithmic HBM bytes: z in + z out (+ h: C, + hF: 2C) fp32 per level-pixel
+  snprintf(g_prof_tag, sizeof g_prof_tag, "flowstep%s C%d %dx%d%s%s", inv ? "-inv" : "-fwd", w.C, a.H, a.W, h ? " h" : "", hF ? " hF" : "");
   ProfScope prof(PK_FLOWSTEP, 4.0 * (double)a.npix * w.C * (2 + (h ? 1 : 0) + (hF ? 2 : 0)), s);
   // small-C fast path (levels 1 and 2 of the shipped topology)
   const bool px_ok = (w.C == 12 || w.C == 24) && zin.fmt == F32 && zout.fmt == F32 && (sq_in || vec4_ok(zin)) &&
@@ -263,6 +264,8 @@ __global__ void coupling_finish_kernel(View z, View h, View out, long long n, in
 void coupling_finish(const View& z, const View& h, const View& z_out, cudaStream_t s) {
   const long long n = z.npix() * z.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "coupling_finish C%d", z.C);
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   coupling_finish_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, h, z_out, n, z.C);
   count_launch();
 }
@@ -281,6 +284,8 @@ __global__ void split_fwd_kernel(View z, View h, View z1, View eps, long long n,
 void split_fwd(const View& z, const View& h, const View& z1_out, const View& eps_out, cudaStream_t s) {
   const long long n = z.npix() * z.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "split_fwd");
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   split_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, h, z1_out, eps_out, n, z1_out.C, eps_out.C);
   count_launch();
 }
@@ -298,6 +303,8 @@ __global__ void split_inv_kernel(View z1, View h, View eps, View out, long long 
 void split_inv(const View& z1, const View& h, const View& eps, const View& z_out, cudaStream_t s) {
   const long long n = z_out.npix() * z_out.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "split_inv");
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   split_inv_kernel<<<cdiv(n, 256), 256, 0, s>>>(z1, h, eps, z_out, n, z1.C, eps.C);
   count_launch();
 }
@@ -315,6 +322,8 @@ __global__ void normalise_kernel(View e, View out, long long npix, int C) {
 }
 void normalise_latent(const View& e, const View& out, cudaStream_t s) {
   if (!e.npix()) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "normalise C%d", e.C);
+  ProfScope prof(PK_OTHER, 8.0 * e.npix() * e.C, s);
   normalise_kernel<<<cdiv(e.npix(), 128), 128, 0, s>>>(e, out, e.npix(), e.C);
   count_launch();
 }
@@ -354,6 +363,8 @@ __global__ void nchw_to_nhwc_kernel(const float* src, View dst, long long n, int
 void nchw_to_nhwc(const float* src, const View& dst, cudaStream_t s) {
   const long long n = dst.npix() * dst.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "nchw_to_nhwc C%d", dst.C);
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   nchw_to_nhwc_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, dst.C, dst.H * dst.W);
   count_launch();
 }
@@ -367,6 +378,8 @@ __global__ void nhwc_to_nchw_kernel(View src, float* dst, long long n, int C, in
 void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s) {
   const long long n = src.npix() * src.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "nhwc_to_nchw C%d", src.C);
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   nhwc_to_nchw_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, src.C, src.H * src.W);
   count_launch();
 }
@@ -426,6 +439,8 @@ void resample(const View& src, const View& dst, int mode, cudaStream_t s) {
   }
   const long long n = dst.npix() * dst.C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "resample m%d C%d %dx%d", mode, dst.C, dst.H, dst.W);
+  ProfScope prof(PK_OTHER, 8.0 * n, s);
   resample_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, mode, oy, ox);
   count_launch();
 }
@@ -450,6 +465,8 @@ void bilinear_up_nchw(const float* src, int N, int C, int h, int w, int scale, c
   BFSR_CHECK(dst.N == N && dst.C == C && dst.H == h * scale && dst.W == w * scale, "bilinear_up: shape");
   const long long n = dst.npix() * C;
   if (!n) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "bilinear_up");
+  ProfScope prof(PK_OTHER, 4.0 * n, s);
   bilinear_up_nchw_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, C, h, w, scale, dst, n);
   count_launch();
 }

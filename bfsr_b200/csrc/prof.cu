@@ -1,10 +1,14 @@
 // Optional per-launch device timing with CUDA events (used by bench.py for the roofline numbers; off by default).
 #include "common.cuh"
 #include <vector>
+#include <map>
+#include <string>
+#include <cstring>
 
 namespace bfsr {
 
-struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+struct ProfRec { cudaEvent_t a, b; int kind; double work; std::string tag; };
+thread_local char g_prof_tag[96] = "";
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec> g_recs;
 static thread_local std::vector<cudaEvent_t> g_pool;
@@ -16,7 +20,7 @@ static cudaEvent_t get_event() {
 
 void prof_begin(int kind, double work, cudaStream_t s) {
   if (!g_prof_on) return;
-  ProfRec r; r.a = get_event(); r.b = get_event(); r.kind = kind; r.work = work;
+  ProfRec r; r.a = get_event(); r.b = get_event(); r.kind = kind; r.work = work; r.tag = g_prof_tag; g_prof_tag[0] = 0;
   CUDA_OK(cudaEventRecord(r.a, s));
   g_recs.push_back(r);
 }
@@ -50,5 +54,25 @@ int bfsr_prof_summary(int kind, double* total_ms, double* total_work, int64_t* c
   if (total_work) *total_work = work;
   if (count) *count = n;
   return 0;
+}
+// Per-shape breakdown of the recorded launches: "tag<TAB>launches<TAB>ms<TAB>work" lines into buf (truncated to cap).
+int bfsr_prof_dump(char* buf, int cap) {
+  if (cudaDeviceSynchronize() != cudaSuccess || !buf || cap <= 0) return -1;
+  struct Agg { double ms = 0, work = 0; long long n = 0; };
+  std::map<std::string, Agg> m;
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return -1;
+    Agg& a = m[r.tag.empty() ? std::string("kind") + std::to_string(r.kind) : r.tag];
+    a.ms += t; a.work += r.work; ++a.n;
+  }
+  std::string out;
+  for (auto& kv : m) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\t%lld\t%.4f\t%.6g\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.work);
+    out += line;
+  }
+  strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0;
+  return (int)out.size();
 }
 }

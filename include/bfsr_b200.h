@@ -41,6 +41,8 @@ int64_t bfsr_launch_count(int reset);
  * kind: 0 fp32 conv, 1 tcgen05 conv, 2 fused flow step, 3 other.  work = algorithmic FLOPs (convs) or bytes (flow steps). */
 int bfsr_prof_enable(int on);
 int bfsr_prof_summary(int kind, double* total_ms, double* total_work, int64_t* count);
+/* per-shape breakdown of the recorded launches as "tag\tlaunches\tms\twork\n" text; returns the untruncated length */
+int bfsr_prof_dump(char* buf, int cap);
 
 /* ------------------------------------------------------------------ SRFlow generator
  * Stands behind SRFlowNet.forward (SRFlow-LP/code/models/modules/SRFlowNet_arch.py:60-82),
