@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfsr_b200.so")
+# BFSR_LIB_PATH selects an instrumented build of the same library (tools only; e.g. `make trace`)
+LIB_PATH = os.environ.get("BFSR_LIB_PATH") or os.path.join(_HERE, "libbfsr_b200.so")
 
 
 class BfsrError(RuntimeError):

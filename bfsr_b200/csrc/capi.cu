@@ -258,7 +258,7 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
   BFSR_CHECK(x_dev && w_host && y_dev, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   ConvW cw = pack_conv(w_host, Cout, Cin, ks, bias_host, nullptr, {});
-  float *xn = nullptr, *yn = nullptr;
+  float *xn = nullptr, *yn = nullptr, *xb = nullptr, *yb = nullptr;
   const size_t npix = (size_t)B * H * W;
   try {
     CUDA_OK(cudaMalloc((void**)&xn, (npix * Cin + 4) * 4));
@@ -268,7 +268,20 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
     nchw_to_nhwc(x_dev, x, s);
     ConvEpi ep; ep.act = act;
     if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s);
-    else {   // 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass
+    else if (impl == 3) {   // tcgen05 split-bf16 x3 with the operand tensors stored as bf16 (hi, lo) planes: TMA-fed A operand
+      const int saved = g_conv_mode;
+      g_conv_mode = 0;
+      try {
+        CUDA_OK(cudaMalloc((void**)&xb, (npix * Cin + 16) * 4));
+        CUDA_OK(cudaMalloc((void**)&yb, (npix * Cout + 16) * 4));
+        View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * Cin;
+        View yv = y; yv.p = yb; yv.fmt = BF16X2; yv.plane = (long long)npix * Cout;
+        resample(x, xv, RS_COPY, s);
+        conv2d_tc(cw, xv, yv, ep, IN_DIRECT, s);
+        resample(yv, y, RS_COPY, s);
+      } catch (...) { g_conv_mode = saved; throw; }
+      g_conv_mode = saved;
+    } else {   // 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass
       const int saved = g_conv_mode;
       g_conv_mode = impl == 1 ? 0 : 1;
       try { conv2d_tc(cw, x, y, ep, IN_DIRECT, s); } catch (...) { g_conv_mode = saved; throw; }
@@ -276,8 +289,8 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
     }
     nhwc_to_nchw(y, y_dev, s);
     CUDA_OK(cudaStreamSynchronize(s));
-  } catch (...) { cudaFree(xn); cudaFree(yn); free_conv(cw); throw; }
-  cudaFree(xn); cudaFree(yn); free_conv(cw);
+  } catch (...) { cudaFree(xn); cudaFree(yn); cudaFree(xb); cudaFree(yb); free_conv(cw); throw; }
+  cudaFree(xn); cudaFree(yn); cudaFree(xb); cudaFree(yb); free_conv(cw);
   API_END
 }
 

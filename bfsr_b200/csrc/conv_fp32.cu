@@ -21,7 +21,7 @@ namespace bfsr {
 thread_local long long g_launches = 0;
 
 struct ConvArgs {
-  View in, out, pre, res1, res2;
+  View in, out, out2, pre, res1, res2;
   const float* w; const float* bias;
   int cin, cin_pad, cout, cout_pad;
   int H, W;           // output spatial dims
@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(ConvArgs a) {
       for (int j = 0; j < 4; ++j)
         if (co + j < a.cout) st(a.out, p, co + j, o[j]);
     }
+    if (a.out2.p) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co + j < a.cout) st(a.out2, p, co + j, o[j]);
+    }
   }
 }
 
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(ConvArgs a) {
 
 static bool small_ok(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode) {
   auto v2 = [](const View& v) { return v.fmt == F32 && v.cs % 2 == 0 && v.coff % 2 == 0 && ((uintptr_t)v.p % 8) == 0; };
-  return w.ks == 3 && w.cin <= 16 && w.cout == 64 && in_mode == IN_DIRECT && !epi.res1 && !epi.res2 &&
+  return w.ks == 3 && w.cin <= 16 && w.cout == 64 && in_mode == IN_DIRECT && !epi.res1 && !epi.res2 && !epi.out2 &&
          epi.act != ACT_CROSS_SIGMOID && in.fmt == F32 && v2(out) && (!epi.pre || v2(*epi.pre));
 }
 
@@ -260,7 +265,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
   if (in_mode == IN_UP2) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv(up2): spatial mismatch");
   else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv: spatial mismatch %dx%d vs %dx%d", in.H, in.W, out.H, out.W);
   ConvArgs a;
-  a.in = in; a.out = out;
+  a.in = in; a.out = out; a.out2 = epi.out2 ? *epi.out2 : View();
   a.pre = epi.pre ? *epi.pre : View();
   a.res1 = epi.res1 ? *epi.res1 : View();
   a.res2 = epi.res2 ? *epi.res2 : View();

@@ -29,6 +29,7 @@
 // Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMEM allocator + MMA issuer, warp 5 weight TMA
 // producer, warps 6-13 A producers.
 #include "ops.cuh"
+#include <cuda.h>
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -45,13 +46,19 @@ constexpr int NA = 2, NW_MAX = 4;
 constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
 constexpr int NTHREADS = (6 + PROD_WARPS) * 32;
 constexpr int MAX_SMEM = 227 * 1024;
+constexpr int STG_WARP = 8192;               // epilogue staging per warp: two 4 KB buffers (32 pixel rows x 128 B)
+constexpr int STG_BYTES = 4 * STG_WARP;
 constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
-constexpr int STG_PITCH = 36;                // floats per staged epilogue row (32 columns + pad, keeps float4 alignment)
-constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // one 32x32 block per epilogue warp
 }  // namespace tc
 
 struct TcArgs {
-  View in, out, pre, res1, res2;
+  alignas(64) CUtensorMap tmap;          // BF16X2 input: 5-D (C, W, H, N, plane) tiled map, box = one halo tile x 32 channels
+  alignas(64) CUtensorMap tmap_out;      // output(s): box = 32 channels x 8 x 4 pixels (one epilogue warp's rows of a sub-tile)
+  alignas(64) CUtensorMap tmap_out2;
+  int tma_out, tma_out2;                 // epilogue leaves through TMA bulk tensor stores (else per-lane direct stores)
+  View in, out, out2, pre, res1, res2;
+  int tma;                               // A operand arrives by TMA (input already split into bf16 hi/lo planes in HBM)
+  int in_bf;                             // register producer reads a BF16X2 view (IN_UP2 / phase modes)
   const unsigned char* w; const float* bias;
   int cin, cout, nt, n_chunks, n_ct;     // n_ct = cout tiles
   int H, W, N, in_mode, act;
@@ -101,6 +108,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 5-D tiled TMA load (SASS UTMALDG): box of the tensor map at signed coordinates -> swizzled smem, completes on an mbarrier
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// TMA bulk tensor stores (SASS UTMASTG): swizzled smem box -> global, clipped at the tensor bounds
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -130,6 +151,15 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// 4 consecutive channels of one pixel -> bf16 (hi, lo) planes of a BF16X2 view (the operand format of the next conv)
+__device__ __forceinline__ void store_split(const View& v, long long pix, int c, const float4& o) {
+  const float h0 = __bfloat162float(__float2bfloat16_rn(o.x)), h1 = __bfloat162float(__float2bfloat16_rn(o.y));
+  const float h2 = __bfloat162float(__float2bfloat16_rn(o.z)), h3 = __bfloat162float(__float2bfloat16_rn(o.w));
+  __nv_bfloat16* d = (__nv_bfloat16*)v.p + pix * v.cs + v.coff + c;
+  *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+  *reinterpret_cast<uint2*>(d + v.plane) = make_uint2(pack_bf16(o.x - h0, o.y - h1), pack_bf16(o.z - h2, o.w - h3));
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -166,11 +196,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
   const uint32_t w_smem = base + NA * a.a_slot;                   // NW slots
-  const uint32_t bars = w_smem + a.nw * a.w_stage;                // mbarriers (8 B each)
+  const uint32_t stg_smem = w_smem + a.nw * a.w_stage;            // epilogue staging (1024-aligned: every slot size is)
+  const uint32_t bars = stg_smem + STG_BYTES;                     // mbarriers (8 B each), then the per-warp bias copies
   const uint32_t a_full = bars, a_empty = bars + 8 * NA, w_full = bars + 16 * NA, w_empty = w_full + 8 * NW_MAX;
   const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
-  float* stage_all = reinterpret_cast<float*>(smem_gen + NA * a.a_slot + a.nw * a.w_stage + 256);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // provably warp-uniform role index
@@ -178,7 +208,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const int acc_cols = a.mt * (a.wide ? 2 * nt : nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, NPROD); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, a.tma ? 1 : NPROD); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,7 +224,30 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-  if (warp >= 6) {
+  if (warp >= 6 && a.tma) {
+    // ===================== A by TMA: the input already lives in HBM as bf16 (hi, lo) planes =====================
+    // One tiled TMA load per plane brings the whole halo tile of a 32-channel chunk straight into the UMMA SWIZZLE_64B
+    // layout (one pixel = one 64-byte row); out-of-image pixels and channels past the view are zero-filled by the TMA
+    // unit, which is exactly the conv's zero padding.
+    if (warp == 6) {
+      const uint32_t box_bytes = (uint32_t)(a.pitch * a.hrows) * ROWB;
+      int a_it = 0;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        const TileCoord tcd = tile_coord(a, t);
+        for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
+          const int slot = a_it % NA;
+          mbar_wait(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+          if (elect_one()) {
+            const uint32_t dst = a_smem + slot * a.a_slot, bar = a_full + 8 * slot;
+            mbar_expect_tx(bar, a.fast ? box_bytes : 2 * box_bytes);
+            tma_load_5d(dst, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 0);
+            if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 1);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 6) {
     // ===================== A producers: fp32 halo tile -> (hi, lo) bf16 planes, swizzled =====================
     // Each thread owns up to MAXI (pixel, 8-channel) items of a chunk.  The global loads of chunk i+1 are issued
     // into registers BEFORE waiting for its smem slot, so their latency hides behind the MMAs of chunk i-1.
@@ -216,9 +269,19 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && cb < a.cin) {
             const int sy_ = a.in_mode == IN_UP2 ? gy >> 1 : gy, sx_ = a.in_mode == IN_UP2 ? gx >> 1 : gx;
             const long long p = img + (long long)sy_ * inW + sx_;
-            {   // eligibility guarantees 128-bit addressable views and Cin % 8 == 0
+            if (a.in_bf) {   // already split: 8 channels = 16 bytes of the hi plane and 16 of the lo plane
+              const __nv_bfloat16* src = (const __nv_bfloat16*)a.in.p + p * a.in.cs + a.in.coff + cb;
+              v[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+              v[u][1] = __ldg(reinterpret_cast<const float4*>(src + a.in.plane));
+            } else if (cb + 8 <= a.cin) {   // eligibility guarantees 128-bit addressable views
               const float4* src = reinterpret_cast<const float4*>((const float*)a.in.p + p * a.in.cs + a.in.coff + cb);
               v[u][0] = __ldg(src); v[u][1] = __ldg(src + 1);
+            } else {          // ragged last group (Cin % 8 != 0, e.g. the 6-channel z1 of the first coupling level)
+              const float* src = (const float*)a.in.p + p * a.in.cs + a.in.coff + cb;
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = cb + e < a.cin ? __ldg(src + e) : 0.f;
+              v[u][0] = make_float4(x[0], x[1], x[2], x[3]); v[u][1] = make_float4(x[4], x[5], x[6], x[7]);
             }
           }
         }
@@ -230,11 +293,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         const int it = ptid + u * NPROD;
         if (it < items) {
           const int q = it >> 2, j = it & 3;
+          const uint32_t off = (uint32_t)q * ROWB + (uint32_t)((j ^ ((q >> 1) & 3)) << 4);
+          if (a.in_bf) {
+            *reinterpret_cast<float4*>(pl_hi + off) = v[u][0];
+            if (!a.fast) *reinterpret_cast<float4*>(pl_hi + a.a_plane + off) = v[u][1];
+            continue;
+          }
           const float x[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
           float hi[8], lo[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { hi[e] = __bfloat162float(__float2bfloat16_rn(x[e])); lo[e] = x[e] - hi[e]; }
-          const uint32_t off = (uint32_t)q * ROWB + (uint32_t)((j ^ ((q >> 1) & 3)) << 4);
           *reinterpret_cast<uint4*>(pl_hi + off) =
               make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
           if (!a.fast)
@@ -265,21 +333,86 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     if (blockIdx.x == 0 && ptid == 0) printf("[tc trace] producer: total %lld wait_a_empty %lld fill %lld (chunks %d)\n", clock64() - tr_start, tr_wait, tr_fill, a_it);
 #endif
   } else if (warp < 4) {
-    // ===================== epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> coalesced stores ============
-    float* stg = stage_all + warp * 32 * STG_PITCH;   // this warp's 32 x 32 staging block
+    // ===================== epilogue: TMEM -> registers -> fused epilogue -> swizzled smem -> TMA bulk tensor store ==========
+    // tcgen05.ld 32x32b hands every lane one accumulator ROW = the channels of one output pixel.  The lane applies bias /
+    // pre-activation / activation / residuals to its pixel, writes the 32-channel piece into a per-warp staging tile in
+    // the TMA swizzle pattern (conflict-free) and one lane issues a bulk tensor store of the warp's 8 x 4 pixel box: the
+    // TMA unit writes whole lines asynchronously and clips ragged edges / channel tails, the LSU only sees the (few)
+    // operand loads.  Views that TMA cannot address (phase outputs, odd strides) fall back to per-lane 16-byte stores.
     const int sub_cols = a.wide ? 2 * nt : nt;
-    int t_it = 0;
+    const float slope = a.act == ACT_LRELU ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+    unsigned char* stg_gen = smem_gen + (stg_smem - base) + warp * STG_WARP;
+    const uint32_t stg_u32 = stg_smem + warp * STG_WARP;
+    float* bias_s = reinterpret_cast<float*>(smem_gen + (bars + 256 - base)) + warp * 128;
+    int sb = 0, cur_ct = -1, t_it = 0;
+    // stage one 32-pixel x 32-channel block of this warp and launch its bulk store (out and out2 share the two buffers)
+    auto stage_store = [&](const View& v, const CUtensorMap* tm, const float* o, int ncol, int c0, int x0, int y0, int n) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the older store has drained its buffer
+      __syncwarp();
+      unsigned char* buf = stg_gen + sb * 4096;
+      if (v.fmt == F32) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (4 * k < ncol)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (8 * k < ncol) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0f = o[8 * k + 2 * e], x1f = o[8 * k + 2 * e + 1];
+              const float h0 = __bfloat162float(__float2bfloat16_rn(x0f)), h1 = __bfloat162float(__float2bfloat16_rn(x1f));
+              hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(x0f - h0, x1f - h1);
+            }
+            const uint32_t off = lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(buf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(buf + 2048 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = stg_u32 + sb * 4096;
+        if (v.fmt == F32) tma_store_4d(tm, src, v.coff + c0, x0, y0, n);
+        else { tma_store_5d(tm, src, v.coff + c0, x0, y0, n, 0); tma_store_5d(tm, src + 2048, v.coff + c0, x0, y0, n, 1); }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      sb ^= 1;
+    };
+    auto direct_store = [&](const View& v, long long p, int co, const float4& o) {
+      if (v.fmt == F32) *reinterpret_cast<float4*>((float*)v.p + p * v.cs + v.coff + co) = o;
+      else store_split(v, p, co, o);
+    };
     TR_DECL(tr_wait = 0, tr_work = 0); TR_T(tr_start);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
       const TileCoord tcd = tile_coord(a, t);
       const int as = t_it % a.nacc;
+      const int co_base = tcd.ct * nt;
+      if (tcd.ct != cur_ct) {   // bias of this cout tile -> the warp's smem copy, fetched before the accumulator wait
+        cur_ct = tcd.ct;
+        __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane * 4 < nt && co_base + lane * 4 < a.cout) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + co_base + lane * 4));
+        *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+        __syncwarp();
+      }
       TR_T(tr0);
       mbar_wait(acc_full + 8 * as, (t_it / a.nacc) & 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int co_base = tcd.ct * nt;
       for (int sub = 0; sub < a.mt; ++sub) {
+        const int idx = warp * 32 + lane;                  // accumulator row = pixel of the 8 x 16 sub-tile
         const int sy0 = tcd.ty0 + (sub / a.sx) * 16, sx0 = tcd.tx0 + (sub % a.sx) * 8;
+        const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
+        const bool valid = gy < a.H && gx < a.W;
+        const long long p = a.phase ? ((long long)tcd.n * 2 * a.H + 2 * gy + (tcd.ph >> 1)) * (2 * a.W) + 2 * gx + (tcd.ph & 1)
+                                    : ((long long)tcd.n * a.H + gy) * a.W + gx;
+        const long long pl = valid ? p : 0;                // rows past the image edge read pixel 0 (their results are clipped)
+        const float* prep = (const float*)a.pre.p + pl * a.pre.cs + a.pre.coff;
+        const float* r1p = (const float*)a.res1.p + pl * a.res1.cs + a.res1.coff;
+        const float* r2p = (const float*)a.res2.p + pl * a.res2.cs + a.res2.coff;
         const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols + sub * sub_cols;
         for (int n0 = 0; n0 < nt; n0 += 32) {
           if (co_base + n0 >= a.cout) break;             // warp-uniform
@@ -297,58 +430,72 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
           } else {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
-          // phase A: accumulator row (one pixel per lane) -> staging row
+          // The fused epilogue runs as a few whole-row passes with warp-uniform branches around them (a per-group
+          // formulation costs ~2000 issue slots per 32x32 block and made every small-K conv epilogue-bound).
+          const int ng = ncol >> 2;                        // 4-channel groups in this block; Cout % 4 == 0 (eligibility)
+          const int co0 = co_base + n0;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            if (4 * k < ncol)
-              *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * k) = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-          __syncwarp();
-          // phase B: lanes sweep channels first, so every global access covers whole 64/128-byte pixel runs
-          const int q4 = ncol >> 2, ppi = 32 / q4;
-          const int c4 = (lane % q4) * 4, rsub = lane / q4;
-          const int co = co_base + n0 + c4;              // this lane's 4 output channels (same for every pixel it touches)
-          const bool cok = co < a.cout;                  // Cout % 4 == 0 (eligibility), so a live lane owns 4 valid channels
-          float bb[4] = {0.f, 0.f, 0.f, 0.f};
-          if (cok) { const float4 b4 = *reinterpret_cast<const float4*>(a.bias + co); bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w; }
-          if (cok) {
-            // lean path (every operand 128-bit addressable, block fully inside Cout): ~40 instructions per 4 outputs
-            const float slope = a.act == ACT_LRELU ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
-            const float* prep = (const float*)a.pre.p + a.pre.coff + co;
-            const float* r1p = (const float*)a.res1.p + a.res1.coff + co;
-            const float* r2p = (const float*)a.res2.p + a.res2.coff + co;
-            float* outp = (float*)a.out.p + a.out.coff + co;
-#pragma unroll 2
-            for (int i = 0; i < q4; ++i) {
-              const int r = i * ppi + rsub;
-              const int idx = warp * 32 + r;
-              const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
-              if (gy < a.H && gx < a.W) {
-                const long long p = a.phase ? ((long long)tcd.n * 2 * a.H + 2 * gy + (tcd.ph >> 1)) * (2 * a.W) + 2 * gx + (tcd.ph & 1)
-                                            : ((long long)tcd.n * a.H + gy) * a.W + gx;
-                float4 o = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
-                o.x += bb[0]; o.y += bb[1]; o.z += bb[2]; o.w += bb[3];
-                if (a.pre.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(prep + p * a.pre.cs)); o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
-                if (a.act == ACT_CROSS_SIGMOID) {
-                  o.y = 1.f / (1.f + expf(-(o.y + 2.f))) + a.eps;      // co % 4 == 0: the odd channels are .y and .w
-                  o.w = 1.f / (1.f + expf(-(o.w + 2.f))) + a.eps;
-                } else {
-                  o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
-                  o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
-                }
-                o.x *= a.alpha; o.y *= a.alpha; o.z *= a.alpha; o.w *= a.alpha;
-                if (a.res1.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(r1p + p * a.res1.cs)); o.x = fmaf(a.beta1, t4.x, o.x); o.y = fmaf(a.beta1, t4.y, o.y); o.z = fmaf(a.beta1, t4.z, o.z); o.w = fmaf(a.beta1, t4.w, o.w); }
-                if (a.res2.p) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(r2p + p * a.res2.cs)); o.x = fmaf(a.beta2, t4.x, o.x); o.y = fmaf(a.beta2, t4.y, o.y); o.z = fmaf(a.beta2, t4.z, o.z); o.w = fmaf(a.beta2, t4.w, o.w); }
-                *reinterpret_cast<float4*>(outp + p * a.out.cs) = o;
-              }
+            if (k < ng) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + 4 * k);
+              acc[4 * k] += b4.x; acc[4 * k + 1] += b4.y; acc[4 * k + 2] += b4.z; acc[4 * k + 3] += b4.w;
             }
+          if (a.pre.p) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < ng && co0 + 4 * k < a.cout) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(prep + co0 + 4 * k));
+                acc[4 * k] += t4.x; acc[4 * k + 1] += t4.y; acc[4 * k + 2] += t4.z; acc[4 * k + 3] += t4.w;
+              }
           }
-          __syncwarp();
+          if (a.act == ACT_CROSS_SIGMOID) {                // co0 % 4 == 0: the odd channels are the scales
+#pragma unroll
+            for (int i = 1; i < 32; i += 2) acc[i] = 1.f / (1.f + expf(-(acc[i] + 2.f))) + a.eps;
+          } else if (a.act != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * slope;
+          }
+          if (a.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] *= a.alpha;
+          }
+          if (a.res1.p) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < ng && co0 + 4 * k < a.cout) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(r1p + co0 + 4 * k));
+                acc[4 * k] = fmaf(a.beta1, t4.x, acc[4 * k]); acc[4 * k + 1] = fmaf(a.beta1, t4.y, acc[4 * k + 1]);
+                acc[4 * k + 2] = fmaf(a.beta1, t4.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(a.beta1, t4.w, acc[4 * k + 3]);
+              }
+          }
+          if (a.res2.p) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < ng && co0 + 4 * k < a.cout) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(r2p + co0 + 4 * k));
+                acc[4 * k] = fmaf(a.beta2, t4.x, acc[4 * k]); acc[4 * k + 1] = fmaf(a.beta2, t4.y, acc[4 * k + 1]);
+                acc[4 * k + 2] = fmaf(a.beta2, t4.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(a.beta2, t4.w, acc[4 * k + 3]);
+              }
+          }
+          if ((!a.tma_out || (a.out2.p && !a.tma_out2)) && valid) {   // views the TMA unit cannot address: per-lane stores
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < ng && co0 + 4 * k < a.cout) {
+                const float4 o = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+                if (!a.tma_out) direct_store(a.out, p, co0 + 4 * k, o);
+                if (a.out2.p && !a.tma_out2) direct_store(a.out2, p, co0 + 4 * k, o);
+              }
+          }
+          if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, sx0, sy0 + 4 * warp, tcd.n);
+          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, sx0, sy0 + 4 * warp, tcd.n);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(acc_empty + 8 * as);                 // 128 arrivals free the accumulator stage
       TR_ADD(tr_work, tr1);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores of this warp have completed
+    __syncwarp();
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
 #endif
@@ -517,13 +664,74 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
   c.tc_kchunks = n_chunks; c.tc_npad = nt;
 }
 
+static bool vec4(const View& v);
+static void make_tmap_out(CUtensorMap* tm, const View& v);
+static bool tma_out_ok(const View& v);
 static bool vec4(const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; }
+// BF16X2 operand views: TMA needs 16-byte global strides and base; the register producer needs 16-byte channel groups
+static bool bf_in_ok(const View& v) {
+  return v.fmt == BF16X2 && v.cs % 8 == 0 && v.coff % 8 == 0 && v.plane % 8 == 0 && ((uintptr_t)v.p % 16) == 0;
+}
+static bool out_ok(const View& v) {
+  return vec4(v) || (v.fmt == BF16X2 && v.cs % 4 == 0 && v.coff % 4 == 0 && v.plane % 4 == 0 && ((uintptr_t)v.p % 8) == 0);
+}
+static bool shapes_ok(const ConvW& w, const View& in, const View& out, const ConvEpi& epi) {
+  return w.cout % 4 == 0 && (bf_in_ok(in) || (vec4(in) && (w.cin % 8 == 0 || w.cin <= 16))) && out_ok(out) &&
+         (!epi.out2 || out_ok(*epi.out2)) && (!epi.pre || vec4(*epi.pre)) && (!epi.res1 || vec4(*epi.res1)) &&
+         (!epi.res2 || vec4(*epi.res2));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {   // resolved through the runtime so the library has no link-time dependency on libcuda
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    BFSR_CHECK(p && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// (C, W, H, N, plane) map over a BF16X2 NHWC view; box = [32 channels, pitch, hrows, 1, 1], SWIZZLE_64B, zero OOB fill
+static void make_tmap(CUtensorMap* tm, const View& v, int pitch, int hrows) {
+  const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)v.cs * 2, (cuuint64_t)v.W * v.cs * 2, (cuuint64_t)v.H * v.W * v.cs * 2,
+                                 (cuuint64_t)v.plane * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)pitch, (cuuint32_t)hrows, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.p, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BFSR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for view C=%d cs=%d %dx%dx%d", (int)r, v.C, v.cs, v.N, v.H, v.W);
+}
 
 // Shapes the tensor-core kernel takes (everything else runs on the fp32 CUDA-core kernels).  Batch-independent, so results
 // do not depend on chunking.  The kernel has no scalar fallbacks (keeps its instruction footprint small).
 bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const ConvEpi& epi) {
-  return w.w_tc != nullptr && !w.tc_phase && g_conv_mode != 2 && w.cin % 8 == 0 && w.cout % 4 == 0 && vec4(in) && vec4(out) &&
-         (!epi.pre || vec4(*epi.pre)) && (!epi.res1 || vec4(*epi.res1)) && (!epi.res2 || vec4(*epi.res2));
+  return w.w_tc != nullptr && !w.tc_phase && g_conv_mode != 2 && shapes_ok(w, in, out, epi);
+}
+
+static bool tma_out_ok(const View& v) {
+  if (((uintptr_t)v.p % 16) != 0) return false;
+  return v.fmt == F32 ? v.cs % 4 == 0 : (v.cs % 8 == 0 && v.plane % 8 == 0);
+}
+// output map: box = [32 channels, 8, 4 pixels] = the accumulator rows of one epilogue warp; fp32 rows are 128 B
+// (SWIZZLE_128B), bf16 rows 64 B per plane (SWIZZLE_64B); the channel extent stops at the end of the view (tail clipped)
+static void make_tmap_out(CUtensorMap* tm, const View& v) {
+  const int es_b = v.fmt == F32 ? 4 : 2;
+  const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)v.cs * es_b, (cuuint64_t)v.W * v.cs * es_b, (cuuint64_t)v.H * v.W * v.cs * es_b,
+                                 (cuuint64_t)v.plane * es_b};
+  const cuuint32_t box[5] = {32, 8, 4, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = v.fmt == F32
+      ? encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+      : encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BFSR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed (%d) for view C=%d cs=%d %dx%dx%d", (int)r, v.C, v.cs, v.N, v.H, v.W);
 }
 
 static int g_num_sms = 0;
@@ -535,15 +743,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
-  BFSR_CHECK(w.cin % 8 == 0 && w.cout % 4 == 0 && vec4(in) && vec4(out) && (!epi.pre || vec4(*epi.pre)) &&
-             (!epi.res1 || vec4(*epi.res1)) && (!epi.res2 || vec4(*epi.res2)),
-             "conv_tc: operands must be fp32, 16-byte addressable, Cin %% 8 == 0 and Cout %% 4 == 0");
+  BFSR_CHECK(shapes_ok(w, in, out, epi), "conv_tc: operand views are not addressable by the tensor-core kernel "
+             "(16-byte aligned fp32 or BF16X2 views, Cout %% 4 == 0)");
   if (in_mode == IN_UP2 || phase) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
   else BFSR_CHECK(in.H == out.H && in.W == out.W, "conv_tc: spatial mismatch");
   if (out.npix() == 0) return;
   const int gH = phase ? in.H : out.H, gW = phase ? in.W : out.W;      // grid the GEMM rows live on
   TcArgs a;
-  a.in = in; a.out = out;
+  a.in = in; a.out = out; a.out2 = epi.out2 ? *epi.out2 : View();
   a.pre = epi.pre ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
   a.w = (const unsigned char*)w.w_tc; a.bias = w.bias;
   a.cin = w.cin; a.cout = w.cout; a.nt = w.tc_npad; a.n_chunks = w.tc_kchunks;
@@ -555,11 +762,12 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
-  // accurate mode: NT >= 64 issues the three products as separate N = NT MMAs into the same columns (half the TMEM, the
-  // epilogue reads each value once); NT < 64 keeps A_hi x [W_hi;W_lo] as one N = 2NT MMA (an N < 64 MMA is bound by the
-  // shared-memory read of A, so fewer, wider MMAs win there)
+  // accurate mode.  Measured M=128,K=16 SS-mode MMA cost on B200 (tools/micro/umma_rate.cu): 45.5 clk for N <= 32, 48 @ 64,
+  // 56 @ 96, then N/2 (64 @ 128, 128 @ 256): an MMA narrower than N = 128 is bound by its fixed cost, so NT <= 64 issues
+  // A_hi x [W_hi;W_lo] as ONE N = 2NT MMA plus A_lo x W_hi (e.g. NT = 64: 64 + 48 clk instead of 3 x 48); NT > 64 issues the
+  // three products as separate N = NT MMAs into the same columns (same MMA time, half the TMEM -> two accumulator stages)
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
-  a.wide = (!a.fast && (a.nt < 64 || force_wide)) ? 1 : 0;
+  a.wide = (!a.fast && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
   int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
   a.sx = 1; a.sy = 1;
@@ -585,7 +793,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.tps = 1;
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
-  const int fixed = NA * a.a_slot + 1024 + 256 + STG_BYTES;
+  const int fixed = NA * a.a_slot + 1024 + STG_BYTES + 256 + 4 * 128 * 4;
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
@@ -595,6 +803,16 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   const int smem = fixed + a.nw * a.w_stage;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
   BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
+  a.tma = (in.fmt == BF16X2 && in_mode == IN_DIRECT && !phase) ? 1 : 0;
+  a.in_bf = in.fmt == BF16X2 ? 1 : 0;
+  memset(&a.tmap, 0, sizeof a.tmap);
+  if (a.tma) make_tmap(&a.tmap, in, a.pitch, a.hrows);
+  memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
+  static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
+  a.tma_out = (!phase && !no_tma_out && tma_out_ok(out)) ? 1 : 0;
+  a.tma_out2 = (epi.out2 && !phase && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
+  if (a.tma_out) make_tmap_out(&a.tmap_out, out);
+  if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2);
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;

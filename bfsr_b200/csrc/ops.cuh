@@ -27,6 +27,7 @@ struct ConvEpi {
   float alpha = 1.f;            // out = act(acc+bias+pre)*alpha + beta1*res1 + beta2*res2
   const View* res1 = nullptr; float beta1 = 0.f;
   const View* res2 = nullptr; float beta2 = 0.f;
+  const View* out2 = nullptr;   // second copy of the result (e.g. fp32 residual stream + BF16X2 operand copy)
 };
 
 // out(N,H,W,Cout) = conv_ks(in) ; `in` has spatial dims (H,W) or (H/2,W/2) for IN_UP2.

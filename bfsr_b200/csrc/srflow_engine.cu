@@ -219,6 +219,7 @@ struct Run {
   std::vector<View> bufA;                  // per level: n_coupling*64 pre-activations of fAffine.0 (ft part)
   std::vector<std::vector<View>> hF;       // per level, per step: (shiftFt, scaleFt) pairs, 2C channels
   bool plan() const { return A.plan; }
+  int opfmt() const { return g_conv_mode == 2 ? (int)F32 : (int)BF16X2; }   // format of conv-operand-only tensors
   int lvH(int level) const { return (h * e->d.scale) >> level; }
   int lvW(int level) const { return (w * e->d.scale) >> level; }
 };
@@ -229,39 +230,51 @@ static void run_encoder(Run& r, const View& x) {
   bfsr_srflow* e = r.e; const auto& d = e->d;
   const int B = r.B, h = r.h, w = r.w, nf = d.nf, gc = d.gc, L = d.L;
   const int log2s = d.scale == 4 ? 2 : 3;
+  // Tensors that are only ever consumed as conv operands live in HBM already split into bf16 (hi, lo) planes (BF16X2:
+  // same bytes as fp32, bit-identical MMA operands) so the tensor-core convs fetch them by TMA with no conversion pass.
+  const int fmt = r.opfmt();
+  const bool split = fmt == BF16X2;
   r.ft.assign(L + 1, View());
-  for (int lv = 1; lv <= L; ++lv) r.ft[lv] = make_view(r.A, B, r.lvH(lv), r.lvW(lv), e->n_cond);
+  for (int lv = 1; lv <= L; ++lv) r.ft[lv] = make_view(r.A, B, r.lvH(lv), r.lvW(lv), e->n_cond, fmt);
   const int lv0 = log2s;                           // level whose features live at LR resolution ('fea_up1')
   BFSR_CHECK(lv0 <= L, "L=%d too small for scale %d", L, d.scale);
   View& ft0 = r.ft[lv0];
   const size_t mark = r.A.off;
-  View D[3];
-  for (int i = 0; i < 3; ++i) D[i] = make_view(r.A, B, h, w, nf + 4 * gc);
+  // Dense-block buffers: D[i] = [x (64) | conv1..4 outputs (4 x 32)] in operand format; the residual stream x also keeps
+  // an fp32 copy X[i] (the 69 chained `x5*0.2 + x` updates must not be re-rounded to 16 mantissa bits each time).
+  View D[3], X[3];
+  for (int i = 0; i < 3; ++i) {
+    D[i] = make_view(r.A, B, h, w, nf + 4 * gc, fmt);
+    X[i] = split ? make_view(r.A, B, h, w, nf) : D[i].slice(0, nf);
+  }
   ConvEpi lrelu; lrelu.act = ACT_LRELU;
-  K_(conv2d(e->rrdb.conv_first, x, D[0].slice(0, nf), ConvEpi(), IN_DIRECT, r.s));
+  {
+    ConvEpi ep; View op0 = D[0].slice(0, nf); if (split) ep.out2 = &op0;
+    K_(conv2d(e->rrdb.conv_first, x, X[0], ep, IN_DIRECT, r.s));
+  }
   int tap = 0;
   for (int i = 0; i < d.nb; ++i) {
     for (int rb = 0; rb < 3; ++rb) {
-      View& cur = D[rb]; View& nxt = D[(rb + 1) % 3];
+      View& cur = D[rb]; const int nx = (rb + 1) % 3;
       const ConvW* cw = &e->rrdb.rdb[(size_t)(i * 3 + rb) * 5];
       for (int c = 0; c < 4; ++c)
         K_(conv2d(cw[c], cur.slice(0, nf + c * gc), cur.slice(nf + c * gc, gc), lrelu, IN_DIRECT, r.s));
       ConvEpi ep;
-      View x_rdb = cur.slice(0, nf), x_rrdb = D[0].slice(0, nf);
-      if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &x_rdb; ep.beta1 = 1.f; }                      // x5*0.2 + x
-      else { ep.alpha = 0.04f; ep.res1 = &x_rdb; ep.beta1 = 0.2f; ep.res2 = &x_rrdb; ep.beta2 = 1.f; }  // (x5*0.2+x)*0.2 + x_rrdb
-      K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), nxt.slice(0, nf), ep, IN_DIRECT, r.s));
+      View op_next = D[nx].slice(0, nf); if (split) ep.out2 = &op_next;
+      if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &X[rb]; ep.beta1 = 1.f; }                      // x5*0.2 + x
+      else { ep.alpha = 0.04f; ep.res1 = &X[rb]; ep.beta1 = 0.2f; ep.res2 = &X[0]; ep.beta2 = 1.f; }  // (x5*0.2+x)*0.2 + x_rrdb
+      K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), X[nx], ep, IN_DIRECT, r.s));
     }
     for (int b = 0; b < d.n_blocks; ++b)
       if (d.blocks[b] == i) {   // block_{i} tap -> its slot in the conditioning tensor (order of stackRRDB.blocks)
-        K_(resample(D[0].slice(0, nf), ft0.slice(nf * (1 + b), nf), RS_COPY, r.s));
+        K_(resample(X[0], ft0.slice(nf * (1 + b), nf), RS_COPY, r.s));
         ++tap;
       }
   }
   BFSR_CHECK(tap == d.n_blocks, "stackRRDB.blocks reference RRDB indices outside [0, nb)");
   {  // last_lr_fea = fea + trunk_conv(fea)
-    ConvEpi ep; View fea = D[0].slice(0, nf); ep.res1 = &fea; ep.beta1 = 1.f;
-    K_(conv2d(e->rrdb.trunk_conv, fea, ft0.slice(0, nf), ep, IN_DIRECT, r.s));
+    ConvEpi ep; ep.res1 = &X[0]; ep.beta1 = 1.f;
+    K_(conv2d(e->rrdb.trunk_conv, D[0].slice(0, nf), ft0.slice(0, nf), ep, IN_DIRECT, r.s));
   }
   r.A.off = mark;
   // finer levels: fea_up2 = lrelu(upconv1(nearest2x(last_lr_fea))) etc. (post-activation: in-place LeakyReLU aliasing)
@@ -294,8 +307,9 @@ static void run_ft_convs(Run& r) {
     const LevelW& L = e->levels[lv];
     const int H = r.lvH(lv), W = r.lvW(lv);
     const size_t mark = r.A.off;
-    View bufF = make_view(r.A, r.B, H, W, L.n_coupling * Hd);
-    View t = make_view(r.A, r.B, H, W, Hd);
+    const bool two_pass_phase = L.has_phase && g_conv_mode != 2;   // accumulates into bufF through the fp32 `pre` operand
+    View bufF = make_view(r.A, r.B, H, W, L.n_coupling * Hd, two_pass_phase ? (int)F32 : r.opfmt());
+    View t = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     ConvEpi relu; relu.act = ACT_RELU;
     ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
     if (L.has_phase && g_conv_mode != 2) {
@@ -341,7 +355,7 @@ struct LevelBufs {
   void alloc(Run& r, int H, int W, int C) {
     const int Hd = r.e->d.hidden;
     z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
-    t1 = make_view(r.A, r.B, H, W, Hd); t2 = make_view(r.A, r.B, H, W, Hd);
+    t1 = make_view(r.A, r.B, H, W, Hd); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
     pp = 0;
   }

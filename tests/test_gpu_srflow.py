@@ -143,9 +143,10 @@ def test_rejects_odd_lr_size():
 @pytest.mark.parametrize("cin,cout,H,W,act", [
     (64, 32, 16, 8, 0), (64, 64, 32, 24, 1), (96, 32, 17, 23, 1), (192, 64, 40, 40, 0), (160, 32, 33, 9, 2),
     (320, 128, 24, 16, 2), (72, 64, 20, 12, 0), (64, 24, 16, 16, 3), (352, 64, 8, 8, 0), (64, 192, 10, 10, 3)])
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
-    """tcgen05 implicit-GEMM conv: split-bf16 x3 (impl 1) must be fp32-accurate; single-pass bf16 (impl 2) is the fast mode."""
+    """tcgen05 implicit-GEMM conv: split-bf16 x3 (impl 1) must be fp32-accurate; single-pass bf16 (impl 2) is the fast mode;
+    impl 3 = x3 with input and output stored as bf16 (hi, lo) planes in HBM (TMA-fed A operand, split-store epilogue)."""
     g = torch.Generator().manual_seed(cin * 1000 + cout + H)
     x = torch.randn(2, cin, H, W, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
@@ -159,11 +160,12 @@ def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
     lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 3, act, impl,
                                       y.data_ptr(), None))
     err = rel_l2(ref, y)
-    assert err < (2e-5 if impl == 1 else 1e-2), err
+    assert err < ({1: 2e-5, 2: 1e-2, 3: 2.5e-5}[impl]), err
 
 
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("cin,cout,H,W,act", [(64, 64, 20, 24, 2), (256, 28, 9, 9, 0), (1024, 256, 33, 5, 2), (96, 540, 8, 8, 0)])
-def test_conv1x1_tcgen05(lib, cin, cout, H, W, act):
+def test_conv1x1_tcgen05(lib, cin, cout, H, W, act, impl):
     """1x1 convs (coupling hidden layers, LINF MLP) on the tcgen05 kernel (single tap, no halo), split-bf16 x3."""
     g = torch.Generator().manual_seed(cin + cout)
     x = torch.randn(2, cin, H, W, generator=g)
@@ -172,9 +174,9 @@ def test_conv1x1_tcgen05(lib, cin, cout, H, W, act):
     ref = F.conv2d(x.double(), w.double(), b.double())
     ref = {0: lambda t: t, 2: F.relu}[act](ref)
     y = torch.empty(2, cout, H, W, device="cuda")
-    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 1, act, 1,
+    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 1, act, impl,
                                       y.data_ptr(), None))
-    assert rel_l2(ref, y) < 2e-5
+    assert rel_l2(ref, y) < (2e-5 if impl == 1 else 2.5e-5)
 
 
 @pytest.mark.parametrize("impl,tol", [(0, 2e-6), (1, 2e-5), (2, 2e-5)])
