@@ -257,13 +257,13 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
   API_BEGIN
   BFSR_CHECK(x_dev && w_host && y_dev, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  ConvW cw = pack_conv(w_host, Cout, Cin, ks, bias_host, nullptr, {});
+  ConvW cw = pack_conv(w_host, Cout, Cin, ks, bias_host, nullptr, {}, impl ? 1 : -1);
   float *xn = nullptr, *yn = nullptr, *xb = nullptr, *yb = nullptr;
   const size_t npix = (size_t)B * H * W;
   try {
-    CUDA_OK(cudaMalloc((void**)&xn, (npix * Cin + 4) * 4));
+    CUDA_OK(cudaMalloc((void**)&xn, (npix * ((Cin + 3) & ~3) + 4) * 4));
     CUDA_OK(cudaMalloc((void**)&yn, (npix * Cout + 4) * 4));
-    View x; x.p = xn; x.N = B; x.H = H; x.W = W; x.C = Cin; x.cs = Cin;
+    View x; x.p = xn; x.N = B; x.H = H; x.W = W; x.C = Cin; x.cs = (Cin + 3) & ~3;   // pixel stride padded to 16 bytes
     View y; y.p = yn; y.N = B; y.H = H; y.W = W; y.C = Cout; y.cs = Cout;
     nchw_to_nhwc(x_dev, x, s);
     ConvEpi ep; ep.act = act;
@@ -272,9 +272,9 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
       const int saved = g_conv_mode;
       g_conv_mode = 0;
       try {
-        CUDA_OK(cudaMalloc((void**)&xb, (npix * Cin + 16) * 4));
+        CUDA_OK(cudaMalloc((void**)&xb, (npix * x.cs + 16) * 4));
         CUDA_OK(cudaMalloc((void**)&yb, (npix * Cout + 16) * 4));
-        View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * Cin;
+        View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * x.cs;
         View yv = y; yv.p = yb; yv.fmt = BF16X2; yv.plane = (long long)npix * Cout;
         resample(x, xv, RS_COPY, s);
         conv2d_tc(cw, xv, yv, ep, IN_DIRECT, s);

@@ -300,7 +300,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
 }
 
 ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float* bias, const float* out_scale,
-                const std::vector<int>& cin_map) {
+                const std::vector<int>& cin_map, int tc_min_cin) {
   BFSR_CHECK(ks == 1 || ks == 3, "conv kernel size %d unsupported", ks);
   ConvW c;
   c.ks = ks; c.cout = cout;
@@ -325,7 +325,7 @@ ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float*
   CUDA_OK(cudaMalloc((void**)&c.bias, hb.size() * 4));
   CUDA_OK(cudaMemcpy(c.w, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(c.bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
-  pack_conv_tc(c, h);   // split-bf16 image for the tcgen05 path when the shape is eligible
+  pack_conv_tc(c, h, tc_min_cin);   // split-bf16 image for the tcgen05 path when the shape is eligible
   return c;
 }
 

@@ -44,7 +44,8 @@ constexpr int KC = 32;                       // channels per chunk = one 64-byte
 constexpr int ROWB = 64;                     // bytes per smem row
 constexpr int NA = 2, NW_MAX = 4;
 constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
-constexpr int NTHREADS = (6 + PROD_WARPS) * 32;
+constexpr int ISSUER_B = 6 + PROD_WARPS;       // warp index of the second MMA issuer
+constexpr int NTHREADS = (7 + PROD_WARPS) * 32;
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr int STG_WARP = 8192;               // epilogue staging per warp: two 4 KB buffers (32 pixel rows x 128 B)
 constexpr int STG_BYTES = 4 * STG_WARP;
@@ -64,6 +65,7 @@ struct TcArgs {
   int H, W, N, in_mode, act;
   float eps, alpha, beta1, beta2;
   int fast, vec_in, vec_out;
+  int n_iss;                             // MMA issuing warps (1 or 2)
   int wide;                              // accurate mode with NT < 64: A_hi x [W_hi;W_lo] as one N = 2NT MMA (column halves summed by the epilogue)
   int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
   int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
@@ -208,9 +210,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const int acc_cols = a.mt * (a.wide ? 2 * nt : nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, a.tma ? 1 : NPROD); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, a.tma ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
+    for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-  if (warp >= 6 && a.tma) {
+  if (warp >= 6 && warp < ISSUER_B && a.tma) {
     // ===================== A by TMA: the input already lives in HBM as bf16 (hi, lo) planes =====================
     // One tiled TMA load per plane brings the whole halo tile of a 32-channel chunk straight into the UMMA SWIZZLE_64B
     // layout (one pixel = one 64-byte row); out-of-image pixels and channels past the view are zero-filled by the TMA
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && warp < ISSUER_B) {
     // ===================== A producers: fp32 halo tile -> (hi, lo) bf16 planes, swizzled =====================
     // Each thread owns up to MAXI (pixel, 8-channel) items of a chunk.  The global loads of chunk i+1 are issued
     // into registers BEFORE waiting for its smem slot, so their latency hides behind the MMAs of chunk i-1.
@@ -499,8 +501,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
 #endif
-  } else if (warp == 4) {
-    // ===================== MMA issuer: whole warp walks the (uniform) loop, one elected lane issues =====================
+  } else if (warp == 4 || warp == ISSUER_B) {
+    // ===================== MMA issuers: whole warp walks the (uniform) loop, one elected lane issues =====================
+    // A single thread sustains one small MMA per ~45-55 clk, the tensor pipe accepts one per ~40 (tools/micro/umma_rate.cu),
+    // so macro tiles with several sub-tiles are split between two issuing warps (even / odd sub-tiles); every barrier
+    // that recycles operand slots or releases the epilogue counts one tcgen05.commit per issuer.
+    const int iss = warp == 4 ? 0 : 1;
+    if (iss < a.n_iss) {
     const uint32_t idesc_wide = make_idesc(a.wide ? 2 * nt : nt), idesc_nt = make_idesc(nt);
     const uint32_t lo_rows = (uint32_t)nt * (ROWB >> 4);               // descriptor offset of the W_lo rows inside a tap image
     const uint32_t sbo = (uint32_t)a.pitch * ROWB;
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
             if (elect_one()) {
 #pragma unroll
               for (int sub = 0; sub < 4; ++sub) {
-                if (sub < a.mt) {
+                if (sub < a.mt && (sub & (a.n_iss - 1)) == iss) {
                   const uint32_t d = d_base + sub * sub_cols;
                   const uint64_t ah = a_hi_d + tap_off + sub_off[sub], al = a_lo_d + tap_off + sub_off[sub];
                   umma_f16(d, ah, bd0, idesc_wide, accf0);
@@ -578,8 +585,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
       __syncwarp();
     }
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && lane == 0) printf("[tc trace] mma: total %lld wait_acc_empty %lld wait_a_full %lld wait_w_full %lld issue %lld (taps %d)\n", clock64() - tr_start, tr_acc, tr_a, tr_w, tr_issue, w_it);
+    if (blockIdx.x == 0 && lane == 0 && iss == 0) printf("[tc trace] mma: total %lld wait_acc_empty %lld wait_a_full %lld wait_w_full %lld issue %lld (taps %d)\n", clock64() - tr_start, tr_acc, tr_a, tr_w, tr_issue, w_it);
 #endif
+    }
   } else {
     // ===================== weight producer: cp.async.bulk of pre-swizzled [W_hi;W_lo] images =====================
     const size_t tap_stride = (size_t)2 * nt * ROWB;    // packed image always holds both planes
@@ -632,10 +640,10 @@ static int pick_nt(int cout) {
 }
 
 // h: host fp32 packed [tap][cin_pad][cout_pad] (the fp32 kernel's layout)
-void pack_conv_tc(ConvW& c, const std::vector<float>& h) {
+void pack_conv_tc(ConvW& c, const std::vector<float>& h, int min_cin_arg) {
   using namespace tc;
-  static const int min_cin = getenv("BFSR_TC_MIN_CIN") ? atoi(getenv("BFSR_TC_MIN_CIN")) : 32;
-  if (c.cin < min_cin) return;
+  static const int min_cin_env = getenv("BFSR_TC_MIN_CIN") ? atoi(getenv("BFSR_TC_MIN_CIN")) : 32;
+  if (c.cin < (min_cin_arg >= 0 ? min_cin_arg : min_cin_env)) return;
   const int taps = c.ks * c.ks;
   const int nt = pick_nt(c.cout);
   const int n_tiles = (c.cout + nt - 1) / nt, n_chunks = (c.cin + KC - 1) / KC;
@@ -780,6 +788,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   }
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
+  static const int max_iss = getenv("BFSR_TC_ISSUERS") ? atoi(getenv("BFSR_TC_ISSUERS")) : 2;
+  a.n_iss = (a.mt >= 2 && max_iss >= 2) ? 2 : 1;
   a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
   a.a_plane = (a.pitch * a.hrows * ROWB + 1023) / 1024 * 1024;
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;

@@ -36,7 +36,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
 // tcgen05 path (conv_tc.cu).  g_conv_mode: 0 = split-bf16 x3 (fp32-accurate), 1 = bf16 single pass (fast),
 // 2 = never use the tensor-core path (all convs on the fp32 CUDA-core kernel).
 extern thread_local int g_conv_mode;
-void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed);
+void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed, int min_cin = -1);
 bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const ConvEpi& epi);
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);
 // 3x3 conv over nearest2x(in_lowres) as four 2x2 phase convs on the low-res grid (16/36 of the MACs); out is (N,2H,2W)
@@ -47,7 +47,7 @@ void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out,
 // output channel, `bias` is the FINAL bias (already scaled); the input-channel gather map makes packed input channel
 // i read source channel map[i] (-1 = zero) so callers can split / pad / reorder concatenated inputs.
 ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float* bias, const float* out_scale,
-                const std::vector<int>& cin_map);
+                const std::vector<int>& cin_map, int tc_min_cin = -1 /* smallest Cin packed for the tcgen05 path; -1 = default (32) */);
 void free_conv(ConvW& w);
 
 // ------------------------------------------------------------------ layout / resampling

@@ -97,13 +97,13 @@ static StepW pack_step(const Weights& W, const std::string& p, int C, bool coupl
 
 // flow.Conv2d (bias-free conv + ActNorm): W' = W*e^logs, b' = b_an*e^logs   (flow.py:41-65)
 static ConvW pack_conv_actnorm(const Weights& W, const std::string& p, int cout, int cin_src, int ks,
-                               const std::vector<int>& cin_map, bool with_bias) {
+                               const std::vector<int>& cin_map, bool with_bias, int tc_min_cin = -1) {
   const float* w = W.data(p + ".weight", {cout, cin_src, ks, ks});
   const float* ab = W.data(p + ".actnorm.bias", {1, cout, 1, 1});
   const float* al = W.data(p + ".actnorm.logs", {1, cout, 1, 1});
   std::vector<float> sc(cout), bi(cout);
   for (int i = 0; i < cout; ++i) { sc[i] = std::exp(al[i]); bi[i] = with_bias ? ab[i] * sc[i] : 0.f; }
-  return pack_conv(w, cout, cin_src, ks, bi.data(), sc.data(), cin_map);
+  return pack_conv(w, cout, cin_src, ks, bi.data(), sc.data(), cin_map, tc_min_cin);
 }
 // flow.Conv2dZeros: (conv + b) * exp(3*logs)   (flow.py:68-83)
 static ConvW pack_conv_zeros(const Weights& W, const std::string& p, int cout, int cin) {
@@ -177,7 +177,7 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
           sA[k * Hd + o] = std::exp(al[o]); bA[k * Hd + o] = ab[o] * sA[k * Hd + o];
         }
         std::vector<int> zmap(Cn); for (int i = 0; i < Cn; ++i) zmap[i] = i;
-        l.cp.fA0z = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, zmap, /*with_bias=*/false);
+        l.cp.fA0z = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, zmap, /*with_bias=*/false, /*tc_min_cin=*/1);
       }
       l.cp.fF2 = pack_conv_actnorm(W, p + ".affine.fFeatures.2", Hd, Hd, 1, {}, true);
       l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
@@ -334,14 +334,16 @@ static void run_ft_convs(Run& r) {
   }
 }
 
+static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
 // z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
 static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& t1, const View& t2, const View& hout) {
   const int Hd = r.e->d.hidden;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
-  static const bool tc_z = getenv("BFSR_TC_Z") && atoi(getenv("BFSR_TC_Z"));
-  if (tc_z) K_(conv2d(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
-  else K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  // z-dependent first conv: split-bf16 x3 on the tensor cores like every other conv (products exact to ~2^-17); BFSR_FP32_Z=1
+  // keeps it on the fp32 CUDA-core kernel (the round-1 default) for A/B parity runs
+  if (fp32_z()) K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  else K_(conv2d(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
   ConvEpi relu; relu.act = ACT_RELU;
   K_(conv2d(l.cp.fA2, t1, t2, relu, IN_DIRECT, r.s));
   ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
@@ -355,7 +357,7 @@ struct LevelBufs {
   void alloc(Run& r, int H, int W, int C) {
     const int Hd = r.e->d.hidden;
     z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
-    t1 = make_view(r.A, r.B, H, W, Hd); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
+    t1 = make_view(r.A, r.B, H, W, Hd, fp32_z() ? (int)F32 : r.opfmt()); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
     pp = 0;
   }

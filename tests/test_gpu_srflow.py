@@ -163,6 +163,21 @@ def test_conv2d_tcgen05(lib, cin, cout, H, W, act, impl):
     assert err < ({1: 2e-5, 2: 1e-2, 3: 2.5e-5}[impl]), err
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(6, 64, 20, 24), (12, 64, 17, 9), (48, 64, 10, 10), (8, 64, 16, 8)])
+def test_conv_small_cin_tcgen05(lib, cin, cout, H, W):
+    """z-dependent first conv of a coupling (Cin = C/2 = 6, 12, 48): fp32 input through the register producer with a ragged
+    channel group, split-bf16 x3."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    y = torch.empty(2, cout, H, W, device="cuda")
+    lib.check(lib.lib().bfsr_op_conv2d(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 3, 2, 1,
+                                      y.data_ptr(), None))
+    assert rel_l2(ref, y) < 2e-5
+
+
 @pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("cin,cout,H,W,act", [(64, 64, 20, 24, 2), (256, 28, 9, 9, 0), (1024, 256, 33, 5, 2), (96, 540, 8, 8, 0)])
 def test_conv1x1_tcgen05(lib, cin, cout, H, W, act, impl):
