@@ -44,11 +44,21 @@ constexpr int KC = 32;                       // channels per chunk = one 64-byte
 constexpr int ROWB = 64;                     // bytes per smem row
 constexpr int NA = 2, NW_MAX = 4;
 constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
-constexpr int ISSUER_B = 6 + PROD_WARPS;       // warp index of the second MMA issuer
-constexpr int NTHREADS = (7 + PROD_WARPS) * 32;
+// Warp roles.  TMA-fed variant (input already in bf16 hi/lo planes): 8 epilogue warps (two per TMEM lane quarter -- one
+// warp per scheduler cannot hide its own ALU latency and made every small-K conv epilogue-bound), MMA issuer A, weight
+// loader, TMA loader for A, MMA issuer B = 12 warps.  Register-producer variant (fp32 / upsampled / phase inputs): 4 epilogue
+// warps, MMA issuer A, weight loader, 8 producer warps, MMA issuer B = 15 warps.
+template <bool TMA_IN> struct Roles {
+  static constexpr int EPI_WARPS = TMA_IN ? 8 : 4;
+  static constexpr int W_MMA = EPI_WARPS, W_WPROD = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
+  static constexpr int N_PROD = TMA_IN ? 1 : PROD_WARPS;
+  static constexpr int W_MMAB = W_PROD0 + N_PROD;
+  static constexpr int NTHREADS = (W_MMAB + 1) * 32;
+};
 constexpr int MAX_SMEM = 227 * 1024;
-constexpr int STG_WARP = 8192;               // epilogue staging per warp: two 4 KB buffers (32 pixel rows x 128 B)
-constexpr int STG_BYTES = 4 * STG_WARP;
+constexpr int STG_WARP = 4096;               // epilogue staging per warp: 32 pixel rows x 128 B
+constexpr int STG_BYTES = 8 * STG_WARP;
+constexpr int BIAS_BYTES = 8 * 128 * 4;        // per-epilogue-warp copy of the cout tile's bias
 constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
 }  // namespace tc
 
@@ -100,6 +110,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("bfsr conv_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+      __trap();
+    }
+  }
+}
+// wait of a role that runs AHEAD of the critical path (operand producers): back off between polls so the 8 producer warps
+// do not take issue slots from the epilogue / MMA warps sharing their schedulers while the pipeline is full
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned ns = 64;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;
     if (clock64() - t0 > 8000000000LL) {
       printf("bfsr conv_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
       __trap();
@@ -192,8 +217,10 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
   return c;
 }
 
-__global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+template <bool TMA_IN>
+__global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
+  using R = Roles<TMA_IN>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
@@ -210,12 +237,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   const int acc_cols = a.mt * (a.wide ? 2 * nt : nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, a.tma ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, TMA_IN ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
     for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == R::W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -226,19 +253,19 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-  if (warp >= 6 && warp < ISSUER_B && a.tma) {
+  if (TMA_IN && warp == R::W_PROD0) {
     // ===================== A by TMA: the input already lives in HBM as bf16 (hi, lo) planes =====================
     // One tiled TMA load per plane brings the whole halo tile of a 32-channel chunk straight into the UMMA SWIZZLE_64B
     // layout (one pixel = one 64-byte row); out-of-image pixels and channels past the view are zero-filled by the TMA
     // unit, which is exactly the conv's zero padding.
-    if (warp == 6) {
+    {
       const uint32_t box_bytes = (uint32_t)(a.pitch * a.hrows) * ROWB;
       int a_it = 0;
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         const TileCoord tcd = tile_coord(a, t);
         for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
           const int slot = a_it % NA;
-          mbar_wait(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+          mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
           if (elect_one()) {
             const uint32_t dst = a_smem + slot * a.a_slot, bar = a_full + 8 * slot;
             mbar_expect_tx(bar, a.fast ? box_bytes : 2 * box_bytes);
@@ -249,11 +276,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= 6 && warp < ISSUER_B) {
+  } else if (!TMA_IN && warp >= R::W_PROD0 && warp < R::W_MMAB) {
     // ===================== A producers: fp32 halo tile -> (hi, lo) bf16 planes, swizzled =====================
     // Each thread owns up to MAXI (pixel, 8-channel) items of a chunk.  The global loads of chunk i+1 are issued
     // into registers BEFORE waiting for its smem slot, so their latency hides behind the MMAs of chunk i-1.
-    const int ptid = tid - 6 * 32;
+    const int ptid = tid - R::W_PROD0 * 32;
     const int inH = a.in_mode == IN_UP2 ? a.H >> 1 : a.H, inW = a.in_mode == IN_UP2 ? a.W >> 1 : a.W;
     const int items = a.hrows * a.pitch * 4;           // (pixel, 8-channel group) pairs per chunk
     float4 v[MAXI][2];
@@ -281,8 +308,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
             } else {          // ragged last group (Cin % 8 != 0, e.g. the 6-channel z1 of the first coupling level)
               const float* src = (const float*)a.in.p + p * a.in.cs + a.in.coff + cb;
               float x[8];
+              if (cb + 4 <= a.cin) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(src));
+                x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = cb + e < a.cin ? __ldg(src + e) : 0.f;
+                for (int e = 0; e < 4; ++e) x[e] = cb + e < a.cin ? __ldg(src + e) : 0.f;
+              }
+#pragma unroll
+              for (int e = 4; e < 8; ++e) x[e] = cb + e < a.cin ? __ldg(src + e) : 0.f;
               v[u][0] = make_float4(x[0], x[1], x[2], x[3]); v[u][1] = make_float4(x[4], x[5], x[6], x[7]);
             }
           }
@@ -321,7 +355,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     while (have) {
       const int slot = a_it % NA;
       TR_T(tr0);
-      mbar_wait(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+      mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       store_chunk(smem_gen + slot * a.a_slot);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -334,7 +368,9 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && ptid == 0) printf("[tc trace] producer: total %lld wait_a_empty %lld fill %lld (chunks %d)\n", clock64() - tr_start, tr_wait, tr_fill, a_it);
 #endif
-  } else if (warp < 4) {
+  } else if (warp < R::EPI_WARPS) {
+    const int q = warp & 3, grp = warp >> 2;             // TMEM lane quarter of this warp; block-interleave group
+    constexpr int N_GRP = R::EPI_WARPS / 4;
     // ===================== epilogue: TMEM -> registers -> fused epilogue -> swizzled smem -> TMA bulk tensor store ==========
     // tcgen05.ld 32x32b hands every lane one accumulator ROW = the channels of one output pixel.  The lane applies bias /
     // pre-activation / activation / residuals to its pixel, writes the 32-channel piece into a per-warp staging tile in
@@ -346,12 +382,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
     unsigned char* stg_gen = smem_gen + (stg_smem - base) + warp * STG_WARP;
     const uint32_t stg_u32 = stg_smem + warp * STG_WARP;
     float* bias_s = reinterpret_cast<float*>(smem_gen + (bars + 256 - base)) + warp * 128;
-    int sb = 0, cur_ct = -1, t_it = 0;
+    int cur_ct = -1, t_it = 0;
     // stage one 32-pixel x 32-channel block of this warp and launch its bulk store (out and out2 share the two buffers)
     auto stage_store = [&](const View& v, const CUtensorMap* tm, const float* o, int ncol, int c0, int x0, int y0, int n) {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the older store has drained its buffer
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has drained the buffer
       __syncwarp();
-      unsigned char* buf = stg_gen + sb * 4096;
+      unsigned char* buf = stg_gen;
       if (v.fmt == F32) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -376,12 +412,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        const uint32_t src = stg_u32 + sb * 4096;
+        const uint32_t src = stg_u32;
         if (v.fmt == F32) tma_store_4d(tm, src, v.coff + c0, x0, y0, n);
         else { tma_store_5d(tm, src, v.coff + c0, x0, y0, n, 0); tma_store_5d(tm, src + 2048, v.coff + c0, x0, y0, n, 1); }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      sb ^= 1;
     };
     auto direct_store = [&](const View& v, long long p, int co, const float4& o) {
       if (v.fmt == F32) *reinterpret_cast<float4*>((float*)v.p + p * v.cs + v.coff + co) = o;
@@ -401,11 +436,16 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         __syncwarp();
       }
       TR_T(tr0);
-      mbar_wait(acc_full + 8 * as, (t_it / a.nacc) & 1);
+      mbar_wait_relaxed(acc_full + 8 * as, (t_it / a.nacc) & 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int sub = 0; sub < a.mt; ++sub) {
-        const int idx = warp * 32 + lane;                  // accumulator row = pixel of the 8 x 16 sub-tile
+      // 32-channel blocks of this cout tile that hold real channels, and the flattened (sub-tile, block) sequence
+      const int nblk = min((nt + 31) >> 5, (a.cout - co_base + 31) >> 5);
+      const int nb_total = a.mt * nblk;
+      for (int b = grp; b < nb_total; b += N_GRP) {      // the warps sharing a lane quarter take alternate blocks
+        const int sub = b / nblk, n0 = (b - sub * nblk) << 5;
+        {
+        const int idx = q * 32 + lane;                     // accumulator row = pixel of the 8 x 16 sub-tile
         const int sy0 = tcd.ty0 + (sub / a.sx) * 16, sx0 = tcd.tx0 + (sub % a.sx) * 8;
         const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
         const bool valid = gy < a.H && gx < a.W;
@@ -415,9 +455,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
         const float* prep = (const float*)a.pre.p + pl * a.pre.cs + a.pre.coff;
         const float* r1p = (const float*)a.res1.p + pl * a.res1.cs + a.res1.coff;
         const float* r2p = (const float*)a.res2.p + pl * a.res2.cs + a.res2.coff;
-        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols + sub * sub_cols;
-        for (int n0 = 0; n0 < nt; n0 += 32) {
-          if (co_base + n0 >= a.cout) break;             // warp-uniform
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + sub * sub_cols;
+        {
           const int ncol = nt - n0 < 32 ? 16 : 32;
           float acc[32];
           tmem_ld16(t_row + n0, acc);
@@ -488,12 +527,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
                 if (a.out2.p && !a.tma_out2) direct_store(a.out2, p, co0 + 4 * k, o);
               }
           }
-          if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, sx0, sy0 + 4 * warp, tcd.n);
-          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, sx0, sy0 + 4 * warp, tcd.n);
+          if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, sx0, sy0 + 4 * q, tcd.n);
+          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, sx0, sy0 + 4 * q, tcd.n);
+        }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(acc_empty + 8 * as);                 // 128 arrivals free the accumulator stage
+      mbar_arrive(acc_empty + 8 * as);                 // every epilogue thread arrives: the accumulator stage is free
       TR_ADD(tr_work, tr1);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores of this warp have completed
@@ -501,12 +541,12 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
 #endif
-  } else if (warp == 4 || warp == ISSUER_B) {
+  } else if (warp == R::W_MMA || warp == R::W_MMAB) {
     // ===================== MMA issuers: whole warp walks the (uniform) loop, one elected lane issues =====================
     // A single thread sustains one small MMA per ~45-55 clk, the tensor pipe accepts one per ~40 (tools/micro/umma_rate.cu),
     // so macro tiles with several sub-tiles are split between two issuing warps (even / odd sub-tiles); every barrier
     // that recycles operand slots or releases the epilogue counts one tcgen05.commit per issuer.
-    const int iss = warp == 4 ? 0 : 1;
+    const int iss = warp == R::W_MMA ? 0 : 1;
     if (iss < a.n_iss) {
     const uint32_t idesc_wide = make_idesc(a.wide ? 2 * nt : nt), idesc_nt = make_idesc(nt);
     const uint32_t lo_rows = (uint32_t)nt * (ROWB >> 4);               // descriptor offset of the W_lo rows inside a tap image
@@ -528,7 +568,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
       const int ph = a.phase ? (t / a.n_ct) & 3 : 0;
       const uint32_t tap_base = a.phase ? (uint32_t)((ph >> 1) * a.pitch + (ph & 1)) * (ROWB >> 4) : 0u;
       TR_T(tr0);
-      mbar_wait(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
+      mbar_wait_relaxed(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
       TR_ADD(tr_acc, tr0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_base = tmem_base + as * acc_cols;
@@ -602,7 +642,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
       for (int wi = 0; wi < total; ++wi, ++w_it) {
         const int ws = w_it % a.nw;
         TR_T(tr0);
-        mbar_wait(w_empty + 8 * ws, ((w_it / a.nw) & 1) ^ 1);
+        mbar_wait_relaxed(w_empty + 8 * ws, ((w_it / a.nw) & 1) ^ 1);
         TR_ADD(tr_wait, tr0);
         if (elect_one()) {
           const uint32_t dst = w_smem + ws * a.w_stage;
@@ -619,7 +659,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) conv_tc_kernel(const __grid_c
 #endif
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == R::W_MMA) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
@@ -803,7 +843,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.tps = 1;
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
-  const int fixed = NA * a.a_slot + 1024 + STG_BYTES + 256 + 4 * 128 * 4;
+  const int fixed = NA * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES;
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
@@ -824,13 +864,15 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (a.tma_out) make_tmap_out(&a.tmap_out, out);
   if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2);
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
-  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
   snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", phase ? "-phase" : "", w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
-  conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
+  if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
+  else conv_tc_kernel<false><<<grid, Roles<false>::NTHREADS, smem, s>>>(a);
   count_launch();
 }
 

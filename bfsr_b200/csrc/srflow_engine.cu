@@ -176,7 +176,10 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
           memcpy(&wA[((size_t)(k * Hd + o) * 320) * 9], &w[((size_t)o * (Cn + 320) + Cn) * 9], (size_t)320 * 9 * 4);
           sA[k * Hd + o] = std::exp(al[o]); bA[k * Hd + o] = ab[o] * sA[k * Hd + o];
         }
-        std::vector<int> zmap(Cn); for (int i = 0; i < Cn; ++i) zmap[i] = i;
+        // z-part input channels padded to a multiple of 8 (zero weights): the operand copy of z1 is a BF16X2 tensor whose
+        // pixel stride must be 16-byte aligned for TMA
+        const int Cnp = (Cn + 7) & ~7;
+        std::vector<int> zmap(Cnp, -1); for (int i = 0; i < Cn; ++i) zmap[i] = i;
         l.cp.fA0z = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, zmap, /*with_bias=*/false, /*tc_min_cin=*/1);
       }
       l.cp.fF2 = pack_conv_actnorm(W, p + ".affine.fFeatures.2", Hd, Hd, 1, {}, true);
@@ -336,14 +339,19 @@ static void run_ft_convs(Run& r) {
 
 static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
 // z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
-static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& t1, const View& t2, const View& hout) {
+static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, const View& t1, const View& t2, const View& hout) {
   const int Hd = r.e->d.hidden;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
   // z-dependent first conv: split-bf16 x3 on the tensor cores like every other conv (products exact to ~2^-17); BFSR_FP32_Z=1
   // keeps it on the fp32 CUDA-core kernel (the round-1 default) for A/B parity runs
-  if (fp32_z()) K_(conv2d_fp32(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
-  else K_(conv2d(l.cp.fA0z, z.slice(0, l.C / 2), t1, e1, IN_DIRECT, r.s));
+  const int Cnp = l.cp.fA0z.cin;                    // C/2 padded to a multiple of 8 (the padding weights are zero)
+  if (fp32_z() || r.opfmt() != BF16X2) K_(conv2d_fp32(l.cp.fA0z, z.slice(0, Cnp), t1, e1, IN_DIRECT, r.s));
+  else {
+    // operand copy of z1 in bf16 (hi, lo) planes so the conv is TMA-fed like every other one (no register producers)
+    K_(resample(z.slice(0, l.C / 2), z1op, RS_COPY, r.s));
+    K_(conv2d(l.cp.fA0z, z1op, t1, e1, IN_DIRECT, r.s));
+  }
   ConvEpi relu; relu.act = ACT_RELU;
   K_(conv2d(l.cp.fA2, t1, t2, relu, IN_DIRECT, r.s));
   ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
@@ -353,12 +361,13 @@ static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& t
 // Per-level scratch: the flow state ping-pongs between two buffers; the affine-net intermediates are reused by
 // every step of the level (all work is ordered on one stream).
 struct LevelBufs {
-  View z[2], t1, t2, h; int pp = 0;
+  View z[2], z1op, t1, t2, h; int pp = 0;
   void alloc(Run& r, int H, int W, int C) {
     const int Hd = r.e->d.hidden;
     z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
     t1 = make_view(r.A, r.B, H, W, Hd, fp32_z() ? (int)F32 : r.opfmt()); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
+    z1op = make_view(r.A, r.B, H, W, (C / 2 + 7) & ~7, r.opfmt());
     pp = 0;
   }
   View& next() { View& v = z[pp]; pp ^= 1; return v; }
@@ -384,7 +393,7 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
       K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s));
       pending = false;
       z = zo;
-      if (l.kind == 2) { run_affine_net(r, l, z, lb.t1, lb.t2, lb.h); pending = true; }
+      if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, lb.t1, lb.t2, lb.h); pending = true; }
       const bool level_end = (i + 1 == e->layers.size()) || e->layers[i + 1].kind == 0 || e->layers[i + 1].kind == 3;
       if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
     } else {   // Split2d forward (Split.py:49-61)
@@ -425,7 +434,7 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
     const bool unsq = e->layers[i - 1].kind == 0;
     View zo = unsq ? make_view(r.A, r.B, 2 * H, 2 * W, l.C / 4) : lb.next();
     if (l.kind == 2) {
-      run_affine_net(r, l, z, lb.t1, lb.t2, lb.h);
+      run_affine_net(r, l, z, lb.z1op, lb.t1, lb.t2, lb.h);
       K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s));
     } else {
       K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s));
