@@ -73,6 +73,7 @@ SYMBOLS = {
     "bfsr_linf_lp_sr": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "bfsr_linf_lp_sr_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "bfsr_op_conv2d": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "bfsr_op_conv2d_hi_lo": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_conv2d_up2": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_squeeze2d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
 }

@@ -332,6 +332,41 @@ int bfsr_op_conv2d_up2(const float* x_dev, int32_t B, int32_t Cin, int32_t H, in
   API_END
 }
 
+// y = conv3x3(cat[x_hi, nearest2x(x_lo)]) through the single-pass phase evaluation of the tcgen05 kernel (BF16X2 operands)
+int bfsr_op_conv2d_hi_lo(const float* xhi_dev, const float* xlo_dev, int32_t B, int32_t Chi, int32_t Clo, int32_t H, int32_t W,
+                         const float* w_host, const float* bias_host, int32_t Cout, int32_t act, float* y_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(xhi_dev && xlo_dev && w_host && y_dev, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvW cw = pack_conv_tc_phase1(w_host, Cout, Chi + Clo, 0, Chi, Chi, Clo, nullptr, bias_host);
+  float *tmp = nullptr, *hb = nullptr, *lb = nullptr, *yb = nullptr;
+  const size_t nlo = (size_t)B * H * W, nhi = nlo * 4;
+  const int saved = g_conv_mode;
+  try {
+    CUDA_OK(cudaMalloc((void**)&tmp, (nhi * (Chi > Cout ? Chi : Cout) + nlo * Clo + 16) * 4));
+    CUDA_OK(cudaMalloc((void**)&hb, (nhi * Chi + 16) * 4));
+    CUDA_OK(cudaMalloc((void**)&lb, (nlo * Clo + 16) * 4));
+    CUDA_OK(cudaMalloc((void**)&yb, (nhi * Cout + 16) * 4));
+    View xh; xh.p = tmp; xh.N = B; xh.H = 2 * H; xh.W = 2 * W; xh.C = xh.cs = Chi;
+    View xhb = xh; xhb.p = hb; xhb.fmt = BF16X2; xhb.plane = (long long)nhi * Chi;
+    nchw_to_nhwc(xhi_dev, xh, s); resample(xh, xhb, RS_COPY, s);
+    View xl; xl.p = tmp; xl.N = B; xl.H = H; xl.W = W; xl.C = xl.cs = Clo;
+    View xlb = xl; xlb.p = lb; xlb.fmt = BF16X2; xlb.plane = (long long)nlo * Clo;
+    nchw_to_nhwc(xlo_dev, xl, s); resample(xl, xlb, RS_COPY, s);
+    View y; y.p = tmp; y.N = B; y.H = 2 * H; y.W = 2 * W; y.C = y.cs = Cout;
+    View ybv = y; ybv.p = yb; ybv.fmt = BF16X2; ybv.plane = (long long)nhi * Cout;
+    ConvEpi ep; ep.act = act;
+    g_conv_mode = 0;
+    conv2d_tc_phase1(cw, xhb, xlb, ybv, ep, s);
+    g_conv_mode = saved;
+    resample(ybv, y, RS_COPY, s);
+    nhwc_to_nchw(y, y_dev, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { g_conv_mode = saved; cudaFree(tmp); cudaFree(hb); cudaFree(lb); cudaFree(yb); free_conv(cw); throw; }
+  cudaFree(tmp); cudaFree(hb); cudaFree(lb); cudaFree(yb); free_conv(cw);
+  API_END
+}
+
 int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
                       void* stream) {
   API_BEGIN

@@ -39,6 +39,9 @@ namespace bfsr {
 
 thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
 
+#ifndef BFSR_EPI_WARPS
+#define BFSR_EPI_WARPS 8   // epilogue warps of the TMA-fed variant (multiple of 4)
+#endif
 namespace tc {
 constexpr int KC = 32;                       // channels per chunk = one 64-byte bf16 row (SWIZZLE_64B)
 constexpr int ROWB = 64;                     // bytes per smem row
@@ -49,7 +52,7 @@ constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
 // loader, TMA loader for A, MMA issuer B = 12 warps.  Register-producer variant (fp32 / upsampled / phase inputs): 4 epilogue
 // warps, MMA issuer A, weight loader, 8 producer warps, MMA issuer B = 15 warps.
 template <bool TMA_IN> struct Roles {
-  static constexpr int EPI_WARPS = TMA_IN ? 8 : 4;
+  static constexpr int EPI_WARPS = TMA_IN ? BFSR_EPI_WARPS : 4;
   static constexpr int W_MMA = EPI_WARPS, W_WPROD = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
   static constexpr int N_PROD = TMA_IN ? 1 : PROD_WARPS;
   static constexpr int W_MMAB = W_PROD0 + N_PROD;
@@ -57,13 +60,14 @@ template <bool TMA_IN> struct Roles {
 };
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr int STG_WARP = 4096;               // epilogue staging per warp: 32 pixel rows x 128 B
-constexpr int STG_BYTES = 8 * STG_WARP;
-constexpr int BIAS_BYTES = 8 * 128 * 4;        // per-epilogue-warp copy of the cout tile's bias
+constexpr int STG_BYTES = BFSR_EPI_WARPS * STG_WARP;
+constexpr int BIAS_BYTES = BFSR_EPI_WARPS * 128 * 4;        // per-epilogue-warp copy of the cout tile's bias
 constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
 }  // namespace tc
 
 struct TcArgs {
   alignas(64) CUtensorMap tmap;          // BF16X2 input: 5-D (C, W, H, N, plane) tiled map, box = one halo tile x 32 channels
+  alignas(64) CUtensorMap tmap_pl[4];    // phase 2: hi-res input seen as four parity planes (py, px): base offset + doubled strides
   alignas(64) CUtensorMap tmap_out;      // output(s): box = 32 channels x 8 x 4 pixels (one epilogue warp's rows of a sub-tile)
   alignas(64) CUtensorMap tmap_out2;
   int tma_out, tma_out2;                 // epilogue leaves through TMA bulk tensor stores (else per-lane direct stores)
@@ -79,6 +83,13 @@ struct TcArgs {
   int wide;                              // accurate mode with NT < 64: A_hi x [W_hi;W_lo] as one N = 2NT MMA (column halves summed by the epilogue)
   int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
   int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
+                                         // 2: single pass over [hi-res channels | nearest2x(low-res channels)]: per output phase
+                                         //    the low-res chunks take 4 pre-summed taps, the hi-res channels arrive as four
+                                         //    parity planes (stride-2 TMA boxes), each serving the 3x3 taps that land on it
+  int n_lo, taps_tile;                   // phase 2: low-res chunks per tile; tap images per (cout tile, phase)
+  unsigned short pl_off[4][4][4];        // phase 2: [phase][parity plane][i] view offset (16-byte units) of the plane's i-th tap
+  unsigned char pl_nt[4][4];             // phase 2: taps served by a parity plane for an output phase (1, 2, 2 or 4)
+  View in2;                              // phase 2: hi-res part of the input (BF16X2)
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
   int a_plane, a_slot, w_slot;           // bytes (w_slot = one tap image)
@@ -269,8 +280,14 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           if (elect_one()) {
             const uint32_t dst = a_smem + slot * a.a_slot, bar = a_full + 8 * slot;
             mbar_expect_tx(bar, a.fast ? box_bytes : 2 * box_bytes);
-            tma_load_5d(dst, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 0);
-            if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 1);
+            if (a.phase == 2 && c >= a.n_lo) {   // parity plane (py, px) of a hi-res channel chunk: every second pixel
+              const int pc = c - a.n_lo, pl = pc & 3, cc = pc >> 2;
+              tma_load_5d(dst, &a.tmap_pl[pl], bar, a.in2.coff + cc * KC, tcd.tx0 - 1, tcd.ty0 - 1, tcd.n, 0);
+              if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap_pl[pl], bar, a.in2.coff + cc * KC, tcd.tx0 - 1, tcd.ty0 - 1, tcd.n, 1);
+            } else {
+              tma_load_5d(dst, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 0);
+              if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap, bar, a.in.coff + c * KC, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 1);
+            }
           }
           __syncwarp();
         }
@@ -527,8 +544,10 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
                 if (a.out2.p && !a.tma_out2) direct_store(a.out2, p, co0 + 4 * k, o);
               }
           }
-          if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, sx0, sy0 + 4 * q, tcd.n);
-          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, sx0, sy0 + 4 * q, tcd.n);
+          // phase outputs: the map strides over every second pixel, the box starts at the phase's own (fy, fx) offset
+          const int ox = a.phase ? 2 * sx0 + (tcd.ph & 1) : sx0, oy = a.phase ? 2 * (sy0 + 4 * q) + (tcd.ph >> 1) : sy0 + 4 * q;
+          if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, ox, oy, tcd.n);
+          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, ox, oy, tcd.n);
         }
         }
       }
@@ -583,7 +602,14 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
         // running tap geometry (no divisions on the issue path): kw taps per filter row, start offset of the phase
         int tdx = 0;
         uint32_t tap_off = tap_base;
-        for (int st = 0; st < stages; ++st, ++w_it) {
+        int stages_c = stages, pl = -1;
+        if (a.phase == 2) {                                  // one tap per weight stage; hi-res plane chunks use the tap table
+          nk = 2;
+          if (c < a.n_lo) stages_c = 4;
+          else { pl = (c - a.n_lo) & 3; stages_c = a.pl_nt[ph][pl]; }
+        }
+        for (int st = 0; st < stages_c; ++st, ++w_it) {
+          if (pl >= 0) tap_off = a.pl_off[ph][pl][st];
           const int ws = w_it % a.nw;
           TR_T(tr2);
           mbar_wait(w_full + 8 * ws, (w_it / a.nw) & 1);
@@ -637,8 +663,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       const int ct = t % a.n_ct;
       const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
-      const unsigned char* wsrc = a.w + (size_t)wsel * a.n_chunks * a.ntaps * tap_stride;
-      const int total = a.n_chunks * (a.ntaps / a.tps);
+      const unsigned char* wsrc = a.w + (size_t)wsel * (a.phase == 2 ? a.taps_tile : a.n_chunks * a.ntaps) * tap_stride;
+      const int total = a.phase == 2 ? a.taps_tile : a.n_chunks * (a.ntaps / a.tps);
       for (int wi = 0; wi < total; ++wi, ++w_it) {
         const int ws = w_it % a.nw;
         TR_T(tr0);
@@ -713,7 +739,7 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h, int min_cin_arg) {
 }
 
 static bool vec4(const View& v);
-static void make_tmap_out(CUtensorMap* tm, const View& v);
+static void make_tmap_out(CUtensorMap* tm, const View& v, int estride);
 static bool tma_out_ok(const View& v);
 static bool vec4(const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; }
 // BF16X2 operand views: TMA needs 16-byte global strides and base; the register producer needs 16-byte channel groups
@@ -729,6 +755,7 @@ static bool shapes_ok(const ConvW& w, const View& in, const View& out, const Con
          (!epi.res2 || vec4(*epi.res2));
 }
 
+static void make_tmap_plane(CUtensorMap* tm, const View& v, int py, int px, int pitch, int hrows);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -743,12 +770,13 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 // (C, W, H, N, plane) map over a BF16X2 NHWC view; box = [32 channels, pitch, hrows, 1, 1], SWIZZLE_64B, zero OOB fill
-static void make_tmap(CUtensorMap* tm, const View& v, int pitch, int hrows) {
+static void make_tmap(CUtensorMap* tm, const View& v, int pitch, int hrows, int estride = 1) {
   const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)v.cs * 2, (cuuint64_t)v.W * v.cs * 2, (cuuint64_t)v.H * v.W * v.cs * 2,
                                  (cuuint64_t)v.plane * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)pitch, (cuuint32_t)hrows, 1, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // estride = 2: the box traverses every second pixel (one parity plane of the tensor); boxDim counts traversed elements
+  const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)(pitch * estride), (cuuint32_t)(hrows * estride), 1, 1};
+  const cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   const CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.p, dims, strides, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -761,19 +789,33 @@ bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const Con
   return w.w_tc != nullptr && !w.tc_phase && g_conv_mode != 2 && shapes_ok(w, in, out, epi);
 }
 
+// parity plane (py, px) of a BF16X2 NHWC view with even H, W: pixels (2Y+py, 2X+px) as a dense (C, W/2, H/2, N, plane) tensor
+static void make_tmap_plane(CUtensorMap* tm, const View& v, int py, int px, int pitch, int hrows) {
+  BFSR_CHECK(v.H % 2 == 0 && v.W % 2 == 0, "parity planes need even spatial dims");
+  const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)(v.W / 2), (cuuint64_t)(v.H / 2), (cuuint64_t)v.N, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)v.cs * 4, (cuuint64_t)v.W * v.cs * 4, (cuuint64_t)v.H * v.W * v.cs * 2,
+                                 (cuuint64_t)v.plane * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)tc::KC, (cuuint32_t)pitch, (cuuint32_t)hrows, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  void* base = (void*)((__nv_bfloat16*)v.p + ((long long)py * v.W + px) * v.cs);
+  const CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BFSR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(plane) failed (%d) for view C=%d cs=%d %dx%dx%d", (int)r, v.C, v.cs, v.N, v.H, v.W);
+}
 static bool tma_out_ok(const View& v) {
   if (((uintptr_t)v.p % 16) != 0) return false;
   return v.fmt == F32 ? v.cs % 4 == 0 : (v.cs % 8 == 0 && v.plane % 8 == 0);
 }
 // output map: box = [32 channels, 8, 4 pixels] = the accumulator rows of one epilogue warp; fp32 rows are 128 B
 // (SWIZZLE_128B), bf16 rows 64 B per plane (SWIZZLE_64B); the channel extent stops at the end of the view (tail clipped)
-static void make_tmap_out(CUtensorMap* tm, const View& v) {
+static void make_tmap_out(CUtensorMap* tm, const View& v, int estride) {
   const int es_b = v.fmt == F32 ? 4 : 2;
   const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)v.cs * es_b, (cuuint64_t)v.W * v.cs * es_b, (cuuint64_t)v.H * v.W * v.cs * es_b,
                                  (cuuint64_t)v.plane * es_b};
-  const cuuint32_t box[5] = {32, 8, 4, 1, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t box[5] = {32, (cuuint32_t)(8 * estride), (cuuint32_t)(4 * estride), 1, 1};   // estride 2: every second pixel (phase outputs)
+  const cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   const CUresult r = v.fmt == F32
       ? encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
@@ -787,10 +829,11 @@ static int g_num_sms = 0;
 // phase = false: out (N,H,W) = conv_ks(in) (+ optional nearest-2x folded into the loader).
 // phase = true : out (N,2H,2W) (+)= conv3x3(nearest2x(in)) evaluated on the LOW-RES grid as four 2x2 phase convs with
 //                pre-summed weights (exact in real arithmetic, 16/36 of the MACs); `in` is the low-res tensor.
-static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, bool phase, cudaStream_t s) {
+static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, int phase, cudaStream_t s,
+                      const View* in2 = nullptr) {
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
-  BFSR_CHECK(in.C == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
+  BFSR_CHECK(in.C + (in2 ? in2->C : 0) == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
   BFSR_CHECK(shapes_ok(w, in, out, epi), "conv_tc: operand views are not addressable by the tensor-core kernel "
              "(16-byte aligned fp32 or BF16X2 views, Cout %% 4 == 0)");
   if (in_mode == IN_UP2 || phase) BFSR_CHECK(in.H * 2 == out.H && in.W * 2 == out.W, "conv_tc(up2): spatial mismatch");
@@ -806,7 +849,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.H = gH; a.W = gW; a.N = out.N; a.in_mode = phase ? (int)IN_DIRECT : in_mode; a.act = epi.act;
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
   a.fast = g_conv_mode == 1;
-  a.phase = phase ? 1 : 0;
+  a.phase = phase;
   a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
   a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
@@ -828,6 +871,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   }
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
+  a.n_lo = 0; a.taps_tile = 0; a.in2 = in2 ? *in2 : View();
+  memset(a.pl_off, 0, sizeof a.pl_off); memset(a.pl_nt, 0, sizeof a.pl_nt);
   static const int max_iss = getenv("BFSR_TC_ISSUERS") ? atoi(getenv("BFSR_TC_ISSUERS")) : 2;
   a.n_iss = (a.mt >= 2 && max_iss >= 2) ? 2 : 1;
   a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
@@ -841,6 +886,25 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
   // weight stages: as many taps per stage as fit ~48 KB (fewer barrier round trips on the MMA issue path), 2-4 stages
   a.tps = 1;
+  if (phase == 2) {
+    BFSR_CHECK(in2 && bf_in_ok(in) && bf_in_ok(*in2) && in.C % KC == 0 && in2->C % KC == 0 && in2->H == out.H && in2->W == out.W &&
+               in2->N == out.N && in_mode == IN_DIRECT && w.ks == 3, "conv_tc(single-pass phase): operand views");
+    a.n_lo = in.C / KC;
+    a.n_chunks = a.n_lo + 4 * (in2->C / KC);
+    a.taps_tile = a.n_lo * 4 + (in2->C / KC) * 9;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int pl = 0; pl < 4; ++pl) {
+        int n = 0;
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            const int u = (ph >> 1) + dy - 1, v = (ph & 1) + dx - 1;               // hi-res offset of the tap from (2y, 2x)
+            if ((u & 1) != (pl >> 1) || (v & 1) != (pl & 1)) continue;
+            const int sy_ = u < 0 ? -1 : u >> 1, sx_ = v < 0 ? -1 : v >> 1;        // floor(u / 2): row / col shift inside the plane
+            a.pl_off[ph][pl][n++] = (unsigned short)(((1 + sy_) * a.pitch + (1 + sx_)) * (ROWB >> 4));
+          }
+        a.pl_nt[ph][pl] = (unsigned char)n;
+      }
+  } else
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
   const int fixed = NA * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES;
@@ -853,22 +917,24 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   const int smem = fixed + a.nw * a.w_stage;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
   BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
-  a.tma = (in.fmt == BF16X2 && in_mode == IN_DIRECT && !phase) ? 1 : 0;
+  a.tma = (in.fmt == BF16X2 && in_mode == IN_DIRECT && phase != 1) ? 1 : 0;
   a.in_bf = in.fmt == BF16X2 ? 1 : 0;
   memset(&a.tmap, 0, sizeof a.tmap);
   if (a.tma) make_tmap(&a.tmap, in, a.pitch, a.hrows);
+  memset(a.tmap_pl, 0, sizeof a.tmap_pl);
+  if (phase == 2) for (int pl = 0; pl < 4; ++pl) make_tmap_plane(&a.tmap_pl[pl], *in2, pl >> 1, pl & 1, a.pitch, a.hrows);
   memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
   static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
-  a.tma_out = (!phase && !no_tma_out && tma_out_ok(out)) ? 1 : 0;
-  a.tma_out2 = (epi.out2 && !phase && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
-  if (a.tma_out) make_tmap_out(&a.tmap_out, out);
-  if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2);
+  a.tma_out = (!no_tma_out && tma_out_ok(out)) ? 1 : 0;
+  a.tma_out2 = (epi.out2 && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
+  if (a.tma_out) make_tmap_out(&a.tmap_out, out, phase ? 2 : 1);
+  if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2, phase ? 2 : 1);
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
-  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", phase ? "-phase" : "", w.ks, w.cin, w.cout, out.H, out.W,
+  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", phase == 2 ? "-phase1p" : (phase ? "-phase" : ""), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
@@ -878,11 +944,83 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
 
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
   BFSR_CHECK(!w.tc_phase, "conv_tc: phase-packed weights need conv2d_tc_up2_phase");
-  launch_tc(w, in, out, epi, in_mode, false, s);
+  launch_tc(w, in, out, epi, in_mode, 0, s);
 }
 void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s) {
-  BFSR_CHECK(w.tc_phase, "conv_tc: weights are not phase-packed");
-  launch_tc(w, in_lowres, out, epi, IN_DIRECT, true, s);
+  BFSR_CHECK(w.tc_phase == 1, "conv_tc: weights are not phase-packed");
+  launch_tc(w, in_lowres, out, epi, IN_DIRECT, 1, s);
+}
+
+void conv2d_tc_phase1(const ConvW& w, const View& in_hi, const View& in_lo, const View& out, const ConvEpi& epi, cudaStream_t s) {
+  BFSR_CHECK(w.tc_phase == 2, "conv_tc: weights are not packed for the single-pass phase evaluation");
+  launch_tc(w, in_lo, out, epi, IN_DIRECT, 2, s, &in_hi);
+}
+
+// Single-pass packing of a 3x3 conv over [hi (hi_cn channels at full resolution) | nearest2x(lo) (lo_cn channels)]
+// (the level-1 conditioning tensor, SRFlowNet_arch.py:136).  Per (cout tile, output phase) the tap images are laid out in
+// the order the kernel walks them: low-res chunks x 4 pre-summed taps, then per hi chunk the four parity planes with the
+// original 3x3 taps that land on each plane (dy-major).  w_oihw: [cout][cin_src][3][3]; bias is the final bias.
+ConvW pack_conv_tc_phase1(const float* w_oihw, int cout, int cin_src, int hi_c0, int hi_cn, int lo_c0, int lo_cn,
+                          const float* out_scale, const float* bias) {
+  using namespace tc;
+  BFSR_CHECK(hi_cn % KC == 0 && lo_cn % KC == 0, "pack_conv_tc_phase1: channel counts must be multiples of %d", KC);
+  ConvW c;
+  c.ks = 3; c.cin = hi_cn + lo_cn; c.cout = cout; c.cin_pad = c.cin; c.co_tile = 64; c.cout_pad = (cout + 63) / 64 * 64;
+  c.tc_phase = 2;
+  const int nt = pick_nt(cout);
+  const int n_tiles = (cout + nt - 1) / nt, n_lo = lo_cn / KC, n_hi = hi_cn / KC;
+  const int taps_tile = n_lo * 4 + n_hi * 9;
+  const size_t tap_elems = (size_t)2 * nt * (ROWB / 2);
+  std::vector<unsigned short> img((size_t)n_tiles * 4 * taps_tile * tap_elems, 0);
+  auto members = [](int f, int a, int* d) {   // taps of the 3-tap filter that land on low-res offset a for phase f
+    if (f == 0) { if (a == 0) { d[0] = 0; return 1; } d[0] = 1; d[1] = 2; return 2; }
+    if (a == 0) { d[0] = 0; d[1] = 1; return 2; } d[0] = 2; return 1;
+  };
+  auto put = [&](unsigned short* dst, int t, int ci0, int ny, const int* dys, int nx, const int* dxs) {
+    for (int r = 0; r < nt; ++r) {
+      const int co = t * nt + r;
+      for (int k = 0; k < KC; ++k) {
+        double acc = 0.0;
+        if (co < cout)
+          for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix)
+              acc += (double)w_oihw[(((size_t)co * cin_src + ci0 + k) * 3 + dys[iy]) * 3 + dxs[ix]];
+        const float w = (float)(acc * (out_scale && co < cout ? (double)out_scale[co] : 1.0));
+        const unsigned short hi = f2bf(w), lo = f2bf(w - bf2f(hi));
+        const int j = k >> 3, e = k & 7;
+        dst[(size_t)r * 32 + ((j ^ ((r >> 1) & 3)) << 3) + e] = hi;
+        const int r2 = nt + r;
+        dst[(size_t)r2 * 32 + ((j ^ ((r2 >> 1) & 3)) << 3) + e] = lo;
+      }
+    }
+  };
+  for (int t = 0; t < n_tiles; ++t)
+    for (int ph = 0; ph < 4; ++ph) {
+      unsigned short* dst = img.data() + ((size_t)t * 4 + ph) * taps_tile * tap_elems;
+      for (int ch = 0; ch < n_lo; ++ch)
+        for (int tap = 0; tap < 4; ++tap, dst += tap_elems) {
+          int dys[2], dxs[2];
+          const int ny = members(ph >> 1, tap >> 1, dys), nx = members(ph & 1, tap & 1, dxs);
+          put(dst, t, lo_c0 + ch * KC, ny, dys, nx, dxs);
+        }
+      for (int ch = 0; ch < n_hi; ++ch)
+        for (int pl = 0; pl < 4; ++pl)
+          for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+              const int u = (ph >> 1) + dy - 1, v = (ph & 1) + dx - 1;
+              if ((u & 1) != (pl >> 1) || (v & 1) != (pl & 1)) continue;
+              put(dst, t, hi_c0 + ch * KC, 1, &dy, 1, &dx);
+              dst += tap_elems;
+            }
+    }
+  CUDA_OK(cudaMalloc(&c.w_tc, img.size() * 2));
+  CUDA_OK(cudaMemcpy(c.w_tc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> hb(c.cout_pad + 128, 0.f);
+  if (bias) for (int i = 0; i < cout; ++i) hb[i] = bias[i];
+  CUDA_OK(cudaMalloc((void**)&c.bias, hb.size() * 4));
+  CUDA_OK(cudaMemcpy(c.bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  c.tc_kchunks = n_lo + 4 * n_hi; c.tc_npad = nt;
+  return c;
 }
 
 // Phase packing of a 3x3 conv applied to nearest2x(x) (SRFlowNet_arch.py:136 feeds such tensors to every level-1 coupling):

@@ -44,10 +44,10 @@ struct LevelW {
   int C = 0, n_coupling = 0;
   ConvW fF0_all;           // ft -> n_coupling*64, ReLU            (fFeatures.0 of every step, ActNorm folded)
   ConvW fA0ft_all;         // ft -> n_coupling*64, pre-activation  (ft slice of fAffine.0 of every step)
-  // level fed by [hi-res base 64 | nearest2x(taps)] (SRFlowNet_arch.py:136): the same two convs split by linearity into
-  // a 3x3 over the 64 hi-res channels and a four-phase 2x2 evaluation over the LOW-RES taps (16/36 of those MACs)
+  // level fed by [hi-res base 64 | nearest2x(taps)] (SRFlowNet_arch.py:136): the same two convs packed for the single-pass
+  // phase evaluation (low-res taps: four pre-summed 2x2 taps per output phase; hi-res part: parity planes)
   bool has_phase = false;
-  ConvW fF0_hi, fA0ft_hi, fF0_ph, fA0ft_ph;
+  ConvW fF0_1p, fA0ft_1p;
 };
 
 struct RRDBW {

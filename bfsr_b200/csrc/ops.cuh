@@ -42,6 +42,11 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
 // 3x3 conv over nearest2x(in_lowres) as four 2x2 phase convs on the low-res grid (16/36 of the MACs); out is (N,2H,2W)
 ConvW pack_conv_tc_phase(const float* w_oihw, int cout, int cin_src, int c0, int cn, const float* out_scale);
 void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s);
+// single pass over [in_hi (N,2H,2W,hi_cn) | nearest2x(in_lo (N,H,W,lo_cn))] (both BF16X2): out (N,2H,2W,cout); 1600/2880 of the MACs
+// of the plain 3x3 for the level-1 conditioning tensor (64 hi-res + 256 upsampled channels)
+ConvW pack_conv_tc_phase1(const float* w_oihw, int cout, int cin_src, int hi_c0, int hi_cn, int lo_c0, int lo_cn,
+                          const float* out_scale, const float* bias);
+void conv2d_tc_phase1(const ConvW& w, const View& in_hi, const View& in_lo, const View& out, const ConvEpi& epi, cudaStream_t s);
 
 // Host-side packing: src is OIHW fp32 [cout][cin_src][ks][ks]; `out_scale` (optional) multiplies the weights per
 // output channel, `bias` is the FINAL bias (already scaled); the input-channel gather map makes packed input channel

@@ -34,7 +34,7 @@ bfsr_srflow::~bfsr_srflow() {
   }
   for (auto& l : levels) {
     free_conv(l.fF0_all); free_conv(l.fA0ft_all);
-    free_conv(l.fF0_hi); free_conv(l.fA0ft_hi); free_conv(l.fF0_ph); free_conv(l.fA0ft_ph);
+    free_conv(l.fF0_1p); free_conv(l.fA0ft_1p);
   }
   if (stage_in) cudaFree(stage_in);
   if (stage_out) cudaFree(stage_out);
@@ -190,17 +190,13 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
     }
     lv.fF0_all = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), {});
     lv.fA0ft_all = pack_conv(wA.data(), d.K * Hd, 320, 3, bA.data(), sA.data(), {});
-    // Two-pass phase evaluation (3x3 on the 64 hi-res channels, then four 2x2 phase convs accumulating on top).  Measured
-    // on B200: 44 % fewer MACs but a second exposed epilogue over the 1024-channel output -> slower (592 vs 499 ms/step),
-    // so it is opt-in until the single-pass variant (parity planes of the hi-res part) exists.
-    static const bool use_phase = getenv("BFSR_PHASE") && atoi(getenv("BFSR_PHASE"));
+    // Level fed by [hi-res base 64 | nearest2x(taps of the next level)]: single-pass phase evaluation (1600/2880 of the MACs,
+    // and the upsampled copy of the 256 tap channels is never materialised).  BFSR_PHASE=0 keeps the plain 3x3.
+    static const bool use_phase = !(getenv("BFSR_PHASE") && atoi(getenv("BFSR_PHASE")) == 0);
     if (use_phase && level == log2s - 1) {   // conditioning = [upconv output | nearest2x(taps of the LR-resolution level)]
-      std::vector<int> hi_map(nf); for (int i = 0; i < nf; ++i) hi_map[i] = i;
       lv.has_phase = true;
-      lv.fF0_hi = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), hi_map);
-      lv.fA0ft_hi = pack_conv(wA.data(), d.K * Hd, 320, 3, bA.data(), sA.data(), hi_map);
-      lv.fF0_ph = pack_conv_tc_phase(wF.data(), d.K * Hd, 320, nf, 320 - nf, sF.data());
-      lv.fA0ft_ph = pack_conv_tc_phase(wA.data(), d.K * Hd, 320, nf, 320 - nf, sA.data());
+      lv.fF0_1p = pack_conv_tc_phase1(wF.data(), d.K * Hd, 320, 0, nf, nf, 320 - nf, sF.data(), bF.data());
+      lv.fA0ft_1p = pack_conv_tc_phase1(wA.data(), d.K * Hd, 320, 0, nf, nf, 320 - nf, sA.data(), bA.data());
     }
     if (d.split_enable && level < d.L - 1) {
       LayerW l; l.kind = 3; l.C = C; l.level = level;
@@ -310,20 +306,15 @@ static void run_ft_convs(Run& r) {
     const LevelW& L = e->levels[lv];
     const int H = r.lvH(lv), W = r.lvW(lv);
     const size_t mark = r.A.off;
-    const bool two_pass_phase = L.has_phase && g_conv_mode != 2;   // accumulates into bufF through the fp32 `pre` operand
-    View bufF = make_view(r.A, r.B, H, W, L.n_coupling * Hd, two_pass_phase ? (int)F32 : r.opfmt());
+    View bufF = make_view(r.A, r.B, H, W, L.n_coupling * Hd, r.opfmt());
     View t = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     ConvEpi relu; relu.act = ACT_RELU;
     ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
     if (L.has_phase && g_conv_mode != 2) {
       const int nf = d.nf;
-      View taps = r.ft[lv + 1].slice(nf, e->n_cond - nf);
-      ConvEpi acc_relu; acc_relu.act = ACT_RELU; acc_relu.pre = &bufF;
-      ConvEpi acc; acc.pre = &r.bufA[lv];
-      K_(conv2d(L.fF0_hi, r.ft[lv].slice(0, nf), bufF, ConvEpi(), IN_DIRECT, r.s));
-      K_(conv2d_tc_up2_phase(L.fF0_ph, taps, bufF, acc_relu, r.s));
-      K_(conv2d(L.fA0ft_hi, r.ft[lv].slice(0, nf), r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));
-      K_(conv2d_tc_up2_phase(L.fA0ft_ph, taps, r.bufA[lv], acc, r.s));
+      View hi = r.ft[lv].slice(0, nf), lo = r.ft[lv + 1].slice(nf, e->n_cond - nf);
+      K_(conv2d_tc_phase1(L.fF0_1p, hi, lo, bufF, relu, r.s));
+      K_(conv2d_tc_phase1(L.fA0ft_1p, hi, lo, r.bufA[lv], ConvEpi(), r.s));
     } else {
       K_(conv2d(L.fF0_all, r.ft[lv], bufF, relu, IN_DIRECT, r.s));
       K_(conv2d(L.fA0ft_all, r.ft[lv], r.bufA[lv], ConvEpi(), IN_DIRECT, r.s));

@@ -163,6 +163,11 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
  * folded loader; 2 = tcgen05, four 2x2 phase convs on the low-res grid with pre-summed weights (16/36 of the MACs). */
 int bfsr_op_conv2d_up2(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                        const float* bias_host, int32_t Cout, int32_t impl, float* y_dev, void* stream);
+/* conv3x3(cat[x_hi (B,Chi,2H,2W), nearest2x(x_lo (B,Clo,H,W))]) + bias + activation: the level-1 coupling conditioning of
+ * SRFlowNet_arch.py:118-138 evaluated in ONE pass per output phase (low-res channels: four pre-summed 2x2 taps; hi-res
+ * channels: stride-2 parity planes); Chi, Clo multiples of 32; operands stored as bf16 (hi, lo) planes, split-bf16 x3. */
+int bfsr_op_conv2d_hi_lo(const float* xhi_dev, const float* xlo_dev, int32_t B, int32_t Chi, int32_t Clo, int32_t H, int32_t W,
+                         const float* w_host, const float* bias_host, int32_t Cout, int32_t act, float* y_dev, void* stream);
 /* flow.squeeze2d / unsqueeze2d (flow.py:122-152) */
 int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
                       void* stream);

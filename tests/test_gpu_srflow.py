@@ -207,3 +207,24 @@ def test_conv_over_nearest_up2(lib, cin, cout, H, W, impl, tol):
     lib.check(lib.lib().bfsr_op_conv2d_up2(x.cuda().data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, impl,
                                           y.data_ptr(), None))
     assert rel_l2(ref, y) < tol
+
+
+@pytest.mark.parametrize("chi,clo,cout,H,W,act", [(64, 256, 128, 12, 10, 2), (32, 64, 64, 17, 9, 0), (64, 256, 1024, 8, 16, 2),
+                                                 (64, 32, 24, 20, 24, 0)])
+def test_conv_hi_lo_single_pass_phase(lib, chi, clo, cout, H, W, act):
+    """conv3x3(cat[x_hi, nearest2x(x_lo)]) evaluated per output phase in one pass (TMA parity planes + pre-summed taps)
+    equals the plain op on the materialised tensor (SRFlowNet_arch.py:136 conditioning of the finest level)."""
+    g = torch.Generator().manual_seed(chi + clo + cout + H)
+    xh = torch.randn(2, chi, 2 * H, 2 * W, generator=g)
+    xl = torch.randn(2, clo, H, W, generator=g)
+    w = torch.randn(cout, chi + clo, 3, 3, generator=g) / ((chi + clo) * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xin = torch.cat([xh, F.interpolate(xl, scale_factor=2, mode="nearest")], 1)
+    ref = F.conv2d(xin.double(), w.double(), b.double(), padding=1)
+    if act == 2:
+        ref = F.relu(ref)
+    y = torch.empty(2, cout, 2 * H, 2 * W, device="cuda")
+    xh_d, xl_d = xh.cuda(), xl.cuda()    # keep both device tensors alive: two temporaries would share one cached block
+    lib.check(lib.lib().bfsr_op_conv2d_hi_lo(xh_d.data_ptr(), xl_d.data_ptr(), 2, chi, clo, H, W, w.data_ptr(),
+                                            b.data_ptr(), cout, act, y.data_ptr(), None))
+    assert rel_l2(ref, y) < 3e-5
