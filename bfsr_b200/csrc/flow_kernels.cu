@@ -20,7 +20,9 @@ namespace bfsr {
 // ------------------------------------------------------------------ fused flow steps
 struct StepArgs {
   View zin, zout, h, hF;
+  View z1op;           // optional: bf16 (hi, lo) operand copy of the first C/2 output channels, padded to a multiple of 8
   const float* M;      // [C][C] row-major (out, in)
+  const float* MT;     // [C][C] transposed (in, out), or null
   const float* cvec;   // [C]
   int C, H, W;         // dims of the squeezed (level) tensor
   long long npix;
@@ -45,7 +47,8 @@ __global__ void __launch_bounds__(256) flowstep_kernel(StepArgs a) {
   const int tid = threadIdx.x, P = a.pix_per_block;
   const long long p0 = (long long)blockIdx.x * P;
 
-  for (int e = tid; e < C * C; e += 256) { const int co = e / C, ci = e % C; Mt[ci * C + co] = a.M[e]; }
+  if (a.MT) { for (int e = tid; e < C * C; e += 256) Mt[e] = a.MT[e]; }
+  else { for (int e = tid; e < C * C; e += 256) { const int co = e / C, ci = e % C; Mt[ci * C + co] = a.M[e]; } }
 
   // ---- phase 1: gather z, apply the elementwise part that precedes the channel mix
   for (int e = tid; e < P * C; e += 256) {
@@ -176,6 +179,24 @@ __global__ void __launch_bounds__(128) flowstep_px_kernel(StepArgs a) {
 #pragma unroll
     for (int k = 0; k < C / 2; ++k) { const float4 v = fp[k]; o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
   }
+  if (a.z1op.p) {   // operand copy of z1 for the next coupling conv: C/2 channels zero-padded to a multiple of 8, bf16 (hi, lo)
+    constexpr int CP = (C / 2 + 7) & ~7;
+    __nv_bfloat16* d = (__nv_bfloat16*)a.z1op.p + pix * a.z1op.cs + a.z1op.coff;
+#pragma unroll
+    for (int k = 0; k < CP / 8; ++k) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = 8 * k + 2 * e;
+        const float x0 = c0 < C / 2 ? o[c0] : 0.f, x1 = c0 + 1 < C / 2 ? o[c0 + 1] : 0.f;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+        hi[e] = *reinterpret_cast<const uint32_t*>(&hh); lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(d + 8 * k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(d + a.z1op.plane + 8 * k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
   if (a.unsqueeze_out) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
@@ -191,12 +212,108 @@ __global__ void __launch_bounds__(128) flowstep_px_kernel(StepArgs a) {
   }
 }
 
+
+// ---- wide-C variant (C = 96, level 3 of the shipped topology): tile of 64 pixels per CTA staged in shared memory with
+// 128-bit loads (coupling / ft-affine inverse applied on the way in), C x C mix with a 2-pixel x 12-channel register tile
+// per thread (5 shared loads per 24 FMA), 128-bit epilogue.  No squeeze folding (the two boundary steps of a level use the
+// generic kernel).
+template <int C, bool INV>
+__global__ void __launch_bounds__(256) flowstep_wide_kernel(StepArgs a) {
+  constexpr int P = 64, ZP = C + 4, C4 = C / 4, NG = C / 12;
+  static_assert(C % 12 == 0 && C % 8 == 0 && (P / 2) * NG == 256, "tile shape");
+  extern __shared__ __align__(16) float sm[];
+  float* Mt = sm;                      // [ci][co]
+  float* zs = sm + C * C;              // [P][ZP]
+  const int tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * P;
+  if (a.MT) {     // pre-transposed copy: straight 128-bit copy (a transposing fill is a 32-way bank conflict per store)
+    for (int e = tid; e < C * C / 4; e += 256) reinterpret_cast<float4*>(Mt)[e] = __ldg(reinterpret_cast<const float4*>(a.MT) + e);
+  } else {
+    for (int e = tid; e < C * C; e += 256) { const int co = e / C, ci = e % C; Mt[ci * C + co] = a.M[e]; }
+  }
+  // ---- phase 1
+  for (int e = tid; e < P * C4; e += 256) {
+    const int p = e / C4, k = e % C4, c = 4 * k;
+    const long long pix = p0 + p;
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pix < a.npix) {
+      z = *reinterpret_cast<const float4*>((const float*)a.zin.p + pix * a.zin.cs + a.zin.coff + c);
+      if (a.has_h && c >= C / 2) {
+        const float4* hp = reinterpret_cast<const float4*>((const float*)a.h.p + pix * a.h.cs + a.h.coff + 2 * (c - C / 2));
+        const float4 h0 = hp[0], h1 = hp[1];          // (shift, scale) pairs of channels c..c+3
+        if (INV) { z.x = z.x / h0.y - h0.x; z.y = z.y / h0.w - h0.z; z.z = z.z / h1.y - h1.x; z.w = z.w / h1.w - h1.z; }
+        else { z.x = (z.x + h0.x) * h0.y; z.y = (z.y + h0.z) * h0.w; z.z = (z.z + h1.x) * h1.y; z.w = (z.w + h1.z) * h1.w; }
+      }
+      if (INV && a.has_hF) {
+        const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff + 2 * c);
+        const float4 f0 = fp[0], f1 = fp[1];
+        z.x = z.x / f0.y - f0.x; z.y = z.y / f0.w - f0.z; z.z = z.z / f1.y - f1.x; z.w = z.w / f1.w - f1.z;
+      }
+    }
+    *reinterpret_cast<float4*>(zs + p * ZP + c) = z;
+  }
+  __syncthreads();
+  // ---- phase 2: thread = (pixel pair, group of 12 output channels)
+  const int g = tid % NG, pq = tid / NG;
+  float acc[2][12];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[i][j] = 0.f;
+  const float* z0 = zs + (2 * pq) * ZP;
+  const float* mr = Mt + 12 * g;
+#pragma unroll 4
+  for (int ci = 0; ci < C; ++ci) {
+    const float4 m0 = *reinterpret_cast<const float4*>(mr + ci * C), m1 = *reinterpret_cast<const float4*>(mr + ci * C + 4),
+                 m2 = *reinterpret_cast<const float4*>(mr + ci * C + 8);
+    const float m[12] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
+    const float za = z0[ci], zb = z0[ZP + ci];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { acc[0][j] = fmaf(m[j], za, acc[0][j]); acc[1][j] = fmaf(m[j], zb, acc[1][j]); }
+  }
+  float cv[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) cv[j] = a.cvec[12 * g + j];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long pix = p0 + 2 * pq + i;
+    if (pix >= a.npix) continue;
+    float o[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) o[j] = INV ? acc[i][j] - cv[j] : acc[i][j] + cv[j];
+    if (!INV && a.has_hF) {
+      const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff + 24 * g);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const float4 v = fp[k]; o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
+    }
+    float4* dst = reinterpret_cast<float4*>((float*)a.zout.p + pix * a.zout.cs + a.zout.coff + 12 * g);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    if (a.z1op.p && 12 * g < C / 2) {     // C/2 is a multiple of 12 here: whole groups fall into the first half
+      __nv_bfloat16* d = (__nv_bfloat16*)a.z1op.p + pix * a.z1op.cs + a.z1op.coff + 12 * g;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        uint32_t hi[2], lo[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float x0 = o[4 * k + 2 * e], x1 = o[4 * k + 2 * e + 1];
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+          hi[e] = *reinterpret_cast<const uint32_t*>(&hh); lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint2*>(d + 4 * k) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(d + a.z1op.plane + 4 * k) = make_uint2(lo[0], lo[1]);
+      }
+    }
+  }
+}
+
 static bool vec4_ok(const View& v) {
   return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0;
 }
 
 static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, const View* h, const View* hF,
-                        const View& zout, bool unsq_out, cudaStream_t s) {
+                        const View& zout, bool unsq_out, cudaStream_t s, const View* z1op) {
   StepArgs a;
   a.C = w.C;
   BFSR_CHECK(w.C % 4 == 0, "flow step: C=%d not divisible by 4", w.C);
@@ -214,8 +331,10 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   a.zin = zin; a.zout = zout;
   a.h = h ? *h : View(); a.hF = hF ? *hF : View();
   a.has_h = h != nullptr; a.has_hF = hF != nullptr;
-  a.M = inv ? w.Mi : w.Mf; a.cvec = inv ? w.ci : w.cf;
+  a.M = inv ? w.Mi : w.Mf; a.cvec = inv ? w.ci : w.cf; a.MT = inv ? w.MiT : w.MfT;
   a.squeeze_in = sq_in; a.unsqueeze_out = unsq_out;
+  a.z1op = View();
+  bool z1_done = false;
   a.pix_per_block = w.C <= 24 ? 256 : (w.C <= 96 ? 128 : 32);
   if (a.npix == 0) return;
   const size_t smem = ((size_t)w.C * w.C + (size_t)a.pix_per_block * (w.C + 1)) * 4;
@@ -226,30 +345,50 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   // small-C fast path (levels 1 and 2 of the shipped topology)
   const bool px_ok = (w.C == 12 || w.C == 24) && zin.fmt == F32 && zout.fmt == F32 && (sq_in || vec4_ok(zin)) &&
                      (unsq_out || vec4_ok(zout)) && (!h || vec4_ok(*h)) && (!hF || vec4_ok(*hF));
+  // the fused operand copy of z1 needs the output at level resolution and a BF16X2 view with 16-byte pixel rows
+  const bool z1_ok = z1op && !unsq_out && z1op->fmt == BF16X2 && z1op->C == ((w.C / 2 + 7) & ~7) && z1op->cs % 8 == 0 &&
+                     z1op->coff % 8 == 0 && z1op->plane % 8 == 0 && ((uintptr_t)z1op->p % 16) == 0 && z1op->npix() == a.npix;
+  const bool wide_ok = w.C == 96 && !sq_in && !unsq_out && vec4_ok(zin) && vec4_ok(zout) && (!h || vec4_ok(*h)) && (!hF || vec4_ok(*hF));
+  if (wide_ok) {
+    if (z1_ok) { a.z1op = *z1op; z1_done = true; }
+    const size_t smem96 = (size_t)(96 * 96 + 64 * 100) * 4;
+    const int g = cdiv(a.npix, 64);
+    if (inv) { CUDA_OK(cudaFuncSetAttribute(flowstep_wide_kernel<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem96));
+               flowstep_wide_kernel<96, true><<<g, 256, smem96, s>>>(a); }
+    else { CUDA_OK(cudaFuncSetAttribute(flowstep_wide_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem96));
+           flowstep_wide_kernel<96, false><<<g, 256, smem96, s>>>(a); }
+    count_launch();
+  } else
   if (px_ok) {
+    if (z1_ok) { a.z1op = *z1op; z1_done = true; }
     const int g = cdiv(a.npix, 128);
     if (w.C == 12) { if (inv) flowstep_px_kernel<12, true><<<g, 128, 0, s>>>(a); else flowstep_px_kernel<12, false><<<g, 128, 0, s>>>(a); }
     else { if (inv) flowstep_px_kernel<24, true><<<g, 128, 0, s>>>(a); else flowstep_px_kernel<24, false><<<g, 128, 0, s>>>(a); }
     count_launch();
-    return;
-  }
-  if (inv) {
-    CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    flowstep_kernel<true><<<grid, 256, smem, s>>>(a);
   } else {
-    CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    flowstep_kernel<false><<<grid, 256, smem, s>>>(a);
+    if (inv) {
+      CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      flowstep_kernel<true><<<grid, 256, smem, s>>>(a);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(flowstep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      flowstep_kernel<false><<<grid, 256, smem, s>>>(a);
+    }
+    count_launch();
   }
-  count_launch();
+  // operand copy of z1 requested but not producible in the step kernel (boundary steps, odd layouts): plain converting copy
+  if (z1op && !z1_done) {
+    BFSR_CHECK(!unsq_out, "flowstep: z1 operand copy of an unsqueezed output is not supported");
+    resample(zout.slice(0, w.C / 2), *z1op, RS_COPY, s);
+  }
 }
 
 void flowstep_fwd(const StepW& w, const View& z_in, bool squeeze_in, const View* h_prev, const View* hF,
-                  const View& z_out, cudaStream_t s) {
-  launch_step(false, w, z_in, squeeze_in, h_prev, hF, z_out, false, s);
+                  const View& z_out, cudaStream_t s, const View* z1op) {
+  launch_step(false, w, z_in, squeeze_in, h_prev, hF, z_out, false, s, z1op);
 }
 void flowstep_inv(const StepW& w, const View& z_in, const View* h, const View* hF, const View& z_out,
-                  bool unsqueeze_out, cudaStream_t s) {
-  launch_step(true, w, z_in, false, h, hF, z_out, unsqueeze_out, s);
+                  bool unsqueeze_out, cudaStream_t s, const View* z1op) {
+  launch_step(true, w, z_in, false, h, hF, z_out, unsqueeze_out, s, z1op);
 }
 
 // ------------------------------------------------------------------ small elementwise flow ops

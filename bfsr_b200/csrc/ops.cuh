@@ -69,16 +69,19 @@ struct StepW {      // one FlowStep (device pointers, fp32)
   int C = 0; bool coupling = false;
   float* Mf = nullptr;  float* cf = nullptr;   // forward: y = Mf z + cf   (W diag(e^logs), W (b*e^logs))
   float* Mi = nullptr;  float* ci = nullptr;   // inverse: z = Mi y - ci   (diag(e^-logs) W^-1, bias)
+  float* MfT = nullptr; float* MiT = nullptr;  // the same matrices transposed ([in][out]) for the shared-memory tile kernels
 };
 // encode half-step: [finish previous coupling with h_prev] -> actnorm -> invconv -> [ft-affine with hF]
 //   squeeze_in: z_in is the un-squeezed tensor (N,2H,2W,C/4) read through the Squeeze2d index map (flow.py:122-134)
+//   z1op (optional, both directions): BF16X2 view that receives the operand copy of the first C/2 output channels (zero-padded
+//   to a multiple of 8) for the next coupling's z-dependent conv, written by the same kernel
 void flowstep_fwd(const StepW& w, const View& z_in, bool squeeze_in, const View* h_prev, const View* hF,
-                  const View& z_out, cudaStream_t s);
+                  const View& z_out, cudaStream_t s, const View* z1op = nullptr);
 // z2 = (z2 + shift) * scale with (shift,scale) pairs in h   (FlowAffineCouplingsAblation.py:72-76)
 void coupling_finish(const View& z, const View& h, const View& z_out, cudaStream_t s);
 // decode step: coupling^-1 (h) -> ft-affine^-1 (hF) -> invconv^-1 -> actnorm^-1 ; unsqueeze_out folds Unsqueeze2d
 void flowstep_inv(const StepW& w, const View& z_in, const View* h, const View* hF, const View& z_out,
-                  bool unsqueeze_out, cudaStream_t s);
+                  bool unsqueeze_out, cudaStream_t s, const View* z1op = nullptr);
 // Split2d (Split.py:49-77): h holds (mean,logs) pairs
 void split_fwd(const View& z, const View& h, const View& z1_out, const View& eps_out, cudaStream_t s);
 void split_inv(const View& z1, const View& h, const View& eps, const View& z_out, cudaStream_t s);

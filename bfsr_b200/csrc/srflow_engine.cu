@@ -29,6 +29,8 @@ bfsr_srflow::~bfsr_srflow() {
     if (l.step.cf) cudaFree(l.step.cf);
     if (l.step.Mi) cudaFree(l.step.Mi);
     if (l.step.ci) cudaFree(l.step.ci);
+    if (l.step.MfT) cudaFree(l.step.MfT);
+    if (l.step.MiT) cudaFree(l.step.MiT);
     free_conv(l.cp.fF2); free_conv(l.cp.fF4); free_conv(l.cp.fA0z); free_conv(l.cp.fA2); free_conv(l.cp.fA4);
     free_conv(l.split_conv);
   }
@@ -92,6 +94,9 @@ static StepW pack_step(const Weights& W, const std::string& p, int C, bool coupl
     ci[o] = b[o];
   }
   s.Mf = to_device(Mf); s.cf = to_device(cf); s.Mi = to_device(Mi); s.ci = to_device(ci);
+  std::vector<float> MfT((size_t)C * C), MiT((size_t)C * C);
+  for (int o = 0; o < C; ++o) for (int i = 0; i < C; ++i) { MfT[(size_t)i * C + o] = Mf[(size_t)o * C + i]; MiT[(size_t)i * C + o] = Mi[(size_t)o * C + i]; }
+  s.MfT = to_device(MfT); s.MiT = to_device(MiT);
   return s;
 }
 
@@ -330,7 +335,9 @@ static void run_ft_convs(Run& r) {
 
 static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
 // z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
-static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, const View& t1, const View& t2, const View& hout) {
+static bool z1_fused(const Run& r) { return !fp32_z() && r.opfmt() == BF16X2; }   // step kernels emit the z1 operand copy
+static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, bool z1_ready, const View& t1, const View& t2,
+                           const View& hout) {
   const int Hd = r.e->d.hidden;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
@@ -340,7 +347,7 @@ static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z
   if (fp32_z() || r.opfmt() != BF16X2) K_(conv2d_fp32(l.cp.fA0z, z.slice(0, Cnp), t1, e1, IN_DIRECT, r.s));
   else {
     // operand copy of z1 in bf16 (hi, lo) planes so the conv is TMA-fed like every other one (no register producers)
-    K_(resample(z.slice(0, l.C / 2), z1op, RS_COPY, r.s));
+    if (!z1_ready) K_(resample(z.slice(0, l.C / 2), z1op, RS_COPY, r.s));
     K_(conv2d(l.cp.fA0z, z1op, t1, e1, IN_DIRECT, r.s));
   }
   ConvEpi relu; relu.act = ACT_RELU;
@@ -381,10 +388,11 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
       BFSR_CHECK(!(sq && pending), "internal: pending coupling across a squeeze");
       View zo = lb.next();
       const View* hF = l.kind == 2 ? &r.hF[l.level][l.k_in_level] : nullptr;
-      K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s));
+      const bool emit_z1 = l.kind == 2 && z1_fused(r);     // this step's output feeds its own affine net
+      K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s, emit_z1 ? &lb.z1op : nullptr));
       pending = false;
       z = zo;
-      if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, lb.t1, lb.t2, lb.h); pending = true; }
+      if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h); pending = true; }
       const bool level_end = (i + 1 == e->layers.size()) || e->layers[i + 1].kind == 0 || e->layers[i + 1].kind == 3;
       if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
     } else {   // Split2d forward (Split.py:49-61)
@@ -407,6 +415,7 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
   int li = (int)lat.size() - 1;
   View z = lat[li--];
   LevelBufs lb; int cur_level = 0;
+  bool z1_ready = false;
   for (int i = (int)e->layers.size() - 1; i >= 0; --i) {
     const LayerW& l = e->layers[i];
     if (l.kind == 0) continue;   // unsqueeze: folded into the previous step's store
@@ -418,18 +427,21 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
       View zo = make_view(r.A, r.B, H, W, l.C);
       K_(conv2d_fp32(l.split_conv, z, hs, ConvEpi(), IN_DIRECT, r.s));
       K_(split_inv(z, hs, lat[li], zo, r.s));
-      --li; z = zo;
+      --li; z = zo; z1_ready = false;
       continue;
     }
     if (l.level != cur_level) { lb.alloc(r, H, W, l.C); cur_level = l.level; }
     const bool unsq = e->layers[i - 1].kind == 0;
     View zo = unsq ? make_view(r.A, r.B, 2 * H, 2 * W, l.C / 4) : lb.next();
+    // the step's output is the input of the next processed layer: if that is a coupling of the same level, emit its z1 copy
+    const bool next_cpl = i > 0 && e->layers[i - 1].kind == 2 && e->layers[i - 1].level == l.level && !unsq && z1_fused(r);
     if (l.kind == 2) {
-      run_affine_net(r, l, z, lb.z1op, lb.t1, lb.t2, lb.h);
-      K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s));
+      run_affine_net(r, l, z, lb.z1op, z1_ready, lb.t1, lb.t2, lb.h);
+      K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s, next_cpl ? &lb.z1op : nullptr));
     } else {
-      K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s));
+      K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s, next_cpl ? &lb.z1op : nullptr));
     }
+    z1_ready = next_cpl;
     z = zo;
   }
   BFSR_CHECK(z.C == 3, "decode: final tensor has %d channels", z.C);

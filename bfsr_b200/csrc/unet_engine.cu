@@ -43,9 +43,9 @@ static void pack_double_conv(const Weights& W, const std::string& p, int cin, in
   out2[1] = pack_conv_bn(W, p + ".double_conv.3", p + ".double_conv.4", cout, mid);
 }
 
-// DenseBlock_5C with the nf input channels padded to a multiple of 4 inside the dense buffer
+// DenseBlock_5C with the nf input channels padded to a multiple of 8 inside the dense buffer (16-byte bf16 pixel rows for TMA)
 void pack_dense5(const Weights& W, const std::string& p, int nf, int gc, int out_dim, ConvW* out5, int* nf_pad_out) {
-  const int nf_pad = (nf + 3) / 4 * 4;
+  const int nf_pad = (nf + 7) / 8 * 8;
   *nf_pad_out = nf_pad;
   for (int c = 1; c <= 5; ++c) {
     const int cin_src = nf + (c - 1) * gc, cout = c < 5 ? gc : out_dim;
@@ -54,7 +54,7 @@ void pack_dense5(const Weights& W, const std::string& p, int nf, int gc, int out
     for (int i = 0; i < (c - 1) * gc; ++i) map[nf_pad + i] = nf + i;
     const std::string q = p + ".conv" + std::to_string(c);
     out5[c - 1] = pack_conv(W.data(q + ".weight", {cout, cin_src, 3, 3}), cout, cin_src, 3, W.data(q + ".bias", {cout}),
-                            nullptr, map);
+                            nullptr, map, /*tc_min_cin=*/1);
   }
 }
 
@@ -119,19 +119,21 @@ View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const Vie
   for (int i = 0; i < depth; ++i) { Hs[i + 1] = Hs[i] / 2; Ws[i + 1] = Ws[i] / 2; Cs[i + 1] = B.down[2 * i + 1].cout; }
   BFSR_CHECK(Hs[depth] >= 1 && Ws[depth] >= 1, "UNet: latent %dx%d too small for depth %d", x.H, x.W, depth);
   // skip-concat buffers: cat[i] = [features[i] | upsampled] at resolution i (i < depth)
+  // every intermediate is only ever a conv operand: stored as bf16 (hi, lo) planes so the tcgen05 convs are TMA-fed
+  const int fmt = g_conv_mode == 2 ? (int)F32 : (int)BF16X2;
   std::vector<View> cat(depth);
-  for (int i = 0; i < depth; ++i) cat[i] = make_view(A, N, Hs[i], Ws[i], 2 * Cs[i]);
-  View t = make_view(A, N, Hs[0], Ws[0], B.inc[0].cout);
+  for (int i = 0; i < depth; ++i) cat[i] = make_view(A, N, Hs[i], Ws[i], 2 * Cs[i], fmt);
+  View t = make_view(A, N, Hs[0], Ws[0], B.inc[0].cout, fmt);
   K_(conv2d(B.inc[0], x, t, lrelu, IN_DIRECT, s));
   K_(conv2d(B.inc[1], t, cat[0].slice(0, Cs[0]), lrelu, IN_DIRECT, s));
   View cur = cat[0].slice(0, Cs[0]);
   View bottom;
   for (int i = 0; i < depth; ++i) {
-    View p = make_view(A, N, Hs[i + 1], Ws[i + 1], Cs[i]);
+    View p = make_view(A, N, Hs[i + 1], Ws[i + 1], Cs[i], fmt);
     K_(resample(cur, p, RS_MAXPOOL2, s));
-    View m = make_view(A, N, Hs[i + 1], Ws[i + 1], B.down[2 * i].cout);
+    View m = make_view(A, N, Hs[i + 1], Ws[i + 1], B.down[2 * i].cout, fmt);
     K_(conv2d(B.down[2 * i], p, m, lrelu, IN_DIRECT, s));
-    View o = i + 1 < depth ? cat[i + 1].slice(0, Cs[i + 1]) : make_view(A, N, Hs[i + 1], Ws[i + 1], Cs[i + 1]);
+    View o = i + 1 < depth ? cat[i + 1].slice(0, Cs[i + 1]) : make_view(A, N, Hs[i + 1], Ws[i + 1], Cs[i + 1], fmt);
     K_(conv2d(B.down[2 * i + 1], m, o, lrelu, IN_DIRECT, s));
     cur = o;
     if (i + 1 == depth) bottom = o;
@@ -141,9 +143,9 @@ View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const Vie
     const int lvl = depth - 1 - i;
     BFSR_CHECK(z.C == Cs[lvl], "UNet: up path channel mismatch (%d vs %d)", z.C, Cs[lvl]);
     K_(resample(z, cat[lvl].slice(Cs[lvl], Cs[lvl]), RS_BILINEAR_UP2_AC, s));
-    View m = make_view(A, N, Hs[lvl], Ws[lvl], B.up[2 * i].cout);
+    View m = make_view(A, N, Hs[lvl], Ws[lvl], B.up[2 * i].cout, fmt);
     K_(conv2d(B.up[2 * i], cat[lvl], m, lrelu, IN_DIRECT, s));
-    View o = make_view(A, N, Hs[lvl], Ws[lvl], B.up[2 * i + 1].cout);
+    View o = make_view(A, N, Hs[lvl], Ws[lvl], B.up[2 * i + 1].cout, fmt);
     K_(conv2d(B.up[2 * i + 1], m, o, lrelu, IN_DIRECT, s));
     z = o;
   }
@@ -155,11 +157,12 @@ View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const Vie
 // DenseBlock_5C (unet.py:30-36): x -> dense buffer -> conv5 output (out_dim channels)
 View run_dense5(const ConvW* dense, int nf, int nf_pad, int gc, Arena& A, const View& x, cudaStream_t s) {
   ConvEpi lrelu; lrelu.act = ACT_LRELU;
-  View D = make_view(A, x.N, x.H, x.W, nf_pad + 4 * gc);
+  const int fmt = g_conv_mode == 2 ? (int)F32 : (int)BF16X2;
+  View D = make_view(A, x.N, x.H, x.W, nf_pad + 4 * gc, fmt);
   K_(resample(x, D.slice(0, nf_pad), RS_COPY, s));
   for (int c = 0; c < 4; ++c)
     K_(conv2d(dense[c], D.slice(0, nf_pad + c * gc), D.slice(nf_pad + c * gc, gc), lrelu, IN_DIRECT, s));
-  View o = make_view(A, x.N, x.H, x.W, dense[4].cout);
+  View o = make_view(A, x.N, x.H, x.W, dense[4].cout, fmt);
   K_(conv2d(dense[4], D, o, ConvEpi(), IN_DIRECT, s));
   (void)nf;
   return o;
@@ -171,7 +174,7 @@ View run_unet_linf(bfsr_unet* u, Arena& A, const View& x, const float* lr_nchw, 
   const UNetBranchW& B = u->br[0];
   BFSR_CHECK(x.C == B.nf, "prior: latent has %d channels, expected %d", x.C, B.nf);
   const int dim = u->d.dim, half = dim / 2;
-  View cat = make_view(A, x.N, x.H, x.W, dim);
+  View cat = make_view(A, x.N, x.H, x.W, dim, g_conv_mode == 2 ? (int)F32 : (int)BF16X2);
   View xa = run_dense5(B.dense, B.nf, B.nf_pad, B.gc, A, x, s);
   K_(resample(xa, cat.slice(0, half), RS_COPY, s));
   const int eh = (h + 2 - 3) / 3 + 1, ew = (w + 2 - 3) / 3 + 1;
