@@ -89,7 +89,9 @@ struct TcArgs {
   int n_lo, taps_tile;                   // phase 2: low-res chunks per tile; tap images per (cout tile, phase)
   unsigned short pl_off[4][4][4];        // phase 2: [phase][parity plane][i] view offset (16-byte units) of the plane's i-th tap
   unsigned char pl_nt[4][4];             // phase 2: taps served by a parity plane for an output phase (1, 2, 2 or 4)
-  View in2;                              // phase 2: hi-res part of the input (BF16X2)
+  View in2;                              // phase 2: hi-res part of the input (BF16X2); n_pre: the pre-activation tensor
+  int n_pre, n_main;                     // pre-activation folded into the GEMM: n_pre extra 32-channel chunks of `in2` with ONE
+                                         // centre tap and identity weights follow the n_main chunks of the conv proper
   int mt, sx, sy;                        // sub-tiles per macro tile and their arrangement (sx * sy = mt)
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
   int a_plane, a_slot, w_slot;           // bytes (w_slot = one tap image)
@@ -280,7 +282,11 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           if (elect_one()) {
             const uint32_t dst = a_smem + slot * a.a_slot, bar = a_full + 8 * slot;
             mbar_expect_tx(bar, a.fast ? box_bytes : 2 * box_bytes);
-            if (a.phase == 2 && c >= a.n_lo) {   // parity plane (py, px) of a hi-res channel chunk: every second pixel
+            if (a.n_pre && c >= a.n_main) {     // pre-activation chunk: same halo tile geometry, read through the second map
+              const int c0 = a.in2.coff + (c - a.n_main) * KC;
+              tma_load_5d(dst, &a.tmap_pl[0], bar, c0, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 0);
+              if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap_pl[0], bar, c0, tcd.tx0 - a.halo, tcd.ty0 - a.halo, tcd.n, 1);
+            } else if (a.phase == 2 && c >= a.n_lo) {   // parity plane (py, px) of a hi-res channel chunk: every second pixel
               const int pc = c - a.n_lo, pl = pc & 3, cc = pc >> 2;
               tma_load_5d(dst, &a.tmap_pl[pl], bar, a.in2.coff + cc * KC, tcd.tx0 - 1, tcd.ty0 - 1, tcd.n, 0);
               if (!a.fast) tma_load_5d(dst + a.a_plane, &a.tmap_pl[pl], bar, a.in2.coff + cc * KC, tcd.tx0 - 1, tcd.ty0 - 1, tcd.n, 1);
@@ -603,7 +609,9 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
         int tdx = 0;
         uint32_t tap_off = tap_base;
         int stages_c = stages, pl = -1;
-        if (a.phase == 2) {                                  // one tap per weight stage; hi-res plane chunks use the tap table
+        if (a.n_pre) {                                       // one tap per weight stage; identity chunks take the centre tap only
+          if (c >= a.n_main) { nk = 2; stages_c = 1; tap_off = (uint32_t)(a.halo * a.pitch + a.halo) * (ROWB >> 4); }
+        } else if (a.phase == 2) {                           // one tap per weight stage; hi-res plane chunks use the tap table
           nk = 2;
           if (c < a.n_lo) stages_c = 4;
           else { pl = (c - a.n_lo) & 3; stages_c = a.pl_nt[ph][pl]; }
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       const int ct = t % a.n_ct;
       const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
       const unsigned char* wsrc = a.w + (size_t)wsel * (a.phase == 2 ? a.taps_tile : a.n_chunks * a.ntaps) * tap_stride;
-      const int total = a.phase == 2 ? a.taps_tile : a.n_chunks * (a.ntaps / a.tps);
+      const int total = a.phase == 2 ? a.taps_tile : (a.n_pre ? a.n_main * a.ntaps + a.n_pre : a.n_chunks * (a.ntaps / a.tps));
       for (int wi = 0; wi < total; ++wi, ++w_it) {
         const int ws = w_it % a.nw;
         TR_T(tr0);
@@ -714,7 +722,19 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h, int min_cin_arg) {
   const int nt = pick_nt(c.cout);
   const int n_tiles = (c.cout + nt - 1) / nt, n_chunks = (c.cin + KC - 1) / KC;
   const size_t tap_elems = (size_t)2 * nt * (ROWB / 2);
-  std::vector<unsigned short> img((size_t)n_tiles * n_chunks * taps * tap_elems, 0);
+  // single-tile convs with Cout % 32 == 0 carry Cout/32 identity tap images after the conv's own taps: a BF16X2 pre-activation
+  // tensor is then added INSIDE the GEMM as extra K chunks (hi*1 + lo*1 is exact in the fp32 accumulator) instead of by
+  // epilogue loads
+  const int n_id = (n_tiles == 1 && c.cout % KC == 0) ? c.cout / KC : 0;
+  std::vector<unsigned short> img(((size_t)n_tiles * n_chunks * taps + n_id) * tap_elems, 0);
+  for (int j = 0; j < n_id; ++j) {
+    unsigned short* dst = img.data() + ((size_t)n_chunks * taps + j) * tap_elems;
+    for (int k = 0; k < KC; ++k) {
+      const int r = j * KC + k;             // output channel r takes input channel k of identity chunk j
+      dst[(size_t)r * 32 + (((k >> 3) ^ ((r >> 1) & 3)) << 3) + (k & 7)] = 0x3F80;   // bf16(1.0) in the W_hi rows; W_lo stays 0
+    }
+  }
+  c.tc_n_id = n_id;
   for (int t = 0; t < n_tiles; ++t)
     for (int ch = 0; ch < n_chunks; ++ch)
       for (int tap = 0; tap < taps; ++tap) {
@@ -751,7 +771,7 @@ static bool out_ok(const View& v) {
 }
 static bool shapes_ok(const ConvW& w, const View& in, const View& out, const ConvEpi& epi) {
   return w.cout % 4 == 0 && (bf_in_ok(in) || (vec4(in) && (w.cin % 8 == 0 || w.cin <= 16))) && out_ok(out) &&
-         (!epi.out2 || out_ok(*epi.out2)) && (!epi.pre || vec4(*epi.pre)) && (!epi.res1 || vec4(*epi.res1)) &&
+         (!epi.out2 || out_ok(*epi.out2)) && (!epi.pre || vec4(*epi.pre) || (bf_in_ok(*epi.pre) && bf_in_ok(in) && w.tc_n_id * tc::KC == w.cout)) && (!epi.res1 || vec4(*epi.res1)) &&
          (!epi.res2 || vec4(*epi.res2));
 }
 
@@ -842,7 +862,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   const int gH = phase ? in.H : out.H, gW = phase ? in.W : out.W;      // grid the GEMM rows live on
   TcArgs a;
   a.in = in; a.out = out; a.out2 = epi.out2 ? *epi.out2 : View();
-  a.pre = epi.pre ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
+  const bool pre_gemm = epi.pre && epi.pre->fmt == BF16X2;    // pre-activation enters as identity K chunks (checked below)
+  a.pre = (epi.pre && !pre_gemm) ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
   a.w = (const unsigned char*)w.w_tc; a.bias = w.bias;
   a.cin = w.cin; a.cout = w.cout; a.nt = w.tc_npad; a.n_chunks = w.tc_kchunks;
   a.n_ct = cdiv(w.cout, w.tc_npad);
@@ -872,6 +893,13 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
   a.n_lo = 0; a.taps_tile = 0; a.in2 = in2 ? *in2 : View();
+  a.n_pre = 0; a.n_main = a.n_chunks;
+  if (pre_gemm) {
+    BFSR_CHECK(phase == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && w.tc_n_id * KC == w.cout && epi.pre->C == w.cout &&
+               bf_in_ok(*epi.pre) && epi.pre->npix() == out.npix(),
+               "conv_tc: a BF16X2 pre-activation needs a TMA-fed single-tile conv with Cout %% 32 == 0");
+    a.n_pre = w.tc_n_id; a.n_chunks = a.n_main + a.n_pre; a.in2 = *epi.pre;
+  }
   memset(a.pl_off, 0, sizeof a.pl_off); memset(a.pl_nt, 0, sizeof a.pl_nt);
   static const int max_iss = getenv("BFSR_TC_ISSUERS") ? atoi(getenv("BFSR_TC_ISSUERS")) : 2;
   a.n_iss = (a.mt >= 2 && max_iss >= 2) ? 2 : 1;
@@ -886,7 +914,9 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
   // weight stages: as many taps per stage as fit ~48 KB (fewer barrier round trips on the MMA issue path), 2-4 stages
   a.tps = 1;
-  if (phase == 2) {
+  if (a.n_pre) {
+    // one tap per weight stage (the identity chunks have a single tap)
+  } else if (phase == 2) {
     BFSR_CHECK(in2 && bf_in_ok(in) && bf_in_ok(*in2) && in.C % KC == 0 && in2->C % KC == 0 && in2->H == out.H && in2->W == out.W &&
                in2->N == out.N && in_mode == IN_DIRECT && w.ks == 3, "conv_tc(single-pass phase): operand views");
     a.n_lo = in.C / KC;
@@ -923,6 +953,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (a.tma) make_tmap(&a.tmap, in, a.pitch, a.hrows);
   memset(a.tmap_pl, 0, sizeof a.tmap_pl);
   if (phase == 2) for (int pl = 0; pl < 4; ++pl) make_tmap_plane(&a.tmap_pl[pl], *in2, pl >> 1, pl & 1, a.pitch, a.hrows);
+  if (a.n_pre) make_tmap(&a.tmap_pl[0], a.in2, a.pitch, a.hrows);
   memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
   static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
   a.tma_out = (!no_tma_out && tma_out_ok(out)) ? 1 : 0;

@@ -561,6 +561,86 @@ __global__ void resample_kernel(View src, View dst, long long n, int mode, int o
   }
   st(dst, pix, c, v);
 }
+// 8 consecutive channels of one pixel (views with 8-channel-aligned strides / offsets): two 128-bit loads for fp32, one per
+// plane for BF16X2
+__device__ __forceinline__ void ld8(const View& v, long long pix, int c, float* x) {
+  if (v.fmt == F32) {
+    const float4* p = reinterpret_cast<const float4*>((const float*)v.p + pix * v.cs + v.coff + c);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+    const __nv_bfloat16* p = (const __nv_bfloat16*)v.p + pix * v.cs + v.coff + c;
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(p)), l = __ldg(reinterpret_cast<const uint4*>(p + v.plane));
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a 16-bit shift
+      x[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+      x[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ void st8(const View& v, long long pix, int c, const float* x) {
+  if (v.fmt == F32) {
+    float4* p = reinterpret_cast<float4*>((float*)v.p + pix * v.cs + v.coff + c);
+    p[0] = make_float4(x[0], x[1], x[2], x[3]); p[1] = make_float4(x[4], x[5], x[6], x[7]);
+  } else {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - __low2float(hh), x[2 * i + 1] - __high2float(hh));
+      hi[i] = *reinterpret_cast<const uint32_t*>(&hh); lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    __nv_bfloat16* p = (__nv_bfloat16*)v.p + pix * v.cs + v.coff + c;
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p + v.plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+// channel-vectorised twin of resample_kernel: one thread = 8 channels of one output pixel
+__global__ void resample8_kernel(View src, View dst, long long n8, int mode, int oy, int ox) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n8) return;
+  const int C8 = dst.C >> 3;
+  const long long pix = e / C8; const int c = (int)(e % C8) << 3;
+  const int x = (int)(pix % dst.W); const long long t = pix / dst.W; const int y = (int)(t % dst.H); const long long b = t / dst.H;
+  const long long sb = b * src.H * src.W;
+  float v[8];
+  if (mode == RS_COPY) ld8(src, pix, c, v);
+  else if (mode == RS_NEAREST_UP2) ld8(src, sb + (long long)(y >> 1) * src.W + (x >> 1), c, v);
+  else if (mode == RS_NEAREST_DOWN2) ld8(src, sb + (long long)(2 * y) * src.W + 2 * x, c, v);
+  else if (mode == RS_AVG_DOWN2 || mode == RS_MAXPOOL2) {
+    const long long p = sb + (long long)(2 * y) * src.W + 2 * x;
+    float a[8], bq[8], cq[8], d[8];
+    ld8(src, p, c, a); ld8(src, p + 1, c, bq); ld8(src, p + src.W, c, cq); ld8(src, p + src.W + 1, c, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = mode == RS_MAXPOOL2 ? fmaxf(fmaxf(a[i], bq[i]), fmaxf(cq[i], d[i]))
+                                 : 0.5f * (0.5f * a[i] + 0.5f * bq[i]) + 0.5f * (0.5f * cq[i] + 0.5f * d[i]);   // same op order as the scalar kernel
+  } else {  // RS_BILINEAR_UP2_AC
+    const int uy = y - oy, ux = x - ox, UH = 2 * src.H, UW = 2 * src.W;
+    if (uy < 0 || uy >= UH || ux < 0 || ux >= UW) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    } else {
+      const float sh = UH > 1 ? (float)(src.H - 1) / (float)(UH - 1) : 0.f;
+      const float sw = UW > 1 ? (float)(src.W - 1) / (float)(UW - 1) : 0.f;
+      const float fy = sh * uy, fx = sw * ux;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < src.H - 1 ? 1 : 0), x1 = x0 + (x0 < src.W - 1 ? 1 : 0);
+      const float ly = fy - y0, lx = fx - x0;
+      float a00[8], a01[8], a10[8], a11[8];
+      ld8(src, sb + (long long)y0 * src.W + x0, c, a00); ld8(src, sb + (long long)y0 * src.W + x1, c, a01);
+      ld8(src, sb + (long long)y1 * src.W + x0, c, a10); ld8(src, sb + (long long)y1 * src.W + x1, c, a11);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) + ly * ((1.f - lx) * a10[i] + lx * a11[i]);
+    }
+  }
+  st8(dst, pix, c, v);
+}
+static bool vec8_ok(const View& v) {
+  return v.C % 8 == 0 && v.cs % 8 == 0 && v.coff % 8 == 0 && ((uintptr_t)v.p % 16) == 0 && (v.fmt == F32 || v.plane % 8 == 0);
+}
+
 void resample(const View& src, const View& dst, int mode, cudaStream_t s) {
   BFSR_CHECK((src.C == dst.C || (mode == RS_COPY && src.C < dst.C)) && src.N == dst.N,
              "resample: channel/batch mismatch (%d vs %d)", src.C, dst.C);
@@ -580,7 +660,8 @@ void resample(const View& src, const View& dst, int mode, cudaStream_t s) {
   if (!n) return;
   snprintf(g_prof_tag, sizeof g_prof_tag, "resample m%d C%d %dx%d", mode, dst.C, dst.H, dst.W);
   ProfScope prof(PK_OTHER, 8.0 * n, s);
-  resample_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, mode, oy, ox);
+  if (src.C == dst.C && vec8_ok(src) && vec8_ok(dst)) resample8_kernel<<<cdiv(n / 8, 256), 256, 0, s>>>(src, dst, n / 8, mode, oy, ox);
+  else resample_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, mode, oy, ox);
   count_launch();
 }
 

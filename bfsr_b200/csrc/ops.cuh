@@ -17,7 +17,7 @@ struct ConvW {
   float* bias = nullptr;   // [cout_pad] (zeros if the conv has none)
   // split-bf16 packing for the tcgen05 path (built lazily by conv_tc.cu)
   void* w_tc = nullptr;
-  int tc_kchunks = 0, tc_npad = 0, tc_phase = 0;
+  int tc_kchunks = 0, tc_npad = 0, tc_phase = 0, tc_n_id = 0;   // tc_n_id: identity tap images appended (pre-activation as K chunks)
 };
 
 struct ConvEpi {

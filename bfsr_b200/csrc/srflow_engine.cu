@@ -295,6 +295,7 @@ static void run_encoder(Run& r, const View& x) {
   }
 }
 
+static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
 // feature-only halves of every coupling step of every level
 static void run_ft_convs(Run& r) {
   bfsr_srflow* e = r.e; const auto& d = e->d;
@@ -304,7 +305,8 @@ static void run_ft_convs(Run& r) {
   for (int lv = 1; lv <= d.L; ++lv) {
     const LevelW& L = e->levels[lv];
     const int H = r.lvH(lv), W = r.lvW(lv);
-    r.bufA[lv] = make_view(r.A, r.B, H, W, L.n_coupling * Hd);
+    // pre-activations of fAffine.0 (ft part): consumed as identity K chunks of the z-dependent conv -> operand format
+    r.bufA[lv] = make_view(r.A, r.B, H, W, L.n_coupling * Hd, fp32_z() ? (int)F32 : r.opfmt());
     for (int k = 0; k < L.n_coupling; ++k) r.hF[lv].push_back(make_view(r.A, r.B, H, W, 2 * L.C));
   }
   for (int lv = 1; lv <= d.L; ++lv) {
@@ -333,7 +335,6 @@ static void run_ft_convs(Run& r) {
   }
 }
 
-static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
 // z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
 static bool z1_fused(const Run& r) { return !fp32_z() && r.opfmt() == BF16X2; }   // step kernels emit the z1 operand copy
 static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, bool z1_ready, const View& t1, const View& t2,
