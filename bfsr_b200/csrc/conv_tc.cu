@@ -45,7 +45,7 @@ thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 
 namespace tc {
 constexpr int KC = 32;                       // channels per chunk = one 64-byte bf16 row (SWIZZLE_64B)
 constexpr int ROWB = 64;                     // bytes per smem row
-constexpr int NA = 2, NW_MAX = 4;
+constexpr int NA_MAX = 4, NW_MAX = 4;          // A-operand slots are 2..4 per launch (a.na): deep enough to hide the TMA latency of HBM-bound convs
 constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
 // Warp roles.  TMA-fed variant (input already in bf16 hi/lo planes): 8 epilogue warps (two per TMEM lane quarter -- one
 // warp per scheduler cannot hide its own ALU latency and made every small-K conv epilogue-bound), MMA issuer A, weight
@@ -80,6 +80,7 @@ struct TcArgs {
   float eps, alpha, beta1, beta2;
   int fast, vec_in, vec_out;
   int n_iss;                             // MMA issuing warps (1 or 2)
+  int na;                                // A-operand slots in the ring (2..4)
   int wide;                              // accurate mode with NT < 64: A_hi x [W_hi;W_lo] as one N = 2NT MMA (column halves summed by the epilogue)
   int ks, ntaps, halo;                   // 3x3 (9 taps, halo 1) or 1x1 (1 tap, halo 0)
   int phase;                             // 1: conv over a nearest-2x-upsampled input evaluated as four 2x2 phase convs
@@ -237,10 +238,10 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
-  const uint32_t w_smem = base + NA * a.a_slot;                   // NW slots
+  const uint32_t w_smem = base + a.na * a.a_slot;                 // NW slots
   const uint32_t stg_smem = w_smem + a.nw * a.w_stage;            // epilogue staging (1024-aligned: every slot size is)
   const uint32_t bars = stg_smem + STG_BYTES;                     // mbarriers (8 B each), then the per-warp bias copies
-  const uint32_t a_full = bars, a_empty = bars + 8 * NA, w_full = bars + 16 * NA, w_empty = w_full + 8 * NW_MAX;
+  const uint32_t a_full = bars, a_empty = bars + 8 * NA_MAX, w_full = bars + 16 * NA_MAX, w_empty = w_full + 8 * NW_MAX;
   const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
   const int acc_cols = a.mt * (a.wide ? 2 * nt : nt);            // TMEM columns per accumulator stage
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, TMA_IN ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
+    for (int i = 0; i < NA_MAX; ++i) { mbar_init(a_full + 8 * i, TMA_IN ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
     for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         const TileCoord tcd = tile_coord(a, t);
         for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
-          const int slot = a_it % NA;
-          mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+          const int slot = a_it % a.na;
+          mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / a.na) & 1) ^ 1);
           if (elect_one()) {
             const uint32_t dst = a_smem + slot * a.a_slot, bar = a_full + 8 * slot;
             mbar_expect_tx(bar, a.fast ? box_bytes : 2 * box_bytes);
@@ -376,9 +377,9 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     TR_DECL(tr_wait = 0, tr_fill = 0); TR_T(tr_start);
     if (have) load_chunk(tcd, 0);
     while (have) {
-      const int slot = a_it % NA;
+      const int slot = a_it % a.na;
       TR_T(tr0);
-      mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / NA) & 1) ^ 1);
+      mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / a.na) & 1) ^ 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       store_chunk(smem_gen + slot * a.a_slot);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -598,9 +599,9 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_base = tmem_base + as * acc_cols;
       for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
-        const int slot = a_it % NA;
+        const int slot = a_it % a.na;
         TR_T(tr1);
-        mbar_wait(a_full + 8 * slot, (a_it / NA) & 1);
+        mbar_wait(a_full + 8 * slot, (a_it / a.na) & 1);
         TR_ADD(tr_a, tr1);
         const uint32_t a_hi = a_smem + slot * a.a_slot, a_lo = a_hi + a.a_plane;
         const uint64_t a_hi_d = desc_a_hi | (uint64_t)((a_hi & 0x3FFFF) >> 4), a_lo_d = desc_a_hi | (uint64_t)((a_lo & 0x3FFFF) >> 4);
@@ -882,6 +883,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.wide = (!a.fast && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
   int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
+  static const int mt_cap = getenv("BFSR_TC_MT_MAX") ? atoi(getenv("BFSR_TC_MT_MAX")) : 4;
+  if (mt > mt_cap) mt = mt_cap;
   a.sx = 1; a.sy = 1;
   if (mt == 4) {
     if (gW > 8 && gH > 16) { a.sx = 2; a.sy = 2; }
@@ -937,14 +940,18 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   } else
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
-  const int fixed = NA * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES;
+  a.na = 2;
+  const int fixed = a.na * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES;
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
     a.tps = next; a.w_stage = a.tps * a.w_slot; a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   }
   BFSR_CHECK(a.nw >= 2, "conv_tc: no room for two weight stages");
-  const int smem = fixed + a.nw * a.w_stage;
+  // left-over shared memory deepens the A ring (convs with little MMA work per chunk are bound by TMA latency otherwise)
+  static const int na_max = getenv("BFSR_TC_NA") ? atoi(getenv("BFSR_TC_NA")) : NA_MAX;
+  while (a.na < na_max && a.na < NA_MAX && fixed + (a.na - 1) * a.a_slot + a.nw * a.w_stage <= MAX_SMEM) ++a.na;
+  const int smem = fixed + (a.na - 2) * a.a_slot + a.nw * a.w_stage;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
   BFSR_CHECK(a.hrows * a.pitch * 4 <= MAXI * NPROD, "conv_tc: producer item budget exceeded");
   a.tma = (in.fmt == BF16X2 && in_mode == IN_DIRECT && phase != 1) ? 1 : 0;

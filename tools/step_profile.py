@@ -1,5 +1,5 @@
 """Per-shape device-time breakdown of one SRFlow-LP step at BASELINE config 2 (CUDA events around every launch):
-    python tools/step_profile.py [batch] [precision] > gpurun_out/step_profile.tsv"""
+    python tools/step_profile.py [batch] [precision] [tile_chunk] > gpurun_out/step_profile.tsv"""
 import ctypes as C
 import sys
 
@@ -11,10 +11,11 @@ from tools import synth  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 t = synth.SRFlowTopo()
 sd = synth.synth_srflow_state_dict(t, seed=0)
 usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(), seed=1)
-net = models.define_Flow(t.opt(), device="cuda:0", precision=prec)
+net = models.define_Flow(t.opt(), device="cuda:0", precision=prec, tile_chunk=chunk)
 net.load_state_dict(sd, strict=True)
 prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
 lr = synth.img(B, 160, 160, 1236).cuda()
