@@ -62,6 +62,7 @@ constexpr int MAX_SMEM = 227 * 1024;
 constexpr int STG_WARP = 4096;               // epilogue staging per warp: 32 pixel rows x 128 B
 constexpr int STG_BYTES = BFSR_EPI_WARPS * STG_WARP;
 constexpr int BIAS_BYTES = BFSR_EPI_WARPS * 128 * 4;        // per-epilogue-warp copy of the cout tile's bias
+constexpr int FLOW_BYTES = (24 * 24 + 32) * 4;   // channel-mix matrix + offset vector of a fused FlowStep (C <= 24)
 constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
 }  // namespace tc
 
@@ -90,6 +91,7 @@ struct TcArgs {
   int n_lo, taps_tile;                   // phase 2: low-res chunks per tile; tap images per (cout tile, phase)
   unsigned short pl_off[4][4][4];        // phase 2: [phase][parity plane][i] view offset (16-byte units) of the plane's i-th tap
   unsigned char pl_nt[4][4];             // phase 2: taps served by a parity plane for an output phase (1, 2, 2 or 4)
+  FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
   View in2;                              // phase 2: hi-res part of the input (BF16X2); n_pre: the pre-activation tensor
   int n_pre, n_main;                     // pre-activation folded into the GEMM: n_pre extra 32-channel chunks of `in2` with ONE
                                          // centre tap and identity weights follow the n_main chunks of the conv proper
@@ -203,6 +205,65 @@ __device__ __forceinline__ void store_split(const View& v, long long pix, int c,
   *reinterpret_cast<uint2*>(d + v.plane) = make_uint2(pack_bf16(o.x - h0, o.y - h1), pack_bf16(o.z - h2, o.w - h3));
 }
 
+// FlowStep on one pixel (one lane): h = accumulator row after bias + cross-sigmoid; Ms / cs = mix matrix and vector in smem
+template <int C>
+__device__ __forceinline__ void flow_epilogue(const FlowEpi& f, const float* h, const float* Ms, const float* cs, long long pix) {
+  float z[C], o[C];
+  const float4* zp = reinterpret_cast<const float4*>((const float*)f.z_in.p + pix * f.z_in.cs + f.z_in.coff);
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) { const float4 v = __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+#pragma unroll
+  for (int j = 0; j < C / 2; ++j) {
+    if (f.inv) z[C / 2 + j] = z[C / 2 + j] / h[2 * j + 1] - h[2 * j];
+    else z[C / 2 + j] = (z[C / 2 + j] + h[2 * j]) * h[2 * j + 1];
+  }
+  const float4* fp = reinterpret_cast<const float4*>((const float*)f.hF.p + pix * f.hF.cs + f.hF.coff);
+  if (f.inv && f.hF.p) {
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) { const float4 v = __ldg(fp + k); z[2 * k] = z[2 * k] / v.y - v.x; z[2 * k + 1] = z[2 * k + 1] / v.w - v.z; }
+  }
+  if (f.has_mix) {
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 m = *reinterpret_cast<const float4*>(Ms + co * C + 4 * k);
+        acc = fmaf(m.x, z[4 * k], acc); acc = fmaf(m.y, z[4 * k + 1], acc);
+        acc = fmaf(m.z, z[4 * k + 2], acc); acc = fmaf(m.w, z[4 * k + 3], acc);
+      }
+      o[co] = f.inv ? acc - cs[co] : acc + cs[co];
+    }
+    if (!f.inv && f.hF.p) {
+#pragma unroll
+      for (int k = 0; k < C / 2; ++k) { const float4 v = __ldg(fp + k); o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = z[c];
+  }
+  float4* dst = reinterpret_cast<float4*>((float*)f.z_out.p + pix * f.z_out.cs + f.z_out.coff);
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  if (f.z1op.p) {
+    constexpr int CP = (C / 2 + 7) & ~7;
+    __nv_bfloat16* d = (__nv_bfloat16*)f.z1op.p + pix * f.z1op.cs + f.z1op.coff;
+#pragma unroll
+    for (int k = 0; k < CP / 8; ++k) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = 8 * k + 2 * e;
+        const float x0 = c0 < C / 2 ? o[c0] : 0.f, x1 = c0 + 1 < C / 2 ? o[c0 + 1] : 0.f;
+        const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+        hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(x0 - h0, x1 - h1);
+      }
+      *reinterpret_cast<uint4*>(d + 8 * k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(d + f.z1op.plane + 8 * k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -255,6 +316,11 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float* flow_s = reinterpret_cast<float*>(smem_gen + (bars + 256 + BIAS_BYTES - base));   // [C*C] mix matrix, then [C] vector
+  if (a.flow.C && a.flow.has_mix) {
+    for (int i = tid; i < a.flow.C * a.flow.C; i += blockDim.x) flow_s[i] = a.flow.M[i];
+    for (int i = tid; i < a.flow.C; i += blockDim.x) flow_s[24 * 24 + i] = a.flow.cvec[i];
   }
   if (warp == R::W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
@@ -541,6 +607,13 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
                 acc[4 * k] = fmaf(a.beta2, t4.x, acc[4 * k]); acc[4 * k + 1] = fmaf(a.beta2, t4.y, acc[4 * k + 1]);
                 acc[4 * k + 2] = fmaf(a.beta2, t4.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(a.beta2, t4.w, acc[4 * k + 3]);
               }
+          }
+          if (TMA_IN && a.flow.C) {   // fused FlowStep: the conv output (shift, scale pairs) is consumed here and never stored
+            if (valid) {
+              if (a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+              else flow_epilogue<24>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+            }
+            continue;
           }
           if ((!a.tma_out || (a.out2.p && !a.tma_out2)) && valid) {   // views the TMA unit cannot address: per-lane stores
 #pragma unroll
@@ -895,6 +968,17 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   }
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
+  a.flow = FlowEpi();
+  if (epi.flow) {
+    const FlowEpi& f = *epi.flow;
+    BFSR_CHECK((f.C == 12 || f.C == 24) && w.cout == f.C && a.n_ct == 1 && phase == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && epi.act == ACT_CROSS_SIGMOID && !epi.out2 &&
+               vec4(f.z_in) && vec4(f.z_out) && f.z_in.C == f.C && f.z_out.C == f.C && f.z_in.npix() == out.npix() &&
+               f.z_out.npix() == out.npix() && (!f.hF.p || (vec4(f.hF) && f.hF.C == 2 * f.C)) && (!f.has_mix || (f.M && f.cvec)) &&
+               (!f.z1op.p || (f.z1op.fmt == BF16X2 && f.z1op.cs % 8 == 0 && f.z1op.coff % 8 == 0 && f.z1op.plane % 8 == 0 &&
+                              f.z1op.C == ((f.C / 2 + 7) & ~7))),
+               "conv_tc: fused FlowStep epilogue needs C in {12,24}, a single cout tile and 16-byte addressable fp32 z / hF views");
+    a.flow = f;
+  }
   a.n_lo = 0; a.taps_tile = 0; a.in2 = in2 ? *in2 : View();
   a.n_pre = 0; a.n_main = a.n_chunks;
   if (pre_gemm) {
@@ -941,7 +1025,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
   a.na = 2;
-  const int fixed = a.na * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES;
+  const int fixed = a.na * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES + FLOW_BYTES;
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
@@ -963,7 +1047,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (a.n_pre) make_tmap(&a.tmap_pl[0], a.in2, a.pitch, a.hrows);
   memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
   static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
-  a.tma_out = (!no_tma_out && tma_out_ok(out)) ? 1 : 0;
+  a.tma_out = (!no_tma_out && tma_out_ok(out) && !epi.flow) ? 1 : 0;
   a.tma_out2 = (epi.out2 && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
   if (a.tma_out) make_tmap_out(&a.tmap_out, out, phase ? 2 : 1);
   if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2, phase ? 2 : 1);

@@ -20,7 +20,21 @@ struct ConvW {
   int tc_kchunks = 0, tc_npad = 0, tc_phase = 0, tc_n_id = 0;   // tc_n_id: identity tap images appended (pre-activation as K chunks)
 };
 
+// FlowStep fused into the epilogue of a coupling's last conv (whose output h = (shift, scale) pairs never reaches HBM):
+//   inverse: z2 = z2/scale - shift ; z = z/scaleF - shiftF (hF) ; z_out = M z - cvec        (FlowStep.reverse_flow, FlowStep.py:113-129)
+//   forward: z2 = (z2 + shift)*scale ; [z_out = M z + cvec ; z_out = (z_out + shiftF)*scaleF]  (coupling of step k, then actnorm /
+//            invconv / ft-affine of step k+1; has_mix = 0 at the end of a level)
+struct FlowEpi {
+  int inv = 0, C = 0, has_mix = 1;
+  const float* M = nullptr;     // [C][C] row-major (out, in): Mi of this step (inverse) or Mf of the next step (forward)
+  const float* cvec = nullptr;  // [C]
+  View z_in, z_out;             // fp32, C channels, same resolution as the conv output
+  View hF;                      // (shiftF, scaleF) pairs, 2C channels; p == nullptr: none
+  View z1op;                    // optional BF16X2 operand copy of the first C/2 output channels (padded to a multiple of 8)
+};
+
 struct ConvEpi {
+  const FlowEpi* flow = nullptr;   // tcgen05 path only, C in {12, 24}
   int act = ACT_NONE;
   float eps = 1e-4f;            // ACT_CROSS_SIGMOID epsilon
   const View* pre = nullptr;    // added before the activation

@@ -337,8 +337,14 @@ static void run_ft_convs(Run& r) {
 
 // z-dependent half of fAffine: h = (shift, scale) pairs for z2   (FlowAffineCouplingsAblation.py:114-119)
 static bool z1_fused(const Run& r) { return !fp32_z() && r.opfmt() == BF16X2; }   // step kernels emit the z1 operand copy
+// Levels whose FlowStep is fused into the epilogue of the coupling's last conv (C = 12, 24): h never reaches HBM and the
+// step costs no launch of its own.  BFSR_FUSE_FLOW=0 keeps the separate step kernels.
+static bool flow_fused(const Run& r, int C) {
+  static const bool off = getenv("BFSR_FUSE_FLOW") && atoi(getenv("BFSR_FUSE_FLOW")) == 0;
+  return !off && z1_fused(r) && (C == 12 || C == 24);
+}
 static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, bool z1_ready, const View& t1, const View& t2,
-                           const View& hout) {
+                           const View& hout, const FlowEpi* flow = nullptr) {
   const int Hd = r.e->d.hidden;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
@@ -353,8 +359,9 @@ static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z
   }
   ConvEpi relu; relu.act = ACT_RELU;
   K_(conv2d(l.cp.fA2, t1, t2, relu, IN_DIRECT, r.s));
-  ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
-  K_(conv2d(l.cp.fA4, t2, hout, cs, IN_DIRECT, r.s));
+  ConvEpi cs; cs.act = ACT_CROSS_SIGMOID; cs.flow = flow;
+  if (flow) { View none = hout; none.p = nullptr; K_(conv2d_tc(l.cp.fA4, t2, none, cs, IN_DIRECT, r.s)); }
+  else K_(conv2d(l.cp.fA4, t2, hout, cs, IN_DIRECT, r.s));
 }
 
 // Per-level scratch: the flow state ping-pongs between two buffers; the affine-net intermediates are reused by
@@ -378,6 +385,7 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
   std::vector<View> lat;
   View z = gt;                    // current flow state
   bool pending = false;           // coupling whose second half has not been applied to z yet
+  bool premixed = false;          // the previous coupling's fused epilogue already applied this step's actnorm/invconv/ft-affine
   LevelBufs lb; int cur_level = 0;
   for (size_t i = 0; i < e->layers.size(); ++i) {
     const LayerW& l = e->layers[i];
@@ -387,15 +395,32 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
       if (l.level != cur_level) { lb.alloc(r, H, W, l.C); cur_level = l.level; }
       const bool sq = e->layers[i - 1].kind == 0;
       BFSR_CHECK(!(sq && pending), "internal: pending coupling across a squeeze");
-      View zo = lb.next();
       const View* hF = l.kind == 2 ? &r.hF[l.level][l.k_in_level] : nullptr;
       const bool emit_z1 = l.kind == 2 && z1_fused(r);     // this step's output feeds its own affine net
-      K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s, emit_z1 ? &lb.z1op : nullptr));
-      pending = false;
-      z = zo;
-      if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h); pending = true; }
       const bool level_end = (i + 1 == e->layers.size()) || e->layers[i + 1].kind == 0 || e->layers[i + 1].kind == 3;
-      if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
+      if (!premixed) {
+        View zo = lb.next();
+        K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s, emit_z1 ? &lb.z1op : nullptr));
+        pending = false;
+        z = zo;
+      }
+      const bool z1_have = emit_z1;      // premixed steps received their z1 copy from the previous coupling's epilogue
+      premixed = false;
+      if (l.kind == 2 && flow_fused(r, l.C)) {
+        // coupling of this step + actnorm / invconv / ft-affine of the next step run in the epilogue of fAffine's last conv
+        FlowEpi f; f.inv = 0; f.C = l.C; f.z_in = z; f.z_out = lb.next();
+        if (!level_end) {
+          const LayerW& nx = e->layers[i + 1];
+          BFSR_CHECK(nx.kind == 2 && nx.level == l.level, "internal: coupling followed by a non-coupling step inside a level");
+          f.has_mix = 1; f.M = nx.step.Mf; f.cvec = nx.step.cf; f.hF = r.hF[nx.level][nx.k_in_level]; f.z1op = lb.z1op;
+        } else f.has_mix = 0;
+        run_affine_net(r, l, z, lb.z1op, z1_have, lb.t1, lb.t2, lb.h, &f);
+        z = f.z_out;
+        premixed = !level_end;
+      } else {
+        if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, z1_have, lb.t1, lb.t2, lb.h); pending = true; }
+        if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
+      }
     } else {   // Split2d forward (Split.py:49-61)
       const int cons = (int)std::lround(l.C * 0.5), pass = l.C - cons;
       View hs = make_view(r.A, r.B, H, W, 2 * cons);
@@ -436,7 +461,12 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
     View zo = unsq ? make_view(r.A, r.B, 2 * H, 2 * W, l.C / 4) : lb.next();
     // the step's output is the input of the next processed layer: if that is a coupling of the same level, emit its z1 copy
     const bool next_cpl = i > 0 && e->layers[i - 1].kind == 2 && e->layers[i - 1].level == l.level && !unsq && z1_fused(r);
-    if (l.kind == 2) {
+    if (l.kind == 2 && flow_fused(r, l.C) && !unsq) {
+      FlowEpi f; f.inv = 1; f.C = l.C; f.z_in = z; f.z_out = zo; f.has_mix = 1; f.M = l.step.Mi; f.cvec = l.step.ci;
+      f.hF = r.hF[l.level][l.k_in_level];
+      if (next_cpl) f.z1op = lb.z1op;
+      run_affine_net(r, l, z, lb.z1op, z1_ready, lb.t1, lb.t2, lb.h, &f);
+    } else if (l.kind == 2) {
       run_affine_net(r, l, z, lb.z1op, z1_ready, lb.t1, lb.t2, lb.h);
       K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s, next_cpl ? &lb.z1op : nullptr));
     } else {
