@@ -489,10 +489,10 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           if (8 * k < ncol) {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; ++e) {   // packed conversion; bf16 -> fp32 of the hi part is a shift / mask of the packed word
               const float x0f = o[8 * k + 2 * e], x1f = o[8 * k + 2 * e + 1];
-              const float h0 = __bfloat162float(__float2bfloat16_rn(x0f)), h1 = __bfloat162float(__float2bfloat16_rn(x1f));
-              hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(x0f - h0, x1f - h1);
+              hi[e] = pack_bf16(x0f, x1f);
+              lo[e] = pack_bf16(x0f - __uint_as_float(hi[e] << 16), x1f - __uint_as_float(hi[e] & 0xffff0000u));
             }
             const uint32_t off = lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(buf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -582,9 +582,12 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           if (a.act == ACT_CROSS_SIGMOID) {                // co0 % 4 == 0: the odd channels are the scales
 #pragma unroll
             for (int i = 1; i < 32; i += 2) acc[i] = 1.f / (1.f + expf(-(acc[i] + 2.f))) + a.eps;
+          } else if (a.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
           } else if (a.act != ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * slope;
+            for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f) + slope * fminf(acc[i], 0.f);
           }
           if (a.alpha != 1.f) {
 #pragma unroll
@@ -873,7 +876,7 @@ static void make_tmap(CUtensorMap* tm, const View& v, int pitch, int hrows, int 
   const cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   const CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.p, dims, strides, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BFSR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for view C=%d cs=%d %dx%dx%d", (int)r, v.C, v.cs, v.N, v.H, v.W);
 }
 
@@ -894,7 +897,7 @@ static void make_tmap_plane(CUtensorMap* tm, const View& v, int py, int px, int 
   void* base = (void*)((__nv_bfloat16*)v.p + ((long long)py * v.W + px) * v.cs);
   const CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BFSR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(plane) failed (%d) for view C=%d cs=%d %dx%dx%d", (int)r, v.C, v.cs, v.N, v.H, v.W);
 }
 static bool tma_out_ok(const View& v) {
