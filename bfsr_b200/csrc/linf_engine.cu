@@ -86,38 +86,48 @@ static View run_linf_encoder(bfsr_linf* e, Arena& A, const View& x, cudaStream_t
   const int B = x.N, h = x.H, w = x.W;
   View feat = make_view(A, B, h, w, 64);
   const size_t mark = A.off;
+  // conv-operand-only tensors are stored as bf16 (hi, lo) planes (TMA-fed tcgen05 convs); the residual
+  // streams keep fp32 copies (the conv epilogue writes both through `out2`)
+  const int fmt = g_conv_mode == 2 ? (int)F32 : (int)BF16X2;
+  const bool split = fmt == BF16X2;
   if (e->d.encoder == 0) {
-    View head = make_view(A, B, h, w, 64), res = make_view(A, B, h, w, 64), t = make_view(A, B, h, w, 64);
-    K_(conv2d(e->head, x, head, ConvEpi(), IN_DIRECT, s));
+    View head = make_view(A, B, h, w, 64), res = make_view(A, B, h, w, 64);
+    View head_op = split ? make_view(A, B, h, w, 64, fmt) : head, res_op = split ? make_view(A, B, h, w, 64, fmt) : res;
+    View t = make_view(A, B, h, w, 64, fmt);
+    { ConvEpi ep; if (split) ep.out2 = &head_op; K_(conv2d(e->head, x, head, ep, IN_DIRECT, s)); }
     ConvEpi relu; relu.act = ACT_RELU;
-    View cur = head;
+    View cur = head, cur_op = head_op;
     for (int i = 0; i < e->d.nb; ++i) {   // ResBlock: conv-ReLU-conv, res_scale 1, += x (edsr.py:45-49)
-      K_(conv2d(e->body[2 * i], cur, t, relu, IN_DIRECT, s));
-      ConvEpi ep; ep.res1 = &cur; ep.beta1 = 1.f;
+      K_(conv2d(e->body[2 * i], cur_op, t, relu, IN_DIRECT, s));
+      ConvEpi ep; ep.res1 = &cur; ep.beta1 = 1.f; if (split) ep.out2 = &res_op;
       K_(conv2d(e->body[2 * i + 1], t, res, ep, IN_DIRECT, s));   // res may alias cur: each element is read then written by one thread
-      cur = res;
+      cur = res; cur_op = res_op;
     }
     ConvEpi ep; ep.res1 = &head; ep.beta1 = 1.f;                  // res += x (edsr.py:138-139)
-    K_(conv2d(e->body[2 * e->d.nb], cur, feat, ep, IN_DIRECT, s));
+    K_(conv2d(e->body[2 * e->d.nb], cur_op, feat, ep, IN_DIRECT, s));
   } else {
     const int nf = 64, gc = 32;
     View first = make_view(A, B, h, w, nf);
-    View D[3];
-    for (int i = 0; i < 3; ++i) D[i] = make_view(A, B, h, w, nf + 4 * gc);
+    View D[3], X[3];
+    for (int i = 0; i < 3; ++i) {
+      D[i] = make_view(A, B, h, w, nf + 4 * gc, fmt);
+      X[i] = split ? make_view(A, B, h, w, nf) : D[i].slice(0, nf);
+    }
     ConvEpi lrelu; lrelu.act = ACT_LRELU;
     K_(conv2d(e->head, x, first, ConvEpi(), IN_DIRECT, s));
     K_(resample(first, D[0].slice(0, nf), RS_COPY, s));
+    if (split) K_(resample(first, X[0], RS_COPY, s));
     for (int i = 0; i < e->d.nb; ++i)
       for (int rb = 0; rb < 3; ++rb) {
-        View& cur = D[rb]; View& nxt = D[(rb + 1) % 3];
+        View& cur = D[rb]; const int nx = (rb + 1) % 3;
         const ConvW* cw = &e->body[(size_t)(i * 3 + rb) * 5];
         for (int c = 0; c < 4; ++c)
           K_(conv2d(cw[c], cur.slice(0, nf + c * gc), cur.slice(nf + c * gc, gc), lrelu, IN_DIRECT, s));
         ConvEpi ep;
-        View x_rdb = cur.slice(0, nf), x_rrdb = D[0].slice(0, nf);
-        if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &x_rdb; ep.beta1 = 1.f; }
-        else { ep.alpha = 0.04f; ep.res1 = &x_rdb; ep.beta1 = 0.2f; ep.res2 = &x_rrdb; ep.beta2 = 1.f; }
-        K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), nxt.slice(0, nf), ep, IN_DIRECT, s));
+        View op_next = D[nx].slice(0, nf); if (split) ep.out2 = &op_next;
+        if (rb < 2) { ep.alpha = 0.2f; ep.res1 = &X[rb]; ep.beta1 = 1.f; }
+        else { ep.alpha = 0.04f; ep.res1 = &X[rb]; ep.beta1 = 0.2f; ep.res2 = &X[0]; ep.beta2 = 1.f; }
+        K_(conv2d(cw[4], cur.slice(0, nf + 4 * gc), X[nx], ep, IN_DIRECT, s));
       }
     ConvEpi ep; ep.res1 = &first; ep.beta1 = 1.f;                 // fea = conv_first(x) + trunk (rrdb.py:106-108)
     K_(conv2d(e->body.back(), D[0].slice(0, nf), feat, ep, IN_DIRECT, s));
@@ -134,10 +144,11 @@ static View run_affine_info(bfsr_linf* e, Arena& A, const View& feat, const floa
   const size_t mark = A.off;
   View cfm = make_view(A, B, feat.H, feat.W, 2 * hid);
   K_(conv2d(e->cf, feat, cfm, ConvEpi(), IN_DIRECT, s));
-  View f = make_view(A, B, qh, qw, 4 * hid);
+  const int fmt = g_conv_mode == 2 ? (int)F32 : (int)BF16X2;     // the MLP's activations are conv operands only
+  View f = make_view(A, B, qh, qw, 4 * hid, fmt);
   K_(linf_features(cfm, coord, cell, e->phase, f, qh, qw, s));
   ConvEpi relu; relu.act = ACT_RELU;
-  View a1 = make_view(A, B, qh, qw, hid), a2 = make_view(A, B, qh, qw, hid);
+  View a1 = make_view(A, B, qh, qw, hid, fmt), a2 = make_view(A, B, qh, qw, hid, fmt);
   K_(conv2d(e->mlp[0], f, a1, relu, IN_DIRECT, s));
   K_(conv2d(e->mlp[1], a1, a2, relu, IN_DIRECT, s));
   K_(conv2d(e->mlp[2], a2, a1, relu, IN_DIRECT, s));
