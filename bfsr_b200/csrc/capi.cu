@@ -250,6 +250,29 @@ int bfsr_linf_lp_sr_host(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_ho
   API_END
 }
 
+int bfsr_linf_build_inputs(const float* lr01_dev, int32_t B, int32_t lr_h, int32_t lr_w, int32_t out_h, int32_t out_w,
+                           int32_t patch_size, int32_t always_pad, float* inp_dev, float* coord_dev, float* cell_dev,
+                           float* gt_lr_up_dev, int32_t* qh_out, int32_t* qw_out, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0 && out_h > 0 && out_w > 0 && patch_size > 0, "bad shape");
+  const int ps = patch_size;
+  const int pad_h = always_pad ? ps - out_h % ps : (ps - out_h % ps) % ps, pad_w = always_pad ? ps - out_w % ps : (ps - out_w % ps) % ps;
+  const int qh = (out_h + pad_h) / ps, qw = (out_w + pad_w) / ps;
+  if (qh_out) *qh_out = qh;
+  if (qw_out) *qw_out = qw;
+  if (!inp_dev && !coord_dev && !cell_dev && !gt_lr_up_dev) return 0;     // shape query
+  BFSR_CHECK(B == 0 || (lr01_dev && inp_dev && coord_dev && cell_dev && gt_lr_up_dev), "null argument");
+  if (B == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* scratch = nullptr;
+  CUDA_OK(cudaMallocAsync((void**)&scratch, (size_t)B * 3 * ((size_t)2 * out_h * out_w + (size_t)lr_h * lr_w) * 4, s));
+  try { linf_build_inputs(lr01_dev, B, lr_h, lr_w, out_h, out_w, ps, qh, qw, scratch, inp_dev, coord_dev, cell_dev, gt_lr_up_dev, s); }
+  catch (...) { cudaFreeAsync(scratch, s); throw; }
+  CUDA_OK(cudaFreeAsync(scratch, s));
+  CUDA_OK(cudaGetLastError());
+  API_END
+}
+
 // ------------------------------------------------------------------ single operators
 int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                    const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,

@@ -255,4 +255,69 @@ void bilinear_resize(const View& src, const View& dst, cudaStream_t s) {
   count_launch();
 }
 
+
+// ------------------------------------------------------------------ test-time input construction (datasets/wrappers.py:154-238, 516-613)
+// F.interpolate(x, size, mode='bilinear', align_corners=False) on NCHW planes (area_pixel_compute_source_index semantics)
+__global__ void bilinear_nchw_kernel(const float* src, float* dst, long long n, int hi, int wi, int ho, int wo, float sub, float mul) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int x = (int)(e % wo); const long long t = e / wo; const int y = (int)(t % ho); const long long pl = t / ho;
+  const float sh = (float)hi / (float)ho, sw = (float)wi / (float)wo;
+  float fy = sh * (y + 0.5f) - 0.5f, fx = sw * (x + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const float* sp = src + pl * (long long)hi * wi;
+  const float a00 = (sp[y0 * wi + x0] - sub) * mul, a01 = (sp[y0 * wi + x1] - sub) * mul;
+  const float a10 = (sp[y1 * wi + x0] - sub) * mul, a11 = (sp[y1 * wi + x1] - sub) * mul;
+  dst[e] = (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11);
+}
+static void bilinear_nchw(const float* src, float* dst, long long planes, int hi, int wi, int ho, int wo, float sub, float mul, cudaStream_t s) {
+  const long long n = planes * ho * wo;
+  if (!n) return;
+  bilinear_nchw_kernel<<<cdiv(n, 256), 256, 0, s>>>(src, dst, n, hi, wi, ho, wo, sub, mul);
+  count_launch();
+}
+// inp = (lr - 0.5) / 0.5 ; gt_lr_up = unfold_ps(lr_up - up(down(lr_up))) zero padded ; coord = patch-centre coords (0 in the pad) ; cell
+__global__ void linf_inputs_kernel(const float* lr01, const float* lr_up, const float* lr_udu, int B, int h, int w, int H, int W,
+                                   int ps, int qh, int qw, float* inp, float* coord, float* cell, float* gt, long long n_gt,
+                                   long long n_inp, float ay, float by, float ax, float bx, float cy, float cx) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_gt) {   // gt[b][c*ps*ps + ky*ps + kx][a][q]
+    const int q = (int)(e % qw); long long t = e / qw; const int a = (int)(t % qh); t /= qh;
+    const int D = 3 * ps * ps; const int d = (int)(t % D); const int b = (int)(t / D);
+    const int c = d / (ps * ps), ky = (d / ps) % ps, kx = d % ps;
+    const int Y = a * ps + ky, X = q * ps + kx;
+    float v = 0.f;
+    if (Y < H && X < W) { const long long i = (((long long)b * 3 + c) * H + Y) * W + X; v = lr_up[i] - lr_udu[i]; }
+    gt[e] = v;
+  }
+  if (e < n_inp) inp[e] = (lr01[e] - 0.5f) / 0.5f;
+  if (e < (long long)B * qh * qw) {
+    const int q = (int)(e % qw); const int a = (int)((e / qw) % qh);
+    const int Y = a * ps + ps / 2, X = q * ps + ps / 2;
+    float vy = 0.f, vx = 0.f;
+    if (Y < H && X < W) { vy = __fadd_rn(ay, __fmul_rn(by, (float)Y)); vx = __fadd_rn(ax, __fmul_rn(bx, (float)X)); }   // make_coord, utils.py:105-120
+    coord[2 * e] = vy; coord[2 * e + 1] = vx;
+  }
+  if (e < B) { cell[2 * e] = cy; cell[2 * e + 1] = cx; }
+}
+void linf_build_inputs(const float* lr01, int B, int h, int w, int H, int W, int ps, int qh, int qw, float* scratch, float* inp,
+                       float* coord, float* cell, float* gt, cudaStream_t s) {
+  if (B == 0) return;
+  const long long nHR = (long long)B * 3 * H * W, nLR = (long long)B * 3 * h * w;
+  float* lr_up = scratch; float* down = scratch + nHR; float* udu = down + nLR;
+  bilinear_nchw(lr01, lr_up, (long long)B * 3, h, w, H, W, 0.5f, 2.0f, s);     // lr_up = bilinear((lr-0.5)/0.5)  ((x-0.5)*2 == (x-0.5)/0.5 exactly)
+  bilinear_nchw(lr_up, down, (long long)B * 3, H, W, h, w, 0.f, 1.f, s);
+  bilinear_nchw(down, udu, (long long)B * 3, h, w, H, W, 0.f, 1.f, s);
+  const long long n_gt = (long long)B * 3 * ps * ps * qh * qw;
+  const long long n = n_gt > nLR ? n_gt : nLR;
+  const double ry = 1.0 / H, rx = 1.0 / W;
+  linf_inputs_kernel<<<cdiv(n, 256), 256, 0, s>>>(lr01, lr_up, udu, B, h, w, H, W, ps, qh, qw, inp, coord, cell, gt, n_gt, nLR,
+                                                (float)(-1.0 + ry), (float)(2.0 * ry), (float)(-1.0 + rx), (float)(2.0 * rx),
+                                                (float)(2.0 / H), (float)(2.0 / W));
+  count_launch();
+}
+
 }  // namespace bfsr

@@ -116,5 +116,9 @@ void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, co
 void conv3x3_s3_lrelu(const float* x_nchw, int B, int Cin, int h, int w, const float* w_oihw_dev, const float* bias_dev,
                       const View& out, cudaStream_t s);
 void bilinear_resize(const View& src, const View& dst, cudaStream_t s);
+// test-time inputs of the LINF wrappers (datasets/wrappers.py:154-238, 516-613) for a batch of LR images in [0,1];
+// scratch: B*3*(2*H*W + h*w) floats
+void linf_build_inputs(const float* lr01, int B, int h, int w, int H, int W, int ps, int qh, int qw, float* scratch, float* inp,
+                       float* coord, float* cell, float* gt, cudaStream_t s);
 
 }  // namespace bfsr

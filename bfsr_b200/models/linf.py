@@ -275,3 +275,29 @@ def batched_predict_log_p(model, inp, coord, cell, gt):
             preds.append(z)
             row += 256
         return torch.cat(preds, dim=2)
+
+
+# ---- LINF-LP/datasets/wrappers.py:154-238, 516-613 -------------------------------------------
+def build_inputs(lr01, scale, patch_size=3, always_pad=True):
+    """Test-time inputs of the LINF wrappers for a batch of LR images in [0,1] (B,3,h,w) on a CUDA device:
+    returns inp (B,3,h,w) in [-1,1], coord (B,qh,qw,2), cell (B,2), gt_lr_up (B,3*ps*ps,qh,qw), (H,W).
+    always_pad=True is the paired test wrapper (one extra patch row/column even when H % ps == 0, wrappers.py:218-219),
+    False the arbitrary-scale wrapper (wrappers.py:587-594)."""
+    import ctypes as C
+    assert lr01.is_cuda and lr01.dtype == torch.float32 and lr01.dim() == 4 and lr01.shape[1] == 3
+    lr01 = lr01.contiguous()
+    B, _, h, w = lr01.shape
+    H, W = round(h * scale), round(w * scale)
+    qh, qw = C.c_int32(), C.c_int32()
+    L = _lib.lib()
+    _lib.check(L.bfsr_linf_build_inputs(None, B, h, w, H, W, patch_size, int(always_pad), None, None, None, None, C.byref(qh), C.byref(qw), None))
+    dev = lr01.device
+    inp = torch.empty_like(lr01)
+    coord = torch.empty((B, qh.value, qw.value, 2), device=dev, dtype=torch.float32)
+    cell = torch.empty((B, 2), device=dev, dtype=torch.float32)
+    gt = torch.empty((B, 3 * patch_size ** 2, qh.value, qw.value), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(L.bfsr_linf_build_inputs(lr01.data_ptr(), B, h, w, H, W, patch_size, int(always_pad), inp.data_ptr(), coord.data_ptr(),
+                                            cell.data_ptr(), gt.data_ptr(), C.byref(qh), C.byref(qw), _lib.stream_ptr(dev)))
+    return inp, coord, cell, gt, (H, W)
+

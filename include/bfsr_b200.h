@@ -150,6 +150,14 @@ int bfsr_linf_lp_sr(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_dev, in
 int bfsr_linf_lp_sr_host(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_host, int32_t B, int32_t lr_h, int32_t lr_w,
                          const float* coord_host, const float* cell_host, const float* gt_lr_up_host, int32_t qh,
                          int32_t qw, int32_t out_h, int32_t out_w, float* pred_host, void* stream);
+/* Test-time input construction of the LINF dataset wrappers (LINF-LP/datasets/wrappers.py:154-238 paired / always_pad = 1,
+ * :516-613 arbitrary scale / always_pad = 0; utils.make_coord utils.py:105-120) for a batch of LR images in [0,1]:
+ * inp = (lr-0.5)/0.5 (B,3,h,w); coord = centres of the ps x ps HR patches (B,qh,qw,2), zeros in the padded row/column;
+ * cell = (2/out_h, 2/out_w) (B,2); gt_lr_up = unfold_ps(lr_up - up(down(lr_up))) (B,3*ps*ps,qh,qw), all bilinear
+ * align_corners=False.  With every output pointer NULL only (qh, qw) are returned. */
+int bfsr_linf_build_inputs(const float* lr01_dev, int32_t B, int32_t lr_h, int32_t lr_w, int32_t out_h, int32_t out_w,
+                           int32_t patch_size, int32_t always_pad, float* inp_dev, float* coord_dev, float* cell_dev,
+                           float* gt_lr_up_dev, int32_t* qh_out, int32_t* qw_out, void* stream);
 
 /* ------------------------------------------------------------------ single operators (parity tests, P1 in SURVEY.md §8c)
  * fp32 NCHW in / out on the device; weights in the reference's per-module layout (host). */

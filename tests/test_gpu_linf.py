@@ -62,3 +62,22 @@ def test_linf_rejects_bad_prior():
     srflow_prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}})
     with pytest.raises(BfsrError):
         model.lp_sr(inp, coord, cell, gt, srflow_prior, hw)
+
+
+@pytest.mark.parametrize("h,w,scale,always_pad", [(24, 24, 4, True), (20, 16, 3, False), (16, 16, 2, False), (17, 23, 4, True),
+                                                  (12, 10, 3.5, False)])
+def test_linf_build_inputs_vs_wrapper_restatement(h, w, scale, always_pad):
+    """Device-side input construction (datasets/wrappers.py:154-238, 516-613) equals the oracle's restatement: coord / cell /
+    inp bit-exact, the bilinear residual patches to fp32 rounding."""
+    from bfsr_b200 import models
+    from oracle import linf_oracle as LO
+    from tools import synth
+    lr = synth.img(3, h, w, 77)
+    inp, coord, cell, gt, hw = models.build_inputs(lr.cuda(), scale, 3, always_pad)
+    for i in range(3):
+        r_inp, r_coord, r_cell, r_gt, r_hw = LO.build_inputs(lr[i], scale, 3, always_pad)
+        assert tuple(hw) == tuple(r_hw)
+        assert torch.equal(inp[i].cpu(), r_inp)
+        assert torch.equal(coord[i].cpu(), r_coord)
+        assert torch.equal(cell[i].cpu(), r_cell)
+        assert gt[i].shape == r_gt.shape and max_abs(r_gt, gt[i]) < 2e-6
