@@ -55,8 +55,9 @@ template <bool TMA_IN> struct Roles {
   static constexpr int EPI_WARPS = TMA_IN ? BFSR_EPI_WARPS : 4;
   static constexpr int W_MMA = EPI_WARPS, W_WPROD = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
   static constexpr int N_PROD = TMA_IN ? 1 : PROD_WARPS;
-  static constexpr int W_MMAB = W_PROD0 + N_PROD;
-  static constexpr int NTHREADS = (W_MMAB + 1) * 32;
+  static constexpr int W_MMAB = W_PROD0 + N_PROD;                    // first of the extra MMA issuing warps
+  static constexpr int N_ISS_MAX = 2;                                // issuing warps incl. W_MMA; 4 measured no faster (the pipe's small-N floor binds)
+  static constexpr int NTHREADS = (W_MMAB + N_ISS_MAX - 1) * 32;
 };
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr int STG_WARP = 4096;               // epilogue staging per warp: 32 pixel rows x 128 B
@@ -643,12 +644,12 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
 #endif
-  } else if (warp == R::W_MMA || warp == R::W_MMAB) {
+  } else if (warp == R::W_MMA || (warp >= R::W_MMAB && warp < R::W_MMAB + R::N_ISS_MAX - 1)) {
     // ===================== MMA issuers: whole warp walks the (uniform) loop, one elected lane issues =====================
     // A single thread sustains one small MMA per ~45-55 clk, the tensor pipe accepts one per ~40 (tools/micro/umma_rate.cu),
     // so macro tiles with several sub-tiles are split between two issuing warps (even / odd sub-tiles); every barrier
     // that recycles operand slots or releases the epilogue counts one tcgen05.commit per issuer.
-    const int iss = warp == R::W_MMA ? 0 : 1;
+    const int iss = warp == R::W_MMA ? 0 : warp - R::W_MMAB + 1;
     if (iss < a.n_iss) {
     const uint32_t idesc_wide = make_idesc(a.wide ? 2 * nt : nt), idesc_nt = make_idesc(nt);
     const uint32_t lo_rows = (uint32_t)nt * (ROWB >> 4);               // descriptor offset of the W_lo rows inside a tap image
