@@ -291,7 +291,19 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
     nchw_to_nhwc(x_dev, x, s);
     ConvEpi ep; ep.act = act;
     if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s);
-    else if (impl == 3) {   // tcgen05 split-bf16 x3 with the operand tensors stored as bf16 (hi, lo) planes: TMA-fed A operand
+    else if (impl == 4) {   // as 3, but the output stays fp32 (the layout of the coupling-parameter convs: tap-folded when Cin = 64, Cout <= 24)
+      const int saved = g_conv_mode;
+      g_conv_mode = 0;
+      try {
+        CUDA_OK(cudaMalloc((void**)&xb, (npix * x.cs + 16) * 4));
+        View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * x.cs;
+        resample(x, xv, RS_COPY, s);
+        g_tc_fold = 1;
+        conv2d_tc(cw, xv, y, ep, IN_DIRECT, s);
+        g_tc_fold = -1;
+      } catch (...) { g_conv_mode = saved; g_tc_fold = -1; throw; }
+      g_conv_mode = saved;
+    } else if (impl == 3) {   // tcgen05 split-bf16 x3 with the operand tensors stored as bf16 (hi, lo) planes: TMA-fed A operand
       const int saved = g_conv_mode;
       g_conv_mode = 0;
       try {

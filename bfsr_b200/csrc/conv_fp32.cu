@@ -333,7 +333,8 @@ void free_conv(ConvW& w) {
   if (w.w) cudaFree(w.w);
   if (w.bias) cudaFree(w.bias);
   if (w.w_tc) cudaFree(w.w_tc);
-  w.w = w.bias = nullptr; w.w_tc = nullptr;
+  if (w.w_tc_fold) cudaFree(w.w_tc_fold);
+  w.w = w.bias = nullptr; w.w_tc = nullptr; w.w_tc_fold = nullptr;
 }
 
 }  // namespace bfsr

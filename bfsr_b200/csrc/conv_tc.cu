@@ -37,7 +37,8 @@
 
 namespace bfsr {
 
-thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
+thread_local int g_conv_mode = 0;
+thread_local int g_tc_fold = -1;    // tap-folded small-Cout convs: -1 = environment default (off), 0 = off, 1 = on   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
 
 #ifndef BFSR_EPI_WARPS
 #define BFSR_EPI_WARPS 8   // epilogue warps of the TMA-fed variant (multiple of 4)
@@ -92,6 +93,11 @@ struct TcArgs {
   int n_lo, taps_tile;                   // phase 2: low-res chunks per tile; tap images per (cout tile, phase)
   unsigned short pl_off[4][4][4];        // phase 2: [phase][parity plane][i] view offset (16-byte units) of the plane's i-th tap
   unsigned char pl_nt[4][4];             // phase 2: taps served by a parity plane for an output phase (1, 2, 2 or 4)
+  int fold;                              // tap folding (3x3, Cin = 64, Cout <= 24): one GEMM over the HALO tile with N = 9*Cout
+                                         // columns (u[r, tap*Cout+co] = x[r,:] . W[tap][:, co]) and a shift-add epilogue
+                                         // out[p] = sum_tap u[p + off_tap, tap] -- 9x fewer MMAs for convs that sit on the
+                                         // small-N MMA floor
+  int tile_w, tile_h;                    // output pixels of a macro tile (fold: 16x16 or 14x14; else 8*sx x 16*sy)
   FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
   View in2;                              // phase 2: hi-res part of the input (BF16X2); n_pre: the pre-activation tensor
   int n_pre, n_main;                     // pre-activation folded into the GEMM: n_pre extra 32-channel chunks of `in2` with ONE
@@ -289,7 +295,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
   if (a.phase) { c.ph = t & 3; t >>= 2; }
   const int tx = t % a.tiles_x; t /= a.tiles_x;
   const int ty = t % a.tiles_y; c.n = t / a.tiles_y;
-  c.ty0 = ty * 16 * a.sy; c.tx0 = tx * 8 * a.sx;
+  c.ty0 = ty * a.tile_h; c.tx0 = tx * a.tile_w;
   return c;
 }
 
@@ -530,6 +536,65 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       mbar_wait_relaxed(acc_full + 8 * as, (t_it / a.nacc) & 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (TMA_IN && a.fold) {
+        // ---- tap-folded conv: TMEM holds u[halo row][tap*Cout + co]; shift-add the nine taps through a shared-memory
+        // accumulator (fixed tap order, block barriers between taps: deterministic), then bias / activation / FlowStep
+        const int Cc = a.cout, P = a.pitch, nrows = a.pitch * a.hrows;
+        float* oacc = reinterpret_cast<float*>(smem_gen + (stg_smem - base));     // [tile_h*tile_w][Cc], reuses the staging area
+        const int n_out = a.tile_h * a.tile_w;
+        for (int i = tid; i < n_out * Cc; i += 32 * R::EPI_WARPS) oacc[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * R::EPI_WARPS) : "memory");
+        for (int tp = 0; tp < 9; ++tp) {
+          const int dy = tp / 3, dx = tp - 3 * dy;
+          for (int m = grp; m < a.mt; m += N_GRP) {
+            const int r = m * 128 + q * 32 + lane;           // halo-tile raster position of this accumulator row
+            const int ry = r / P, rx = r - ry * P;
+            const int oy = ry - dy, ox = rx - dx;
+            float u[32];
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + m * nt + tp * Cc;
+            tmem_ld16(t_row, u);
+            if (Cc > 16) tmem_ld16(t_row + 16, u + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (r < nrows && oy >= 0 && oy < a.tile_h && ox >= 0 && ox < a.tile_w) {
+              float4* dst = reinterpret_cast<float4*>(oacc + (oy * a.tile_w + ox) * Cc);
+#pragma unroll
+              for (int k = 0; k < 6; ++k)
+                if (4 * k < Cc) { float4 v = dst[k]; v.x += u[4 * k]; v.y += u[4 * k + 1]; v.z += u[4 * k + 2]; v.w += u[4 * k + 3]; dst[k] = v; }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * R::EPI_WARPS) : "memory");
+        }
+        // the accumulators are consumed: the MMA warps may start the next tile while the outputs are finished
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(acc_empty + 8 * as);
+        for (int pix = tid; pix < n_out; pix += 32 * R::EPI_WARPS) {
+          const int oy = pix / a.tile_w, ox = pix - oy * a.tile_w;
+          const int gy = tcd.ty0 + oy, gx = tcd.tx0 + ox;
+          if (gy >= a.H || gx >= a.W) continue;
+          const long long p = ((long long)tcd.n * a.H + gy) * a.W + gx;
+          float hv[24];
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (4 * k < Cc) {
+              const float4 v = *reinterpret_cast<const float4*>(oacc + pix * Cc + 4 * k), b4 = *reinterpret_cast<const float4*>(bias_s + 4 * k);
+              hv[4 * k] = v.x + b4.x; hv[4 * k + 1] = v.y + b4.y; hv[4 * k + 2] = v.z + b4.z; hv[4 * k + 3] = v.w + b4.w;
+            }
+          if (a.act == ACT_CROSS_SIGMOID) {
+#pragma unroll
+            for (int i = 1; i < 24; i += 2) if (i < Cc) hv[i] = 1.f / (1.f + expf(-(hv[i] + 2.f))) + a.eps;
+          }
+          if (a.flow.C == 12) flow_epilogue<12>(a.flow, hv, flow_s, flow_s + 24 * 24, p);
+          else if (a.flow.C == 24) flow_epilogue<24>(a.flow, hv, flow_s, flow_s + 24 * 24, p);
+          else {
+            float4* dst = reinterpret_cast<float4*>((float*)a.out.p + p * a.out.cs + a.out.coff);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (4 * k < Cc) dst[k] = make_float4(hv[4 * k], hv[4 * k + 1], hv[4 * k + 2], hv[4 * k + 3]);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * R::EPI_WARPS) : "memory");   // oacc is reused by the next tile
+        TR_ADD(tr_work, tr1);
+        continue;
+      }
       // 32-channel blocks of this cout tile that hold real channels, and the flattened (sub-tile, block) sequence
       const int nblk = min((nt + 31) >> 5, (a.cout - co_base + 31) >> 5);
       const int nb_total = a.mt * nblk;
@@ -653,14 +718,15 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     if (iss < a.n_iss) {
     const uint32_t idesc_wide = make_idesc(a.wide ? 2 * nt : nt), idesc_nt = make_idesc(nt);
     const uint32_t lo_rows = (uint32_t)nt * (ROWB >> 4);               // descriptor offset of the W_lo rows inside a tap image
-    const uint32_t sbo = (uint32_t)a.pitch * ROWB;
+    const uint32_t sbo = a.fold ? 8u * ROWB : (uint32_t)a.pitch * ROWB;   // fold: M tiles are runs of 128 consecutive halo-tile rows
     const int sub_cols = a.wide ? 2 * nt : nt;
     const bool merged = !a.fast && !a.wide;                             // three N = NT MMAs into the same accumulator columns
     // constant descriptor fields (LBO=1, SBO, version 1, SWIZZLE_64B); the start address is added per operand
     const uint64_t desc_a_hi = make_desc(0, sbo), desc_b_hi = make_desc(0, 8 * ROWB);
     uint32_t sub_off[4];
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) sub_off[sub] = (uint32_t)((sub / a.sx) * 16 * a.pitch + (sub % a.sx) * 8) * (ROWB >> 4);
+    for (int sub = 0; sub < 4; ++sub)
+      sub_off[sub] = a.fold ? (uint32_t)(sub * 128) * (ROWB >> 4) : (uint32_t)((sub / a.sx) * 16 * a.pitch + (sub % a.sx) * 8) * (ROWB >> 4);
     const int kw = a.phase ? 2 : a.ks;                                   // taps per filter row
     const uint32_t row_step = (uint32_t)(a.pitch - (kw - 1)) * (ROWB >> 4);   // from the last tap of a row to the first of the next
     const int stages = a.ntaps / a.tps;
@@ -834,6 +900,26 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h, int min_cin_arg) {
   CUDA_OK(cudaMalloc(&c.w_tc, img.size() * 2));
   CUDA_OK(cudaMemcpy(c.w_tc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   c.tc_kchunks = n_chunks; c.tc_npad = nt;
+  if (c.ks == 3 && c.cin == 64 && c.cout <= 24 && c.cout % 4 == 0) {   // tap-folded image (see TcArgs::fold)
+    const int np = (9 * c.cout + 15) / 16 * 16;
+    std::vector<unsigned short> f((size_t)2 * 2 * np * (ROWB / 2), 0);
+    for (int ch = 0; ch < 2; ++ch)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int co = 0; co < c.cout; ++co) {
+          const int r = tap * c.cout + co;
+          for (int k = 0; k < KC; ++k) {
+            const float w = h[((size_t)tap * c.cin_pad + ch * KC + k) * c.cout_pad + co];
+            const unsigned short hi = f2bf(w), lo = f2bf(w - bf2f(hi));
+            unsigned short* dst = f.data() + (size_t)ch * 2 * np * 32;
+            const int j = k >> 3, e = k & 7, r2 = np + r;
+            dst[(size_t)r * 32 + ((j ^ ((r >> 1) & 3)) << 3) + e] = hi;
+            dst[(size_t)r2 * 32 + ((j ^ ((r2 >> 1) & 3)) << 3) + e] = lo;
+          }
+        }
+    CUDA_OK(cudaMalloc(&c.w_tc_fold, f.size() * 2));
+    CUDA_OK(cudaMemcpy(c.w_tc_fold, f.data(), f.size() * 2, cudaMemcpyHostToDevice));
+    c.tc_fold_np = np;
+  }
 }
 
 static bool vec4(const View& v);
@@ -928,7 +1014,7 @@ static int g_num_sms = 0;
 // phase = true : out (N,2H,2W) (+)= conv3x3(nearest2x(in)) evaluated on the LOW-RES grid as four 2x2 phase convs with
 //                pre-summed weights (exact in real arithmetic, 16/36 of the MACs); `in` is the low-res tensor.
 static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, int phase, cudaStream_t s,
-                      const View* in2 = nullptr) {
+                      const View* in2 = nullptr, bool fold = false) {
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C + (in2 ? in2->C : 0) == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
@@ -942,8 +1028,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.in = in; a.out = out; a.out2 = epi.out2 ? *epi.out2 : View();
   const bool pre_gemm = epi.pre && epi.pre->fmt == BF16X2;    // pre-activation enters as identity K chunks (checked below)
   a.pre = (epi.pre && !pre_gemm) ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
-  a.w = (const unsigned char*)w.w_tc; a.bias = w.bias;
-  a.cin = w.cin; a.cout = w.cout; a.nt = w.tc_npad; a.n_chunks = w.tc_kchunks;
+  a.w = (const unsigned char*)(fold ? w.w_tc_fold : w.w_tc); a.bias = w.bias;
+  a.cin = w.cin; a.cout = w.cout; a.nt = fold ? w.tc_fold_np : w.tc_npad; a.n_chunks = w.tc_kchunks;
   a.n_ct = cdiv(w.cout, w.tc_npad);
   a.H = gH; a.W = gW; a.N = out.N; a.in_mode = phase ? (int)IN_DIRECT : in_mode; a.act = epi.act;
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
@@ -957,7 +1043,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // A_hi x [W_hi;W_lo] as ONE N = 2NT MMA plus A_lo x W_hi (e.g. NT = 64: 64 + 48 clk instead of 3 x 48); NT > 64 issues the
   // three products as separate N = NT MMAs into the same columns (same MMA time, half the TMEM -> two accumulator stages)
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
-  a.wide = (!a.fast && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
+  a.wide = (!a.fast && !fold && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
   int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
   static const int mt_cap = getenv("BFSR_TC_MT_MAX") ? atoi(getenv("BFSR_TC_MT_MAX")) : 4;
@@ -972,6 +1058,19 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   }
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
+  a.fold = fold ? 1 : 0; a.tile_w = 8 * a.sx; a.tile_h = 16 * a.sy;
+  int fold_p = 0, fold_r = 0;
+  if (fold) {
+    BFSR_CHECK(w.w_tc_fold && phase == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && !a.fast && !epi.pre && !epi.res1 && !epi.res2 &&
+               !epi.out2 && epi.alpha == 1.f && (epi.act == ACT_NONE || epi.act == ACT_CROSS_SIGMOID) && (epi.flow || vec4(out)),
+               "conv_tc(fold): unsupported epilogue / operand combination");
+    // one GEMM "tap" per chunk over the whole halo tile; M tiles = runs of 128 halo-raster rows; N = 9*Cout (padded to 16)
+    a.tile_w = a.tile_h = w.cout <= 12 ? 16 : 14;            // 3 x 112 / 2 x 224 accumulator columns
+    fold_p = a.tile_w + 2; fold_r = a.tile_h + 2;
+    a.mt = cdiv(fold_p * fold_r, 128); a.sx = a.sy = 1;
+    a.ks = 1; a.ntaps = 1; a.halo = 1;
+    BFSR_CHECK(a.mt * a.nt <= 512 && a.mt <= 4, "conv_tc(fold): accumulators do not fit TMEM");
+  }
   a.flow = FlowEpi();
   if (epi.flow) {
     const FlowEpi& f = *epi.flow;
@@ -995,13 +1094,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   static const int max_iss = getenv("BFSR_TC_ISSUERS") ? atoi(getenv("BFSR_TC_ISSUERS")) : 2;
   a.n_iss = (a.mt >= 2 && max_iss >= 2) ? 2 : 1;
   a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
-  a.a_plane = (a.pitch * a.hrows * ROWB + 1023) / 1024 * 1024;
+  if (fold) { a.pitch = fold_p; a.hrows = fold_r; }
+  a.a_plane = ((fold ? a.mt * 128 : a.pitch * a.hrows) * ROWB + 1023) / 1024 * 1024;
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
   a.w_slot = 2 * a.nt * ROWB;
   a.nacc = 2 * a.mt * sub_cols <= 512 ? 2 : 1;
   uint32_t cols = 32; while ((int)cols < a.nacc * a.mt * sub_cols) cols <<= 1;
   a.tmem_cols = cols;
-  a.tiles_x = cdiv(gW, 8 * a.sx); a.tiles_y = cdiv(gH, 16 * a.sy);
+  a.tiles_x = cdiv(gW, a.tile_w); a.tiles_y = cdiv(gH, a.tile_h);
   a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
   // weight stages: as many taps per stage as fit ~48 KB (fewer barrier round trips on the MMA issue path), 2-4 stages
   a.tps = 1;
@@ -1051,7 +1151,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (a.n_pre) make_tmap(&a.tmap_pl[0], a.in2, a.pitch, a.hrows);
   memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
   static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
-  a.tma_out = (!no_tma_out && tma_out_ok(out) && !epi.flow) ? 1 : 0;
+  a.tma_out = (!no_tma_out && tma_out_ok(out) && !epi.flow && !fold) ? 1 : 0;
   a.tma_out2 = (epi.out2 && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
   if (a.tma_out) make_tmap_out(&a.tmap_out, out, phase ? 2 : 1);
   if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2, phase ? 2 : 1);
@@ -1060,7 +1160,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
-  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", phase == 2 ? "-phase1p" : (phase ? "-phase" : ""), w.ks, w.cin, w.cout, out.H, out.W,
+  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
@@ -1070,7 +1170,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
 
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s) {
   BFSR_CHECK(!w.tc_phase, "conv_tc: phase-packed weights need conv2d_tc_up2_phase");
-  launch_tc(w, in, out, epi, in_mode, 0, s);
+  // Tap folding is correct but not a win on B200 as built (measured 64->12 @ 320x320: 0.99 ms folded vs 0.56 ms): the nine-tap
+  // shift-add through shared memory costs what the 9x fewer MMAs save, and its 336-448 accumulator columns leave no second
+  // TMEM stage to hide it.  Opt-in: BFSR_TC_FOLD=1 (or g_tc_fold = 1 from the per-op test entry).
+  static const bool env_fold = getenv("BFSR_TC_FOLD") && atoi(getenv("BFSR_TC_FOLD")) == 1;
+  const bool fold = (g_tc_fold == 1 || (g_tc_fold < 0 && env_fold)) && w.w_tc_fold && g_conv_mode == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && !epi.pre && !epi.res1 &&
+                    !epi.res2 && !epi.out2 && epi.alpha == 1.f && (epi.act == ACT_NONE || epi.act == ACT_CROSS_SIGMOID) &&
+                    (epi.flow || (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0));
+  launch_tc(w, in, out, epi, in_mode, 0, s, nullptr, fold);
 }
 void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s) {
   BFSR_CHECK(w.tc_phase == 1, "conv_tc: weights are not phase-packed");

@@ -18,6 +18,8 @@ struct ConvW {
   // split-bf16 packing for the tcgen05 path (built lazily by conv_tc.cu)
   void* w_tc = nullptr;
   int tc_kchunks = 0, tc_npad = 0, tc_phase = 0, tc_n_id = 0;   // tc_n_id: identity tap images appended (pre-activation as K chunks)
+  void* w_tc_fold = nullptr;   // tap-folded image (3x3, Cin = 64, Cout <= 24): per 32-channel chunk [9*Cout rows hi ; lo], N padded to tc_fold_np
+  int tc_fold_np = 0;
 };
 
 // FlowStep fused into the epilogue of a coupling's last conv (whose output h = (shift, scale) pairs never reaches HBM):
@@ -50,6 +52,7 @@ void conv2d_fp32(const ConvW& w, const View& in, const View& out, const ConvEpi&
 // tcgen05 path (conv_tc.cu).  g_conv_mode: 0 = split-bf16 x3 (fp32-accurate), 1 = bf16 single pass (fast),
 // 2 = never use the tensor-core path (all convs on the fp32 CUDA-core kernel).
 extern thread_local int g_conv_mode;
+extern thread_local int g_tc_fold;
 void pack_conv_tc(ConvW& c, const std::vector<float>& host_packed, int min_cin = -1);
 bool conv_tc_eligible(const ConvW& w, const View& in, const View& out, const ConvEpi& epi);
 void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, cudaStream_t s);

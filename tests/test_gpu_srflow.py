@@ -228,3 +228,20 @@ def test_conv_hi_lo_single_pass_phase(lib, chi, clo, cout, H, W, act):
     lib.check(lib.lib().bfsr_op_conv2d_hi_lo(xh_d.data_ptr(), xl_d.data_ptr(), 2, chi, clo, H, W, w.data_ptr(),
                                             b.data_ptr(), cout, act, y.data_ptr(), None))
     assert rel_l2(ref, y) < 3e-5
+
+
+@pytest.mark.parametrize("cout,H,W,act", [(12, 20, 24, 3), (24, 16, 16, 3), (24, 33, 17, 0), (12, 7, 40, 0), (8, 16, 16, 0), (16, 30, 30, 3)])
+def test_conv_tap_folded_small_cout(lib, cout, H, W, act):
+    """3x3 convs with 64 input and <= 24 output channels (the (shift, scale) heads of every coupling): one GEMM over the halo tile
+    with N = 9*Cout columns plus a shift-add epilogue must equal the plain conv (split-bf16 x3)."""
+    g = torch.Generator().manual_seed(cout * 100 + H)
+    x = torch.randn(2, 64, H, W, generator=g)
+    w = torch.randn(cout, 64, 3, 3, generator=g) / (64 * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if act == 3:
+        ref = ref.clone(); ref[:, 1::2] = torch.sigmoid(ref[:, 1::2] + 2.0) + 1e-4
+    y = torch.empty(2, cout, H, W, device="cuda")
+    x_d = x.cuda()
+    lib.check(lib.lib().bfsr_op_conv2d(x_d.data_ptr(), 2, 64, H, W, w.data_ptr(), b.data_ptr(), cout, 3, act, 4, y.data_ptr(), None))
+    assert rel_l2(ref, y) < 2e-5
