@@ -1,33 +1,37 @@
-// tcgen05 implicit-GEMM 3x3 convolution for sm_100a (replaces cuDNN behind every wide nn.Conv2d of the path:
-// RRDBNet_arch.py:25-45, the feature-only coupling convs of FlowAffineCouplingsAblation.py:45-55, unet.py:10-107).
+// tcgen05 implicit-GEMM 3x3 / 1x1 convolution for sm_100a (replaces cuDNN behind every wide nn.Conv2d of the path:
+// RRDBNet_arch.py:25-45, the coupling convs of FlowAffineCouplingsAblation.py:45-55, unet.py:10-107, linf.py:228-240).
 //
 // Persistent, warp-specialised kernel.  One CTA per SM walks a static round-robin list of work tiles; a work tile is a
 // MACRO tile of MT sub-tiles (each 8 wide x 16 tall = 128 output pixels = one UMMA M=128 accumulator) times NT output
-// channels.  GEMM view per sub-tile: M = 128 pixels, N = NT, K = 9 taps x Cin, walked in 32-channel chunks.
+// channels.  GEMM view per sub-tile: M = 128 pixels, N = NT, K = taps x Cin, walked in 32-channel chunks.
 //
-//  * A operand (pixels x channels).  The fp32 NHWC halo tile of the whole macro tile (e.g. 18 x 34 pixels for 2x2
-//    sub-tiles) of one 32-channel chunk is loaded ONCE by the producer warps with coalesced 128-bit loads, split on the
-//    fly into bf16 (hi, lo) planes and written to shared memory in the UMMA K-major SWIZZLE_64B layout (one pixel = one
-//    64-byte row).  Every (sub-tile, tap) operand is then just a shifted VIEW of that tile: the smem descriptor's start
-//    address moves by ((sy*16+dy)*pitch + sx*8+dx) rows and its stride-byte-offset (distance between 8-row groups =
-//    one image row of the tile) is the halo pitch.  The swizzle is a function of the absolute smem address
-//    (Swizzle<2,4,3> o smem_ptr), so shifted views stay consistent.  Conv zero padding / ragged edges are written as
-//    zeros by the producer; nearest-2x upsampling of the input (RRDBNet_arch.py:105) is folded into its index math.
+//  * A operand (pixels x channels).  One halo tile of the whole macro tile (e.g. 18 x 34 pixels for 2x2 sub-tiles) per
+//    32-channel chunk lands in shared memory in the UMMA K-major SWIZZLE_64B layout (one pixel = one 64-byte row), as bf16
+//    (hi, lo) planes.  Inputs stored in HBM in that split format (BF16X2 views: every conv-operand-only tensor of the
+//    engines) arrive by ONE TMA tile load per plane (kernel variant TMA_IN; zero OOB fill = the conv's padding); fp32 /
+//    nearest-2x-upsampled inputs are loaded, split and written by 8 producer warps (variant !TMA_IN).  Every (sub-tile,
+//    tap) operand is then a shifted VIEW of that tile: the smem descriptor's start address moves by
+//    ((sy*16+dy)*pitch + sx*8+dx) rows and its stride-byte-offset (distance between 8-row groups = one image row of
+//    the tile) is the halo pitch.  The swizzle is a function of the absolute smem address, so shifted views stay
+//    consistent.
 //  * B operand (weights), pre-packed at load time as [cout tile][chunk][tap] images of the exact smem layout
-//    ([W_hi ; W_lo] rows of 64 B, swizzled), streamed through a 4-slot ring with cp.async.bulk (TMA bulk copy, SASS
-//    UBLKCP) completing on mbarriers; one weight slot serves all MT sub-tiles of the macro tile.
+//    ([W_hi ; W_lo] rows of 64 B, swizzled), streamed through a 2-4 stage ring with cp.async.bulk (SASS UBLKCP)
+//    completing on mbarriers; one weight stage serves all MT sub-tiles of the macro tile.
 //  * fp32-accurate arithmetic on bf16 tensor cores (split-bf16 x3):
 //        x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi      (dropped term ~2^-16 relative)
-//    issued as TWO tcgen05.mma per K=16 step:  A_hi x [W_hi;W_lo] (N = 2*NT, accumulator columns [0,2NT)) and
-//    A_lo x W_hi (N = NT, accumulating into columns [0,NT)); the epilogue adds the two column halves.  The fast mode
-//    issues only A_hi x W_hi.
-//  * Accumulators live in TMEM (MT x 2NT columns per stage, double-buffered when 2 stages fit in 512 columns so the
-//    epilogue of tile i overlaps the MMAs of tile i+1); one elected thread issues the MMAs; tcgen05.commit arrives on
-//    the mbarriers that recycle the A / W slots and release the epilogue.  Epilogue: tcgen05.ld 32x32b -> bias,
-//    pre-activation add, activation, scaled residuals -> fp32 NHWC channel-slice store.
+//    NT <= 64: A_hi x [W_hi;W_lo] as one N = 2*NT MMA + A_lo x W_hi (the epilogue adds the column halves); NT > 64: three
+//    N = NT MMAs into the same columns (the small-N MMA floor decides, see launch_tc).  The fast mode issues A_hi x W_hi.
+//  * Accumulators live in TMEM (two stages whenever they fit 512 columns); two warps issue the MMAs (even / odd
+//    sub-tiles); tcgen05.commit arrives on the mbarriers that recycle the A / W slots and release the epilogue.
+//  * Epilogue (8 warps in the TMA variant, two per TMEM lane quarter): tcgen05.ld 32x32b -> bias / pre-activation /
+//    activation / residual passes on whole rows -> swizzled staging tile -> TMA bulk tensor store (fp32 or bf16 planes,
+//    optionally a second copy); or a FlowStep applied in place of the store (FlowEpi).
+//  * Modes: phase 1/2 = conv over nearest-2x-upsampled channels evaluated per output phase with pre-summed 2x2 taps
+//    (phase 2 adds the hi-res channels as TMA parity planes in the same pass); n_pre = a BF16X2 pre-activation tensor
+//    enters the GEMM as identity K chunks; fold = nine taps folded into N with a shift-add epilogue (opt-in).
 //
-// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMEM allocator + MMA issuer, warp 5 weight TMA
-// producer, warps 6-13 A producers.
+// Warp roles (Roles<TMA_IN>): epilogue warps, MMA issuer A (+ TMEM allocator), weight loader, TMA loader or 8 A producers,
+// MMA issuer B.
 #include "ops.cuh"
 #include <cuda.h>
 #include <vector>
@@ -81,7 +85,7 @@ struct TcArgs {
   int cin, cout, nt, n_chunks, n_ct;     // n_ct = cout tiles
   int H, W, N, in_mode, act;
   float eps, alpha, beta1, beta2;
-  int fast, vec_in, vec_out;
+  int fast;
   int n_iss;                             // MMA issuing warps (1 or 2)
   int na;                                // A-operand slots in the ring (2..4)
   int wide;                              // accurate mode with NT < 64: A_hi x [W_hi;W_lo] as one N = 2NT MMA (column halves summed by the epilogue)
@@ -1035,8 +1039,6 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
   a.fast = g_conv_mode == 1;
   a.phase = phase;
-  a.vec_in = (in.fmt == F32 && in.cs % 4 == 0 && in.coff % 4 == 0 && ((uintptr_t)in.p % 16) == 0);
-  a.vec_out = (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0);
   // macro tile: as many 128-pixel sub-tiles as fit in 512 TMEM columns (and the image); weights shared by all of them
   // accurate mode.  Measured M=128,K=16 SS-mode MMA cost on B200 (tools/micro/umma_rate.cu): 45.5 clk for N <= 32, 48 @ 64,
   // 56 @ 96, then N/2 (64 @ 128, 128 @ 256): an MMA narrower than N = 128 is bound by its fixed cost, so NT <= 64 issues
