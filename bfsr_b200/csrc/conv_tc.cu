@@ -110,6 +110,7 @@ struct TcArgs {
   int pitch, hrows;                      // halo tile: pitch = 8*sx+2 pixels, hrows = 16*sy+2
   int a_plane, a_slot, w_slot;           // bytes (w_slot = one tap image)
   int tps, nw, w_stage;                  // taps per weight stage, number of stages, bytes per stage
+  int w_res;                             // all weight stages fit in smem: loaded once per CTA, never recycled (nw = stages per tile)
   int nacc;                              // TMEM accumulator stages (1 or 2)
   int tiles_x, tiles_y, total_tiles;     // macro tiles per image and total work tiles (incl. cout tiles, batch)
   uint32_t tmem_cols;
@@ -736,9 +737,11 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     const int stages = a.ntaps / a.tps;
     int a_it = 0, w_it = 0, t_it = 0;
     TR_DECL(tr_acc = 0, tr_a = 0, tr_w = 0, tr_issue = 0); TR_T(tr_start);
+    if (a.w_res && (int)blockIdx.x < a.total_tiles) mbar_wait(w_full, 0);     // resident weights: one wait for the whole set
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
       const int as = t_it % a.nacc;
       const int ph = a.phase ? (t / a.n_ct) & 3 : 0;
+      if (a.w_res) w_it = 0;                                                    // stage index = position inside the tile
       const uint32_t tap_base = a.phase ? (uint32_t)((ph >> 1) * a.pitch + (ph & 1)) * (ROWB >> 4) : 0u;
       TR_T(tr0);
       mbar_wait_relaxed(acc_empty + 8 * as, ((t_it / a.nacc) & 1) ^ 1);
@@ -768,7 +771,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           if (pl >= 0) tap_off = a.pl_off[ph][pl][st];
           const int ws = w_it % a.nw;
           TR_T(tr2);
-          mbar_wait(w_full + 8 * ws, (w_it / a.nw) & 1);
+          if (!a.w_res) mbar_wait(w_full + 8 * ws, (w_it / a.nw) & 1);
           TR_ADD(tr_w, tr2); TR_T(tr3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           // One elected lane issues the whole stage.  Descriptors differ only in the 14-bit start-address field, so each
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
             bd0 += (uint32_t)a.w_slot >> 4;
             if (++tdx == kw) { tdx = 0; tap_off += row_step; } else tap_off += ROWB >> 4;
           }
-          if (elect_one()) umma_commit(w_empty + 8 * ws);      // weight stage reusable once these MMAs retire
+          if (!a.w_res && elect_one()) umma_commit(w_empty + 8 * ws);      // weight stage reusable once these MMAs retire
           __syncwarp();
           TR_ADD(tr_issue, tr3);
         }
@@ -816,6 +819,14 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     const uint32_t w_bytes = (uint32_t)(a.fast ? nt : 2 * nt) * ROWB;
     int w_it = 0;
     TR_DECL(tr_wait = 0); TR_T(tr_start);
+    if (a.w_res) {     // the whole weight set of the (single) cout tile stays resident: one barrier, a.nw bulk copies, done
+      if ((int)blockIdx.x < a.total_tiles && elect_one()) {
+        mbar_expect_tx(w_full, w_bytes * a.tps * a.nw);
+        for (int wi = 0; wi < a.nw; ++wi)
+          bulk_g2s(w_smem + wi * a.w_stage, a.w + (size_t)wi * a.tps * tap_stride, w_bytes * a.tps, w_full);
+      }
+      __syncwarp();
+    } else
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       const int ct = t % a.n_ct;
       const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
@@ -1138,6 +1149,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     a.tps = next; a.w_stage = a.tps * a.w_slot; a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   }
   BFSR_CHECK(a.nw >= 2, "conv_tc: no room for two weight stages");
+  // weight-stationary when the whole set fits next to two A slots (tiny-K convs re-streamed as many weight bytes per tile
+  // from L2 as activations: the z-dependent coupling conv moved 5.9 TB/s L2->SM under ncu)
+  a.w_res = 0;
+  {
+    static const bool no_res = getenv("BFSR_TC_WRES") && atoi(getenv("BFSR_TC_WRES")) == 0;
+    const int stages_tile = a.n_pre ? a.n_main * a.ntaps + a.n_pre : a.n_chunks * (a.ntaps / a.tps);
+    if (!no_res && phase == 0 && !fold && !a.fast && a.n_ct == 1 && fixed + stages_tile * a.w_stage <= MAX_SMEM) { a.w_res = 1; a.nw = stages_tile; }
+  }
   // left-over shared memory deepens the A ring (convs with little MMA work per chunk are bound by TMA latency otherwise)
   static const int na_max = getenv("BFSR_TC_NA") ? atoi(getenv("BFSR_TC_NA")) : NA_MAX;
   while (a.na < na_max && a.na < NA_MAX && fixed + (a.na - 1) * a.a_slot + a.nw * a.w_stage <= MAX_SMEM) ++a.na;
