@@ -1,0 +1,127 @@
+// Evaluation metrics of the reference's test drivers on the device:
+//   PSNR  — LINF-LP/utils.py:132-151 (calc_psnr: plain / 'benchmark' luma + shave / 'div2k' shave)
+//   SSIM  — LINF-LP/utils.py:154-193 (11x11 Gaussian window sigma 1.5, 'valid' region, float64, mean over channels), the
+//           same definition Measure.py:46-53 takes from skimage for SRFlow-LP.
+// Both accumulate in fp64 (the reference's SSIM is fp64; its PSNR is an fp32 mean whose rounding we do not reproduce).
+#include "common.cuh"
+#include "../../include/bfsr_b200.h"
+#include <cmath>
+#include <string>
+
+namespace bfsr {
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;   // valid in thread 0
+}
+
+// sum of squared (optionally luma-weighted) differences over the shaved region
+__global__ void psnr_kernel(const float* sr, const float* hr, int B, int C, int H, int W, int luma, int shave, float inv_range,
+                            double* acc) {
+  const int h = H - 2 * shave, w = W - 2 * shave, Ce = luma ? 1 : C;
+  const long long n = (long long)B * Ce * h * w;
+  double s = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % w) + shave; long long t = e / w; const int y = (int)(t % h) + shave; t /= h;
+    const int c = (int)(t % Ce); const long long b = t / Ce;
+    float d;
+    if (luma) {   // diff.mul(convert).sum(dim=1), convert = [65.738, 129.057, 25.064] / 256 (utils.py:137-140)
+      const long long i = (b * C * H + y) * W + x, pl = (long long)H * W;
+      const float d0 = (sr[i] - hr[i]) * inv_range, d1 = (sr[i + pl] - hr[i + pl]) * inv_range, d2 = (sr[i + 2 * pl] - hr[i + 2 * pl]) * inv_range;
+      d = d0 * (65.738f / 256.f) + d1 * (129.057f / 256.f) + d2 * (25.064f / 256.f);
+    } else {
+      const long long i = ((b * C + c) * H + y) * W + x;
+      d = (sr[i] - hr[i]) * inv_range;
+    }
+    s += (double)d * (double)d;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+// one thread per valid pixel of one channel plane; images are (C,H,W) fp32 scaled by `mul` (255 for [0,1] inputs)
+__global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W, float mul, const double* __restrict__ win, double* acc) {
+  const int h = H - 10, w = W - 10;
+  const long long n = (long long)C * h * w;
+  const double C1 = (0.01 * 255) * (0.01 * 255), C2 = (0.03 * 255) * (0.03 * 255);
+  double s = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % w); const long long t = e / w; const int y = (int)(t % h); const int c = (int)(t / h);
+    const float* pa = a + ((long long)c * H + y) * W + x;
+    const float* pb = b + ((long long)c * H + y) * W + x;
+    double m1 = 0, m2 = 0, s11 = 0, s22 = 0, s12 = 0;
+    for (int i = 0; i < 11; ++i)
+      for (int j = 0; j < 11; ++j) {
+        const double wgt = win[i * 11 + j];
+        const double u = (double)(pa[i * W + j] * mul), v = (double)(pb[i * W + j] * mul);
+        m1 += wgt * u; m2 += wgt * v; s11 += wgt * u * u; s22 += wgt * v * v; s12 += wgt * u * v;
+      }
+    const double v1 = s11 - m1 * m1, v2 = s22 - m2 * m2, cov = s12 - m1 * m2;
+    s += ((2 * m1 * m2 + C1) * (2 * cov + C2)) / ((m1 * m1 + m2 * m2 + C1) * (v1 + v2 + C2));
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+}  // namespace bfsr
+
+using namespace bfsr;
+static thread_local std::string g_merr;
+extern "C" {
+
+int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode,
+                     int32_t scale, float rgb_range, double* psnr_out, void* stream) {
+  try {
+    BFSR_CHECK(sr_dev && hr_dev && psnr_out && B > 0 && C > 0 && H > 0 && W > 0, "psnr: bad arguments");
+    BFSR_CHECK(mode >= 0 && mode <= 2, "psnr: mode must be 0 (none), 1 ('benchmark') or 2 ('div2k')");
+    const int shave = mode ? scale : 0, luma = (mode == 1 && C > 1) ? 1 : 0;
+    BFSR_CHECK(!luma || C == 3, "psnr('benchmark'): luma conversion needs 3 channels");
+    BFSR_CHECK(H > 2 * shave && W > 2 * shave, "psnr: image smaller than the shaved border");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* acc = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&acc, 8, s));
+    CUDA_OK(cudaMemsetAsync(acc, 0, 8, s));
+    const long long n = (long long)B * (luma ? 1 : C) * (H - 2 * shave) * (W - 2 * shave);
+    psnr_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, s>>>(sr_dev, hr_dev, B, C, H, W, luma, shave, 1.f / rgb_range, acc);
+    double sum = 0;
+    CUDA_OK(cudaMemcpyAsync(&sum, acc, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaFreeAsync(acc, s));
+    *psnr_out = -10.0 * std::log10(sum / (double)n);
+  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  return 0;
+}
+
+int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul, double* ssim_out,
+                     void* stream) {
+  try {
+    BFSR_CHECK(img1_dev && img2_dev && ssim_out && C > 0 && H > 10 && W > 10, "ssim: bad arguments (images must exceed the 11x11 window)");
+    cudaStream_t s = (cudaStream_t)stream;
+    // cv2.getGaussianKernel(11, 1.5): exp(-(i-5)^2 / (2 sigma^2)) normalised to sum 1; window = outer product (utils.py:160-161)
+    double k[11], ksum = 0, win[121];
+    for (int i = 0; i < 11; ++i) { k[i] = std::exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); ksum += k[i]; }
+    for (int i = 0; i < 11; ++i) k[i] /= ksum;
+    for (int i = 0; i < 11; ++i) for (int j = 0; j < 11; ++j) win[i * 11 + j] = k[i] * k[j];
+    double* buf = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&buf, 122 * 8, s));
+    CUDA_OK(cudaMemcpyAsync(buf, win, 121 * 8, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(buf + 121, 0, 8, s));
+    const long long n = (long long)C * (H - 10) * (W - 10);
+    ssim_kernel<<<(int)((n + 127) / 128 > 2368 ? 2368 : (n + 127) / 128), 128, 0, s>>>(img1_dev, img2_dev, C, H, W, mul, buf, buf + 121);
+    double sum = 0;
+    CUDA_OK(cudaMemcpyAsync(&sum, buf + 121, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaFreeAsync(buf, s));
+    *ssim_out = sum / (double)n;
+  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  return 0;
+}
+
+const char* bfsr_metric_last_error(void) { return g_merr.c_str(); }
+
+}  // extern "C"

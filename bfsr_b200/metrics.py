@@ -1,0 +1,52 @@
+"""Evaluation metrics of the reference's test drivers, computed on the device through the C ABI.
+
+Mirrors LINF-LP/utils.py:132-193 (`calc_psnr(sr, hr, dataset, scale, rgb_range)`, `calculate_ssim(img1, img2)`); the SRFlow-LP
+driver uses the same definitions through skimage (SRFlow-LP/code/Measure.py:46-53).  Inputs are CUDA tensors; there is no CPU
+fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_MODES = {None: 0, "benchmark": 1, "div2k": 2}
+
+
+def _check(rc):
+    if rc != 0:
+        raise _lib.BfsrError(_lib.lib().bfsr_metric_last_error().decode("utf-8", "replace"))
+
+
+def calc_psnr(sr, hr, dataset=None, scale=1, rgb_range=1):
+    """utils.calc_psnr: -10 log10(mean(((sr - hr) / rgb_range)^2)) over the whole (B,C,H,W) tensor; dataset='benchmark' takes the
+    luma of the difference and shaves `scale` border pixels, 'div2k' only shaves."""
+    if dataset not in _MODES:
+        raise NotImplementedError(dataset)
+    assert sr.is_cuda and hr.is_cuda and sr.shape == hr.shape and sr.dim() == 4
+    sr, hr = sr.contiguous().float(), hr.contiguous().float()
+    B, Cc, H, W = sr.shape
+    out = C.c_double()
+    with torch.cuda.device(sr.device):
+        _check(_lib.lib().bfsr_metric_psnr(sr.data_ptr(), hr.data_ptr(), B, Cc, H, W, _MODES[dataset], int(scale), float(rgb_range),
+                                           C.byref(out), _lib.stream_ptr(sr.device)))
+    return out.value
+
+
+def calculate_ssim(img1, img2, mul=1.0):
+    """utils.calculate_ssim on (C,H,W) CUDA tensors (the reference takes HWC numpy arrays in [0,255]: pass mul=255 for [0,1]
+    inputs).  11x11 Gaussian window, sigma 1.5, valid region, fp64, mean over channels."""
+    assert img1.is_cuda and img2.is_cuda and img1.shape == img2.shape
+    if img1.dim() == 2:
+        img1, img2 = img1[None], img2[None]
+    if img1.dim() != 3:
+        raise ValueError("Wrong input image dimensions.")
+    img1, img2 = img1.contiguous().float(), img2.contiguous().float()
+    Cc, H, W = img1.shape
+    out = C.c_double()
+    with torch.cuda.device(img1.device):
+        _check(_lib.lib().bfsr_metric_ssim(img1.data_ptr(), img2.data_ptr(), Cc, H, W, float(mul), C.byref(out),
+                                           _lib.stream_ptr(img1.device)))
+    return out.value

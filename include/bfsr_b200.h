@@ -171,6 +171,17 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
  * folded loader; 2 = tcgen05, four 2x2 phase convs on the low-res grid with pre-summed weights (16/36 of the MACs). */
 int bfsr_op_conv2d_up2(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                        const float* bias_host, int32_t Cout, int32_t impl, float* y_dev, void* stream);
+/* ---- evaluation metrics on the device (the reference computes them on the host with numpy / cv2) ----
+ * calc_psnr (LINF-LP/utils.py:132-151) over a whole (B,C,H,W) tensor: mode 0 = plain, 1 = 'benchmark' (luma of the difference,
+ * border of `scale` pixels shaved), 2 = 'div2k' (shave only).  fp64 accumulation; result on the host. */
+int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode,
+                     int32_t scale, float rgb_range, double* psnr_out, void* stream);
+/* calculate_ssim (LINF-LP/utils.py:154-193): (C,H,W) fp32 images, each multiplied by `mul` first (255 for [0,1] inputs); 11x11
+ * Gaussian window (sigma 1.5), valid region, fp64, mean over channels. */
+int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul, double* ssim_out,
+                     void* stream);
+const char* bfsr_metric_last_error(void);
+
 /* conv3x3(cat[x_hi (B,Chi,2H,2W), nearest2x(x_lo (B,Clo,H,W))]) + bias + activation: the level-1 coupling conditioning of
  * SRFlowNet_arch.py:118-138 evaluated in ONE pass per output phase (low-res channels: four pre-summed 2x2 taps; hi-res
  * channels: stride-2 parity planes); Chi, Clo multiples of 32; operands stored as bf16 (hi, lo) planes, split-bf16 x3. */

@@ -1,0 +1,58 @@
+"""TEST INFRASTRUCTURE ONLY — numpy restatement of the reference's evaluation metrics (LINF-LP/utils.py:132-193).
+
+Pinned against outputs of the unmodified reference functions (tests/golden/metrics.npz, oracle/make_golden_metrics.py)."""
+import numpy as np
+
+
+def calc_psnr(sr, hr, dataset=None, scale=1, rgb_range=1):
+    """utils.py:132-151.  sr, hr: (B,C,H,W) float arrays."""
+    diff = (sr.astype(np.float64) - hr.astype(np.float64)) / rgb_range
+    if dataset is not None:
+        if dataset == "benchmark":
+            shave = scale
+            if diff.shape[1] > 1:
+                conv = np.array([65.738, 129.057, 25.064], dtype=np.float32).astype(np.float64).reshape(1, 3, 1, 1) / 256
+                diff = (diff * conv).sum(axis=1)
+        elif dataset == "div2k":
+            shave = scale
+        else:
+            raise NotImplementedError
+        diff = diff[..., shave:-shave, shave:-shave]
+    return float(-10 * np.log10((diff ** 2).mean()))
+
+
+def _gauss_window():
+    k = np.exp(-((np.arange(11) - 5.0) ** 2) / (2 * 1.5 ** 2))   # cv2.getGaussianKernel(11, 1.5)
+    k /= k.sum()
+    return np.outer(k, k)
+
+
+def ssim(img1, img2):
+    """utils.py:154-174 on one 2-D plane in [0,255] (valid region of an 11x11 Gaussian filter, float64)."""
+    C1, C2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    a, b = img1.astype(np.float64), img2.astype(np.float64)
+    win = _gauss_window()
+    H, W = a.shape
+
+    def filt(x):
+        out = np.zeros((H - 10, W - 10))
+        for i in range(11):
+            for j in range(11):
+                out += win[i, j] * x[i:i + H - 10, j:j + W - 10]
+        return out
+
+    mu1, mu2 = filt(a), filt(b)
+    s1, s2, s12 = filt(a * a) - mu1 ** 2, filt(b * b) - mu2 ** 2, filt(a * b) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 ** 2 + mu2 ** 2 + C1) * (s1 + s2 + C2))
+    return float(m.mean())
+
+
+def calculate_ssim(img1, img2):
+    """utils.py:177-193.  HWC (or HW) arrays in [0,255]."""
+    if img1.shape != img2.shape:
+        raise ValueError("Input images must have the same dimensions.")
+    if img1.ndim == 2:
+        return ssim(img1, img2)
+    if img1.ndim == 3:
+        return float(np.mean([ssim(img1[:, :, i], img2[:, :, i]) for i in range(img1.shape[2])]))
+    raise ValueError("Wrong input image dimensions.")
