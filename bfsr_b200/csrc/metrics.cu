@@ -7,6 +7,7 @@
 #include "../../include/bfsr_b200.h"
 #include <cmath>
 #include <string>
+#include <vector>
 
 namespace bfsr {
 
@@ -68,6 +69,56 @@ __global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W,
   if (threadIdx.x == 0) atomicAdd(acc, s);
 }
 
+// MATLAB-compatible antialiased bicubic resize (LINF-LP/imresize.py:53-175; the LR-consistency metric of test.py:183-200):
+// out[o] = sum_p w[o][p] * in[idx[o][p]] along one dimension, fp64; planes are (C, H, W)
+template <typename TI>
+__global__ void resize_dim_kernel(const TI* in, double* out, int C, int H, int W, int dim, int olen, int P, const double* wgt,
+                                  const int* idx) {
+  const int oH = dim == 0 ? olen : H, oW = dim == 1 ? olen : W;
+  const long long n = (long long)C * oH * oW;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % oW); const long long t = e / oW; const int y = (int)(t % oH); const int c = (int)(t / oH);
+    const int o = dim == 0 ? y : x;
+    double acc = 0.0;
+    for (int p = 0; p < P; ++p) {
+      const int i = idx[o * P + p];
+      const double v = dim == 0 ? (double)in[((long long)c * H + i) * W + x] : (double)in[((long long)c * H + y) * W + i];
+      acc += wgt[o * P + p] * v;
+    }
+    out[e] = acc;
+  }
+}
+__global__ void f64_to_f32_kernel(const double* in, float* out, long long n) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = (float)in[e];
+}
+
+static double cubic(double x) {   // imresize.py:30-37
+  const double a = std::fabs(x), a2 = a * a, a3 = a2 * a;
+  return (a <= 1 ? 1.5 * a3 - 2.5 * a2 + 1 : 0.0) + ((1 < a && a <= 2) ? -0.5 * a3 + 2.5 * a2 - 4 * a + 2 : 0.0);
+}
+// imresize.py:40-64 (mirror padding through the `aux` index table; all-zero weight columns are kept: they add exact zeros)
+static void contributions(int in_len, int out_len, double scale, std::vector<double>& w, std::vector<int>& ind, int& P) {
+  const double kw = scale < 1 ? 4.0 / scale : 4.0;
+  P = (int)std::ceil(kw) + 2;
+  w.assign((size_t)out_len * P, 0.0); ind.assign((size_t)out_len * P, 0);
+  const int aux_n = 2 * in_len;
+  for (int o = 0; o < out_len; ++o) {
+    const double u = (o + 1) / scale + 0.5 * (1 - 1 / scale);
+    const double left = std::floor(u - kw / 2);
+    double sum = 0;
+    for (int p = 0; p < P; ++p) {
+      const int i = (int)(left + p - 1);
+      const double d = u - i - 1;
+      const double v = scale < 1 ? scale * cubic(scale * d) : cubic(d);
+      w[(size_t)o * P + p] = v; sum += v;
+      int m = i % aux_n; if (m < 0) m += aux_n;
+      ind[(size_t)o * P + p] = m < in_len ? m : aux_n - 1 - m;
+    }
+    for (int p = 0; p < P; ++p) w[(size_t)o * P + p] /= sum;
+  }
+}
+
 }  // namespace bfsr
 
 using namespace bfsr;
@@ -118,6 +169,39 @@ int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, in
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaFreeAsync(buf, s));
     *ssim_out = sum / (double)n;
+  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  return 0;
+}
+
+int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                          int32_t* out_w, void* stream) {
+  try {
+    BFSR_CHECK(C > 0 && H > 0 && W > 0 && scale > 0, "imresize: bad arguments");
+    const int oh = (int)std::ceil(scale * H), ow = (int)std::ceil(scale * W);     // deriveSizeFromScale, imresize.py:6-10
+    if (out_h) *out_h = oh;
+    if (out_w) *out_w = ow;
+    if (!out_dev) return 0;                                                      // size query
+    BFSR_CHECK(img_dev, "imresize: null input");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<double> w0, w1; std::vector<int> i0, i1; int P0 = 0, P1 = 0;
+    contributions(H, oh, scale, w0, i0, P0);
+    contributions(W, ow, scale, w1, i1, P1);
+    double *dw0 = nullptr, *dw1 = nullptr, *t0 = nullptr, *t1 = nullptr; int *di0 = nullptr, *di1 = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&dw0, w0.size() * 8, s)); CUDA_OK(cudaMallocAsync((void**)&dw1, w1.size() * 8, s));
+    CUDA_OK(cudaMallocAsync((void**)&di0, i0.size() * 4, s)); CUDA_OK(cudaMallocAsync((void**)&di1, i1.size() * 4, s));
+    CUDA_OK(cudaMallocAsync((void**)&t0, (size_t)C * oh * W * 8, s)); CUDA_OK(cudaMallocAsync((void**)&t1, (size_t)C * oh * ow * 8, s));
+    CUDA_OK(cudaMemcpyAsync(dw0, w0.data(), w0.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(dw1, w1.data(), w1.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(di0, i0.data(), i0.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(di1, i1.data(), i1.size() * 4, cudaMemcpyHostToDevice, s));
+    // equal scales: argsort keeps the order (rows first, then columns), imresize.py:150,163-165
+    const long long n0 = (long long)C * oh * W, n1 = (long long)C * oh * ow;
+    resize_dim_kernel<float><<<(int)((n0 + 255) / 256 > 2368 ? 2368 : (n0 + 255) / 256), 256, 0, s>>>(img_dev, t0, C, H, W, 0, oh, P0, dw0, di0);
+    resize_dim_kernel<double><<<(int)((n1 + 255) / 256 > 2368 ? 2368 : (n1 + 255) / 256), 256, 0, s>>>(t0, t1, C, oh, W, 1, ow, P1, dw1, di1);
+    f64_to_f32_kernel<<<(int)((n1 + 255) / 256), 256, 0, s>>>(t1, out_dev, n1);
+    CUDA_OK(cudaStreamSynchronize(s));   // the host weight tables must outlive the copies
+    cudaFreeAsync(dw0, s); cudaFreeAsync(dw1, s); cudaFreeAsync(di0, s); cudaFreeAsync(di1, s); cudaFreeAsync(t0, s); cudaFreeAsync(t1, s);
+    CUDA_OK(cudaGetLastError());
   } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
   return 0;
 }

@@ -50,3 +50,19 @@ def calculate_ssim(img1, img2, mul=1.0):
         _check(_lib.lib().bfsr_metric_ssim(img1.data_ptr(), img2.data_ptr(), Cc, H, W, float(mul), C.byref(out),
                                            _lib.stream_ptr(img1.device)))
     return out.value
+
+
+def imresize(img, scalar_scale):
+    """imresize.imresize(img, scalar_scale) (bicubic, antialiased, MATLAB-compatible) on a (C,H,W) CUDA tensor; returns float32
+    (the reference's float64 result cast as test.py:185 does).  LR consistency: calc_psnr(imresize(sr, 1/s)[None], lr)."""
+    assert img.is_cuda and img.dim() == 3
+    img = img.contiguous().float()
+    Cc, H, W = img.shape
+    oh, ow = C.c_int32(), C.c_int32()
+    L = _lib.lib()
+    _check(L.bfsr_imresize_bicubic(None, Cc, H, W, float(scalar_scale), None, C.byref(oh), C.byref(ow), None))
+    out = torch.empty((Cc, oh.value, ow.value), device=img.device, dtype=torch.float32)
+    with torch.cuda.device(img.device):
+        _check(L.bfsr_imresize_bicubic(img.data_ptr(), Cc, H, W, float(scalar_scale), out.data_ptr(), C.byref(oh), C.byref(ow),
+                                       _lib.stream_ptr(img.device)))
+    return out

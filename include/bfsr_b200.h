@@ -180,6 +180,11 @@ int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_
  * Gaussian window (sigma 1.5), valid region, fp64, mean over channels. */
 int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul, double* ssim_out,
                      void* stream);
+/* imresize(img, scale) of LINF-LP/imresize.py:136-175 (MATLAB-compatible antialiased bicubic, float input, fp64 arithmetic,
+ * mirror padding) on a (C,H,W) image: the LR-consistency metric of test.py:183-200 is calc_psnr(imresize(sr, 1/s), lr).
+ * out_dev == NULL returns only the output size ceil(scale * H), ceil(scale * W). */
+int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                          int32_t* out_w, void* stream);
 const char* bfsr_metric_last_error(void);
 
 /* conv3x3(cat[x_hi (B,Chi,2H,2W), nearest2x(x_lo (B,Clo,H,W))]) + bias + activation: the level-1 coupling conditioning of

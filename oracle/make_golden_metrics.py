@@ -29,6 +29,10 @@ def main():
     b = hr[0].permute(1, 2, 0).numpy() * 255.0
     out["ssim_rgb"] = float(ref_utils.calculate_ssim(a, b))
     out["ssim_gray"] = float(ref_utils.calculate_ssim(a[:, :, 1], b[:, :, 1]))
+    import imresize as ref_imresize   # LINF-LP/imresize.py
+    out["lr_x4"] = ref_imresize.imresize(sr[0].permute(1, 2, 0).numpy(), 1 / 4)
+    out["lr_x3"] = ref_imresize.imresize(sr[1].permute(1, 2, 0).numpy(), 1 / 3)
+    out["up_x2"] = ref_imresize.imresize(sr[0, :, :12, :10].permute(1, 2, 0).numpy(), 2)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), **out)
     print({k: v for k, v in out.items() if not hasattr(v, "shape")})
 

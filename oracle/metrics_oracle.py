@@ -56,3 +56,36 @@ def calculate_ssim(img1, img2):
     if img1.ndim == 3:
         return float(np.mean([ssim(img1[:, :, i], img2[:, :, i]) for i in range(img1.shape[2])]))
     raise ValueError("Wrong input image dimensions.")
+
+
+def _cubic(x):
+    a = np.abs(x); a2 = a * a; a3 = a2 * a
+    return (1.5 * a3 - 2.5 * a2 + 1) * (a <= 1) + (-0.5 * a3 + 2.5 * a2 - 4 * a + 2) * ((1 < a) & (a <= 2))
+
+
+def _contributions(in_len, out_len, scale):
+    """imresize.py:40-64 with the bicubic kernel (width 4), antialiasing when scale < 1, mirror padding."""
+    kw = 4.0 / scale if scale < 1 else 4.0
+    u = np.arange(1, out_len + 1, dtype=np.float64) / scale + 0.5 * (1 - 1 / scale)
+    left = np.floor(u - kw / 2)
+    P = int(np.ceil(kw)) + 2
+    ind = (left[:, None] + np.arange(P) - 1).astype(np.int32)
+    d = u[:, None] - ind - 1
+    w = scale * _cubic(scale * d) if scale < 1 else _cubic(d)
+    w = w / w.sum(axis=1, keepdims=True)
+    aux = np.concatenate((np.arange(in_len), np.arange(in_len - 1, -1, -1))).astype(np.int32)
+    return w, aux[np.mod(ind, aux.size)]
+
+
+def imresize(img, scalar_scale):
+    """imresize.py:136-175 for an HWC (or HW) float image and one scalar scale: rows first, then columns, float64."""
+    s = float(scalar_scale)
+    H, W = img.shape[:2]
+    oh, ow = int(np.ceil(s * H)), int(np.ceil(s * W))
+    x = img.astype(np.float64)
+    x = x[:, :, None] if x.ndim == 2 else x
+    w0, i0 = _contributions(H, oh, s)
+    x = np.einsum("op,opwc->owc", w0, x[i0])
+    w1, i1 = _contributions(W, ow, s)
+    x = np.einsum("op,hopc->hoc", w1, x[:, i1])
+    return x[:, :, 0] if img.ndim == 2 else x

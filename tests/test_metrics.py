@@ -24,6 +24,25 @@ def test_metrics_oracle_vs_reference_golden():
     assert abs(MO.calculate_ssim(a[:, :, 1], b[:, :, 1]) - float(g["ssim_gray"])) < 1e-10
 
 
+def test_imresize_oracle_vs_reference_golden():
+    from oracle import metrics_oracle as MO
+    g = golden("metrics")
+    sr = g["sr"]
+    for key, img, sc in (("lr_x4", sr[0], 1 / 4), ("lr_x3", sr[1], 1 / 3), ("up_x2", sr[0][:, :12, :10], 2)):
+        got = MO.imresize(img.transpose(1, 2, 0), sc)
+        assert got.shape == g[key].shape and np.abs(got - g[key]).max() < 1e-12, key
+
+
+@pytest.mark.gpu
+def test_device_imresize_vs_reference_golden():
+    from bfsr_b200 import metrics as M
+    g = golden("metrics")
+    sr = torch.from_numpy(g["sr"]).cuda()
+    for key, img, sc in (("lr_x4", sr[0], 1 / 4), ("lr_x3", sr[1], 1 / 3), ("up_x2", sr[0][:, :12, :10], 2)):
+        got = M.imresize(img, sc).permute(1, 2, 0).cpu().numpy()
+        assert got.shape == g[key].shape and np.abs(got - g[key].astype(np.float32)).max() < 1e-6, key
+
+
 @pytest.mark.gpu
 def test_device_metrics_vs_reference_golden():
     from bfsr_b200 import metrics as M
