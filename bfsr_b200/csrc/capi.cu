@@ -21,6 +21,7 @@ void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, 
 }
 
 static thread_local std::string g_err;
+namespace bfsr { void set_last_error(const std::string& m) { g_err = m; } }   // shared by the other translation units' entry points
 
 #define API_BEGIN try {
 #define API_END                                                      \

@@ -121,8 +121,8 @@ static void contributions(int in_len, int out_len, double scale, std::vector<dou
 
 }  // namespace bfsr
 
+namespace bfsr { void set_last_error(const std::string& m); }   // capi.cu: message returned by bfsr_last_error()
 using namespace bfsr;
-static thread_local std::string g_merr;
 extern "C" {
 
 int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode,
@@ -144,7 +144,7 @@ int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaFreeAsync(acc, s));
     *psnr_out = -10.0 * std::log10(sum / (double)n);
-  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
   return 0;
 }
 
@@ -169,7 +169,7 @@ int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, in
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaFreeAsync(buf, s));
     *ssim_out = sum / (double)n;
-  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
   return 0;
 }
 
@@ -186,10 +186,13 @@ int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W,
     std::vector<double> w0, w1; std::vector<int> i0, i1; int P0 = 0, P1 = 0;
     contributions(H, oh, scale, w0, i0, P0);
     contributions(W, ow, scale, w1, i1, P1);
-    double *dw0 = nullptr, *dw1 = nullptr, *t0 = nullptr, *t1 = nullptr; int *di0 = nullptr, *di1 = nullptr;
-    CUDA_OK(cudaMallocAsync((void**)&dw0, w0.size() * 8, s)); CUDA_OK(cudaMallocAsync((void**)&dw1, w1.size() * 8, s));
-    CUDA_OK(cudaMallocAsync((void**)&di0, i0.size() * 4, s)); CUDA_OK(cudaMallocAsync((void**)&di1, i1.size() * 4, s));
-    CUDA_OK(cudaMallocAsync((void**)&t0, (size_t)C * oh * W * 8, s)); CUDA_OK(cudaMallocAsync((void**)&t1, (size_t)C * oh * ow * 8, s));
+    // one scratch block: [w0 | w1 | t0 | t1] doubles, then [i0 | i1] ints
+    const size_t nd = w0.size() + w1.size() + (size_t)C * oh * W + (size_t)C * oh * ow;
+    double* blk = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&blk, nd * 8 + (i0.size() + i1.size()) * 4, s));
+    struct Free { double* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{blk, s};
+    double *dw0 = blk, *dw1 = dw0 + w0.size(), *t0 = dw1 + w1.size(), *t1 = t0 + (size_t)C * oh * W;
+    int *di0 = reinterpret_cast<int*>(blk + nd), *di1 = di0 + i0.size();
     CUDA_OK(cudaMemcpyAsync(dw0, w0.data(), w0.size() * 8, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(dw1, w1.data(), w1.size() * 8, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(di0, i0.data(), i0.size() * 4, cudaMemcpyHostToDevice, s));
@@ -200,12 +203,10 @@ int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W,
     resize_dim_kernel<double><<<(int)((n1 + 255) / 256 > 2368 ? 2368 : (n1 + 255) / 256), 256, 0, s>>>(t0, t1, C, oh, W, 1, ow, P1, dw1, di1);
     f64_to_f32_kernel<<<(int)((n1 + 255) / 256), 256, 0, s>>>(t1, out_dev, n1);
     CUDA_OK(cudaStreamSynchronize(s));   // the host weight tables must outlive the copies
-    cudaFreeAsync(dw0, s); cudaFreeAsync(dw1, s); cudaFreeAsync(di0, s); cudaFreeAsync(di1, s); cudaFreeAsync(t0, s); cudaFreeAsync(t1, s);
     CUDA_OK(cudaGetLastError());
-  } catch (const std::exception& ex) { g_merr = ex.what(); return -1; }
+  } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
   return 0;
 }
 
-const char* bfsr_metric_last_error(void) { return g_merr.c_str(); }
 
 }  // extern "C"

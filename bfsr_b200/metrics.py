@@ -15,9 +15,7 @@ from . import _lib
 _MODES = {None: 0, "benchmark": 1, "div2k": 2}
 
 
-def _check(rc):
-    if rc != 0:
-        raise _lib.BfsrError(_lib.lib().bfsr_metric_last_error().decode("utf-8", "replace"))
+_check = _lib.check
 
 
 def calc_psnr(sr, hr, dataset=None, scale=1, rgb_range=1):

@@ -185,7 +185,6 @@ int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, in
  * out_dev == NULL returns only the output size ceil(scale * H), ceil(scale * W). */
 int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
                           int32_t* out_w, void* stream);
-const char* bfsr_metric_last_error(void);
 
 /* conv3x3(cat[x_hi (B,Chi,2H,2W), nearest2x(x_lo (B,Clo,H,W))]) + bias + activation: the level-1 coupling conditioning of
  * SRFlowNet_arch.py:118-138 evaluated in ONE pass per output phase (low-res channels: four pre-summed 2x2 taps; hi-res
