@@ -168,9 +168,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the single JSON line: the pool exports NCCL_DEBUG=VERSION, which prints a banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the single JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
     B, S = args.batch, args.lr_size
