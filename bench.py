@@ -168,9 +168,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the single JSON line: NCCL prints its version banner (NCCL_DEBUG=VERSION in this pool) to stdout while
+        # the communicator is created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     warm = max(args.warmup, 3)
     B, S = args.batch, args.lr_size
 
