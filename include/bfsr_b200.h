@@ -162,7 +162,9 @@ int bfsr_linf_build_inputs(const float* lr01_dev, int32_t B, int32_t lr_h, int32
 /* ------------------------------------------------------------------ single operators (parity tests, P1 in SURVEY.md §8c)
  * fp32 NCHW in / out on the device; weights in the reference's per-module layout (host). */
 /* nn.Conv2d(ks in {1,3}, stride 1, 'same') + bias + activation (0 none, 1 LeakyReLU(0.2), 2 ReLU);
- * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass (3x3, Cin >= 32 only) */
+ * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 split-bf16 x3 (fp32 operand views, register producers), 2 = tcgen05 bf16 single
+ * pass, 3 = x3 with input and output stored as bf16 (hi, lo) planes (TMA-fed A operand, TMA-store epilogue), 4 = as 3 with an
+ * fp32 output and the tap-folded evaluation when Cin = 64 and Cout <= 24 */
 int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                    const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
                    void* stream);
