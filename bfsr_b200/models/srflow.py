@@ -263,6 +263,20 @@ class SRFlowNetEngine(nn.Module):
                                                     sr.data_ptr(), _lib.stream_ptr(lr_d.device)))
         return sr
 
+    def sr_image(self, lr_img, prior, pad_factor=2):
+        """Image-level loop body of SRFlow-LP/code/test.py:121-151 for one HWC uint8 RGB image (numpy): reflect-pad bottom / right
+        to a multiple of `pad_factor` (impad, :80-81,126-130), `t()` (:57), the LP path, clamp, `rgb()` (:59-61: x255 and a
+        truncating uint8 cast) and the crop back to (h*scale, w*scale) (:151).  Returns an HWC uint8 numpy array."""
+        import numpy as np
+        assert lr_img.ndim == 3 and lr_img.shape[2] == 3 and lr_img.dtype == np.uint8
+        h, w, _ = lr_img.shape
+        pb, pr = int(np.ceil(h / pad_factor) * pad_factor - h), int(np.ceil(w / pad_factor) * pad_factor - w)
+        lr = np.pad(lr_img, [(0, pb), (0, pr), (0, 0)], "reflect")
+        lr_t = torch.from_numpy(np.ascontiguousarray(lr.transpose(2, 0, 1))[None].astype(np.float32)) / 255
+        sr_t = self.lp_sr(lr_t, prior)
+        sr = (torch.clamp(sr_t[0], 0, 1) * 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        return sr[:h * self.scale, :w * self.scale]
+
     def lp_sr_host(self, lr_host, prior, out=None):
         """Same through the host-buffer entry point: lr_host is a CPU tensor (pinned for speed), result on the CPU."""
         assert not lr_host.is_cuda and lr_host.dtype == torch.float32 and lr_host.is_contiguous()

@@ -272,3 +272,22 @@ def test_full_size_roundtrip_and_chunk_independence():
     net1 = models.define_Flow(t.opt(), tile_chunk=3)
     net1.load_state_dict(sd, strict=True)
     assert torch.equal(net1.lp_sr(lr, prior), sr)   # chunks of 3 + 3 tiles give the same bits
+
+
+def test_sr_image_driver_odd_size():
+    """Image-level body of test.py:121-151 (reflect pad to even, t(), LP path, clamp, truncating uint8 cast, crop) on an odd-sized
+    uint8 image vs the same steps around the oracle."""
+    import numpy as np
+    from oracle import srflow_oracle as O
+    t, sd, usd, net, prior = _small()
+    rs = np.random.RandomState(3)
+    base = rs.randint(0, 256, size=(4, 6, 3)).astype(np.float32)
+    lr = np.clip(np.kron(base, np.ones((4, 4, 1), np.float32))[:15, :21] + rs.randn(15, 21, 3) * 4, 0, 255).astype(np.uint8)
+    got = net.sr_image(lr, prior)
+    assert got.shape == (60, 84, 3) and got.dtype == np.uint8
+    pad = np.pad(lr, [(0, 1), (0, 1), (0, 0)], "reflect")
+    lr_t = torch.from_numpy(pad.transpose(2, 0, 1)[None].astype(np.float32)) / 255
+    ref = O.lp_sr(sd, usd, t, lr_t, literal=False)
+    ref = (np.clip(ref[0].numpy().transpose(1, 2, 0), 0, 1) * 255).astype(np.uint8)[:60, :84]
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01     # 1e-5-level differences can flip a truncation boundary
