@@ -50,7 +50,8 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 2000;
-  for (int issuers : {1, 2, 4}) for (int n : {16, 32, 64}) {
+  for (int issuers : {1, 2, 4}) for (int n : {16, 32, 64, 96, 128, 192, 256}) {
+    if (issuers > 1 && n > 64) continue;   // accumulator columns: issuers * 128 must fit 512
     const int stride = 128;
     k<<<148, 128, 200 * 1024>>>(n, iters, stride, d, issuers);
     long long c = 0; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
