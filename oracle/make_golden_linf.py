@@ -48,13 +48,22 @@ def golden_linf():
     synth_specs = ({"name": "linf-patch", "args": real["edsr-baseline"][0]["args"], "sd": ssd},
                    {"name": "unet", "args": real["edsr-baseline"][1]["args"], "sd": spd})
 
+    # synthetic RRDB-encoder model: keeps the RRDB branch of the engine under test on the GPU box, where the 89 MB real
+    # rrdb checkpoint does not travel
+    rsd = synth.synth_linf_state_dict(synth.linf_param_shapes("rrdb"), seed=7)
+    synth_rrdb_specs = ({"name": "linf-patch", "args": real["rrdb"][0]["args"], "sd": rsd},
+                        {"name": "unet", "args": real["rrdb"][1]["args"], "sd": spd})
+    only = os.environ.get("BFSR_GOLDEN_ONLY")
     cases = {
         # name: (model spec, prior spec, B, h, w, scale, always_pad, input seed)
         "linf_edsr_real_x4": (*real["edsr-baseline"], 2, 24, 24, 4, True, 301),     # paired wrapper, config-3 shape family
         "linf_edsr_real_x3": (*real["edsr-baseline"], 1, 20, 16, 3, False, 302),    # arbitrary-scale wrapper, ragged
         "linf_rrdb_real_x2": (*real["rrdb"], 1, 16, 16, 2, False, 303),
         "linf_edsr_synth_x4": (*synth_specs, 2, 16, 20, 4, True, 304),
+        "linf_rrdb_synth_x2": (*synth_rrdb_specs, 1, 12, 14, 2, False, 305),
     }
+    if only:
+        cases = {k: v for k, v in cases.items() if k in only.split(",")}
     for name, (mspec, pspec, B, h, w, s, always_pad, seed) in cases.items():
         model = ref_models.make(mspec, load_sd=True).eval()
         prior = ref_models.make(pspec, load_sd=True).eval()

@@ -12,16 +12,16 @@ from tests.util import GOLD, golden, max_abs, rel_l2
 from tools import synth
 
 CASES = {"linf_edsr_real_x4": "edsr-baseline", "linf_edsr_real_x3": "edsr-baseline", "linf_rrdb_real_x2": "rrdb",
-         "linf_edsr_synth_x4": "synth"}
+         "linf_edsr_synth_x4": "synth", "linf_rrdb_synth_x2": "synth-rrdb"}
 
 
 def load_case(name):
     g = golden(name)
     B, h, w, s, always_pad, seed = [int(v) for v in g["meta"]]
     kind = CASES[name]
-    if kind == "synth":
-        enc = "edsr-baseline"
-        sd = synth.synth_linf_state_dict(synth.linf_param_shapes(enc), seed=5)
+    if kind in ("synth", "synth-rrdb"):
+        enc = "edsr-baseline" if kind == "synth" else "rrdb"
+        sd = synth.synth_linf_state_dict(synth.linf_param_shapes(enc), seed=5 if kind == "synth" else 7)
         psd = synth.synth_unet_state_dict(synth.unet_linf_param_shapes(), seed=6)
     else:
         enc = kind

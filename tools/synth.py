@@ -362,6 +362,8 @@ def synth_linf_state_dict(shapes, seed=5):
                 std *= 0.3       # keep the 16 residual adds of EDSR O(1)
             if k.startswith("layers.6"):
                 std *= 0.5
+            if k.startswith("encoder.trunk_conv"):
+                std *= 0.02      # near-identity RDBs make every RRDB a x1.2 gain (x + 0.2 x): keep fea + trunk O(1) after 23 of them
             v = rs.randn(*shp) * std
         elif k == "phase.weight":
             v = rs.randn(*shp) * 0.5
