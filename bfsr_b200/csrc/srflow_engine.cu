@@ -284,7 +284,9 @@ static void run_encoder(Run& r, const View& x) {
   // finer levels: fea_up2 = lrelu(upconv1(nearest2x(last_lr_fea))) etc. (post-activation: in-place LeakyReLU aliasing)
   for (int lv = lv0 - 1, u = 0; lv >= 1; --lv, ++u) {
     K_(conv2d(e->rrdb.upconv[u], r.ft[lv + 1].slice(0, nf), r.ft[lv].slice(0, nf), lrelu, IN_UP2, r.s));
-    if (!(e->levels[lv].has_phase && g_conv_mode != 2))   // the phase path reads the low-res taps directly
+    // the phase path reads the low-res taps directly, so the upsampled copy is only needed by the plain path -- or by a
+    // still finer level (8x: level 1 upsamples level 2's taps once more)
+    if (!(e->levels[lv].has_phase && g_conv_mode != 2) || lv > 1)
       K_(resample(r.ft[lv + 1].slice(nf, e->n_cond - nf), r.ft[lv].slice(nf, e->n_cond - nf), RS_NEAREST_UP2, r.s));
   }
   // coarser level: fea_up0 = bilinear x0.5 (== 2x2 mean), taps nearest x0.5

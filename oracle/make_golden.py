@@ -87,13 +87,45 @@ def golden_srflow():
               "bytes", os.path.getsize(path))
 
 
+def golden_srflow_x8():
+    """8x topology (BASELINE config 4 family: L = 4, conditioning by fea_up4 / fea_up2 / fea_up1 / fea_up0, two Split2d): encode
+    and decode only -- the shipped SRFlow-LP prior hard-codes the 4x latent layout (unet.py:117-118)."""
+    from tools import synth
+    networks, ref_models, option = _ref_srflow_modules()
+    torch.set_num_threads(8)
+    kw, B, h, w, wseed, iseed = dict(scale=8, L=4, nb=2, blocks=(0, 1, 0, 1), K=1), 1, 16, 12, 21, 201
+    topo = synth.SRFlowTopo(**kw)
+    net = networks.define_Flow(option.dict_to_nonedict(topo.opt()), 0)
+    sd = synth.synth_srflow_state_dict(topo, seed=wseed)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    lr = synth.img(B, h, w, iseed)
+    with torch.no_grad():
+        lr_up = torch.nn.functional.interpolate(lr, scale_factor=8, mode="bilinear", align_corners=False)
+        epses = []
+        net(gt=lr_up, lr=lr, reverse=False, epses=epses, add_gt_noise=False)
+        half = [0.5 * e for e in epses]
+        sr, _ = net(lr=lr, z=None, eps_std=None, reverse=True, epses=list(half), reverse_with_grad=True)
+        rt, _ = net(lr=lr, z=None, eps_std=None, reverse=True, epses=list(epses), reverse_with_grad=True)
+    out = {"lr": lr.numpy(), "sr_half": sr.numpy(), "roundtrip_maxabs": np.float32((rt - lr_up).abs().max().item()),
+           "meta": np.array([B, h, w, wseed, iseed], dtype=np.int64)}
+    for i, e in enumerate(epses):
+        out[f"eps{i}"] = e.numpy()
+    path = os.path.join(GOLD, "srflow_x8_small.npz")
+    np.savez_compressed(path, **out)
+    print("srflow_x8_small latents", [tuple(e.shape) for e in epses], "sr range", float(sr.min()), float(sr.max()),
+          "roundtrip", out["roundtrip_maxabs"], "bytes", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "srflow"
     os.makedirs(GOLD, exist_ok=True)
     if which == "srflow":
         golden_srflow()
+    elif which == "srflow_x8":
+        golden_srflow_x8()
     elif which == "linf":
         from oracle.make_golden_linf import golden_linf
         golden_linf()
     else:
-        raise SystemExit("usage: python -m oracle.make_golden [srflow|linf]")
+        raise SystemExit("usage: python -m oracle.make_golden [srflow|srflow_x8|linf]")

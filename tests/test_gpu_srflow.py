@@ -291,3 +291,26 @@ def test_sr_image_driver_odd_size():
     ref = (np.clip(ref[0].numpy().transpose(1, 2, 0), 0, 1) * 255).astype(np.uint8)[:60, :84]
     diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= 1 and (diff != 0).mean() < 0.01     # 1e-5-level differences can flip a truncation boundary
+
+
+def test_x8_topology_encode_decode_vs_reference_golden():
+    """8x SRFlow (BASELINE config 4 family: L = 4, latents at 4h / 2h / h/2, two Split2d, conditioning by fea_up4 / fea_up2 /
+    fea_up1 / fea_up0) against outputs recorded from the unmodified reference."""
+    from tools import synth
+    from bfsr_b200 import models
+    g = golden("srflow_x8_small")
+    B, h, w, wseed, iseed = [int(v) for v in g["meta"]]
+    t = synth.SRFlowTopo(scale=8, L=4, nb=2, blocks=(0, 1, 0, 1), K=1)
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(synth.synth_srflow_state_dict(t, seed=wseed), strict=True)
+    lr = torch.from_numpy(g["lr"])
+    lr_up = F.interpolate(lr, scale_factor=8, mode="bilinear", align_corners=False)
+    epses = []
+    net(gt=lr_up, lr=lr, reverse=False, epses=epses, add_gt_noise=False)
+    assert [tuple(e.shape) for e in epses] == [(1, 6, 64, 48), (1, 12, 32, 24), (1, 192, 8, 6)]
+    for i, e in enumerate(epses):
+        assert rel_l2(g[f"eps{i}"], e) < 1e-4, i
+    sr, _ = net(lr=lr, reverse=True, epses=[0.5 * torch.from_numpy(g[f"eps{i}"]) for i in range(3)])
+    assert rel_l2(g["sr_half"], sr) < 1e-4
+    rt, _ = net(lr=lr, reverse=True, epses=epses)
+    assert max_abs(lr_up, rt) < 5e-5
