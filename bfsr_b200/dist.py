@@ -19,6 +19,23 @@ def shard_range(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def bucket_by_scale(scales, world: int = 1, rank: int = 0):
+    """Mixed-scale batches (BASELINE config 5: LINF-LP at scales {2,3,4,6,8}): images of one scale form a bucket (one query grid
+    per bucket) and EVERY bucket is split into `world` contiguous shares, so each rank gets the same mix and therefore the same
+    cost (work grows with the square of the scale).  Returns {scale: [image indices of this rank]} in
+    ascending scale order; empty shares are omitted."""
+    buckets = {}
+    for i, s in enumerate(scales):
+        buckets.setdefault(s, []).append(i)
+    out = {}
+    for s in sorted(buckets):
+        idx = buckets[s]
+        lo, hi = shard_range(len(idx), world, rank)
+        if hi > lo:
+            out[s] = idx[lo:hi]
+    return out
+
+
 def gather_tiles(local: torch.Tensor, n_total: int, group=None, dst=None):
     """Reassemble the per-rank slices (dim 0) of a sharded batch.  dst=None -> every rank gets the full batch
     (all_gather); dst=r -> only rank r does (gather); other ranks get None.  Ragged slices are padded to the largest."""

@@ -301,3 +301,20 @@ def build_inputs(lr01, scale, patch_size=3, always_pad=True):
                                             cell.data_ptr(), gt.data_ptr(), C.byref(qh), C.byref(qw), _lib.stream_ptr(dev)))
     return inp, coord, cell, gt, (H, W)
 
+
+def lp_sr_mixed(model, prior, lr01, scales, world=1, rank=0, always_pad=False):
+    """LP inference of a batch of equally sized LR images (B,3,h,w) in [0,1] with one scale PER IMAGE (BASELINE config 5).
+    Images are bucketed by scale, every bucket is sharded over `world` ranks (`dist.bucket_by_scale`), each local bucket runs as
+    one `build_inputs` + `lp_sr` call.  Returns {image index: (3, H, W) CUDA tensor} for this rank's images."""
+    from ..dist import bucket_by_scale
+    assert lr01.dim() == 4 and len(scales) == lr01.shape[0]
+    dev = model.device()
+    out = {}
+    for s, idx in bucket_by_scale(list(scales), world, rank).items():
+        sub = lr01[idx].to(dev)
+        inp, coord, cell, gt, hw = build_inputs(sub, s, model.patch_size, always_pad)
+        pred = model.lp_sr(inp, coord, cell, gt, prior, hw)
+        for j, i in enumerate(idx):
+            out[i] = pred[j]
+    return out
+

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bfsr_b200.dist import gather_tiles, shard_range
+from bfsr_b200.dist import bucket_by_scale, gather_tiles, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -45,3 +45,19 @@ def test_gather_tiles_world2_gloo(n):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_bucket_by_scale_balances_every_scale_over_ranks():
+    scales = [[2, 3, 4, 6, 8][i % 5] for i in range(256)]          # BASELINE config 5
+    for world in (1, 2, 8):
+        seen = {}
+        for r in range(world):
+            b = bucket_by_scale(scales, world, r)
+            assert list(b) == sorted(b)
+            for s, idx in b.items():
+                assert all(scales[i] == s for i in idx)
+                seen.setdefault(s, []).extend(idx)
+            sizes = [len(v) for v in b.values()]
+            assert max(sizes) - min(sizes) <= 1                      # every rank gets (almost) the same count of every scale
+        assert sorted(i for v in seen.values() for i in v) == list(range(256))
+    assert bucket_by_scale([4, 4, 2], 4, 3) == {}                     # more ranks than images of any scale

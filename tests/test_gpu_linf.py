@@ -81,3 +81,24 @@ def test_linf_build_inputs_vs_wrapper_restatement(h, w, scale, always_pad):
         assert torch.equal(coord[i].cpu(), r_coord)
         assert torch.equal(cell[i].cpu(), r_cell)
         assert gt[i].shape == r_gt.shape and max_abs(r_gt, gt[i]) < 2e-6
+
+
+def test_linf_mixed_scale_batch_bucketing():
+    """BASELINE config 5 plumbing: per-image scales, buckets sharded over ranks; every image equals its stand-alone result."""
+    from bfsr_b200 import models
+    from tools import synth
+    g, enc, sd, psd, *_ = load_case("linf_edsr_synth_x4")
+    model, prior = _engines(enc, sd, psd)
+    lr = synth.img(5, 12, 12, 41)
+    scales = [2, 3, 4, 2, 3]
+    full = models.lp_sr_mixed(model, prior, lr, scales)
+    assert sorted(full) == [0, 1, 2, 3, 4]
+    for i, s in enumerate(scales):
+        assert tuple(full[i].shape) == (3, 12 * s, 12 * s) and torch.isfinite(full[i]).all()
+        inp, coord, cell, gt, hw = models.build_inputs(lr[i:i + 1].cuda(), s, 3, False)
+        one = model.lp_sr(inp, coord, cell, gt, prior, hw)[0]
+        assert rel_l2(one, full[i]) < 1e-6
+    halves = {}
+    for r in range(2):
+        halves.update(models.lp_sr_mixed(model, prior, lr, scales, world=2, rank=r))
+    assert sorted(halves) == [0, 1, 2, 3, 4] and all(rel_l2(full[i], halves[i]) < 1e-6 for i in range(5))
