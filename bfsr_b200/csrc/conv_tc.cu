@@ -180,6 +180,18 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// cluster variants: the commit arrives on the barrier at the same offset in every CTA of `mask`; the bulk copy lands at the
+// same offset of every CTA's shared memory and signals each one's barrier
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -304,10 +316,27 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
   return c;
 }
 
-template <bool TMA_IN>
+// CL = 2: launched as 2-CTA clusters.  The two CTAs walk tile PAIRS that share (cout tile, phase) -- hence the whole weight
+// stream -- on neighbouring spatial tiles: each CTA fetches half of every weight stage and multicasts it into both shared
+// memories, and a stage is recycled when the MMAs of BOTH CTAs have retired.  Halves the L2 -> SM weight traffic of the
+// convs whose 0.8 MB-per-tile weight stream binds them (level-1 phase convs).  Everything else is per CTA as for CL = 1.
+template <bool TMA_IN, int CL = 1>
 __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   using R = Roles<TMA_IN>;
+  static_assert(CL == 1 || (CL == 2 && TMA_IN), "clusters: TMA-fed variant only");
+  // persistent tile walk: CL = 1 strides the tile list by the grid; CL = 2 strides the PAIR list by the cluster count
+  // (macros, not hoisted constants: the CL = 1 loops stay on the uniform datapath exactly as before)
+#define TC_T_FIRST (CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define TC_T_STEP (CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define TC_T_END (CL == 2 ? a.total_tiles >> 1 : a.total_tiles)
+  const int cl_rank = CL == 2 ? (int)(blockIdx.x & 1u) : 0;
+  auto tile_of = [&](int p) -> int {
+    if (CL == 1) return p;
+    const int g = a.n_ct * (a.phase ? 4 : 1);        // tiles that differ only in (cout tile, phase) are consecutive
+    const int sp = p / g;
+    return (sp * 2 + cl_rank) * g + (p - sp * g);
+  };
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
@@ -325,7 +354,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
 
   if (tid == 0) {
     for (int i = 0; i < NA_MAX; ++i) { mbar_init(a_full + 8 * i, TMA_IN ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
-    for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss); }
+    for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss * CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -340,6 +369,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL == 2) cluster_sync_all();       // the peer's barriers exist before any multicast copy / remote commit targets them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -353,8 +383,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     {
       const uint32_t box_bytes = (uint32_t)(a.pitch * a.hrows) * ROWB;
       int a_it = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        const TileCoord tcd = tile_coord(a, t);
+      for (int p = TC_T_FIRST; p < TC_T_END; p += TC_T_STEP) {
+        const TileCoord tcd = tile_coord(a, tile_of(p));
         for (int c = 0; c < a.n_chunks; ++c, ++a_it) {
           const int slot = a_it % a.na;
           mbar_wait_relaxed(a_empty + 8 * slot, ((a_it / a.na) & 1) ^ 1);
@@ -525,8 +555,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       else store_split(v, p, co, o);
     };
     TR_DECL(tr_wait = 0, tr_work = 0); TR_T(tr_start);
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
-      const TileCoord tcd = tile_coord(a, t);
+    for (int p = TC_T_FIRST; p < TC_T_END; p += TC_T_STEP, ++t_it) {
+      const TileCoord tcd = tile_coord(a, tile_of(p));
       const int as = t_it % a.nacc;
       const int co_base = tcd.ct * nt;
       if (tcd.ct != cur_ct) {   // bias of this cout tile -> the warp's smem copy, fetched before the accumulator wait
@@ -738,7 +768,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     int a_it = 0, w_it = 0, t_it = 0;
     TR_DECL(tr_acc = 0, tr_a = 0, tr_w = 0, tr_issue = 0); TR_T(tr_start);
     if (a.w_res && (int)blockIdx.x < a.total_tiles) mbar_wait(w_full, 0);     // resident weights: one wait for the whole set
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++t_it) {
+    for (int p = TC_T_FIRST; p < TC_T_END; p += TC_T_STEP, ++t_it) {
+      const int t = tile_of(p);
       const int as = t_it % a.nacc;
       const int ph = a.phase ? (t / a.n_ct) & 3 : 0;
       if (a.w_res) w_it = 0;                                                    // stage index = position inside the tile
@@ -799,7 +830,10 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
             bd0 += (uint32_t)a.w_slot >> 4;
             if (++tdx == kw) { tdx = 0; tap_off += row_step; } else tap_off += ROWB >> 4;
           }
-          if (!a.w_res && elect_one()) umma_commit(w_empty + 8 * ws);      // weight stage reusable once these MMAs retire
+          if (!a.w_res && elect_one()) {                                   // weight stage reusable once these MMAs retire
+            if (CL == 2) umma_commit_mc(w_empty + 8 * ws, (uint16_t)3);    // ... in both CTAs of the cluster
+            else umma_commit(w_empty + 8 * ws);
+          }
           __syncwarp();
           TR_ADD(tr_issue, tr3);
         }
@@ -827,7 +861,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       }
       __syncwarp();
     } else
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    for (int p = TC_T_FIRST; p < TC_T_END; p += TC_T_STEP) {
+      const int t = tile_of(p);
       const int ct = t % a.n_ct;
       const int wsel = a.phase ? ct * 4 + ((t / a.n_ct) & 3) : ct;       // phase mode: [cout tile][phase][chunk][tap]
       const unsigned char* wsrc = a.w + (size_t)wsel * (a.phase == 2 ? a.taps_tile : a.n_chunks * a.ntaps) * tap_stride;
@@ -841,17 +876,28 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           const uint32_t dst = w_smem + ws * a.w_stage;
           const unsigned char* src = wsrc + (size_t)wi * a.tps * tap_stride;
           mbar_expect_tx(w_full + 8 * ws, w_bytes * a.tps);
+          if (CL == 2) {      // this CTA's half of every copy, delivered to both CTAs (each one's w_full counts the whole stage)
+            if (!a.fast) { const uint32_t hb = (w_bytes * a.tps) >> 1; bulk_g2s_mc(dst + cl_rank * hb, src + (size_t)cl_rank * hb, hb, w_full + 8 * ws, (uint16_t)3); }
+            else for (int tt = 0; tt < a.tps; ++tt) {
+              const uint32_t hb = w_bytes >> 1;
+              bulk_g2s_mc(dst + tt * a.w_slot + cl_rank * hb, src + (size_t)tt * tap_stride + (size_t)cl_rank * hb, hb, w_full + 8 * ws, (uint16_t)3);
+            }
+          } else
           if (!a.fast) bulk_g2s(dst, src, w_bytes * a.tps, w_full + 8 * ws);        // taps are contiguous: one bulk copy
           else for (int tt = 0; tt < a.tps; ++tt) bulk_g2s(dst + tt * a.w_slot, src + (size_t)tt * tap_stride, w_bytes, w_full + 8 * ws);
         }
         __syncwarp();
       }
     }
+    if (CL == 2) {   // tail: every stage this CTA filled has been released by both CTAs, i.e. no remote arrive is still in flight
+      for (int i = 0; i < a.nw && i < w_it; ++i) { const int it = w_it - 1 - i; mbar_wait_relaxed(w_empty + 8 * (it % a.nw), (it / a.nw) & 1); }
+    }
 #ifdef BFSR_TC_TRACE
     if (blockIdx.x == 0 && lane == 0) printf("[tc trace] wprod: total %lld wait_w_empty %lld (taps %d)\n", clock64() - tr_start, tr_wait, w_it);
 #endif
   }
   __syncthreads();
+  if (CL == 2) cluster_sync_all();       // neither CTA leaves while the other may still signal its barriers
   if (warp == R::W_MMA) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
@@ -1183,7 +1229,34 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-  const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  // 2-CTA clusters with multicast weight stages (opt-in until measured: BFSR_TC_CLUSTER=1 level-1 phase convs, 2 = every
+  // TMA-fed conv that streams its weights): needs an even number of spatial tiles so that the pair list is complete
+  static const int cl_env = getenv("BFSR_TC_CLUSTER") ? atoi(getenv("BFSR_TC_CLUSTER")) : 0;
+  const bool cl2 = cl_env > 0 && (phase == 2 || cl_env >= 2) && a.tma && !a.w_res && !fold && ((a.tiles_x * a.tiles_y * out.N) & 1) == 0 &&
+                   a.total_tiles >= 4 && (a.w_stage & 31) == 0;
+  if (cl2) {
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(Roles<true>::NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
+    static int max_clusters = 0;       // co-schedulable CTA pairs (a GPC with an odd SM count leaves one SM out)
+    if (!max_clusters) {
+      cfg.gridDim = dim3(g_num_sms & ~1); cfg.dynamicSmemBytes = MAX_SMEM;
+      CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, conv_tc_kernel<true, 2>, &cfg));
+      BFSR_CHECK(max_clusters > 0, "conv_tc: no 2-CTA cluster can be scheduled");
+      cfg.dynamicSmemBytes = smem;
+    }
+    const int pairs = a.total_tiles / 2;
+    grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
+    cfg.gridDim = dim3(grid);
+    snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s-cl2 k%d %d->%d %dx%d", phase == 2 ? "-phase1p" : "", w.ks, w.cin, w.cout, out.H, out.W);
+    ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 2>, a));
+    count_launch();
+    return;
+  }
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
   snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");

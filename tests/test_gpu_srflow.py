@@ -2,6 +2,7 @@
 fixtures recorded from the unmodified reference.  Tolerances: bit-exact for index ops; fp32 conv/coupling
 <= 1e-4 relative (BASELINE.json north_star), in practice ~1e-6."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -314,3 +315,17 @@ def test_x8_topology_encode_decode_vs_reference_golden():
     assert rel_l2(g["sr_half"], sr) < 1e-4
     rt, _ = net(lr=lr, reverse=True, epses=epses)
     assert max_abs(lr_up, rt) < 5e-5
+
+
+@pytest.mark.skipif(os.environ.get("BFSR_TEST_CLUSTER") != "1",
+                    reason="2-CTA cluster / multicast weight variant is opt-in until measured (BFSR_TEST_CLUSTER=1)")
+def test_cluster_multicast_variant_subprocess():
+    """conv_tc_kernel<true, 2> (BFSR_TC_CLUSTER=2: every eligible TMA-fed conv runs as 2-CTA clusters with multicast weight
+    stages) must pass the same parity tests as the default kernel.  The knob is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, BFSR_TC_CLUSTER="2", BFSR_TEST_CLUSTER="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_srflow.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "not cluster_multicast"], env=env, cwd=root, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
