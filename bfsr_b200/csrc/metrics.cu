@@ -1,7 +1,8 @@
 // Evaluation metrics of the reference's test drivers on the device:
 //   PSNR  — LINF-LP/utils.py:132-151 (calc_psnr: plain / 'benchmark' luma + shave / 'div2k' shave)
-//   SSIM  — LINF-LP/utils.py:154-193 (11x11 Gaussian window sigma 1.5, 'valid' region, float64, mean over channels), the
-//           same definition Measure.py:46-53 takes from skimage for SRFlow-LP.
+//   SSIM  — LINF-LP/utils.py:154-193 (11x11 Gaussian window sigma 1.5, 'valid' region, float64, mean over channels).
+//           (SRFlow-LP's Measure.py:46-49 calls skimage's default SSIM -- 7x7 uniform window, sample covariance -- which is a
+//           different definition and is not built yet.)
 // Both accumulate in fp64 (the reference's SSIM is fp64; its PSNR is an fp32 mean whose rounding we do not reproduce).
 #include "common.cuh"
 #include "../../include/bfsr_b200.h"

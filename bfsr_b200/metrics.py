@@ -1,8 +1,9 @@
 """Evaluation metrics of the reference's test drivers, computed on the device through the C ABI.
 
-Mirrors LINF-LP/utils.py:132-193 (`calc_psnr(sr, hr, dataset, scale, rgb_range)`, `calculate_ssim(img1, img2)`); the SRFlow-LP
-driver uses the same definitions through skimage (SRFlow-LP/code/Measure.py:46-53).  Inputs are CUDA tensors; there is no CPU
-fallback.
+Mirrors LINF-LP/utils.py:132-193 (`calc_psnr(sr, hr, dataset, scale, rgb_range)`, `calculate_ssim(img1, img2)`).  The SRFlow-LP
+driver takes PSNR and SSIM from skimage (SRFlow-LP/code/Measure.py:46-53): its PSNR on uint8 images is `calc_psnr(..., rgb_range=255)`;
+its SSIM is skimage's default (7x7 uniform window, sample covariance), a different definition from the 11x11 Gaussian one
+implemented here and not built yet.  Inputs are CUDA tensors; there is no CPU fallback.
 """
 from __future__ import annotations
 
