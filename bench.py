@@ -36,8 +36,12 @@ ALG_FLOP_PER_LR_PX = 2 * 57.094e6
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+        try:
+            d = json.load(open(p))
+            tf = d.get("bf16_tflops_sustained") or d["bf16_tflops"]
+            return {"hbm_gbs": float(d["hbm_gbs"]), "tflops": float(tf), "src": "measured"}
+        except Exception as e:   # unreadable / unexpected layout: say so and use the documented fallback
+            sys.stderr.write(f"bench: MEASURED_PEAKS.json not usable ({e!r}); using the fallback peaks\n")
     # B200_PROFILING.md fallback: 6.65 TB/s copy, 1.59 PFLOP/s bf16 burst, ~1.4 PFLOP/s sustained under the 1 kW cap; the step is a
     # ~0.3 s stream of tensor-core kernels, so the sustained figure is the denominator
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (sustained bf16 of B200_PROFILING.md)"}
