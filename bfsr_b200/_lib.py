@@ -77,6 +77,8 @@ SYMBOLS = {
     "bfsr_metric_psnr": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, C.c_float, C.POINTER(C.c_double), _P]),
     "bfsr_metric_ssim": (C.c_int, [_P, _P, _I, _I, _I, C.c_float, C.POINTER(C.c_double), _P]),
     "bfsr_imresize_bicubic": (C.c_int, [_P, _I, _I, _I, C.c_double, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "bfsr_imresize_bicubic_u8": (C.c_int, [_P, _I, _I, _I, C.c_double, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "bfsr_metric_ssim_uniform": (C.c_int, [_P, _P, _I, _I, _I, C.c_float, _I, _I, C.POINTER(C.c_double), _P]),
     "bfsr_op_conv2d_hi_lo": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_conv2d_up2": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_squeeze2d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),

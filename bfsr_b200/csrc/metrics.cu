@@ -46,9 +46,11 @@ __global__ void psnr_kernel(const float* sr, const float* hr, int B, int C, int 
   if (threadIdx.x == 0) atomicAdd(acc, s);
 }
 
-// one thread per valid pixel of one channel plane; images are (C,H,W) fp32 scaled by `mul` (255 for [0,1] inputs)
-__global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W, float mul, const double* __restrict__ win, double* acc) {
-  const int h = H - 10, w = W - 10;
+// one thread per valid pixel of one channel plane; images are (C,H,W) fp32 scaled by `mul` (255 for [0,1] inputs).
+// K x K window `win` (11x11 Gaussian: utils.py; 7x7 uniform: skimage's default), cov_norm = 1 or NP / (NP - 1) (sample covariance)
+__global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W, float mul, int K, double cov_norm,
+                            const double* __restrict__ win, double* acc) {
+  const int h = H - (K - 1), w = W - (K - 1);
   const long long n = (long long)C * h * w;
   const double C1 = (0.01 * 255) * (0.01 * 255), C2 = (0.03 * 255) * (0.03 * 255);
   double s = 0.0;
@@ -57,13 +59,13 @@ __global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W,
     const float* pa = a + ((long long)c * H + y) * W + x;
     const float* pb = b + ((long long)c * H + y) * W + x;
     double m1 = 0, m2 = 0, s11 = 0, s22 = 0, s12 = 0;
-    for (int i = 0; i < 11; ++i)
-      for (int j = 0; j < 11; ++j) {
-        const double wgt = win[i * 11 + j];
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) {
+        const double wgt = win[i * K + j];
         const double u = (double)(pa[i * W + j] * mul), v = (double)(pb[i * W + j] * mul);
         m1 += wgt * u; m2 += wgt * v; s11 += wgt * u * u; s22 += wgt * v * v; s12 += wgt * u * v;
       }
-    const double v1 = s11 - m1 * m1, v2 = s22 - m2 * m2, cov = s12 - m1 * m2;
+    const double v1 = cov_norm * (s11 - m1 * m1), v2 = cov_norm * (s22 - m2 * m2), cov = cov_norm * (s12 - m1 * m2);
     s += ((2 * m1 * m2 + C1) * (2 * cov + C2)) / ((m1 * m1 + m2 * m2 + C1) * (v1 + v2 + C2));
   }
   s = block_sum(s);
@@ -74,7 +76,7 @@ __global__ void ssim_kernel(const float* a, const float* b, int C, int H, int W,
 // out[o] = sum_p w[o][p] * in[idx[o][p]] along one dimension, fp64; planes are (C, H, W)
 template <typename TI>
 __global__ void resize_dim_kernel(const TI* in, double* out, int C, int H, int W, int dim, int olen, int P, const double* wgt,
-                                  const int* idx) {
+                                  const int* idx, int round_u8) {
   const int oH = dim == 0 ? olen : H, oW = dim == 1 ? olen : W;
   const long long n = (long long)C * oH * oW;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -86,7 +88,8 @@ __global__ void resize_dim_kernel(const TI* in, double* out, int C, int H, int W
       const double v = dim == 0 ? (double)in[((long long)c * H + i) * W + x] : (double)in[((long long)c * H + y) * W + i];
       acc += wgt[o * P + p] * v;
     }
-    out[e] = acc;
+    // uint8 images: every pass ends with np.around(np.clip(., 0, 255)).astype(uint8) (imresize.py:108-110,122-124)
+    out[e] = round_u8 ? rint(fmin(fmax(acc, 0.0), 255.0)) : acc;
   }
 }
 __global__ void f64_to_f32_kernel(const double* in, float* out, long long n) {
@@ -149,33 +152,51 @@ int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_
   return 0;
 }
 
+static void ssim_run(const float* img1_dev, const float* img2_dev, int C, int H, int W, float mul, int K, const double* win_host,
+                     double cov_norm, double* ssim_out, cudaStream_t s) {
+  double* buf = nullptr;
+  const int nw = K * K;
+  CUDA_OK(cudaMallocAsync((void**)&buf, (nw + 1) * 8, s));
+  CUDA_OK(cudaMemcpyAsync(buf, win_host, nw * 8, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemsetAsync(buf + nw, 0, 8, s));
+  const long long n = (long long)C * (H - K + 1) * (W - K + 1);
+  ssim_kernel<<<(int)((n + 127) / 128 > 2368 ? 2368 : (n + 127) / 128), 128, 0, s>>>(img1_dev, img2_dev, C, H, W, mul, K, cov_norm, buf, buf + nw);
+  double sum = 0;
+  CUDA_OK(cudaMemcpyAsync(&sum, buf + nw, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));     // also keeps win_host alive until the copy has been made
+  CUDA_OK(cudaFreeAsync(buf, s));
+  *ssim_out = sum / (double)n;
+}
+
 int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul, double* ssim_out,
                      void* stream) {
   try {
     BFSR_CHECK(img1_dev && img2_dev && ssim_out && C > 0 && H > 10 && W > 10, "ssim: bad arguments (images must exceed the 11x11 window)");
-    cudaStream_t s = (cudaStream_t)stream;
     // cv2.getGaussianKernel(11, 1.5): exp(-(i-5)^2 / (2 sigma^2)) normalised to sum 1; window = outer product (utils.py:160-161)
     double k[11], ksum = 0, win[121];
     for (int i = 0; i < 11; ++i) { k[i] = std::exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); ksum += k[i]; }
     for (int i = 0; i < 11; ++i) k[i] /= ksum;
     for (int i = 0; i < 11; ++i) for (int j = 0; j < 11; ++j) win[i * 11 + j] = k[i] * k[j];
-    double* buf = nullptr;
-    CUDA_OK(cudaMallocAsync((void**)&buf, 122 * 8, s));
-    CUDA_OK(cudaMemcpyAsync(buf, win, 121 * 8, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemsetAsync(buf + 121, 0, 8, s));
-    const long long n = (long long)C * (H - 10) * (W - 10);
-    ssim_kernel<<<(int)((n + 127) / 128 > 2368 ? 2368 : (n + 127) / 128), 128, 0, s>>>(img1_dev, img2_dev, C, H, W, mul, buf, buf + 121);
-    double sum = 0;
-    CUDA_OK(cudaMemcpyAsync(&sum, buf + 121, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    CUDA_OK(cudaFreeAsync(buf, s));
-    *ssim_out = sum / (double)n;
+    ssim_run(img1_dev, img2_dev, C, H, W, mul, 11, win, 1.0, ssim_out, (cudaStream_t)stream);
   } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
   return 0;
 }
 
-int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
-                          int32_t* out_w, void* stream) {
+int bfsr_metric_ssim_uniform(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul,
+                             int32_t win_size, int32_t sample_cov, double* ssim_out, void* stream) {
+  try {
+    BFSR_CHECK(img1_dev && img2_dev && ssim_out && C > 0, "ssim_uniform: bad arguments");
+    BFSR_CHECK(win_size >= 3 && win_size <= 31 && (win_size & 1), "ssim_uniform: win_size must be odd, 3..31");
+    BFSR_CHECK(H >= win_size && W >= win_size, "ssim_uniform: win_size exceeds image extent");
+    std::vector<double> win((size_t)win_size * win_size, 1.0 / (double)(win_size * win_size));
+    const double np = (double)(win_size * win_size);
+    ssim_run(img1_dev, img2_dev, C, H, W, mul, win_size, win.data(), sample_cov ? np / (np - 1.0) : 1.0, ssim_out, (cudaStream_t)stream);
+  } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
+  return 0;
+}
+
+static int imresize_run(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                        int32_t* out_w, void* stream, int round_u8) {
   try {
     BFSR_CHECK(C > 0 && H > 0 && W > 0 && scale > 0, "imresize: bad arguments");
     const int oh = (int)std::ceil(scale * H), ow = (int)std::ceil(scale * W);     // deriveSizeFromScale, imresize.py:6-10
@@ -200,8 +221,8 @@ int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W,
     CUDA_OK(cudaMemcpyAsync(di1, i1.data(), i1.size() * 4, cudaMemcpyHostToDevice, s));
     // equal scales: argsort keeps the order (rows first, then columns), imresize.py:150,163-165
     const long long n0 = (long long)C * oh * W, n1 = (long long)C * oh * ow;
-    resize_dim_kernel<float><<<(int)((n0 + 255) / 256 > 2368 ? 2368 : (n0 + 255) / 256), 256, 0, s>>>(img_dev, t0, C, H, W, 0, oh, P0, dw0, di0);
-    resize_dim_kernel<double><<<(int)((n1 + 255) / 256 > 2368 ? 2368 : (n1 + 255) / 256), 256, 0, s>>>(t0, t1, C, oh, W, 1, ow, P1, dw1, di1);
+    resize_dim_kernel<float><<<(int)((n0 + 255) / 256 > 2368 ? 2368 : (n0 + 255) / 256), 256, 0, s>>>(img_dev, t0, C, H, W, 0, oh, P0, dw0, di0, round_u8);
+    resize_dim_kernel<double><<<(int)((n1 + 255) / 256 > 2368 ? 2368 : (n1 + 255) / 256), 256, 0, s>>>(t0, t1, C, oh, W, 1, ow, P1, dw1, di1, round_u8);
     f64_to_f32_kernel<<<(int)((n1 + 255) / 256), 256, 0, s>>>(t1, out_dev, n1);
     CUDA_OK(cudaStreamSynchronize(s));   // the host weight tables must outlive the copies
     CUDA_OK(cudaGetLastError());
@@ -209,5 +230,14 @@ int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W,
   return 0;
 }
 
+int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                          int32_t* out_w, void* stream) {
+  return imresize_run(img_dev, C, H, W, scale, out_dev, out_h, out_w, stream, 0);
+}
+
+int bfsr_imresize_bicubic_u8(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                             int32_t* out_w, void* stream) {
+  return imresize_run(img_dev, C, H, W, scale, out_dev, out_h, out_w, stream, 1);
+}
 
 }  // extern "C"

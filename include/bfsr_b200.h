@@ -187,6 +187,16 @@ int bfsr_metric_ssim(const float* img1_dev, const float* img2_dev, int32_t C, in
  * out_dev == NULL returns only the output size ceil(scale * H), ceil(scale * W). */
 int bfsr_imresize_bicubic(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
                           int32_t* out_w, void* stream);
+/* imresize on a uint8 image (values 0..255 held in fp32): as above, but every pass ends with round-half-even(clip(., 0, 255))
+ * exactly as imresize.py:108-110,122-124 does for uint8 input -- the LR-consistency metric of SRFlow-LP/code/test.py:159-160
+ * (psnr(lq_orig, imresize(sr, 1 / scale))). */
+int bfsr_imresize_bicubic_u8(const float* img_dev, int32_t C, int32_t H, int32_t W, double scale, float* out_dev, int32_t* out_h,
+                             int32_t* out_w, void* stream);
+/* SSIM as SRFlow-LP/code/Measure.py:46-49 takes it from scikit-image (structural_similarity defaults, multichannel): win_size x
+ * win_size UNIFORM window (7), sample covariance (x NP/(NP-1)) when sample_cov != 0, data range 255, K1 = 0.01, K2 = 0.03, mean
+ * over the region the window fits in and over channels.  (C,H,W) fp32 images, each multiplied by `mul` first. */
+int bfsr_metric_ssim_uniform(const float* img1_dev, const float* img2_dev, int32_t C, int32_t H, int32_t W, float mul,
+                             int32_t win_size, int32_t sample_cov, double* ssim_out, void* stream);
 
 /* conv3x3(cat[x_hi (B,Chi,2H,2W), nearest2x(x_lo (B,Clo,H,W))]) + bias + activation: the level-1 coupling conditioning of
  * SRFlowNet_arch.py:118-138 evaluated in ONE pass per output phase (low-res channels: four pre-summed 2x2 taps; hi-res

@@ -33,6 +33,12 @@ def main():
     out["lr_x4"] = ref_imresize.imresize(sr[0].permute(1, 2, 0).numpy(), 1 / 4)
     out["lr_x3"] = ref_imresize.imresize(sr[1].permute(1, 2, 0).numpy(), 1 / 3)
     out["up_x2"] = ref_imresize.imresize(sr[0, :, :12, :10].permute(1, 2, 0).numpy(), 2)
+    # uint8 branch of the same imresize (SRFlow-LP/code/test.py:159: LR consistency of a uint8 SR image)
+    sr8 = (sr.permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+    out["sr8"] = sr8
+    out["lr8_x4"] = ref_imresize.imresize(sr8[0], 1 / 4)
+    out["lr8_x3"] = ref_imresize.imresize(sr8[1], 1 / 3)
+    out["lr8_x8"] = ref_imresize.imresize(sr8[0][:40, :56], 1 / 8)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), **out)
     print({k: v for k, v in out.items() if not hasattr(v, "shape")})
 

@@ -1,6 +1,12 @@
 """TEST INFRASTRUCTURE ONLY — numpy restatement of the reference's evaluation metrics (LINF-LP/utils.py:132-193).
 
-Pinned against outputs of the unmodified reference functions (tests/golden/metrics.npz, oracle/make_golden_metrics.py)."""
+Pinned against outputs of the unmodified reference functions (tests/golden/metrics.npz, oracle/make_golden_metrics.py).
+
+`skimage_ssim` / `skimage_psnr` restate scikit-image's structural_similarity / peak_signal_noise_ratio (third-party dependency of
+SRFlow-LP/code/Measure.py:26-27, `scikit-image` in SRFlow-LP/requirements.txt; the package is absent from this container and
+from /root/reference): PARITY UNPINNED for those two -- they follow the published algorithm (Wang et al. 2004 as implemented by
+skimage >= 0.16: uniform 7x7 filter, sample covariance, border of (win-1)/2 cropped) and are checked only against closed-form
+cases (tests/test_metrics.py)."""
 import numpy as np
 
 
@@ -89,3 +95,42 @@ def imresize(img, scalar_scale):
     w1, i1 = _contributions(W, ow, s)
     x = np.einsum("op,hopc->hoc", w1, x[:, i1])
     return x[:, :, 0] if img.ndim == 2 else x
+
+
+def imresize_u8(img, scalar_scale):
+    """imresize.py:136-175 for a uint8 HWC image: as `imresize`, but each pass ends with around(clip(., 0, 255)).astype(uint8)
+    (imresize.py:122-124)."""
+    assert img.dtype == np.uint8
+    s = float(scalar_scale)
+    H, W = img.shape[:2]
+    oh, ow = int(np.ceil(s * H)), int(np.ceil(s * W))
+    x = img[:, :, None] if img.ndim == 2 else img
+    w0, i0 = _contributions(H, oh, s)
+    x = np.around(np.clip(np.einsum("op,opwc->owc", w0, x[i0].astype(np.float64)), 0, 255)).astype(np.uint8)
+    w1, i1 = _contributions(W, ow, s)
+    x = np.around(np.clip(np.einsum("op,hopc->hoc", w1, x[:, i1].astype(np.float64)), 0, 255)).astype(np.uint8)
+    return x[:, :, 0] if img.ndim == 2 else x
+
+
+def skimage_psnr(img_true, img_test, data_range=255.0):
+    """skimage.metrics.peak_signal_noise_ratio on uint8 images (Measure.py:51-53): 10 log10(R^2 / mse), float64."""
+    err = np.mean((img_true.astype(np.float64) - img_test.astype(np.float64)) ** 2)
+    return float(10 * np.log10(data_range ** 2 / err))
+
+
+def skimage_ssim(img1, img2, win_size=7, data_range=255.0, sample_cov=True):
+    """skimage.metrics.structural_similarity(img1, img2, multichannel=True) on uint8 HWC (or HW) images (Measure.py:46-49)."""
+    from scipy.ndimage import uniform_filter
+    if img1.ndim == 3:
+        return float(np.mean([skimage_ssim(img1[..., c], img2[..., c], win_size, data_range, sample_cov) for c in range(img1.shape[-1])]))
+    x, y = img1.astype(np.float64), img2.astype(np.float64)
+    NP = win_size ** 2
+    cov_norm = NP / (NP - 1) if sample_cov else 1.0
+    f = lambda t: uniform_filter(t, size=win_size)
+    ux, uy = f(x), f(y)
+    uxx, uyy, uxy = f(x * x), f(y * y), f(x * y)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    pad = (win_size - 1) // 2
+    return float(S[pad:S.shape[0] - pad, pad:S.shape[1] - pad].mean())
