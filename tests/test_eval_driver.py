@@ -87,3 +87,124 @@ def test_device_measure_vs_oracle():
     want = MO.skimage_psnr(lr, MO.imresize_u8(sr, 0.25))
     got = m.lr_consistency_psnr(lr, sr, 4)
     assert abs(got - want) < 0.05, (got, want)        # an exact-.5 pixel may round the other way (1 level on a handful of pixels)
+
+
+# ---- LINF-LP eval_psnr (LINF-LP/test.py:50-230): host logic with stand-in model / prior and the oracle as metric backend
+class _FakeLINF:
+    patch_size = 3
+
+    def __init__(self):
+        self.calls = []
+
+    def eval(self):
+        return self
+
+    def __call__(self, op, inp=None, feat=None, coord=None, cell=None, gt=None, temperature=0, zmap=None):
+        import torch
+        self.calls.append(op)
+        if op == "gen_feat":
+            return inp
+        if op in ("query_log_p", "log_p"):
+            return None, gt * 2.0
+        if op in ("query_rgb", "rgb"):
+            B, q1, q2, _ = coord.shape
+            out = torch.zeros(B, 3, 3 * q1, 3 * q2)
+            if zmap is not None:      # make the prior's output visible in the prediction
+                out = out + 0.01 * zmap[:, :3].repeat_interleave(3, 2).repeat_interleave(3, 3)
+            if temperature:
+                out = out + temperature * torch.randn(out.shape, generator=torch.Generator().manual_seed(len(self.calls)))
+            return out
+        raise NotImplementedError(op)
+
+
+class _FakePrior:
+    def eval(self):
+        return self
+
+    def __call__(self, z, inp):
+        return 0.5 * z
+
+
+class _OracleMetrics:
+    @staticmethod
+    def calc_psnr(sr, hr, dataset=None, scale=1, rgb_range=1):
+        from oracle import metrics_oracle as MO
+        return MO.calc_psnr(sr.numpy(), hr.numpy(), dataset, scale, rgb_range)
+
+    @staticmethod
+    def calculate_ssim(a, b, mul=1.0):
+        from oracle import metrics_oracle as MO
+        return MO.calculate_ssim(a.permute(1, 2, 0).numpy() * mul, b.permute(1, 2, 0).numpy() * mul)
+
+    @staticmethod
+    def imresize(img, s):
+        import torch
+        from oracle import metrics_oracle as MO
+        return torch.from_numpy(MO.imresize(img.permute(1, 2, 0).numpy(), s).astype(np.float32)).permute(2, 0, 1)
+
+
+def _linf_batches(n=2, h=12, w=16, s=4):
+    import torch
+    g = torch.Generator().manual_seed(21)
+    out = []
+    for k in range(n):
+        H, W = s * h, s * w
+        q1, q2 = H // 3 + 1, W // 3 + 1                      # the paired wrapper always pads (wrappers.py:218-219)
+        out.append({"inp": torch.rand(1, 3, h, w, generator=g), "gt": torch.rand(1, 3, H, W, generator=g),
+                    "coord": torch.rand(1, q1, q2, 2, generator=g) * 2 - 1, "cell": torch.full((1, 2), 2.0 / H),
+                    "gt_lr_up": 0.1 * torch.randn(1, 27, q1, q2, generator=g)})
+    return out
+
+
+def test_linf_eval_psnr_host_logic():
+    import torch
+    import torch.nn.functional as F
+    from oracle import metrics_oracle as MO
+    norm = {"inp": {"sub": [0.5], "div": [0.5]}, "gt": {"sub": [0.5], "div": [0.5]}}
+    batches = _linf_batches()
+    model = _FakeLINF()
+    res = E.eval_psnr([dict(b) for b in batches], model, _FakePrior(), data_norm=norm, eval_type="div2k-4", eval_bsize=300,
+                      detail=True, patch=True, device="cpu", metrics=_OracleMetrics())
+    assert set(res) == {"psnr", "ssim", "lpips", "LR recon"} and np.isnan(res["lpips"])
+    assert model.calls[:3] == ["gen_feat", "query_log_p", "gen_feat"] and model.calls.count("query_rgb") == 2
+    # independent recomputation: pred = 0.01 * up3(0.5 * 2 * gt_lr_up)[:3] cropped + bilinear(inp_norm), denormalised and clamped
+    want_psnr, want_ssim, want_lr = [], [], []
+    for b in batches:
+        inp = (b["inp"] - 0.5) / 0.5
+        H, W = b["gt"].shape[-2:]
+        pred = (0.01 * b["gt_lr_up"][:, :3].repeat_interleave(3, 2).repeat_interleave(3, 3))[..., :H, :W]
+        pred = pred + F.interpolate(inp, (H, W), mode="bilinear", align_corners=False)
+        p01 = torch.clamp(pred * 0.5 + 0.5, 0, 1)
+        want_psnr.append(MO.calc_psnr(p01.numpy(), b["gt"].numpy(), "div2k", 4))
+        want_ssim.append(MO.calculate_ssim(p01[0].permute(1, 2, 0).numpy() * 255.0, b["gt"][0].permute(1, 2, 0).numpy() * 255.0))
+        lr = MO.imresize(p01[0].permute(1, 2, 0).numpy(), 0.25).astype(np.float32).transpose(2, 0, 1)[None]
+        want_lr.append(MO.calc_psnr(lr, b["inp"].numpy(), "div2k", 4))
+    assert abs(res["psnr"] - np.mean(want_psnr)) < 1e-9 and abs(res["ssim"] - np.mean(want_ssim)) < 1e-9
+    assert abs(res["LR recon"] - np.mean(want_lr)) < 1e-9
+    # plain PSNR return, no prior, un-chunked path of patch mode (evaluation during training, test.py:118-141): the batch holds
+    # one gt pixel per sampled coordinate and only the centre pixel of every 3x3 patch is scored
+    tb = []
+    for b in batches:
+        q1, q2 = b["coord"].shape[1:3]
+        tb.append(dict(b, gt=torch.rand(1, 3, q1, q2, generator=torch.Generator().manual_seed(q1))))
+    v = E.eval_psnr([dict(b) for b in tb], _FakeLINF(), None, data_norm=norm, eval_type=None, eval_bsize=None, patch=True,
+                    device="cpu", metrics=_OracleMetrics())
+    want = []
+    for b in tb:
+        inp = (b["inp"] - 0.5) / 0.5
+        pred = F.grid_sample(inp, b["coord"].flip(-1), mode="bilinear", padding_mode="border", align_corners=False)
+        want.append(MO.calc_psnr(torch.clamp(pred * 0.5 + 0.5, 0, 1).numpy(), b["gt"].numpy()))
+    assert isinstance(v, float) and abs(v - np.mean(want)) < 1e-9
+
+
+def test_linf_eval_psnr_randomness_and_errors(tmp_path):
+    norm = {"inp": {"sub": [0.5], "div": [0.5]}, "gt": {"sub": [0.5], "div": [0.5]}}
+    batches = _linf_batches(n=1)
+    res = E.eval_psnr([dict(b) for b in batches], _FakeLINF(), _FakePrior(), data_norm=norm, eval_type="benchmark-4", eval_bsize=300,
+                      detail=True, randomness=True, temperature=0.2, patch=True, sample=1, save_path=str(tmp_path), device="cpu",
+                      metrics=_OracleMetrics())
+    assert res["diversity"] > 0 and os.path.isfile(tmp_path / "801x4.png")
+    with pytest.raises(NotImplementedError):
+        E.eval_psnr([], _FakeLINF(), None, window_size=8, device="cpu", metrics=_OracleMetrics())
+    with pytest.raises(NotImplementedError):
+        E.eval_psnr([], _FakeLINF(), None, eval_type="set5", device="cpu", metrics=_OracleMetrics())
