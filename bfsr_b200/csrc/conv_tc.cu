@@ -41,8 +41,8 @@
 
 namespace bfsr {
 
-thread_local int g_conv_mode = 0;
-thread_local int g_tc_fold = -1;    // tap-folded small-Cout convs: -1 = environment default (off), 0 = off, 1 = on   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
+thread_local int g_conv_mode = 0;   // 0 = split-bf16 x3 on tcgen05 (accurate), 1 = bf16 (fast), 2 = fp32 CUDA cores only
+thread_local int g_tc_fold = -1;    // tap-folded small-Cout convs: -1 = environment default (off), 0 = off, 1 = on
 
 #ifndef BFSR_EPI_WARPS
 #define BFSR_EPI_WARPS 8   // epilogue warps of the TMA-fed variant (multiple of 4)
