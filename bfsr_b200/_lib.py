@@ -130,6 +130,17 @@ def tensor_table(sd):
     return arr, keep
 
 
+def cuda_device(device=None) -> torch.device:
+    """Indexed CUDA device: `None`, "cuda" and torch.device("cuda") resolve to the CURRENT device (under torchrun each rank has
+    called torch.cuda.set_device(rank), so an un-indexed device must never silently mean GPU 0)."""
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    if d.type != "cuda":
+        raise BfsrError(f"bfsr_b200 runs on CUDA devices only (got {d}); there is no CPU fallback")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
 def stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 

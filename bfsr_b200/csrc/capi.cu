@@ -292,6 +292,23 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
     nchw_to_nhwc(x_dev, x, s);
     ConvEpi ep; ep.act = act;
     if (impl == 0) conv2d_fp32(cw, x, y, ep, IN_DIRECT, s);
+    else if (impl == 5 || impl == 6 || impl == 7) {   // dx-folded 3x3 (Cout <= 32): 5 = fp32 output, 6 = BF16X2 output (TMA store), 7 = 5 in the bf16 single-pass mode
+      const int saved = g_conv_mode;
+      g_conv_mode = impl == 7 ? 1 : 0;
+      try {
+        CUDA_OK(cudaMalloc((void**)&xb, (npix * x.cs + 16) * 4));
+        CUDA_OK(cudaMalloc((void**)&yb, (npix * Cout + 16) * 4));
+        View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * x.cs;
+        View yv = y; yv.p = yb; yv.fmt = BF16X2; yv.plane = (long long)npix * Cout;
+        resample(x, xv, RS_COPY, s);
+        g_tc_fold = 2;
+        BFSR_CHECK(cw.w_tc_f3, "dx-folded packing needs ks = 3 and Cout <= 32");
+        conv2d_tc(cw, xv, impl == 6 ? yv : y, ep, IN_DIRECT, s);
+        g_tc_fold = -1;
+        if (impl == 6) resample(yv, y, RS_COPY, s);
+      } catch (...) { g_conv_mode = saved; g_tc_fold = -1; throw; }
+      g_conv_mode = saved;
+    }
     else if (impl == 4) {   // as 3, but the output stays fp32 (the layout of the coupling-parameter convs: tap-folded when Cin = 64, Cout <= 24)
       const int saved = g_conv_mode;
       g_conv_mode = 0;
@@ -313,9 +330,11 @@ int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_
         View xv = x; xv.p = xb; xv.fmt = BF16X2; xv.plane = (long long)npix * x.cs;
         View yv = y; yv.p = yb; yv.fmt = BF16X2; yv.plane = (long long)npix * Cout;
         resample(x, xv, RS_COPY, s);
+        g_tc_fold = 0;            // the per-tap evaluation (impl 5 / 6 test the dx-folded one)
         conv2d_tc(cw, xv, yv, ep, IN_DIRECT, s);
+        g_tc_fold = -1;
         resample(yv, y, RS_COPY, s);
-      } catch (...) { g_conv_mode = saved; throw; }
+      } catch (...) { g_conv_mode = saved; g_tc_fold = -1; throw; }
       g_conv_mode = saved;
     } else {   // 1 = tcgen05 split-bf16 x3, 2 = tcgen05 bf16 single pass
       const int saved = g_conv_mode;

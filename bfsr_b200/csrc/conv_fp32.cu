@@ -334,7 +334,8 @@ void free_conv(ConvW& w) {
   if (w.bias) cudaFree(w.bias);
   if (w.w_tc) cudaFree(w.w_tc);
   if (w.w_tc_fold) cudaFree(w.w_tc_fold);
-  w.w = w.bias = nullptr; w.w_tc = nullptr; w.w_tc_fold = nullptr;
+  if (w.w_tc_f3) cudaFree(w.w_tc_f3);
+  w.w = w.bias = nullptr; w.w_tc = nullptr; w.w_tc_fold = nullptr; w.w_tc_f3 = nullptr;
 }
 
 }  // namespace bfsr

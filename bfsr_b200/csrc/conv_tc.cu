@@ -101,7 +101,14 @@ struct TcArgs {
                                          // columns (u[r, tap*Cout+co] = x[r,:] . W[tap][:, co]) and a shift-add epilogue
                                          // out[p] = sum_tap u[p + off_tap, tap] -- 9x fewer MMAs for convs that sit on the
                                          // small-N MMA floor
-  int tile_w, tile_h;                    // output pixels of a macro tile (fold: 16x16 or 14x14; else 8*sx x 16*sy)
+                                         // fold = 2 (dx folding, 3x3, Cout <= 32): the tile is a raster of pitch 32 pixels; per filter
+                                         // row dy ONE MMA computes u[r, dx*cb+co] = x[r + 32*dy,:] . W[dy][dx][:, co] for the three dx at
+                                         // once (N = 3*cb), M tiles = runs of 128 raster positions = 4 image rows, and the epilogue
+                                         // forms out[r] = u0[r] + u1[r+1] + u2[r+2] with two warp shuffles per channel (a warp holds one
+                                         // image row of 32 positions, 30 of them valid outputs): 3x fewer MMAs of 3x the width -- the
+                                         // small-N floor of the MMA (A operand read from shared memory, ~40 clk) is paid once per dy
+  int cb;                                // fold = 2: accumulator column stride of a dx block (16 or 32)
+  int tile_w, tile_h;                    // output pixels of a macro tile (fold 1: 16x16 or 14x14; fold 2: 30 x 4*mt; else 8*sx x 16*sy)
   FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
   View in2;                              // phase 2: hi-res part of the input (BF16X2); n_pre: the pre-activation tensor
   int n_pre, n_main;                     // pre-activation folded into the GEMM: n_pre extra 32-channel chunks of `in2` with ONE
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
       mbar_wait_relaxed(acc_full + 8 * as, (t_it / a.nacc) & 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (TMA_IN && a.fold) {
+      if (TMA_IN && a.fold == 1) {
         // ---- tap-folded conv: TMEM holds u[halo row][tap*Cout + co]; shift-add the nine taps through a shared-memory
         // accumulator (fixed tap order, block barriers between taps: deterministic), then bias / activation / FlowStep
         const int Cc = a.cout, P = a.pitch, nrows = a.pitch * a.hrows;
@@ -627,6 +634,66 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * R::EPI_WARPS) : "memory");   // oacc is reused by the next tile
+        TR_ADD(tr_work, tr1);
+        continue;
+      }
+      if (TMA_IN && a.fold == 2) {
+        // ---- dx-folded 3x3: the lane holds raster position (row 4m+q, column lane) of the tile; its accumulator row carries the
+        // three dx partial sums; positions lane+1 / lane+2 of the same image row are the next lanes of this warp
+        const int CB = a.cb;
+        for (int m = grp; m < a.mt; m += N_GRP) {
+          const int gy = tcd.ty0 + 4 * m + q, gx = tcd.tx0 + lane;
+          const bool valid = lane < 30 && gy < a.H && gx < a.W;
+          const long long p = ((long long)tcd.n * a.H + gy) * a.W + gx;
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + m * sub_cols;
+          float acc[32];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g * 16 < CB) {
+              float u0[16], u1[16], u2[16];
+              tmem_ld16(t_row + g * 16, u0); tmem_ld16(t_row + CB + g * 16, u1); tmem_ld16(t_row + 2 * CB + g * 16, u2);
+              if (a.wide) {
+                float v0[16], v1[16], v2[16];
+                tmem_ld16(t_row + nt + g * 16, v0); tmem_ld16(t_row + nt + CB + g * 16, v1); tmem_ld16(t_row + nt + 2 * CB + g * 16, v2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { u0[i] += v0[i]; u1[i] += v1[i]; u2[i] += v2[i]; }
+              } else {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                acc[g * 16 + i] = u0[i] + __shfl_down_sync(0xffffffffu, u1[i], 1) + __shfl_down_sync(0xffffffffu, u2[i], 2) + bias_s[g * 16 + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[g * 16 + i] = 0.f;
+            }
+          }
+          if (a.act == ACT_CROSS_SIGMOID) {
+#pragma unroll
+            for (int i = 1; i < 32; i += 2) acc[i] = 1.f / (1.f + expf(-(acc[i] + 2.f))) + a.eps;
+          } else if (a.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
+          } else if (a.act != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f) + slope * fminf(acc[i], 0.f);
+          }
+          if (a.flow.C) {
+            if (valid) {
+              if (a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+              else flow_epilogue<24>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+            }
+          } else if (a.tma_out) {
+            if (gy < a.H) stage_store(a.out, &a.tmap_out, acc, (a.cout + 7) & ~7, 0, tcd.tx0, gy, tcd.n);   // box = 32 channels x 30 pixels x 1 row
+          } else if (valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (4 * k < a.cout) direct_store(a.out, p, 4 * k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(acc_empty + 8 * as);
         TR_ADD(tr_work, tr1);
         continue;
       }
@@ -762,7 +829,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub)
       sub_off[sub] = a.fold ? (uint32_t)(sub * 128) * (ROWB >> 4) : (uint32_t)((sub / a.sx) * 16 * a.pitch + (sub % a.sx) * 8) * (ROWB >> 4);
-    const int kw = a.phase ? 2 : a.ks;                                   // taps per filter row
+    const int kw = a.phase ? 2 : a.ks;                                   // taps per filter row (fold 2: ks = 1, the three 'taps' are the filter rows)
     const uint32_t row_step = (uint32_t)(a.pitch - (kw - 1)) * (ROWB >> 4);   // from the last tap of a row to the first of the next
     const int stages = a.ntaps / a.tps;
     int a_it = 0, w_it = 0, t_it = 0;
@@ -981,10 +1048,33 @@ void pack_conv_tc(ConvW& c, const std::vector<float>& h, int min_cin_arg) {
     CUDA_OK(cudaMemcpy(c.w_tc_fold, f.data(), f.size() * 2, cudaMemcpyHostToDevice));
     c.tc_fold_np = np;
   }
+  if (c.ks == 3 && c.cout <= 32 && c.cout % 4 == 0) {   // dx-folded image (see TcArgs::fold = 2): [chunk][dy] images of [hi ; lo] rows dx*cb + co
+    const int cb = c.cout <= 16 ? 16 : 32, np = 3 * cb;
+    std::vector<unsigned short> f((size_t)n_chunks * 3 * 2 * np * (ROWB / 2), 0);
+    for (int ch = 0; ch < n_chunks; ++ch)
+      for (int dy = 0; dy < 3; ++dy) {
+        unsigned short* dst = f.data() + ((size_t)ch * 3 + dy) * 2 * np * 32;
+        for (int dx = 0; dx < 3; ++dx)
+          for (int co = 0; co < c.cout; ++co) {
+            const int r = dx * cb + co, r2 = np + r;
+            for (int k = 0; k < KC; ++k) {
+              const int ci = ch * KC + k;
+              const float w = ci < c.cin ? h[((size_t)(dy * 3 + dx) * c.cin_pad + ci) * c.cout_pad + co] : 0.f;
+              const unsigned short hi = f2bf(w), lo = f2bf(w - bf2f(hi));
+              const int j = k >> 3, e = k & 7;
+              dst[(size_t)r * 32 + ((j ^ ((r >> 1) & 3)) << 3) + e] = hi;
+              dst[(size_t)r2 * 32 + ((j ^ ((r2 >> 1) & 3)) << 3) + e] = lo;
+            }
+          }
+      }
+    CUDA_OK(cudaMalloc(&c.w_tc_f3, f.size() * 2));
+    CUDA_OK(cudaMemcpy(c.w_tc_f3, f.data(), f.size() * 2, cudaMemcpyHostToDevice));
+    c.tc_f3_cb = cb;
+  }
 }
 
 static bool vec4(const View& v);
-static void make_tmap_out(CUtensorMap* tm, const View& v, int estride);
+static void make_tmap_out(CUtensorMap* tm, const View& v, int estride, int bw = 8, int bh = 4);
 static bool tma_out_ok(const View& v);
 static bool vec4(const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; }
 // BF16X2 operand views: TMA needs 16-byte global strides and base; the register producer needs 16-byte channel groups
@@ -1054,12 +1144,12 @@ static bool tma_out_ok(const View& v) {
 }
 // output map: box = [32 channels, 8, 4 pixels] = the accumulator rows of one epilogue warp; fp32 rows are 128 B
 // (SWIZZLE_128B), bf16 rows 64 B per plane (SWIZZLE_64B); the channel extent stops at the end of the view (tail clipped)
-static void make_tmap_out(CUtensorMap* tm, const View& v, int estride) {
+static void make_tmap_out(CUtensorMap* tm, const View& v, int estride, int bw, int bh) {
   const int es_b = v.fmt == F32 ? 4 : 2;
   const cuuint64_t dims[5] = {(cuuint64_t)(v.coff + v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)v.cs * es_b, (cuuint64_t)v.W * v.cs * es_b, (cuuint64_t)v.H * v.W * v.cs * es_b,
                                  (cuuint64_t)v.plane * es_b};
-  const cuuint32_t box[5] = {32, (cuuint32_t)(8 * estride), (cuuint32_t)(4 * estride), 1, 1};   // estride 2: every second pixel (phase outputs)
+  const cuuint32_t box[5] = {32, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1, 1};   // estride 2: every second pixel (phase outputs); dx-folded convs: 30 x 1
   const cuuint32_t es[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   const CUresult r = v.fmt == F32
       ? encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1075,7 +1165,7 @@ static int g_num_sms = 0;
 // phase = true : out (N,2H,2W) (+)= conv3x3(nearest2x(in)) evaluated on the LOW-RES grid as four 2x2 phase convs with
 //                pre-summed weights (exact in real arithmetic, 16/36 of the MACs); `in` is the low-res tensor.
 static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, int phase, cudaStream_t s,
-                      const View* in2 = nullptr, bool fold = false) {
+                      const View* in2 = nullptr, int fold = 0) {
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C + (in2 ? in2->C : 0) == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
@@ -1089,8 +1179,9 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.in = in; a.out = out; a.out2 = epi.out2 ? *epi.out2 : View();
   const bool pre_gemm = epi.pre && epi.pre->fmt == BF16X2;    // pre-activation enters as identity K chunks (checked below)
   a.pre = (epi.pre && !pre_gemm) ? *epi.pre : View(); a.res1 = epi.res1 ? *epi.res1 : View(); a.res2 = epi.res2 ? *epi.res2 : View();
-  a.w = (const unsigned char*)(fold ? w.w_tc_fold : w.w_tc); a.bias = w.bias;
-  a.cin = w.cin; a.cout = w.cout; a.nt = fold ? w.tc_fold_np : w.tc_npad; a.n_chunks = w.tc_kchunks;
+  a.w = (const unsigned char*)(fold == 2 ? w.w_tc_f3 : (fold ? w.w_tc_fold : w.w_tc)); a.bias = w.bias;
+  a.cin = w.cin; a.cout = w.cout; a.nt = fold == 2 ? 3 * w.tc_f3_cb : (fold ? w.tc_fold_np : w.tc_npad); a.n_chunks = w.tc_kchunks;
+  a.cb = w.tc_f3_cb;
   a.n_ct = cdiv(w.cout, w.tc_npad);
   a.H = gH; a.W = gW; a.N = out.N; a.in_mode = phase ? (int)IN_DIRECT : in_mode; a.act = epi.act;
   a.eps = epi.eps; a.alpha = epi.alpha; a.beta1 = epi.beta1; a.beta2 = epi.beta2;
@@ -1102,7 +1193,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // A_hi x [W_hi;W_lo] as ONE N = 2NT MMA plus A_lo x W_hi (e.g. NT = 64: 64 + 48 clk instead of 3 x 48); NT > 64 issues the
   // three products as separate N = NT MMAs into the same columns (same MMA time, half the TMEM -> two accumulator stages)
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
-  a.wide = (!a.fast && !fold && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
+  a.wide = (!a.fast && fold != 1 && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
   int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
   static const int mt_cap = getenv("BFSR_TC_MT_MAX") ? atoi(getenv("BFSR_TC_MT_MAX")) : 4;
@@ -1121,9 +1212,9 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   }
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
-  a.fold = fold ? 1 : 0; a.tile_w = 8 * a.sx; a.tile_h = 16 * a.sy;
+  a.fold = fold; a.tile_w = 8 * a.sx; a.tile_h = 16 * a.sy;
   int fold_p = 0, fold_r = 0;
-  if (fold) {
+  if (fold == 1) {
     BFSR_CHECK(w.w_tc_fold && phase == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && !a.fast && !epi.pre && !epi.res1 && !epi.res2 &&
                !epi.out2 && epi.alpha == 1.f && (epi.act == ACT_NONE || epi.act == ACT_CROSS_SIGMOID) && (epi.flow || vec4(out)),
                "conv_tc(fold): unsupported epilogue / operand combination");
@@ -1133,6 +1224,19 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     a.mt = cdiv(fold_p * fold_r, 128); a.sx = a.sy = 1;
     a.ks = 1; a.ntaps = 1; a.halo = 1;
     BFSR_CHECK(a.mt * a.nt <= 512 && a.mt <= 4, "conv_tc(fold): accumulators do not fit TMEM");
+  }
+  if (fold == 2) {
+    BFSR_CHECK(w.w_tc_f3 && phase == 0 && bf_in_ok(in) && in_mode == IN_DIRECT && !epi.pre && !epi.res1 && !epi.res2 && !epi.out2 &&
+               epi.alpha == 1.f && (epi.flow || out_ok(out)), "conv_tc(dx-fold): unsupported epilogue / operand combination");
+    // raster of pitch 32: M tile = 4 image rows of 32 positions (30 valid outputs each); the halo tile adds one row above / below
+    static const int f3_mt = getenv("BFSR_F3_MT") ? atoi(getenv("BFSR_F3_MT")) : 0;
+    a.mt = mt >= 2 ? 2 : 1;
+    if (f3_mt == 4 && 4 * sub_cols <= 512) a.mt = 4;
+    while (a.mt > 1 && 4 * (a.mt - 1) >= gH) --a.mt;              // small images: no M tile entirely below the image
+    a.sx = 1; a.sy = a.mt;
+    a.tile_w = 30; a.tile_h = 4 * a.mt;
+    fold_p = 32; fold_r = a.tile_h + 2;
+    a.ks = 1; a.ntaps = 3; a.halo = 1;
   }
   a.flow = FlowEpi();
   if (epi.flow) {
@@ -1158,7 +1262,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.n_iss = (a.mt >= 2 && max_iss >= 2) ? 2 : 1;
   a.pitch = 8 * a.sx + 2 * a.halo; a.hrows = 16 * a.sy + 2 * a.halo;
   if (fold) { a.pitch = fold_p; a.hrows = fold_r; }
-  a.a_plane = ((fold ? a.mt * 128 : a.pitch * a.hrows) * ROWB + 1023) / 1024 * 1024;
+  a.a_plane = ((fold == 1 ? a.mt * 128 : a.pitch * a.hrows) * ROWB + 1023) / 1024 * 1024;
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
   a.w_slot = 2 * a.nt * ROWB;
   a.nacc = 2 * a.mt * sub_cols <= 512 ? 2 : 1;
@@ -1205,7 +1309,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   {
     static const bool no_res = getenv("BFSR_TC_WRES") && atoi(getenv("BFSR_TC_WRES")) == 0;
     const int stages_tile = a.n_pre ? a.n_main * a.ntaps + a.n_pre : a.n_chunks * (a.ntaps / a.tps);
-    if (!no_res && phase == 0 && !fold && !a.fast && a.n_ct == 1 && fixed + stages_tile * a.w_stage <= MAX_SMEM) { a.w_res = 1; a.nw = stages_tile; }
+    if (!no_res && phase == 0 && fold != 1 && !a.fast && a.n_ct == 1 && fixed + stages_tile * a.w_stage <= MAX_SMEM) { a.w_res = 1; a.nw = stages_tile; }
   }
   // left-over shared memory deepens the A ring (convs with little MMA work per chunk are bound by TMA latency otherwise)
   static const int na_max = getenv("BFSR_TC_NA") ? atoi(getenv("BFSR_TC_NA")) : NA_MAX;
@@ -1222,9 +1326,9 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   if (a.n_pre) make_tmap(&a.tmap_pl[0], a.in2, a.pitch, a.hrows);
   memset(&a.tmap_out, 0, sizeof a.tmap_out); memset(&a.tmap_out2, 0, sizeof a.tmap_out2);
   static const bool no_tma_out = getenv("BFSR_NO_TMA_OUT") && atoi(getenv("BFSR_NO_TMA_OUT"));
-  a.tma_out = (!no_tma_out && tma_out_ok(out) && !epi.flow && !fold) ? 1 : 0;
+  a.tma_out = (!no_tma_out && tma_out_ok(out) && !epi.flow && fold != 1) ? 1 : 0;
   a.tma_out2 = (epi.out2 && !no_tma_out && tma_out_ok(*epi.out2)) ? 1 : 0;
-  if (a.tma_out) make_tmap_out(&a.tmap_out, out, phase ? 2 : 1);
+  if (a.tma_out) { if (fold == 2) make_tmap_out(&a.tmap_out, out, 1, 30, 1); else make_tmap_out(&a.tmap_out, out, phase ? 2 : 1); }
   if (a.tma_out2) make_tmap_out(&a.tmap_out2, *epi.out2, phase ? 2 : 1);
   if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
@@ -1233,7 +1337,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // 2-CTA clusters with multicast weight stages (opt-in until measured: BFSR_TC_CLUSTER=1 level-1 phase convs, 2 = every
   // TMA-fed conv that streams its weights): needs an even number of spatial tiles so that the pair list is complete
   static const int cl_env = getenv("BFSR_TC_CLUSTER") ? atoi(getenv("BFSR_TC_CLUSTER")) : 0;
-  const bool cl2 = cl_env > 0 && (phase == 2 || cl_env >= 2) && a.tma && !a.w_res && !fold && ((a.tiles_x * a.tiles_y * out.N) & 1) == 0 &&
+  const bool cl2 = cl_env > 0 && (phase == 2 || cl_env >= 2) && a.tma && !a.w_res && fold != 1 && ((a.tiles_x * a.tiles_y * out.N) & 1) == 0 &&
                    a.total_tiles >= 4 && (a.w_stage & 31) == 0;
   if (cl2) {
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
@@ -1251,14 +1355,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     const int pairs = a.total_tiles / 2;
     grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
     cfg.gridDim = dim3(grid);
-    snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s-cl2 k%d %d->%d %dx%d", phase == 2 ? "-phase1p" : "", w.ks, w.cin, w.cout, out.H, out.W);
+    snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s-cl2 k%d %d->%d %dx%d", phase == 2 ? "-phase1p" : (fold == 2 ? "-f3" : ""), w.ks, w.cin, w.cout, out.H, out.W);
     ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
     CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 2>, a));
     count_launch();
     return;
   }
   // algorithmic FLOPs are those of the 3x3 conv over the upsampled tensor (what the reference computes)
-  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
+  snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold == 2 ? "-f3" : fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
   if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
@@ -1275,7 +1379,12 @@ void conv2d_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& e
   const bool fold = (g_tc_fold == 1 || (g_tc_fold < 0 && env_fold)) && w.w_tc_fold && g_conv_mode == 0 && in.fmt == BF16X2 && in_mode == IN_DIRECT && !epi.pre && !epi.res1 &&
                     !epi.res2 && !epi.out2 && epi.alpha == 1.f && (epi.act == ACT_NONE || epi.act == ACT_CROSS_SIGMOID) &&
                     (epi.flow || (out.fmt == F32 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0));
-  launch_tc(w, in, out, epi, in_mode, 0, s, nullptr, fold);
+  // dx folding (TcArgs::fold = 2): every TMA-fed 3x3 conv with <= 32 output channels and a plain epilogue -- the RRDB's dense convs,
+  // the (shift, scale) heads of the couplings (with the fused FlowStep) and of fFeatures.  BFSR_TC_F3=0 keeps the per-tap MMAs.
+  static const bool env_f3 = !(getenv("BFSR_TC_F3") && atoi(getenv("BFSR_TC_F3")) == 0);
+  const bool f3 = !fold && (g_tc_fold == 2 || (g_tc_fold < 0 && env_f3)) && w.w_tc_f3 && g_conv_mode != 2 && bf_in_ok(in) && in_mode == IN_DIRECT &&
+                  !epi.pre && !epi.res1 && !epi.res2 && !epi.out2 && epi.alpha == 1.f && (epi.flow || out_ok(out)) && out.W >= 16;
+  launch_tc(w, in, out, epi, in_mode, 0, s, nullptr, f3 ? 2 : (fold ? 1 : 0));
 }
 void conv2d_tc_up2_phase(const ConvW& w, const View& in_lowres, const View& out, const ConvEpi& epi, cudaStream_t s) {
   BFSR_CHECK(w.tc_phase == 1, "conv_tc: weights are not phase-packed");

@@ -197,6 +197,11 @@ void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, co
   a.nq = (long long)B * qh * qw;
   if (!a.nq) return;
   const size_t smem = (size_t)(n_layers + 1) * (FD * FD + FD) * 4;
+  BFSR_CHECK(smem <= 227 * 1024, "linf_flow: %d flow layers need %zu bytes of shared memory (limit 227 KB)", n_layers, smem);
+  if (smem > 48 * 1024) {   // flow_layers >= 16: opt in to the large carve-out (the shipped models have 10 layers = 33 KB)
+    CUDA_OK(cudaFuncSetAttribute(linf_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(linf_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   const int grid = cdiv(a.nq, 128);
   if (inverse) linf_flow_kernel<true><<<grid, 128, smem, s>>>(a);
   else linf_flow_kernel<false><<<grid, 128, smem, s>>>(a);

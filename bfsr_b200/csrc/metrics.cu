@@ -1,14 +1,16 @@
 // Evaluation metrics of the reference's test drivers on the device:
 //   PSNR  — LINF-LP/utils.py:132-151 (calc_psnr: plain / 'benchmark' luma + shave / 'div2k' shave)
 //   SSIM  — LINF-LP/utils.py:154-193 (11x11 Gaussian window sigma 1.5, 'valid' region, float64, mean over channels).
-//           (SRFlow-LP's Measure.py:46-49 calls skimage's default SSIM -- 7x7 uniform window, sample covariance -- which is a
-//           different definition and is not built yet.)
+//           SRFlow-LP's Measure.py:46-49 calls skimage's default SSIM -- 7x7 uniform window, sample covariance -- a different
+//           definition: bfsr_metric_ssim_uniform below (same kernel, uniform window, cov_norm = n/(n-1)).
 // Both accumulate in fp64 (the reference's SSIM is fp64; its PSNR is an fp32 mean whose rounding we do not reproduce).
 #include "common.cuh"
 #include "../../include/bfsr_b200.h"
 #include <cmath>
 #include <string>
 #include <vector>
+
+namespace { struct FreeAsync { void* p; cudaStream_t s; ~FreeAsync() { if (p) cudaFreeAsync(p, s); } }; }   // scratch released on every exit path
 
 namespace bfsr {
 
@@ -140,13 +142,13 @@ int bfsr_metric_psnr(const float* sr_dev, const float* hr_dev, int32_t B, int32_
     cudaStream_t s = (cudaStream_t)stream;
     double* acc = nullptr;
     CUDA_OK(cudaMallocAsync((void**)&acc, 8, s));
+    FreeAsync guard{acc, s};
     CUDA_OK(cudaMemsetAsync(acc, 0, 8, s));
     const long long n = (long long)B * (luma ? 1 : C) * (H - 2 * shave) * (W - 2 * shave);
     psnr_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, s>>>(sr_dev, hr_dev, B, C, H, W, luma, shave, 1.f / rgb_range, acc);
     double sum = 0;
     CUDA_OK(cudaMemcpyAsync(&sum, acc, 8, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
-    CUDA_OK(cudaFreeAsync(acc, s));
     *psnr_out = -10.0 * std::log10(sum / (double)n);
   } catch (const std::exception& ex) { set_last_error(ex.what()); return -1; }
   return 0;
@@ -157,6 +159,7 @@ static void ssim_run(const float* img1_dev, const float* img2_dev, int C, int H,
   double* buf = nullptr;
   const int nw = K * K;
   CUDA_OK(cudaMallocAsync((void**)&buf, (nw + 1) * 8, s));
+  FreeAsync guard{buf, s};
   CUDA_OK(cudaMemcpyAsync(buf, win_host, nw * 8, cudaMemcpyHostToDevice, s));
   CUDA_OK(cudaMemsetAsync(buf + nw, 0, 8, s));
   const long long n = (long long)C * (H - K + 1) * (W - K + 1);
@@ -164,7 +167,6 @@ static void ssim_run(const float* img1_dev, const float* img2_dev, int C, int H,
   double sum = 0;
   CUDA_OK(cudaMemcpyAsync(&sum, buf + nw, 8, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));     // also keeps win_host alive until the copy has been made
-  CUDA_OK(cudaFreeAsync(buf, s));
   *ssim_out = sum / (double)n;
 }
 

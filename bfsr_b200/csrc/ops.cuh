@@ -20,6 +20,8 @@ struct ConvW {
   int tc_kchunks = 0, tc_npad = 0, tc_phase = 0, tc_n_id = 0;   // tc_n_id: identity tap images appended (pre-activation as K chunks)
   void* w_tc_fold = nullptr;   // tap-folded image (3x3, Cin = 64, Cout <= 24): per 32-channel chunk [9*Cout rows hi ; lo], N padded to tc_fold_np
   int tc_fold_np = 0;
+  void* w_tc_f3 = nullptr;     // dx-folded image (3x3, Cout <= 32): per (32-channel chunk, dy) [3 blocks of tc_f3_cb rows hi ; lo], row = dx*cb + co
+  int tc_f3_cb = 0;            // column stride of a dx block (16 or 32); N = 3*cb
 };
 
 // FlowStep fused into the epilogue of a coupling's last conv (whose output h = (shift, scale) pairs never reaches HBM):

@@ -21,16 +21,20 @@ def shard_range(n: int, world: int, rank: int):
 
 def bucket_by_scale(scales, world: int = 1, rank: int = 0):
     """Mixed-scale batches (BASELINE config 5: LINF-LP at scales {2,3,4,6,8}): images of one scale form a bucket (one query grid
-    per bucket) and EVERY bucket is split into `world` contiguous shares, so each rank gets the same mix and therefore the same
-    cost (work grows with the square of the scale).  Returns {scale: [image indices of this rank]} in
+    per bucket) and EVERY bucket is split into `world` contiguous shares, so each rank gets the same mix and therefore (up to the
+    rotated remainders) the same cost (work grows with the square of the scale).  Returns {scale: [image indices of this rank]} in
     ascending scale order; empty shares are omitted."""
     buckets = {}
     for i, s in enumerate(scales):
         buckets.setdefault(s, []).append(i)
     out = {}
+    offset = 0          # ranks that already received an extra image from the smaller-scale buckets
     for s in sorted(buckets):
         idx = buckets[s]
-        lo, hi = shard_range(len(idx), world, rank)
+        # rotate the ranks that take the `len % world` extras from bucket to bucket: with 5 buckets of 9 images on 8 ranks no
+        # rank gets more than one extra instead of rank 0 getting all five (its step time would set the job's)
+        lo, hi = shard_range(len(idx), world, (rank - offset) % world)
+        offset = (offset + len(idx) % world) % world
         if hi > lo:
             out[s] = idx[lo:hi]
     return out

@@ -101,8 +101,7 @@ class LINFEngine(nn.Module):
         return self
 
     def device(self):
-        if self._device is None:
-            self._device = torch.device("cuda", torch.cuda.current_device())
+        self._device = _lib.cuda_device(self._device)
         return self._device
 
     def _destroy(self):
@@ -125,7 +124,7 @@ class LINFEngine(nn.Module):
             d.patch_size, d.tile_chunk, d.precision = self.patch_size, self.tile_chunk, self.precision
             table, keep = _lib.tensor_table(self.state_dict())
             h = C.c_void_p()
-            _lib.check(_lib.lib().bfsr_linf_create(C.byref(h), C.byref(d), table, len(table), self.device().index or 0))
+            _lib.check(_lib.lib().bfsr_linf_create(C.byref(h), C.byref(d), table, len(table), self.device().index))
             del keep
             self._handle = h
         return self._handle

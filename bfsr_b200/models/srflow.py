@@ -153,7 +153,9 @@ class SRFlowNetEngine(nn.Module):
     def device(self):
         if self._device is None:
             p = next(self.parameters())
-            self._device = p.device if p.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            self._device = p.device if p.is_cuda else None
+        # stored with an explicit index: the handle, the buffers and the stream must name the same GPU
+        self._device = _lib.cuda_device(self._device)
         return self._device
 
     def _destroy(self):
@@ -183,7 +185,7 @@ class SRFlowNetEngine(nn.Module):
             table, keep = _lib.tensor_table(self.state_dict())
             h = C.c_void_p()
             dev = self.device()
-            _lib.check(_lib.lib().bfsr_srflow_create(C.byref(h), C.byref(d), table, len(table), dev.index or 0))
+            _lib.check(_lib.lib().bfsr_srflow_create(C.byref(h), C.byref(d), table, len(table), dev.index))
             del keep
             self._handle = h
         return self._handle

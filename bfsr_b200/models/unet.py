@@ -47,6 +47,11 @@ def _body_shapes(s, bufs, depth, dim, sfx):
 
 
 class _PriorBase(nn.Module):
+    # conv arithmetic of the STANDALONE prior calls (0 = split-bf16 x3, 1 = bf16 single pass, 2 = fp32 CUDA cores); inside the
+    # fused lp_sr entry points the prior runs under the generator's precision.  Set it to the generator's value when mixing
+    # step-by-step and fused calls on one model.
+    precision = 0
+
     def __init__(self):
         super().__init__()
         self._handles = {}
@@ -75,15 +80,16 @@ class _PriorBase(nn.Module):
         raise NotImplementedError
 
     def handle(self, device):
-        device = torch.device(device)
-        key = device.index or 0
+        dev_i = _lib.cuda_device(device).index
+        key = (dev_i, int(self.precision))
         if key not in self._handles:
             if not torch.cuda.is_available():
                 raise _lib.BfsrError("bfsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
             table, keep = _lib.tensor_table(self.state_dict())
             h = C.c_void_p()
             d = self._desc()
-            _lib.check(_lib.lib().bfsr_unet_create(C.byref(h), C.byref(d), table, len(table), key))
+            d.precision = int(self.precision)
+            _lib.check(_lib.lib().bfsr_unet_create(C.byref(h), C.byref(d), table, len(table), dev_i))
             del keep
             self._handles[key] = h
         return self._handles[key]

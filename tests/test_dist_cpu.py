@@ -61,3 +61,8 @@ def test_bucket_by_scale_balances_every_scale_over_ranks():
             assert max(sizes) - min(sizes) <= 1                      # every rank gets (almost) the same count of every scale
         assert sorted(i for v in seen.values() for i in v) == list(range(256))
     assert bucket_by_scale([4, 4, 2], 4, 3) == {}                     # more ranks than images of any scale
+    # remainders rotate over the ranks: 5 buckets of 9 images on 8 ranks -> nobody holds more than one extra image
+    scales = [[2, 3, 4, 6, 8][i % 5] for i in range(45)]
+    per_rank = [bucket_by_scale(scales, 8, r) for r in range(8)]
+    assert sorted(i for b in per_rank for v in b.values() for i in v) == list(range(45))
+    assert max(sum(len(v) for v in b.values()) for b in per_rank) == 6

@@ -248,6 +248,29 @@ def test_conv_tap_folded_small_cout(lib, cout, H, W, act):
     assert rel_l2(ref, y) < 2e-5
 
 
+@pytest.mark.parametrize("impl", [5, 6, 7])
+@pytest.mark.parametrize("cin,cout,H,W,act", [(64, 32, 16, 30, 1), (96, 32, 17, 23, 1), (160, 32, 33, 61, 2), (64, 12, 20, 24, 3),
+                                             (64, 24, 16, 16, 3), (64, 24, 9, 95, 0), (128, 32, 40, 40, 1), (64, 8, 5, 31, 0),
+                                             (80, 16, 12, 64, 0)])
+def test_conv_dx_folded(lib, cin, cout, H, W, act, impl):
+    """3x3 convs with <= 32 output channels evaluated with the three dx taps folded into N (one MMA per filter row over a
+    raster of pitch 32, shift-add by warp shuffles): fp32 output (5), BF16X2 output through the 30-pixel TMA store box (6),
+    bf16 single-pass mode (7).  Sizes cover ragged tiles in both directions, Cin % 32 != 0 and a block stride of 16 / 32."""
+    g = torch.Generator().manual_seed(cin * 1000 + cout + H)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if act == 3:
+        ref = ref.clone(); ref[:, 1::2] = torch.sigmoid(ref[:, 1::2] + 2.0) + 1e-4
+    else:
+        ref = {0: lambda t: t, 1: lambda t: F.leaky_relu(t, 0.2), 2: F.relu}[act](ref)
+    y = torch.empty(2, cout, H, W, device="cuda")
+    x_d = x.cuda()
+    lib.check(lib.lib().bfsr_op_conv2d(x_d.data_ptr(), 2, cin, H, W, w.data_ptr(), b.data_ptr(), cout, 3, act, impl, y.data_ptr(), None))
+    assert rel_l2(ref, y) < {5: 2e-5, 6: 2.5e-5, 7: 1e-2}[impl]
+
+
 def test_full_size_roundtrip_and_chunk_independence():
     """BASELINE config-2 geometry (shipped topology nb=23, K=16, L=3; 160x160 LR tiles): size-independent properties at full
     size -- decode(encode(x)) == x (P2), results independent of how the batch is chunked (bit-equal), finite LP output."""
