@@ -290,6 +290,23 @@ def main():
                "kind": "port", "sample": f"1 of {B} tiles ({S}x{S} LR), literal reference work, {dt:.1f} s",
                "parity_rel_l2_vs_gpu": rel}
 
+    # ---- parity of this very run against the UNMODIFIED reference: tile 0 of rank 0's batch is the tile recorded in
+    # tests/golden/srflow_full160.npz by oracle/make_golden_r2.py (stride-4 grid of the reference's SR output, pre-clamp)
+    ref_parity = None
+    if rank == 0 and B >= 1 and S == LR_SIZE:
+        try:
+            import numpy as np
+            g = np.load(os.path.join(ROOT, "tests", "golden", "srflow_full160.npz"))
+            ref_s4 = torch.from_numpy(g["sr_s4"]).double()
+            got_s4 = sr[:1, :, ::4, ::4].cpu().double()
+            rel = float((got_s4 - ref_s4).norm() / ref_s4.norm())
+            a, b = got_s4.clamp(0, 1), ref_s4.clamp(0, 1)
+            mse = float(((a - b) ** 2).mean())
+            ref_parity = {"rel_l2_preclamp": rel, "psnr_db_clamped": (float("inf") if mse == 0 else -10.0 * __import__("math").log10(mse)),
+                          "fixture": "tests/golden/srflow_full160.npz (reference run of tile 0, stride-4 grid)"}
+        except Exception as e:     # fixture missing: say so instead of inventing a number
+            ref_parity = {"unavailable": repr(e)}
+
     if rank == 0:
         print(json.dumps({
             "metric": "HR Mpixels/sec, SRFlow-LP 4x LP inference (160x160 LR tiles)", "value": value, "unit": "HR-Mpix/s",
@@ -304,7 +321,7 @@ def main():
             "alg_tflop_per_step": ALG_FLOP_PER_LR_PX * B * S * S / 1e12,
             "path_tensor_roofline_frac": (ALG_FLOP_PER_LR_PX * B * S * S / (ms * 1e-3) / 1e12) / peaks["tflops"],
             "workspace_gb": L.bfsr_srflow_workspace_bytes(net.handle()) / 1e9,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity_vs_reference": ref_parity,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -102,3 +102,38 @@ def test_linf_mixed_scale_batch_bucketing():
     for r in range(2):
         halves.update(models.lp_sr_mixed(model, prior, lr, scales, world=2, rank=r))
     assert sorted(halves) == [0, 1, 2, 3, 4] and all(rel_l2(full[i], halves[i]) < 1e-6 for i in range(5))
+
+
+# ------------------------------------------------------------------ round-2 pins (oracle/make_golden_r2.py)
+def test_linf_build_inputs_vs_reference_wrappers():
+    """b7 on the device: bfsr_linf_build_inputs against items of the reference's OWN dataset wrappers (recorded by
+    oracle/make_golden_r2.py from SRImplicitPairedFastPatch / SRImplicitDownsampledFastPatchTest): coord / cell / inp bit for
+    bit, the bilinear residual patches to fp32 rounding."""
+    from bfsr_b200 import models
+    from tests.test_oracle_linf import wrapper_cases
+    n = 0
+    for i, paired, h, w, s, lr01, coord, cell, gt, hw in wrapper_cases():
+        inp, d_coord, d_cell, d_gt, d_hw = models.build_inputs(lr01[None].cuda(), s, 3, paired)
+        assert tuple(d_hw) == hw, (i, d_hw, hw)
+        assert torch.equal(inp[0].cpu(), (lr01 - 0.5) / 0.5)
+        assert torch.equal(d_coord[0].cpu(), coord), i
+        assert torch.equal(d_cell[0].cpu(), cell), i
+        assert d_gt[0].shape == gt.shape and max_abs(gt, d_gt[0]) < 2e-6, i
+        n += 1
+    assert n >= 10
+
+
+@pytest.mark.parametrize("name", ["linf_edsr_real_x4_48", "linf_rrdb_real_x6", "linf_rrdb_real_x8"])
+def test_linf_config_shapes_vs_reference(name):
+    """BASELINE config 3 geometry (48x48 LR, q = 65, B = 2, shipped EDSR weights) and the config-5 scales 6 / 8 with the shipped
+    rrdb-linf.pth: inputs built on the device from the wrapper's LR, whole LP path, against the reference's recorded output."""
+    from bfsr_b200 import models
+    from tests.test_oracle_linf import load_case_r2
+    g, enc, sd, psd, lr01, s, paired, inp, coord, cell, gt, hw = load_case_r2(name)
+    model, prior = _engines(enc, sd, psd)
+    z_lr = models.batched_predict_log_p(model, inp, coord, cell, gt)
+    assert rel_l2(g["z_lr"], z_lr) < 1e-4
+    d_inp, d_coord, d_cell, d_gt, d_hw = models.build_inputs(lr01.cuda(), s, 3, paired)
+    fused = model.lp_sr(d_inp, d_coord, d_cell, d_gt, prior, d_hw)
+    assert tuple(d_hw) == tuple(hw)
+    assert rel_l2(g["pred"], fused) < 1e-4 and max_abs(g["pred"], fused) < 1e-3

@@ -352,3 +352,46 @@ def test_cluster_multicast_variant_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_srflow.py"), "-q", "-x", "-m", "gpu",
                         "-k", "not cluster_multicast"], env=env, cwd=root, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ reference-recorded pins at the BASELINE shapes (round 2)
+def test_config2_tile_vs_reference_golden():
+    """BASELINE config 2 geometry: tile 0 of the bench batch (160x160 LR, shipped topology) through the engine -- fused LP path,
+    and encode / prior / decode step by step -- against the values recorded from the UNMODIFIED reference on the same tile."""
+    from tests.test_oracle_golden import check_full160, full160_inputs
+    from bfsr_b200 import models
+    g, t, sd, usd, lr = full160_inputs()
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(sd, strict=True)
+    prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
+    sr = net.lp_sr(lr, prior)
+    assert torch.isfinite(sr).all()
+    check_full160(g, sr.cpu(), tol=1e-4)
+    lr_up = F.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=False)
+    epses = []
+    net(gt=lr_up, lr=lr, reverse=False, epses=epses, add_gt_noise=False)
+    check_full160(g, sr.cpu(), [e.cpu() for e in epses], tol=1e-4)
+
+
+def test_config4_topology_vs_reference_golden():
+    """BASELINE config 4 topology (8x, nb=23, K=16, L=4, two Split2d) on a 40x40 tile: encode, decode(0.9 x latents) and the round
+    trip against the reference's recorded outputs."""
+    from tests.test_oracle_golden import X8K16
+    from tools import synth
+    from bfsr_b200 import models
+    g = golden("srflow_x8_k16")
+    B, h, w, wseed, iseed = [int(v) for v in g["meta"]]
+    t = synth.SRFlowTopo(**X8K16)
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(synth.synth_srflow_state_dict(t, seed=wseed), strict=True)
+    lr = torch.from_numpy(g["lr"])
+    lr_up = F.interpolate(lr, scale_factor=8, mode="bilinear", align_corners=False)
+    epses = []
+    net(gt=lr_up, lr=lr, reverse=False, epses=epses, add_gt_noise=False)
+    assert [list(e.shape) for e in epses] == g["shapes"].tolist()
+    for i, e in enumerate(epses):
+        assert rel_l2(g[f"eps{i}"], e) < 1e-4, i
+    sr, _ = net(lr=lr, reverse=True, epses=[0.9 * torch.from_numpy(g[f"eps{i}"]) for i in range(3)])
+    assert rel_l2(g["sr_s2"], sr[..., ::2, ::2]) < 1e-4 and rel_l2(g["sr_tl"], sr[..., :48, :48]) < 1e-4
+    rt, _ = net(lr=lr, reverse=True, epses=epses)
+    assert max_abs(lr_up, rt) < 1e-3          # the reference's own round trip on this tile: 2.2e-4
