@@ -8,9 +8,12 @@ RRDB encoder, synthetic 160x160 LR tiles, batch 32 per GPU) on 1..8 B200.
     python bench.py --impl reference ...      # the reference algorithm on the host CPU (oracle port, literal work)
 
 One step = one pass of the whole LP path (encoder -> flow forward on bilinear(LR) -> latent normalisation ->
-learned prior -> flow inverse) over one batch of tiles per GPU.  `value` is timed with CUDA events with the LR batch
-already resident in HBM; `e2e` is the same call through the host-buffer C-ABI entry point (pinned host LR in, SR back
-to pinned host memory every step).  Weak scaling: every rank processes its own batch, no collective in the data path.
+learned prior -> flow inverse) over the batch.  `value` is timed with CUDA events with the LR batch already resident in
+HBM; `e2e` is the same call through the host-buffer C-ABI entry point (pinned host LR in, SR back to pinned host memory
+every step).  Scaling: the default is STRONG -- the global batch of 32 tiles is split over the ranks with
+`bfsr_b200.dist.shard_range` (32/N tiles per GPU, 4 at N = 8), no collective in the data path; the same run also times the
+WEAK case (32 tiles per GPU) and reports it under `weak`.  `--scaling weak` swaps the two.  `--gather` adds the optional
+final NCCL gather of the SR tiles to rank 0 inside the timed region.
 """
 from __future__ import annotations
 
@@ -156,6 +159,8 @@ def main():
     ap.add_argument("--tile-chunk", type=int, default=0)
     ap.add_argument("--precision", type=int, default=int(os.environ.get("BFSR_PRECISION", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--gather", action="store_true", help="time the optional final gather of the SR tiles to rank 0 (NCCL) too")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,7 +197,14 @@ def main():
     net = models.define_Flow(t.opt(), device=dev, tile_chunk=args.tile_chunk, precision=args.precision)
     net.load_state_dict(sd, strict=True)
     prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
-    lr_host = synth.img(B, S, S, 1234 + 2 + rank).pin_memory()
+    from bfsr_b200.dist import gather_tiles, shard_range
+    # the global batch (rank 0's seed, so tile 0 is the tile of the reference fixture) and this rank's share of it
+    lr_global = synth.img(B, S, S, 1234 + 2)
+    lo, hi = shard_range(B, world, rank) if args.scaling == "strong" else (0, B)
+    if args.scaling == "weak" and rank:
+        lr_global = synth.img(B, S, S, 1234 + 2 + rank)
+    B_local = hi - lo
+    lr_host = lr_global[lo:hi].contiguous().pin_memory()
     lr = lr_host.to(dev)
     L = _lib.lib()
 
@@ -208,28 +220,53 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    def timed(x, steps, gather=False):
+        """max over ranks of the CUDA-event time of `steps` passes over x, bracketed by barrier + synchronize"""
+        out = None
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = net.lp_sr(x, prior)
+            if gather and world > 1:
+                gather_tiles(out, B if args.scaling == "strong" else B * world, dst=0)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
     # ---- device-resident timing
     for _ in range(warm):
         sr = net.lp_sr(lr, prior)
+        if args.gather and world > 1:
+            gather_tiles(sr, B if args.scaling == "strong" else B * world, dst=0)
     barrier()
     L.bfsr_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            sr = net.lp_sr(lr, prior)
-        e1.record()
-        barrier()
+        ms, sr = timed(lr, args.steps, gather=args.gather)
     launches = int(L.bfsr_launch_count(0))
-    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = cs.summary()
-    hr_px = B * (SCALE * S) ** 2
-    value = world * hr_px / (ms * 1e-3) / 1e6
+    tiles_job = B if args.scaling == "strong" else B * world
+    value = tiles_job * (SCALE * S) ** 2 / (ms * 1e-3) / 1e6
     assert torch.isfinite(sr).all()
+    # the other scaling mode in the same run (N > 1 only; at N = 1 they coincide)
+    other = None
+    if world > 1:
+        if args.scaling == "strong":
+            x2 = synth.img(B, S, S, 1234 + 2 + rank).to(dev)        # weak: 32 tiles per GPU
+            tiles2 = B * world
+        else:
+            l2, h2 = shard_range(B, world, rank)
+            x2 = synth.img(B, S, S, 1234 + 2)[l2:h2].contiguous().to(dev)
+            tiles2 = B
+        for _ in range(2):
+            net.lp_sr(x2, prior)
+        ms2, _ = timed(x2, args.steps)
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "value": tiles2 * (SCALE * S) ** 2 / (ms2 * 1e-3) / 1e6,
+                 "unit": "HR-Mpix/s", "ms_per_step": ms2, "global_batch": tiles2, "tiles_per_gpu": tiles2 // world}
+        del x2
 
     # ---- end to end through the host-buffer C-ABI entry point
-    out_host = torch.empty((B, 3, SCALE * S, SCALE * S), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((B_local, 3, SCALE * S, SCALE * S), dtype=torch.float32).pin_memory()
     net.lp_sr_host(lr_host, prior, out=out_host)
     barrier()
     t0 = time.perf_counter()
@@ -237,8 +274,8 @@ def main():
         net.lp_sr_host(lr_host, prior, out=out_host)     # returns after SR is in host memory
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e = {"value": world * hr_px / (e2e_ms * 1e-3) / 1e6, "unit": "HR-Mpix/s",
-           "h2d_bytes_per_step": lr_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+    e2e = {"value": tiles_job * (SCALE * S) ** 2 / (e2e_ms * 1e-3) / 1e6, "unit": "HR-Mpix/s",
+           "h2d_bytes_per_step": lr_host.numel() * 4 * world, "d2h_bytes_per_step": out_host.numel() * 4 * world,
            "ms_per_step": e2e_ms}
 
     # ---- per-kernel-class device time of one more step (CUDA events around every launch, on the launching stream)
@@ -287,7 +324,7 @@ def main():
         got = sr[:1].cpu().double()
         rel = float((got - ref.double()).norm() / ref.double().norm())
         cpu = {"value": (SCALE * S) ** 2 / dt / 1e6, "unit": "HR-Mpix/s", "cores": torch.get_num_threads(),
-               "kind": "port", "sample": f"1 of {B} tiles ({S}x{S} LR), literal reference work, {dt:.1f} s",
+               "kind": "port", "sample": f"1 of {tiles_job} tiles ({S}x{S} LR), literal reference work, {dt:.1f} s",
                "parity_rel_l2_vs_gpu": rel}
 
     # ---- parity of this very run against the UNMODIFIED reference: tile 0 of rank 0's batch is the tile recorded in
@@ -311,17 +348,17 @@ def main():
         print(json.dumps({
             "metric": "HR Mpixels/sec, SRFlow-LP 4x LP inference (160x160 LR tiles)", "value": value, "unit": "HR-Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
-            "config": {"workload": f"SRFlow-LP 4x RRDB(nb=23,K=16,L=3) {S}x{S} LR tiles, batch {B} per GPU, synthetic weights",
-                       "global_batch": B * world, "precision_mode": {0: "fp32-accurate (split-bf16 x3 on tcgen05, fp32 accumulate)", 1: "bf16-fast", 2: "fp32 CUDA cores"}[args.precision],
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
+            "config": {"workload": f"SRFlow-LP 4x RRDB(nb=23,K=16,L=3) {S}x{S} LR tiles, global batch {tiles_job}, synthetic weights",
+                       "global_batch": tiles_job, "tiles_per_gpu": B_local, "gather_in_timed_region": bool(args.gather and world > 1), "precision_mode": {0: "fp32-accurate (split-bf16 x3 on tcgen05, fp32 accumulate)", 1: "bf16-fast", 2: "fp32 CUDA cores"}[args.precision],
                        "l2": "per-step working set (tens of GB of activations) >> 126 MB L2, no flush needed",
                        "parallelism": f"dp{world} (independent tiles, no data-path collective)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_flowstep": flow_roof,
             "kernel_classes_ms_per_step": {k: round(v["ms"], 3) for k, v in cls.items()},
-            "alg_tflop_per_step": ALG_FLOP_PER_LR_PX * B * S * S / 1e12,
-            "path_tensor_roofline_frac": (ALG_FLOP_PER_LR_PX * B * S * S / (ms * 1e-3) / 1e12) / peaks["tflops"],
+            "alg_tflop_per_step": ALG_FLOP_PER_LR_PX * tiles_job * S * S / 1e12,
+            "path_tensor_roofline_frac": (ALG_FLOP_PER_LR_PX * tiles_job * S * S / world / (ms * 1e-3) / 1e12) / peaks["tflops"],
             "workspace_gb": L.bfsr_srflow_workspace_bytes(net.handle()) / 1e9,
-            "cpu_baseline": cpu, "parity_vs_reference": ref_parity,
+            "cpu_baseline": cpu, "parity_vs_reference": ref_parity, "weak" if args.scaling == "strong" else "strong": other,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -82,6 +82,8 @@ SYMBOLS = {
     "bfsr_op_conv2d_hi_lo": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_conv2d_up2": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "bfsr_op_squeeze2d": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "bfsr_op_flowstep": (C.c_int, [C.POINTER(Tensor), _I, C.c_char_p, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P]),
+    "bfsr_op_split2d": (C.c_int, [C.POINTER(Tensor), _I, C.c_char_p, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
 }
 
 

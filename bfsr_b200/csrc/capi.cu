@@ -12,6 +12,10 @@ void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode, const float* lr, con
 void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n);
 std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s);
 View run_unet_linf(bfsr_unet* u, Arena& A, const View& x, const float* lr_nchw, int h, int w, cudaStream_t s);
+void op_flowstep(const bfsr_tensor_t* weights, int n, const char* prefix, int C, bool coupling, bool reverse, const float* z_nchw,
+                 const float* ft_nchw, int B, int H, int W, float* out_nchw, int reps, cudaStream_t s);
+void op_split2d(const bfsr_tensor_t* weights, int n, const char* prefix, int C, bool reverse, const float* z_nchw, const float* eps_nchw,
+                int B, int H, int W, float* out_z, float* out_eps, cudaStream_t s);
 void linf_build(bfsr_linf* e, const bfsr_tensor_t* weights, int n);
 void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* feat_out, cudaStream_t s);
 void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh,
@@ -275,6 +279,27 @@ int bfsr_linf_build_inputs(const float* lr01_dev, int32_t B, int32_t lr_h, int32
 }
 
 // ------------------------------------------------------------------ single operators
+int bfsr_op_flowstep(const bfsr_tensor_t* weights, int32_t n_weights, const char* prefix, int32_t C, int32_t coupling, int32_t reverse,
+                     const float* z_dev, const float* ft_dev, int32_t B, int32_t H, int32_t W, float* out_dev, int32_t precision,
+                     int32_t reps, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(weights && prefix && z_dev && out_dev && (!coupling || ft_dev), "null argument");
+  BFSR_CHECK(C > 0 && C % 4 == 0 && B > 0 && H > 0 && W > 0, "bad shape");
+  const int saved = g_conv_mode;
+  g_conv_mode = precision;
+  try { op_flowstep(weights, n_weights, prefix, C, coupling != 0, reverse != 0, z_dev, ft_dev, B, H, W, out_dev, reps, (cudaStream_t)stream); }
+  catch (...) { g_conv_mode = saved; throw; }
+  g_conv_mode = saved;
+  API_END
+}
+int bfsr_op_split2d(const bfsr_tensor_t* weights, int32_t n_weights, const char* prefix, int32_t C, int32_t reverse, const float* z_dev,
+                    const float* eps_dev, int32_t B, int32_t H, int32_t W, float* out_z_dev, float* out_eps_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(weights && prefix && z_dev && out_z_dev && (reverse ? eps_dev != nullptr : out_eps_dev != nullptr), "null argument");
+  BFSR_CHECK(C > 0 && C % 2 == 0 && B > 0 && H > 0 && W > 0, "bad shape");
+  op_split2d(weights, n_weights, prefix, C, reverse != 0, z_dev, eps_dev, B, H, W, out_z_dev, out_eps_dev, (cudaStream_t)stream);
+  API_END
+}
 int bfsr_op_conv2d(const float* x_dev, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w_host,
                    const float* bias_host, int32_t Cout, int32_t ks, int32_t act, int32_t impl, float* y_dev,
                    void* stream) {

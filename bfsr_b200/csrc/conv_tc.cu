@@ -56,8 +56,8 @@ constexpr int PROD_WARPS = 8, NPROD = PROD_WARPS * 32;
 // warp per scheduler cannot hide its own ALU latency and made every small-K conv epilogue-bound), MMA issuer A, weight
 // loader, TMA loader for A, MMA issuer B = 12 warps.  Register-producer variant (fp32 / upsampled / phase inputs): 4 epilogue
 // warps, MMA issuer A, weight loader, 8 producer warps, MMA issuer B = 15 warps.
-template <bool TMA_IN> struct Roles {
-  static constexpr int EPI_WARPS = TMA_IN ? BFSR_EPI_WARPS : 4;
+template <bool TMA_IN, int EW = BFSR_EPI_WARPS> struct Roles {
+  static constexpr int EPI_WARPS = TMA_IN ? EW : 4;
   static constexpr int W_MMA = EPI_WARPS, W_WPROD = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
   static constexpr int N_PROD = TMA_IN ? 1 : PROD_WARPS;
   static constexpr int W_MMAB = W_PROD0 + N_PROD;                    // first of the extra MMA issuing warps
@@ -66,8 +66,8 @@ template <bool TMA_IN> struct Roles {
 };
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr int STG_WARP = 4096;               // epilogue staging per warp: 32 pixel rows x 128 B
-constexpr int STG_BYTES = BFSR_EPI_WARPS * STG_WARP;
-constexpr int BIAS_BYTES = BFSR_EPI_WARPS * 128 * 4;        // per-epilogue-warp copy of the cout tile's bias
+constexpr int stg_bytes(int ew) { return ew * STG_WARP; }
+constexpr int bias_bytes(int ew) { return ew * 128 * 4; }   // per-epilogue-warp copy of the cout tile's bias
 constexpr int FLOW_BYTES = (24 * 24 + 32) * 4;   // channel-mix matrix + offset vector of a fused FlowStep (C <= 24)
 constexpr int MAXI = 10;                     // (pixel, 8-channel) items a producer thread prefetches per chunk
 }  // namespace tc
@@ -237,21 +237,40 @@ __device__ __forceinline__ void store_split(const View& v, long long pix, int c,
 }
 
 // FlowStep on one pixel (one lane): h = accumulator row after bias + cross-sigmoid; Ms / cs = mix matrix and vector in smem
+// operands of the step that do not depend on the conv: fetched BEFORE the wait for the accumulator, so the global-load latency hides
+// behind the MMAs (with two to four epilogue warps per scheduler it was fully exposed: 63 % long-scoreboard stalls in this code)
 template <int C>
-__device__ __forceinline__ void flow_epilogue(const FlowEpi& f, const float* h, const float* Ms, const float* cs, long long pix) {
+__device__ __forceinline__ void flow_prefetch(const FlowEpi& f, long long pix, float4* zq, float4* hq) {
+  const float4* zp = reinterpret_cast<const float4*>((const float*)f.z_in.p + pix * f.z_in.cs + f.z_in.coff);
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) zq[k] = __ldg(zp + k);
+  if (f.hF.p) {
+    const float4* fp = reinterpret_cast<const float4*>((const float*)f.hF.p + pix * f.hF.cs + f.hF.coff);
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) hq[k] = __ldg(fp + k);
+  }
+}
+// divisions by the coupling scales: sigmoid(.) + 1e-4 lies in [1e-4, 1.0001], far inside the range where the fast division is
+// accurate to 2 ulp (the reference divides in fp32 too: FlowAffineCouplingsAblation.py:85,92)
+template <int C>
+__device__ __forceinline__ void flow_epilogue(const FlowEpi& f, const float* h, const float* Ms, const float* cs, long long pix,
+                                              const float4* zq = nullptr, const float4* hq = nullptr) {
   float z[C], o[C];
   const float4* zp = reinterpret_cast<const float4*>((const float*)f.z_in.p + pix * f.z_in.cs + f.z_in.coff);
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) { const float4 v = __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+  for (int k = 0; k < C / 4; ++k) { const float4 v = zq ? zq[k] : __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
 #pragma unroll
   for (int j = 0; j < C / 2; ++j) {
-    if (f.inv) z[C / 2 + j] = z[C / 2 + j] / h[2 * j + 1] - h[2 * j];
+    if (f.inv) z[C / 2 + j] = __fdividef(z[C / 2 + j], h[2 * j + 1]) - h[2 * j];
     else z[C / 2 + j] = (z[C / 2 + j] + h[2 * j]) * h[2 * j + 1];
   }
   const float4* fp = reinterpret_cast<const float4*>((const float*)f.hF.p + pix * f.hF.cs + f.hF.coff);
   if (f.inv && f.hF.p) {
 #pragma unroll
-    for (int k = 0; k < C / 2; ++k) { const float4 v = __ldg(fp + k); z[2 * k] = z[2 * k] / v.y - v.x; z[2 * k + 1] = z[2 * k + 1] / v.w - v.z; }
+    for (int k = 0; k < C / 2; ++k) {
+      const float4 v = hq ? hq[k] : __ldg(fp + k);
+      z[2 * k] = __fdividef(z[2 * k], v.y) - v.x; z[2 * k + 1] = __fdividef(z[2 * k + 1], v.w) - v.z;
+    }
   }
   if (f.has_mix) {
 #pragma unroll
@@ -267,7 +286,7 @@ __device__ __forceinline__ void flow_epilogue(const FlowEpi& f, const float* h, 
     }
     if (!f.inv && f.hF.p) {
 #pragma unroll
-      for (int k = 0; k < C / 2; ++k) { const float4 v = __ldg(fp + k); o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
+      for (int k = 0; k < C / 2; ++k) { const float4 v = hq ? hq[k] : __ldg(fp + k); o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w; }
     }
   } else {
 #pragma unroll
@@ -327,10 +346,18 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
 // stream -- on neighbouring spatial tiles: each CTA fetches half of every weight stage and multicasts it into both shared
 // memories, and a stage is recycled when the MMAs of BOTH CTAs have retired.  Halves the L2 -> SM weight traffic of the
 // convs whose 0.8 MB-per-tile weight stream binds them (level-1 phase convs).  Everything else is per CTA as for CL = 1.
-template <bool TMA_IN, int CL = 1>
-__global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+// EW = epilogue warps of the TMA-fed variant (8 or 16).  The convs with little K per output (the z-dependent coupling convs, the 1x1
+// convs, the dx-folded heads) are bound by their epilogue's instruction LATENCY -- ncu (profiles/r2_coupling_l1_summary.md): 19 % of
+// the warp slots occupied, 'wait' / 'short scoreboard' stalls, tensor pipe 11-22 %, DRAM 30-59 % -- so they run with four warps per
+// TMEM lane quarter instead of two.
+template <bool TMA_IN, int CL = 1, int EW = BFSR_EPI_WARPS>
+__global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
-  using R = Roles<TMA_IN>;
+  using R = Roles<TMA_IN, EW>;
+  constexpr int STG_BYTES = stg_bytes(TMA_IN ? EW : BFSR_EPI_WARPS), BIAS_BYTES = bias_bytes(TMA_IN ? EW : BFSR_EPI_WARPS);
+  // the 16-warp instantiation has 96 registers per thread: it carries only the epilogues of the convs that use it (no tap folding,
+  // no C = 24 FlowStep, no residual / fp32 pre-activation / second-output passes; launch_tc checks the same conditions)
+  constexpr bool LEAN = EW == 16;
   static_assert(CL == 1 || (CL == 2 && TMA_IN), "clusters: TMA-fed variant only");
   // persistent tile walk: CL = 1 strides the tile list by the grid; CL = 2 strides the PAIR list by the cluster count
   // (macros, not hoisted constants: the CL = 1 loops stay on the uniform datapath exactly as before)
@@ -523,9 +550,12 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     float* bias_s = reinterpret_cast<float*>(smem_gen + (bars + 256 - base)) + warp * 128;
     int cur_ct = -1, t_it = 0;
     // stage one 32-pixel x 32-channel block of this warp and launch its bulk store (out and out2 share the two buffers)
+    TR_DECL(tr_stw = 0, tr_stg = 0, tr_ld = 0, tr_math = 0);
     auto stage_store = [&](const View& v, const CUtensorMap* tm, const float* o, int ncol, int c0, int x0, int y0, int n) {
+      TR_T(trs0);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has drained the buffer
       __syncwarp();
+      TR_ADD(tr_stw, trs0); TR_T(trs1);
       unsigned char* buf = stg_gen;
       if (v.fmt == F32) {
 #pragma unroll
@@ -556,6 +586,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
         else { tma_store_5d(tm, src, v.coff + c0, x0, y0, n, 0); tma_store_5d(tm, src + 2048, v.coff + c0, x0, y0, n, 1); }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      TR_ADD(tr_stg, trs1);
     };
     auto direct_store = [&](const View& v, long long p, int co, const float4& o) {
       if (v.fmt == F32) *reinterpret_cast<float4*>((float*)v.p + p * v.cs + v.coff + co) = o;
@@ -574,11 +605,21 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
         __syncwarp();
       }
+      // dx-folded head with a fused FlowStep: this warp's (single) M tile of the work tile is known now -- fetch z / hF early
+      float4 zq[LEAN ? 3 : 6], hq[LEAN ? 6 : 12];
+      const bool pf = TMA_IN && a.fold == 2 && a.flow.C && a.mt <= N_GRP && grp < a.mt;
+      if (pf) {
+        const int gy = tcd.ty0 + 4 * grp + q, gx = tcd.tx0 + lane;
+        if (lane < 30 && gy < a.H && gx < a.W) {
+          const long long p = ((long long)tcd.n * a.H + gy) * a.W + gx;
+          if (LEAN || a.flow.C == 12) flow_prefetch<12>(a.flow, p, zq, hq); else flow_prefetch<LEAN ? 12 : 24>(a.flow, p, zq, hq);
+        }
+      }
       TR_T(tr0);
       mbar_wait_relaxed(acc_full + 8 * as, (t_it / a.nacc) & 1);
       TR_ADD(tr_wait, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (TMA_IN && a.fold == 1) {
+      if (TMA_IN && !LEAN && a.fold == 1) {
         // ---- tap-folded conv: TMEM holds u[halo row][tap*Cout + co]; shift-add the nine taps through a shared-memory
         // accumulator (fixed tap order, block barriers between taps: deterministic), then bias / activation / FlowStep
         const int Cc = a.cout, P = a.pitch, nrows = a.pitch * a.hrows;
@@ -671,7 +712,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           }
           if (a.act == ACT_CROSS_SIGMOID) {
 #pragma unroll
-            for (int i = 1; i < 32; i += 2) acc[i] = 1.f / (1.f + expf(-(acc[i] + 2.f))) + a.eps;
+            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + expf(-(acc[i] + 2.f))) + a.eps;
           } else if (a.act == ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
@@ -681,8 +722,8 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           }
           if (a.flow.C) {
             if (valid) {
-              if (a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
-              else flow_epilogue<24>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+              if (LEAN || a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p, pf ? zq : nullptr, pf ? hq : nullptr);
+              else flow_epilogue<LEAN ? 12 : 24>(a.flow, acc, flow_s, flow_s + 24 * 24, p, pf ? zq : nullptr, pf ? hq : nullptr);
             }
           } else if (a.tma_out) {
             if (gy < a.H) stage_store(a.out, &a.tmap_out, acc, (a.cout + 7) & ~7, 0, tcd.tx0, gy, tcd.n);   // box = 32 channels x 30 pixels x 1 row
@@ -717,6 +758,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
         {
           const int ncol = nt - n0 < 32 ? 16 : 32;
           float acc[32];
+          TR_T(trl0);
           tmem_ld16(t_row + n0, acc);
           if (ncol == 32) tmem_ld16(t_row + n0 + 16, acc + 16);
           if (a.wide) {
@@ -729,6 +771,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           } else {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
+          TR_ADD(tr_ld, trl0); TR_T(trm0);
           // The fused epilogue runs as a few whole-row passes with warp-uniform branches around them (a per-group
           // formulation costs ~2000 issue slots per 32x32 block and made every small-K conv epilogue-bound).
           const int ng = ncol >> 2;                        // 4-channel groups in this block; Cout % 4 == 0 (eligibility)
@@ -739,7 +782,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + 4 * k);
               acc[4 * k] += b4.x; acc[4 * k + 1] += b4.y; acc[4 * k + 2] += b4.z; acc[4 * k + 3] += b4.w;
             }
-          if (a.pre.p) {
+          if (!LEAN && a.pre.p) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               if (k < ng && co0 + 4 * k < a.cout) {
@@ -749,7 +792,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           }
           if (a.act == ACT_CROSS_SIGMOID) {                // co0 % 4 == 0: the odd channels are the scales
 #pragma unroll
-            for (int i = 1; i < 32; i += 2) acc[i] = 1.f / (1.f + expf(-(acc[i] + 2.f))) + a.eps;
+            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + expf(-(acc[i] + 2.f))) + a.eps;
           } else if (a.act == ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
@@ -761,7 +804,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] *= a.alpha;
           }
-          if (a.res1.p) {
+          if (!LEAN && a.res1.p) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               if (k < ng && co0 + 4 * k < a.cout) {
@@ -770,7 +813,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
                 acc[4 * k + 2] = fmaf(a.beta1, t4.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(a.beta1, t4.w, acc[4 * k + 3]);
               }
           }
-          if (a.res2.p) {
+          if (!LEAN && a.res2.p) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               if (k < ng && co0 + 4 * k < a.cout) {
@@ -779,10 +822,11 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
                 acc[4 * k + 2] = fmaf(a.beta2, t4.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(a.beta2, t4.w, acc[4 * k + 3]);
               }
           }
+          TR_ADD(tr_math, trm0);
           if (TMA_IN && a.flow.C) {   // fused FlowStep: the conv output (shift, scale pairs) is consumed here and never stored
             if (valid) {
-              if (a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
-              else flow_epilogue<24>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+              if (LEAN || a.flow.C == 12) flow_epilogue<12>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
+              else flow_epilogue<LEAN ? 12 : 24>(a.flow, acc, flow_s, flow_s + 24 * 24, p);
             }
             continue;
           }
@@ -798,7 +842,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
           // phase outputs: the map strides over every second pixel, the box starts at the phase's own (fy, fx) offset
           const int ox = a.phase ? 2 * sx0 + (tcd.ph & 1) : sx0, oy = a.phase ? 2 * (sy0 + 4 * q) + (tcd.ph >> 1) : sy0 + 4 * q;
           if (a.tma_out) stage_store(a.out, &a.tmap_out, acc, ncol, co_base + n0, ox, oy, tcd.n);
-          if (a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, ox, oy, tcd.n);
+          if (!LEAN && a.tma_out2) stage_store(a.out2, &a.tmap_out2, acc, ncol, co_base + n0, ox, oy, tcd.n);
         }
         }
       }
@@ -809,7 +853,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN>::NTHREADS, 1) conv_tc_kernel
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores of this warp have completed
     __syncwarp();
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d)\n", clock64() - tr_start, tr_wait, tr_work, t_it);
+    if (blockIdx.x == 0 && tid == 0) printf("[tc trace] epilogue: total %lld wait_acc_full %lld work %lld (tiles %d) | tmem_ld %lld math %lld store_wait %lld stage+issue %lld\n", clock64() - tr_start, tr_wait, tr_work, t_it, tr_ld, tr_math, tr_stw, tr_stg);
 #endif
   } else if (warp == R::W_MMA || (warp >= R::W_MMAB && warp < R::W_MMAB + R::N_ISS_MAX - 1)) {
     // ===================== MMA issuers: whole warp walks the (uniform) loop, one elected lane issues =====================
@@ -1165,7 +1209,7 @@ static int g_num_sms = 0;
 // phase = true : out (N,2H,2W) (+)= conv3x3(nearest2x(in)) evaluated on the LOW-RES grid as four 2x2 phase convs with
 //                pre-summed weights (exact in real arithmetic, 16/36 of the MACs); `in` is the low-res tensor.
 static void launch_tc(const ConvW& w, const View& in, const View& out, const ConvEpi& epi, int in_mode, int phase, cudaStream_t s,
-                      const View* in2 = nullptr, int fold = 0) {
+                      const View* in2 = nullptr, int fold = 0, bool allow16 = true) {
   using namespace tc;
   BFSR_CHECK(w.w_tc, "conv_tc: weights not packed for the tcgen05 path");
   BFSR_CHECK(in.C + (in2 ? in2->C : 0) == w.cin && out.C == w.cout && in.N == out.N, "conv_tc: shape mismatch");
@@ -1194,6 +1238,14 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // three products as separate N = NT MMAs into the same columns (same MMA time, half the TMEM -> two accumulator stages)
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
   a.wide = (!a.fast && fold != 1 && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
+  // sixteen epilogue warps for the epilogue-latency-bound convs: TMA-fed, few (chunk, tap) MMA groups per output tile (see
+  // conv_tc_kernel); the geometry below must then give at least four (sub-tile, 32-channel block) items per work tile
+  static const int ew16_maxk = getenv("BFSR_TC_EW16_MAXK") ? atoi(getenv("BFSR_TC_EW16_MAXK")) : 0;
+  const bool tma_in = in.fmt == BF16X2 && in_mode == IN_DIRECT && phase != 1;
+  const int k_steps = w.tc_kchunks * (fold == 2 ? 3 : w.ks * w.ks) + (pre_gemm ? w.tc_n_id : 0);
+  bool ew16 = allow16 && tma_in && !a.fast && phase == 0 && fold != 1 && k_steps <= ew16_maxk && a.n_ct == 1 && !epi.res1 && !epi.res2 && !epi.out2 &&
+              (!epi.pre || pre_gemm) && (!epi.flow || epi.flow->C == 12);
+  if (ew16 && fold == 2 && a.nt <= 64) a.wide = 0;                   // 3*cb columns per M tile: four M tiles in two stages
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
   int mt = 256 / sub_cols; mt = mt >= 4 ? 4 : (mt >= 2 ? 2 : 1);      // two accumulator stages whenever they fit
   static const int mt_cap = getenv("BFSR_TC_MT_MAX") ? atoi(getenv("BFSR_TC_MT_MAX")) : 4;
@@ -1230,7 +1282,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
                epi.alpha == 1.f && (epi.flow || out_ok(out)), "conv_tc(dx-fold): unsupported epilogue / operand combination");
     // raster of pitch 32: M tile = 4 image rows of 32 positions (30 valid outputs each); the halo tile adds one row above / below
     static const int f3_mt = getenv("BFSR_F3_MT") ? atoi(getenv("BFSR_F3_MT")) : 0;
-    a.mt = mt >= 2 ? 2 : 1;
+    a.mt = ew16 ? mt : (mt >= 2 ? 2 : 1);
     if (f3_mt == 4 && 4 * sub_cols <= 512) a.mt = 4;
     while (a.mt > 1 && 4 * (a.mt - 1) >= gH) --a.mt;              // small images: no M tile entirely below the image
     a.sx = 1; a.sy = a.mt;
@@ -1296,12 +1348,15 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   for (int cand : {9, 4, 3, 2}) if (a.ntaps % cand == 0 && cand * a.w_slot <= 48 * 1024) { a.tps = cand; break; }
   a.w_stage = a.tps * a.w_slot;
   a.na = 2;
-  const int fixed = a.na * a.a_slot + 1024 + STG_BYTES + 256 + BIAS_BYTES + (epi.flow ? FLOW_BYTES : 0);
+  ew16 = ew16 && a.mt * (fold == 2 ? 1 : cdiv(a.nt > a.cout ? a.cout : a.nt, 32)) >= 4;
+  const int ew = ew16 ? 16 : BFSR_EPI_WARPS;
+  const int fixed = a.na * a.a_slot + 1024 + stg_bytes(ew) + 256 + bias_bytes(ew) + (epi.flow ? FLOW_BYTES : 0);
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
     a.tps = next; a.w_stage = a.tps * a.w_slot; a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   }
+  if (a.nw < 2 && ew16) { launch_tc(w, in, out, epi, in_mode, phase, s, in2, fold, false); return; }   // 16-warp geometry does not fit: 8 warps
   BFSR_CHECK(a.nw >= 2, "conv_tc: no room for two weight stages");
   // weight-stationary when the whole set fits next to two A slots (tiny-K convs re-streamed as many weight bytes per tile
   // from L2 as activations: the z-dependent coupling conv moved 5.9 TB/s L2->SM under ncu)
@@ -1365,7 +1420,10 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold == 2 ? "-f3" : fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
-  if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
+  if (a.tma && ew16) {
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    conv_tc_kernel<true, 1, 16><<<grid, Roles<true, 16>::NTHREADS, smem, s>>>(a);
+  } else if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
   else conv_tc_kernel<false><<<grid, Roles<false>::NTHREADS, smem, s>>>(a);
   count_launch();
 }

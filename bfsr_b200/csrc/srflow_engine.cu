@@ -483,6 +483,130 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
 
 }  // namespace bfsr
 
+// ===================================================================== single modules (P1 parity tests, profiling harness)
+namespace bfsr {
+
+static void pack_coupling(const Weights& W, const std::string& p, int C, int Hd, LayerW& l, ConvW& fF0, ConvW& fA0ft) {
+  const int Cn = C / 2, Cc = C - Cn;
+  fF0 = pack_conv_actnorm(W, p + ".affine.fFeatures.0", Hd, 320, 3, {}, true);
+  std::vector<int> ftmap(320); for (int i = 0; i < 320; ++i) ftmap[i] = Cn + i;
+  fA0ft = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, ftmap, true);
+  const int Cnp = (Cn + 7) & ~7;
+  std::vector<int> zmap(Cnp, -1); for (int i = 0; i < Cn; ++i) zmap[i] = i;
+  l.cp.fA0z = pack_conv_actnorm(W, p + ".affine.fAffine.0", Hd, Cn + 320, 3, zmap, /*with_bias=*/false, /*tc_min_cin=*/1);
+  l.cp.fF2 = pack_conv_actnorm(W, p + ".affine.fFeatures.2", Hd, Hd, 1, {}, true);
+  l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
+  l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
+  l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
+}
+
+// One FlowStep of the reference (FlowStep.py:88-129) through exactly the kernels the engine uses for that step: the feature-only
+// convs, the z-dependent affine net, and the step kernel / fused conv epilogue.  `reps` > 1 repeats the z-dependent part (the
+// per-step cost inside a level) for profiling.
+void op_flowstep(const bfsr_tensor_t* weights, int n, const char* prefix, int C, bool coupling, bool reverse, const float* z_nchw,
+                 const float* ft_nchw, int B, int H, int Wd, float* out_nchw, int reps, cudaStream_t s) {
+  Weights W(weights, n);
+  const std::string p = prefix;
+  bfsr_srflow e; memset(&e.d, 0, sizeof e.d); e.d.hidden = 64; e.d.scale = 4; e.d.L = 1;
+  const int Hd = 64;
+  LayerW l; l.kind = coupling ? 2 : 1; l.C = C; l.level = 1; l.k_in_level = 0;
+  l.step = pack_step(W, p, C, coupling);
+  ConvW fF0, fA0ft;
+  if (coupling) pack_coupling(W, p, C, Hd, l, fF0, fA0ft);
+  e.layers.push_back(l);     // owned (and freed) by e
+  Arena& A = e.arena;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.plan = pass == 0; A.reset();
+    if (pass == 1) A.reserve(A.peak + (1 << 20));
+    Run r{&e, s, A, B, H, Wd};
+    View z = make_view(A, B, H, Wd, C), zo = make_view(A, B, H, Wd, C), zo2 = make_view(A, B, H, Wd, C);
+    K_(nchw_to_nhwc(z_nchw, z, s));
+    View hF, ft;
+    r.bufA.assign(2, View()); r.hF.assign(2, {});
+    if (coupling) {
+      View ftf = make_view(A, B, H, Wd, 320);
+      ft = make_view(A, B, H, Wd, 320, r.opfmt());
+      K_(nchw_to_nhwc(ft_nchw, ftf, s));
+      K_(resample(ftf, ft, RS_COPY, s));
+      View bufF = make_view(A, B, H, Wd, Hd, r.opfmt()), t = make_view(A, B, H, Wd, Hd, r.opfmt());
+      r.bufA[1] = make_view(A, B, H, Wd, Hd, fp32_z() ? (int)F32 : r.opfmt());
+      hF = make_view(A, B, H, Wd, 2 * C);
+      ConvEpi relu; relu.act = ACT_RELU;
+      ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
+      K_(conv2d(fF0, ft, bufF, relu, IN_DIRECT, s));
+      K_(conv2d(fA0ft, ft, r.bufA[1], ConvEpi(), IN_DIRECT, s));
+      K_(conv2d(l.cp.fF2, bufF, t, relu, IN_DIRECT, s));
+      K_(conv2d(l.cp.fF4, t, hF, cs, IN_DIRECT, s));
+      r.hF[1].push_back(hF);
+    }
+    LevelBufs lb; lb.alloc(r, H, Wd, C);
+    const LayerW& L = e.layers[0];
+    for (int it = 0; it < (reps > 0 ? reps : 1); ++it) {
+      if (!reverse) {
+        const bool emit_z1 = coupling && z1_fused(r);
+        K_(flowstep_fwd(L.step, z, false, nullptr, coupling ? &hF : nullptr, zo, s, emit_z1 ? &lb.z1op : nullptr));
+        if (coupling && flow_fused(r, C)) {
+          FlowEpi f; f.inv = 0; f.C = C; f.z_in = zo; f.z_out = zo2; f.has_mix = 0;
+          run_affine_net(r, L, zo, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h, &f);
+        } else if (coupling) {
+          run_affine_net(r, L, zo, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h);
+          K_(coupling_finish(zo, lb.h, zo2, s));
+        } else K_(resample(zo, zo2, RS_COPY, s));
+      } else {
+        if (coupling && flow_fused(r, C)) {
+          FlowEpi f; f.inv = 1; f.C = C; f.z_in = z; f.z_out = zo2; f.has_mix = 1; f.M = L.step.Mi; f.cvec = L.step.ci; f.hF = hF;
+          run_affine_net(r, L, z, lb.z1op, false, lb.t1, lb.t2, lb.h, &f);
+        } else if (coupling) {
+          run_affine_net(r, L, z, lb.z1op, false, lb.t1, lb.t2, lb.h);
+          K_(flowstep_inv(L.step, z, &lb.h, &hF, zo2, false, s, nullptr));
+        } else K_(flowstep_inv(L.step, z, nullptr, nullptr, zo2, false, s, nullptr));
+      }
+    }
+    K_(nhwc_to_nchw(zo2, out_nchw, s));
+  }
+  CUDA_OK(cudaStreamSynchronize(s));
+  free_conv(fF0); free_conv(fA0ft);
+  CUDA_OK(cudaGetLastError());
+}
+
+// Split2d of the reference (Split.py:49-77) through the engine's kernels.  forward: z (C) -> z1 (C - cons), eps (cons);
+// reverse: z1, eps -> z.
+void op_split2d(const bfsr_tensor_t* weights, int n, const char* prefix, int C, bool reverse, const float* z_nchw, const float* eps_nchw,
+                int B, int H, int Wd, float* out_z, float* out_eps, cudaStream_t s) {
+  Weights W(weights, n);
+  const int cons = (int)std::lround(C * 0.5), pass = C - cons;
+  ConvW cw = pack_conv_zeros(W, std::string(prefix) + ".conv", 2 * cons, pass);
+  Arena A;
+  try {
+    for (int ps = 0; ps < 2; ++ps) {
+      A.plan = ps == 0; A.reset();
+      if (ps == 1) A.reserve(A.peak + (1 << 20));
+      View hs = make_view(A, B, H, Wd, 2 * cons);
+      if (!reverse) {
+        View z = make_view(A, B, H, Wd, C), z1 = make_view(A, B, H, Wd, pass), eps = make_view(A, B, H, Wd, cons);
+        if (!A.plan) {
+          nchw_to_nhwc(z_nchw, z, s);
+          conv2d_fp32(cw, z.slice(0, pass), hs, ConvEpi(), IN_DIRECT, s);
+          split_fwd(z, hs, z1, eps, s);
+          nhwc_to_nchw(z1, out_z, s); nhwc_to_nchw(eps, out_eps, s);
+        }
+      } else {
+        View z1 = make_view(A, B, H, Wd, pass), eps = make_view(A, B, H, Wd, cons), zo = make_view(A, B, H, Wd, C);
+        if (!A.plan) {
+          nchw_to_nhwc(z_nchw, z1, s); nchw_to_nhwc(eps_nchw, eps, s);
+          conv2d_fp32(cw, z1, hs, ConvEpi(), IN_DIRECT, s);
+          split_inv(z1, hs, eps, zo, s);
+          nhwc_to_nchw(zo, out_z, s);
+        }
+      }
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { free_conv(cw); throw; }
+  free_conv(cw);
+}
+
+}  // namespace bfsr
+
 // ===================================================================== UNet prior (defined in unet_engine.cu)
 namespace bfsr {
 std::vector<View> run_unet_srflow(bfsr_unet* u, Arena& A, const std::vector<View>& lat, cudaStream_t s);

@@ -203,6 +203,17 @@ int bfsr_metric_ssim_uniform(const float* img1_dev, const float* img2_dev, int32
  * channels: stride-2 parity planes); Chi, Clo multiples of 32; operands stored as bf16 (hi, lo) planes, split-bf16 x3. */
 int bfsr_op_conv2d_hi_lo(const float* xhi_dev, const float* xlo_dev, int32_t B, int32_t Chi, int32_t Clo, int32_t H, int32_t W,
                          const float* w_host, const float* bias_host, int32_t Cout, int32_t act, float* y_dev, void* stream);
+/* One FlowStep of the reference (FlowStep.normal_flow / reverse_flow, FlowStep.py:88-129: ActNorm, InvertibleConv1x1,
+ * CondAffineSeparatedAndCond) through the kernels the engine runs for that step.  `weights` is a state_dict table holding the
+ * keys `<prefix>.actnorm.*`, `<prefix>.invconv.weight` and, for a coupling step, `<prefix>.affine.*`; z (B,C,H,W), ft
+ * (B,320,H,W, ignored without coupling) and out (B,C,H,W) are NCHW device buffers.  reps > 1 repeats the step (profiling). */
+int bfsr_op_flowstep(const bfsr_tensor_t* weights, int32_t n_weights, const char* prefix, int32_t C, int32_t coupling, int32_t reverse,
+                     const float* z_dev, const float* ft_dev, int32_t B, int32_t H, int32_t W, float* out_dev, int32_t precision,
+                     int32_t reps, void* stream);
+/* Split2d (Split.py:49-77, ft = None).  forward: z (B,C,H,W) -> out_z = z1 (B,C-C/2,..), out_eps (B,C/2,..);
+ * reverse: z = z1, eps -> out_z (B,C,H,W).  Keys `<prefix>.conv.{weight,bias,logs}`. */
+int bfsr_op_split2d(const bfsr_tensor_t* weights, int32_t n_weights, const char* prefix, int32_t C, int32_t reverse, const float* z_dev,
+                    const float* eps_dev, int32_t B, int32_t H, int32_t W, float* out_z_dev, float* out_eps_dev, void* stream);
 /* flow.squeeze2d / unsqueeze2d (flow.py:122-152) */
 int bfsr_op_squeeze2d(const float* x_dev, int32_t B, int32_t C, int32_t H, int32_t W, int32_t reverse, float* y_dev,
                       void* stream);

@@ -6,6 +6,7 @@ exist on the GPU box).  Test infrastructure: nothing under bfsr_b200/ imports th
     python -m oracle.make_golden_r2 srflow160    # SRFlow-LP config-2 tile (160x160 LR, shipped topology), strided record
     python -m oracle.make_golden_r2 srflow_x8    # config-4 topology (8x, K=16, L=4, nb=23) encode / decode on a 40x40 tile
     python -m oracle.make_golden_r2 flowstep     # P1: single FlowStep / Split2d modules of the reference, both directions
+    python -m oracle.make_golden_r2 srflow_x8_lp # config 4 LP path: reference SRFlowNet + three-branch prior built from the reference's blocks
 
 Large outputs are recorded on a stride (every 4th pixel) plus full-resolution corner / centre crops: every recorded value
 is an output of the reference itself, and the GPU tests compare the same positions of the engine's output.
@@ -219,6 +220,82 @@ def golden_srflow_x8():
           out["roundtrip_maxabs"], "bytes", os.path.getsize(path))
 
 
+def ref_block_prior(ref_unet, latent_ch, depth=3, dim=64):
+    """The reference's SRFlow-LP UNet (unet.py:109-181) generalised from its hard-coded two latents (6 / 96 channels, :117-118,
+    :151-152) to one branch per latent, built from the reference's OWN blocks (DenseBlock_5C, DoubleConv, Down, Up, OutConv,
+    unet.py:10-107) under the reference's attribute names -- a documented extension: the reference cannot run config 4's prior."""
+    import torch.nn as nn
+
+    class UNetN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.depth = depth
+            for b, nf in enumerate(latent_ch):
+                setattr(self, f"input_proj{b}", ref_unet.DenseBlock_5C(nf=nf, gc=dim, out_dim=dim, bias=True))
+                down, up = nn.ModuleList(), nn.ModuleList()
+                for i in range(depth):
+                    down.append(ref_unet.Down(dim * 2 ** i, dim * 2 ** (i + 1) // (2 if i == depth - 1 else 1)))
+                for i in range(depth):
+                    up.append(ref_unet.Up(dim * 2 ** (depth - i), dim * 2 ** (depth - i - 1) // (2 if i < depth - 1 else 1), True))
+                setattr(self, f"down_layers{b}", down); setattr(self, f"up_layers{b}", up)
+                setattr(self, f"inc{b}", ref_unet.DoubleConv(dim, dim))
+                setattr(self, f"outc{b}", ref_unet.OutConv(dim, nf))
+            self.n = len(latent_ch)
+
+        def forward(self, epses):
+            out = []
+            for b in range(self.n):
+                z = getattr(self, f"inc{b}")(getattr(self, f"input_proj{b}")(epses[b]))
+                feats = [z]
+                for layer in getattr(self, f"down_layers{b}"):
+                    z = layer(z); feats.append(z)
+                for idx, layer in enumerate(getattr(self, f"up_layers{b}")):
+                    z = layer(z, feats[self.depth - 1 - idx])
+                out.append(getattr(self, f"outc{b}")(z))
+            return out
+
+    return UNetN()
+
+
+def golden_srflow_x8_lp():
+    """BASELINE config 4, whole LP path on one 40x40 tile: the reference's SRFlowNet (8x, L=4, nb=23, K=8) + the three-branch prior built
+    from the reference's blocks (`ref_block_prior`): encode -> normalise -> prior -> decode (test.py:135-148)."""
+    from tools import synth
+    networks, ref_models, option = _ref_srflow()
+    from models import unet as ref_unet
+    torch.set_num_threads(8)
+    # K = 8: with UNTRAINED synthetic weights the 64-step inverse of K = 16 overflows for any non-zero prior output (probed: NaN even
+    # at 0.1 x the prior's latents; exact zeros give |SR| ~ 70), the 32-step one stays finite.  K = 16 encode / decode: srflow_x8_k16.
+    topo = synth.SRFlowTopo(scale=8, L=4, K=8)
+    net = networks.define_Flow(option.dict_to_nonedict(topo.opt()), 0)
+    net.load_state_dict(synth.synth_srflow_state_dict(topo, seed=31), strict=True)
+    net.eval()
+    lat_ch = (6, 12, 192)
+    prior = ref_block_prior(ref_unet, lat_ch)
+    usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(latent_ch=lat_ch), seed=32)
+    prior.load_state_dict(usd, strict=True)
+    prior.eval()
+    lr = synth.img(1, 40, 40, 231)
+    with torch.no_grad():
+        lr_up = F.interpolate(lr, scale_factor=8, mode="bilinear", align_corners=False)
+        epses_lr = []
+        net(gt=lr_up, lr=lr, reverse=False, epses=epses_lr, add_gt_noise=False)
+        epses = [e.detach() for e in epses_lr]
+        for i in range(len(epses)):
+            mean = torch.mean(epses[i], dim=[1], keepdim=True)
+            std = torch.std(epses[i], dim=[1], keepdim=True)
+            epses[i] = (epses[i] - mean) / (std + 1e-8)
+        learned = prior(epses)
+        sr, _ = net(lr=lr, z=None, eps_std=None, reverse=True, epses=learned, reverse_with_grad=True)
+    out = {"meta": np.array([1, 40, 40, 31, 231, 32], dtype=np.int64), "sr_s2": strided(sr, 2), "sr_tl": sr[..., :48, :48].numpy()}
+    for i, e in enumerate(learned):
+        out[f"learned{i}_s2"] = strided(e, 2)
+    path = os.path.join(GOLD, "srflow_x8_lp.npz")
+    np.savez_compressed(path, **out)
+    print("srflow_x8_lp sr range", float(sr.min()), float(sr.max()), "finite", bool(torch.isfinite(sr).all()), "learned std",
+          [float(e.std()) for e in learned], "bytes", os.path.getsize(path))
+
+
 def module_inputs(idx, C, H, W, split=False):
     """Seeded inputs of the module-level cases (regenerated by the tests, not stored): z, and ft (320 ch) or eps."""
     g = torch.Generator().manual_seed(1000 + idx)
@@ -287,4 +364,4 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else ""
     os.makedirs(GOLD, exist_ok=True)
     {"wrappers": golden_wrappers, "linf": golden_linf_r2, "srflow160": golden_srflow160, "srflow_x8": golden_srflow_x8,
-     "flowstep": golden_flowstep}.get(which, lambda: sys.exit(__doc__))()
+     "flowstep": golden_flowstep, "srflow_x8_lp": golden_srflow_x8_lp}.get(which, lambda: sys.exit(__doc__))()
