@@ -108,6 +108,7 @@ struct TcArgs {
                                          // image row of 32 positions, 30 of them valid outputs): 3x fewer MMAs of 3x the width -- the
                                          // small-N floor of the MMA (A operand read from shared memory, ~40 clk) is paid once per dy
   int cb;                                // fold = 2: accumulator column stride of a dx block (16 or 32)
+  int stg_bytes;                         // epilogue staging bytes in shared memory (0: the epilogue never stages, e.g. dx-folded head + FlowStep)
   int tile_w, tile_h;                    // output pixels of a macro tile (fold 1: 16x16 or 14x14; fold 2: 30 x 4*mt; else 8*sx x 16*sy)
   FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
   View in2;                              // phase 2: hi-res part of the input (BF16X2); n_pre: the pre-activation tensor
@@ -354,7 +355,7 @@ template <bool TMA_IN, int CL = 1, int EW = BFSR_EPI_WARPS>
 __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   using R = Roles<TMA_IN, EW>;
-  constexpr int STG_BYTES = stg_bytes(TMA_IN ? EW : BFSR_EPI_WARPS), BIAS_BYTES = bias_bytes(TMA_IN ? EW : BFSR_EPI_WARPS);
+  constexpr int BIAS_BYTES = bias_bytes(TMA_IN ? EW : BFSR_EPI_WARPS);
   // the 16-warp instantiation has 96 registers per thread: it carries only the epilogues of the convs that use it (no tap folding,
   // no C = 24 FlowStep, no residual / fp32 pre-activation / second-output passes; launch_tc checks the same conditions)
   constexpr bool LEAN = EW == 16;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
   const uint32_t w_smem = base + a.na * a.a_slot;                 // NW slots
   const uint32_t stg_smem = w_smem + a.nw * a.w_stage;            // epilogue staging (1024-aligned: every slot size is)
-  const uint32_t bars = stg_smem + STG_BYTES;                     // mbarriers (8 B each), then the per-warp bias copies
+  const uint32_t bars = stg_smem + (uint32_t)a.stg_bytes;         // mbarriers (8 B each), then the per-warp bias copies
   const uint32_t a_full = bars, a_empty = bars + 8 * NA_MAX, w_full = bars + 16 * NA_MAX, w_empty = w_full + 8 * NW_MAX;
   const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -1236,14 +1237,19 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // 56 @ 96, then N/2 (64 @ 128, 128 @ 256): an MMA narrower than N = 128 is bound by its fixed cost, so NT <= 64 issues
   // A_hi x [W_hi;W_lo] as ONE N = 2NT MMA plus A_lo x W_hi (e.g. NT = 64: 64 + 48 clk instead of 3 x 48); NT > 64 issues the
   // three products as separate N = NT MMAs into the same columns (same MMA time, half the TMEM -> two accumulator stages)
+  // Round 2, measured on the whole step (profiles/r2_step_knobs.md): the three-MMA form is never slower than the wide one and up to
+  // 23 % faster on the small-K convs (z-dependent coupling conv 0.53 -> 0.41 ms, 1x1 0.33 -> 0.29 ms) -- the wide form doubles the
+  // TMEM loads and adds a pass to an epilogue that is the bottleneck there, and halves the sub-tiles per weight stream everywhere
+  // else.  BFSR_TC_WIDE=1 restores the wide form for NT <= 64.
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
-  a.wide = (!a.fast && fold != 1 && (a.nt <= 64 || force_wide == 1) && force_wide != 2) ? 1 : 0;
+  a.wide = (!a.fast && fold != 1 && a.nt <= 64 && force_wide == 1) ? 1 : 0;
   // sixteen epilogue warps for the epilogue-latency-bound convs: TMA-fed, few (chunk, tap) MMA groups per output tile (see
   // conv_tc_kernel); the geometry below must then give at least four (sub-tile, 32-channel block) items per work tile
-  static const int ew16_maxk = getenv("BFSR_TC_EW16_MAXK") ? atoi(getenv("BFSR_TC_EW16_MAXK")) : 0;
+  static const int ew16_maxk = getenv("BFSR_TC_EW16_MAXK") ? atoi(getenv("BFSR_TC_EW16_MAXK")) : 2;
   const bool tma_in = in.fmt == BF16X2 && in_mode == IN_DIRECT && phase != 1;
   const int k_steps = w.tc_kchunks * (fold == 2 ? 3 : w.ks * w.ks) + (pre_gemm ? w.tc_n_id : 0);
-  bool ew16 = allow16 && tma_in && !a.fast && phase == 0 && fold != 1 && k_steps <= ew16_maxk && a.n_ct == 1 && !epi.res1 && !epi.res2 && !epi.out2 &&
+  static const int ew16_flow = getenv("BFSR_TC_EW16_FLOW") ? atoi(getenv("BFSR_TC_EW16_FLOW")) : 1;   // C = 12 heads: 21.3 -> 17.1 ms per step
+  bool ew16 = allow16 && tma_in && !a.fast && phase == 0 && fold != 1 && (k_steps <= ew16_maxk || (ew16_flow && fold == 2 && epi.flow)) && a.n_ct == 1 && !epi.res1 && !epi.res2 && !epi.out2 &&
               (!epi.pre || pre_gemm) && (!epi.flow || epi.flow->C == 12);
   if (ew16 && fold == 2 && a.nt <= 64) a.wide = 0;                   // 3*cb columns per M tile: four M tiles in two stages
   const int sub_cols = a.wide ? 2 * a.nt : a.nt;
@@ -1254,14 +1260,35 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // MMAs: four sub-tiles per weight stream (one accumulator stage, exposed epilogue) trade 12 % of overlap for 31 % less traffic
   static const bool mt4_phase = getenv("BFSR_TC_MT4") && atoi(getenv("BFSR_TC_MT4")) == 1;
   if (mt4_phase && phase == 2 && sub_cols == 128) mt = 4;
-  a.sx = 1; a.sy = 1;
-  if (mt == 4) {
-    if (gW > 8 && gH > 16) { a.sx = 2; a.sy = 2; }
-    else if (gH > 16) { a.sy = 2; }
-    else if (gW > 8) { a.sx = 2; }
-  } else if (mt == 2) {
-    if (gH > 16) a.sy = 2; else if (gW > 8) a.sx = 2;
+  if (!g_num_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  auto arrange = [&](int m, int& sx, int& sy) {          // sub-tile arrangement of a macro tile of m sub-tiles
+    sx = 1; sy = 1;
+    if (m == 4) {
+      if (gW > 8 && gH > 16) { sx = 2; sy = 2; }
+      else if (gH > 16) { sy = 2; }
+      else if (gW > 8) { sx = 2; }
+    } else if (m == 2) {
+      if (gH > 16) sy = 2; else if (gW > 8) sx = 2;
+    }
+  };
+  // Wave quantisation: one CTA per SM walks the tile list, so a launch with 200 tiles takes two rounds of which the second is a
+  // third full (4 tiles of 160x160 per GPU at 8 GPUs: the RDB's conv5 ran at 64 % of its batch-32 efficiency).  Cost model:
+  // rounds x (sub-tiles per tile + 0.6 for the halo / weight stream / fixed cost of a tile); the cheapest macro tile wins, ties go to
+  // the larger one.  Tile shape never changes the arithmetic of an output pixel, so results stay independent of the batch size.
+  if (fold == 2 && !ew16 && mt > 2 && !(getenv("BFSR_F3_MT") && atoi(getenv("BFSR_F3_MT")) == 4)) mt = 2;   // dx-folded: two M tiles per work tile
+  if (fold != 1) {
+    const long long per = (long long)out.N * a.n_ct * (phase ? 4 : 1);
+    int best = mt; double best_cost = 1e300;
+    for (int m = mt; m >= 1; m >>= 1) {
+      long long tiles;
+      if (fold == 2) tiles = (long long)cdiv(gW, 30) * cdiv(gH, 4 * m) * per;
+      else { int sx, sy; arrange(m, sx, sy); tiles = (long long)cdiv(gW, 8 * sx) * cdiv(gH, 16 * sy) * per; }
+      const double cost = (double)((tiles + g_num_sms - 1) / g_num_sms) * (m + 0.6);
+      if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = m; }
+    }
+    mt = best;
   }
+  arrange(mt, a.sx, a.sy);
   a.mt = a.sx * a.sy;
   a.ks = w.ks; a.ntaps = phase ? 4 : w.ks * w.ks; a.halo = w.ks / 2;
   a.fold = fold; a.tile_w = 8 * a.sx; a.tile_h = 16 * a.sy;
@@ -1284,6 +1311,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     static const int f3_mt = getenv("BFSR_F3_MT") ? atoi(getenv("BFSR_F3_MT")) : 0;
     a.mt = ew16 ? mt : (mt >= 2 ? 2 : 1);
     if (f3_mt == 4 && 4 * sub_cols <= 512) a.mt = 4;
+    if (a.mt > mt) a.mt = mt;
     while (a.mt > 1 && 4 * (a.mt - 1) >= gH) --a.mt;              // small images: no M tile entirely below the image
     a.sx = 1; a.sy = a.mt;
     a.tile_w = 30; a.tile_h = 4 * a.mt;
@@ -1350,7 +1378,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.na = 2;
   ew16 = ew16 && a.mt * (fold == 2 ? 1 : cdiv(a.nt > a.cout ? a.cout : a.nt, 32)) >= 4;
   const int ew = ew16 ? 16 : BFSR_EPI_WARPS;
-  const int fixed = a.na * a.a_slot + 1024 + stg_bytes(ew) + 256 + bias_bytes(ew) + (epi.flow ? FLOW_BYTES : 0);
+  a.stg_bytes = (fold == 2 && epi.flow) ? 0 : stg_bytes(ew);       // the dx-folded head with a FlowStep epilogue stores per lane
+  const int fixed = a.na * a.a_slot + 1024 + a.stg_bytes + 256 + bias_bytes(ew) + (epi.flow ? FLOW_BYTES : 0);
   a.nw = (MAX_SMEM - fixed) / a.w_stage; a.nw = a.nw > NW_MAX ? NW_MAX : a.nw;
   while (a.nw < 2 && a.tps > 1) {   // not enough room for double buffering: shrink the stage
     int next = 1; for (int cand : {4, 3, 2}) if (cand < a.tps && a.ntaps % cand == 0) { next = cand; break; }
@@ -1367,7 +1396,10 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     if (!no_res && phase == 0 && fold != 1 && !a.fast && a.n_ct == 1 && fixed + stages_tile * a.w_stage <= MAX_SMEM) { a.w_res = 1; a.nw = stages_tile; }
   }
   // left-over shared memory deepens the A ring (convs with little MMA work per chunk are bound by TMA latency otherwise)
-  static const int na_max = getenv("BFSR_TC_NA") ? atoi(getenv("BFSR_TC_NA")) : NA_MAX;
+  // the dx-folded heads with a FlowStep epilogue keep TWO A slots: their epilogue's own global loads (z, hF) are latency-critical
+  // and queue behind a deeper TMA prefetch (measured 0.62 -> 0.54 ms per level-1 step)
+  static const int na_env = getenv("BFSR_TC_NA") ? atoi(getenv("BFSR_TC_NA")) : 0;
+  const int na_max = na_env ? na_env : ((fold == 2 && epi.flow) ? 2 : NA_MAX);
   while (a.na < na_max && a.na < NA_MAX && fixed + (a.na - 1) * a.a_slot + a.nw * a.w_stage <= MAX_SMEM) ++a.na;
   const int smem = fixed + (a.na - 2) * a.a_slot + a.nw * a.w_stage;
   BFSR_CHECK(smem <= MAX_SMEM, "conv_tc: smem budget exceeded (%d)", smem);
