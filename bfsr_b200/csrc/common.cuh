@@ -15,6 +15,9 @@
 #include <stdio.h>
 #include <string>
 #include <stdexcept>
+#include <map>
+#include <vector>
+#include <functional>
 
 namespace bfsr {
 
@@ -111,5 +114,24 @@ struct ProfScope {
   ProfScope(int kind, double work, cudaStream_t st) : s(st) { prof_begin(kind, work, st); }
   ~ProfScope() { prof_end(s); }
 };
+
+bool prof_enabled();
+
+// ---------------------------------------------------------------- CUDA-graph replay of a fixed launch sequence
+// The engines' plans are static per (shapes, buffers): the second call with the same key captures the launch sequence on an
+// internal stream and later calls replay the instantiated graph on the caller's stream -- one cudaGraphLaunch instead of hundreds
+// of launches, each with its tensor-map encodes (LINF config 3: ~100 launches for ~2 ms of device work; SRFlow at 4 tiles per GPU:
+// ~860 launches per 40 ms step).  BFSR_GRAPH=0 disables it; it is bypassed while the per-launch profiler is on.  A cache belongs
+// to one engine handle (not re-entrant, like the handle) and must be cleared when the handle's arena moves.
+struct GraphCache {
+  struct Entry { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+  std::map<std::vector<long long>, Entry> m;
+  cudaStream_t cap = nullptr;
+  void clear();
+  ~GraphCache();
+};
+bool graphs_enabled();
+// body(stream) must enqueue everything on the given stream and must not synchronise, allocate or free
+void run_graphed(GraphCache& gc, const std::vector<long long>& key, cudaStream_t s, const std::function<void(cudaStream_t)>& body);
 
 }  // namespace bfsr

@@ -94,6 +94,7 @@ struct bfsr_linf {
   float* phase = nullptr;               // (hidden/2, 2)
   float* Mf = nullptr; float* Mi = nullptr; float* fbias = nullptr;   // flow: W_i, W_i^-1, b_i  (index flow_layers = last)
   bfsr::Arena arena;
+  bfsr::GraphCache graphs;
   float* stage_in = nullptr; size_t stage_in_sz = 0;
   ~bfsr_linf();
 };
@@ -107,6 +108,7 @@ struct bfsr_srflow {
   std::vector<bfsr::LevelW> levels;   // index 1..L
   std::vector<int> latent_C, latent_level;
   bfsr::Arena arena;
+  bfsr::GraphCache graphs;
   float* stage_in = nullptr; float* stage_out = nullptr; size_t stage_in_sz = 0, stage_out_sz = 0;
   ~bfsr_srflow();
 };

@@ -157,9 +157,11 @@ static View run_affine_info(bfsr_linf* e, Arena& A, const View& feat, const floa
   return aff;
 }
 
-static void ensure(Arena& A, cudaStream_t s) {
+// grow the arena to the planned peak; returns true when it moved (captured graphs hold its addresses)
+static bool ensure(Arena& A, cudaStream_t s) {
   const size_t need = A.peak + (1 << 20);
-  if (need > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(need); }
+  if (need > A.cap) { CUDA_OK(cudaStreamSynchronize(s)); A.reserve(need); return true; }
+  return false;
 }
 
 void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* feat_out, cudaStream_t s) {
@@ -172,7 +174,7 @@ void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* f
     K_(nchw_to_nhwc(inp, x, s));
     View feat = run_linf_encoder(e, A, x, s);
     K_(nhwc_to_nchw(feat, feat_out, s));
-    if (pass == 0) { A.plan = false; ensure(A, s); }
+    if (pass == 0) { A.plan = false; if (ensure(A, s)) e->graphs.clear(); }
   }
   CUDA_OK(cudaGetLastError());
 }
@@ -190,7 +192,7 @@ void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const
     View aff = run_affine_info(e, A, feat, coord, cell, qh, qw, s);
     if (mode == 0) K_(linf_flow(false, e->Mf, e->fbias, e->d.flow_layers, aff, zin, B, qh, qw, out, 0, 0, nullptr, 0, 0, ps, s));
     else K_(linf_flow(true, e->Mi, e->fbias, e->d.flow_layers, aff, zin, B, qh, qw, out, qh * ps, qw * ps, nullptr, 0, 0, ps, s));
-    if (pass == 0) { A.plan = false; ensure(A, s); }
+    if (pass == 0) { A.plan = false; if (ensure(A, s)) e->graphs.clear(); }
   }
   CUDA_OK(cudaGetLastError());
 }
@@ -227,13 +229,19 @@ void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, 
   A.plan = true; A.peak = 0;
   linf_lp_chunk(e, prior, nullptr, B < chunk ? B : chunk, h, w, nullptr, nullptr, nullptr, qh, qw, OH, OW, nullptr, s);
   A.plan = false;
-  ensure(A, s);
+  if (ensure(A, s)) e->graphs.clear();
   const int D = 3 * e->d.patch_size * e->d.patch_size;
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int nb = B - b0 < chunk ? B - b0 : chunk;
-    linf_lp_chunk(e, prior, inp + (size_t)b0 * 3 * h * w, nb, h, w, coord + (size_t)b0 * qh * qw * 2, cell + (size_t)b0 * 2,
-                  gt + (size_t)b0 * D * qh * qw, qh, qw, OH, OW, pred + (size_t)b0 * 3 * OH * OW, s);
-  }
+  // the launch sequence is fixed by (shapes, buffers, arena, precision): replayed as a CUDA graph from the third identical call on
+  const std::vector<long long> key = {(long long)(uintptr_t)inp, B, h, w, (long long)(uintptr_t)coord, (long long)(uintptr_t)cell,
+                                      (long long)(uintptr_t)gt, qh, qw, OH, OW, (long long)(uintptr_t)pred, (long long)(uintptr_t)prior,
+                                      (long long)(uintptr_t)A.base, g_conv_mode, chunk};
+  run_graphed(e->graphs, key, s, [&](cudaStream_t st) {
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int nb = B - b0 < chunk ? B - b0 : chunk;
+      linf_lp_chunk(e, prior, inp + (size_t)b0 * 3 * h * w, nb, h, w, coord + (size_t)b0 * qh * qw * 2, cell + (size_t)b0 * 2,
+                    gt + (size_t)b0 * D * qh * qw, qh, qw, OH, OW, pred + (size_t)b0 * 3 * OH * OW, st);
+    }
+  });
   CUDA_OK(cudaGetLastError());
 }
 

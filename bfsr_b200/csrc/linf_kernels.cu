@@ -27,10 +27,14 @@ __device__ __forceinline__ int nearest_index(float c, int n) {
   return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
 }
 
-__global__ void __launch_bounds__(128) linf_features_kernel(FeatArgs a) {
-  const long long q = blockIdx.x;
+// One half-block (64 threads) per query; a thread produces channels 2t, 2t+1 of both halves for the four neighbours, so the
+// stores into the BF16X2 operand tensor of the MLP are packed 4-byte words (256-byte runs per plane) instead of 2-byte scalars.
+__global__ void __launch_bounds__(128) linf_features_kernel(FeatArgs a, long long nq) {
+  const long long q = (long long)blockIdx.x * 2 + (threadIdx.x >> 6);
+  if (q >= nq) return;
+  const int tl = threadIdx.x & 63;
   const int half = a.hid / 2;                      // 128
-  const int qx = (int)(q % a.qw); const long long t = q / a.qw; const int qy = (int)(t % a.qh); const int b = (int)(t / a.qh);
+  const long long t = q / a.qw; const int b = (int)(t / a.qh);
   const float cy = a.coord[q * 2 + 0], cx = a.coord[q * 2 + 1];
   const float cell_y = __fmul_rn(a.cell[b * 2 + 0], (float)a.h), cell_x = __fmul_rn(a.cell[b * 2 + 1], (float)a.w);
   float rel_y[4], rel_x[4], area[4]; long long src[4];
@@ -47,20 +51,45 @@ __global__ void __launch_bounds__(128) linf_features_kernel(FeatArgs a) {
     src[nb] = ((long long)b * a.h + iy) * a.w + ix;
   }
   const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
-  (void)qy; (void)qx;
-  for (int k = threadIdx.x; k < half; k += blockDim.x) {
-    const float ph = fmaf(cell_x, a.phase[k * 2 + 1], __fmul_rn(cell_y, a.phase[k * 2 + 0]));
+  const bool packed = a.out.fmt == BF16X2 && a.cf.fmt == F32 && (a.out.coff & 1) == 0 && (a.out.cs & 1) == 0 && (a.cf.coff & 1) == 0 && (a.cf.cs & 1) == 0;
+  for (int k0 = 2 * tl; k0 < half; k0 += 128) {
+    float ph[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) ph[j] = fmaf(cell_x, a.phase[(k0 + j) * 2 + 1], __fmul_rn(cell_y, a.phase[(k0 + j) * 2 + 0]));
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) {
       const float wgt = __fdiv_rn(area[3 - nb], tot);          // diagonal swap (linf.py:305-306)
-      const float fy = ld(a.cf, src[nb], a.hid + k), fx = ld(a.cf, src[nb], a.hid + half + k);
-      const float f = __fadd_rn(__fadd_rn(__fmul_rn(fy, rel_y[nb]), __fmul_rn(fx, rel_x[nb])), ph);
-      const float ang = __fmul_rn(3.14159265358979323846f, f);
-      float sn, cs;
-      sincosf(ang, &sn, &cs);
-      const float c0 = ld(a.cf, src[nb], k), c1 = ld(a.cf, src[nb], half + k);
-      st(a.out, q, nb * a.hid + k, __fmul_rn(__fmul_rn(wgt, c0), cs));
-      st(a.out, q, nb * a.hid + half + k, __fmul_rn(__fmul_rn(wgt, c1), sn));
+      float oc[2], os[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = k0 + j;
+        const float fy = ld(a.cf, src[nb], a.hid + k), fx = ld(a.cf, src[nb], a.hid + half + k);
+        const float f = __fadd_rn(__fadd_rn(__fmul_rn(fy, rel_y[nb]), __fmul_rn(fx, rel_x[nb])), ph[j]);
+        const float ang = __fmul_rn(3.14159265358979323846f, f);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        const float c0 = ld(a.cf, src[nb], k), c1 = ld(a.cf, src[nb], half + k);
+        oc[j] = __fmul_rn(__fmul_rn(wgt, c0), cs);
+        os[j] = __fmul_rn(__fmul_rn(wgt, c1), sn);
+      }
+      if (packed) {
+        __nv_bfloat16* d = (__nv_bfloat16*)a.out.p + q * a.out.cs + a.out.coff;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const float x0 = hsel ? os[0] : oc[0], x1 = hsel ? os[1] : oc[1];
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(x0, x1);
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - __low2float(hi), x1 - __high2float(hi));
+          const int ch = nb * a.hid + hsel * half + k0;
+          *reinterpret_cast<__nv_bfloat162*>(d + ch) = hi;
+          *reinterpret_cast<__nv_bfloat162*>(d + a.out.plane + ch) = lo;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          st(a.out, q, nb * a.hid + k0 + j, oc[j]);
+          st(a.out, q, nb * a.hid + half + k0 + j, os[j]);
+        }
+      }
     }
   }
 }
@@ -78,12 +107,15 @@ void linf_features(const View& cf, const float* coord, const float* cell, const 
   a.two_rx = (float)(2 * (1.0 / a.w)); a.v0_rx = (float)(-1 + 1.0 / a.w);
   const long long nq = (long long)cf.N * qh * qw;
   if (!nq) return;
-  linf_features_kernel<<<(unsigned)nq, 128, 0, s>>>(a);
+  snprintf(g_prof_tag, sizeof g_prof_tag, "linf_features q%dx%d", qh, qw);
+  ProfScope prof(PK_OTHER, (double)nq * out.C * 4.0, s);
+  BFSR_CHECK(a.hid % 4 == 0, "linf_features: hidden width must be a multiple of 4");
+  linf_features_kernel<<<(unsigned)((nq + 1) / 2), 128, 0, s>>>(a, nq);
   count_launch();
 }
 
 // ------------------------------------------------------------------ conditional flow on D-vectors (flow.py:29-63)
-constexpr int FD = 27;
+constexpr int FD = 27, FDP = 28;
 struct FlowArgs {
   const float* M;      // [n_layers+1][D][D]: forward W_i, inverse W_i^-1 ; index n_layers = `last`
   const float* bias;   // [n_layers+1][D]
@@ -95,75 +127,106 @@ struct FlowArgs {
   long long nq;
 };
 
+__device__ __forceinline__ float dot27(const float* w, const float* x, float acc) {   // w: 28 floats, 16-byte aligned, w[27] = 0
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float4 m = *reinterpret_cast<const float4*>(w + 4 * k);
+    acc = fmaf(m.x, x[4 * k], acc); acc = fmaf(m.y, x[4 * k + 1], acc); acc = fmaf(m.z, x[4 * k + 2], acc);
+    if (4 * k + 3 < FD) acc = fmaf(m.w, x[4 * k + 3], acc);
+  }
+  return acc;
+}
+
+// 256 queries per block, two blocks per SM (<= 128 registers): the kernel is bound by instruction latency, so resident warps count
+// (ncu, 128-thread blocks at 168 registers: 12 warps per SM, 16 % issue-slot utilisation)
+constexpr int FLOW_T = 256;
 template <bool INV>
-__global__ void __launch_bounds__(128) linf_flow_kernel(FlowArgs a) {
+__global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
   extern __shared__ float sm[];
-  const int nm = (a.n_layers + 1) * FD * FD;
+  // weight rows padded to FDP = 28 floats: a row is read as seven 16-byte broadcast loads (one shared-memory load per four FMAs
+  // instead of one per FMA -- the flow passes were bound by the load/store pipe)
+  const int nm = (a.n_layers + 1) * FD * FDP;
   float* Ms = sm; float* bs = sm + nm;
-  for (int e = threadIdx.x; e < nm; e += blockDim.x) Ms[e] = a.M[e];
+  for (int e = threadIdx.x; e < nm; e += blockDim.x) { const int r = e / FDP, c = e - r * FDP; Ms[e] = c < FD ? a.M[r * FD + c] : 0.f; }
   for (int e = threadIdx.x; e < (a.n_layers + 1) * FD; e += blockDim.x) bs[e] = a.bias[e];
+  // per-layer affine parameters of the block's 128 queries, staged through shared memory: a query's 2*D values of a layer are
+  // 216 contiguous bytes of a 2160-byte row, so the block reads them as coalesced runs (a thread walking its own row touched a
+  // different cache line per lane and thrashed L1: 2.9 of the 9.6 ms of a config-3 batch went into the two flow passes)
+  constexpr int AP = 2 * FD + 1;                                   // padded row: conflict-free per-thread reads
+  float* As = bs + (a.n_layers + 1) * FD;                          // [FLOW_T][AP]
+  const long long q0 = (long long)blockIdx.x * blockDim.x;
+  const int nrow = (int)((a.nq - q0) < (long long)blockDim.x ? (a.nq - q0) : (long long)blockDim.x);
+  auto load_layer = [&](int i) {
+    __syncthreads();                                               // the previous layer's rows have been consumed
+    const float* base = (const float*)a.aff.p + q0 * a.aff.cs + a.aff.coff + i * 2 * FD;
+    for (int e = threadIdx.x; e < nrow * 2 * FD; e += blockDim.x) {
+      const int r = e / (2 * FD), c = e - r * 2 * FD;
+      As[r * AP + c] = __ldg(base + (long long)r * a.aff.cs + c);
+    }
+    __syncthreads();
+  };
   __syncthreads();
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= a.nq) return;
-  const int qx = (int)(q % a.qw); const long long t = q / a.qw; const int qy = (int)(t % a.qh); const long long b = t / a.qh;
+  const long long q = q0 + threadIdx.x;
+  const bool live = q < a.nq;
+  const long long qq = live ? q : a.nq - 1;                        // idle lanes of the last block follow the barriers on a valid row
+  const int qx = (int)(qq % a.qw); const long long t = qq / a.qw; const int qy = (int)(t % a.qh); const long long b = t / a.qh;
   const long long plane = (long long)a.qh * a.qw;
   float x[FD], y[FD];
 #pragma unroll
   for (int c = 0; c < FD; ++c) x[c] = a.zin[(b * FD + c) * plane + (long long)qy * a.qw + qx];
-  const float* af = (const float*)a.aff.p + q * a.aff.cs + a.aff.coff;
+  const float* af = As + (live ? threadIdx.x : 0) * AP;
   if (!INV) {
     for (int i = 0; i < a.n_layers; ++i) {
-      const float* W = Ms + i * FD * FD;
+      load_layer(i);
+      const float* W = Ms + i * FD * FDP;
 #pragma unroll
       for (int o = 0; o < FD; ++o) {
         float acc = bs[i * FD + o];
-#pragma unroll
-        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        acc = dot27(W + o * FDP, x, acc);
         y[o] = acc;
       }
 #pragma unroll
       for (int c = 0; c < FD; ++c) {
-        const float scale = 1.f / (1.f + expf(-(af[i * 2 * FD + c] + 2.f))) + 1e-4f;
-        x[c] = fmaf(y[c], scale, af[i * 2 * FD + FD + c]);
+        const float scale = __fdividef(1.f, 1.f + expf(-(af[c] + 2.f))) + 1e-4f;
+        x[c] = fmaf(y[c], scale, af[FD + c]);
       }
     }
-    const float* W = Ms + a.n_layers * FD * FD;
+    const float* W = Ms + a.n_layers * FD * FDP;
 #pragma unroll
     for (int o = 0; o < FD; ++o) {
       float acc = bs[a.n_layers * FD + o];
-#pragma unroll
-      for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
-      a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = acc;
+      acc = dot27(W + o * FDP, x, acc);
+      if (live) a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = acc;
     }
   } else {
     {   // last^-1
-      const float* W = Ms + a.n_layers * FD * FD;
+      const float* W = Ms + a.n_layers * FD * FDP;
 #pragma unroll
       for (int c = 0; c < FD; ++c) x[c] -= bs[a.n_layers * FD + c];
 #pragma unroll
       for (int o = 0; o < FD; ++o) {
         float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        acc = dot27(W + o * FDP, x, acc);
         y[o] = acc;
       }
     }
     for (int i = a.n_layers - 1; i >= 0; --i) {
-      const float* W = Ms + i * FD * FD;
+      load_layer(i);
+      const float* W = Ms + i * FD * FDP;
 #pragma unroll
       for (int c = 0; c < FD; ++c) {
-        const float scale = 1.f / (1.f + expf(-(af[i * 2 * FD + c] + 2.f))) + 1e-4f;
-        x[c] = (y[c] - af[i * 2 * FD + FD + c]) / scale - bs[i * FD + c];
+        const float scale = __fdividef(1.f, 1.f + expf(-(af[c] + 2.f))) + 1e-4f;
+        x[c] = __fdividef(y[c] - af[FD + c], scale) - bs[i * FD + c];
       }
 #pragma unroll
       for (int o = 0; o < FD; ++o) {
         float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < FD; ++c) acc = fmaf(W[o * FD + c], x[c], acc);
+        acc = dot27(W + o * FDP, x, acc);
         y[o] = acc;
       }
     }
     // fold 3x3 patches (== pixel_shuffle(3), linf.py:401-406), crop to (OH,OW), add bilinear(inp) (test.py:168-171)
+    if (!live) return;
     const int ps = a.ps;
     for (int c = 0; c < 3; ++c)
       for (int ky = 0; ky < ps; ++ky)
@@ -196,15 +259,17 @@ void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, co
   a.n_layers = n_layers; a.qh = qh; a.qw = qw; a.OH = OH; a.OW = OW; a.h = h; a.w = w; a.ps = ps;
   a.nq = (long long)B * qh * qw;
   if (!a.nq) return;
-  const size_t smem = (size_t)(n_layers + 1) * (FD * FD + FD) * 4;
+  const size_t smem = ((size_t)(n_layers + 1) * (FD * FDP + FD) + FLOW_T * (2 * FD + 1)) * 4;
   BFSR_CHECK(smem <= 227 * 1024, "linf_flow: %d flow layers need %zu bytes of shared memory (limit 227 KB)", n_layers, smem);
   if (smem > 48 * 1024) {   // flow_layers >= 16: opt in to the large carve-out (the shipped models have 10 layers = 33 KB)
     CUDA_OK(cudaFuncSetAttribute(linf_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(linf_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int grid = cdiv(a.nq, 128);
-  if (inverse) linf_flow_kernel<true><<<grid, 128, smem, s>>>(a);
-  else linf_flow_kernel<false><<<grid, 128, smem, s>>>(a);
+  const int grid = cdiv(a.nq, FLOW_T);
+  snprintf(g_prof_tag, sizeof g_prof_tag, "linf_flow-%s q%dx%d", inverse ? "inv" : "fwd", qh, qw);
+  ProfScope prof(PK_OTHER, (double)a.nq * (2.0 * FD * n_layers + 2 * FD) * 4.0, s);
+  if (inverse) linf_flow_kernel<true><<<grid, FLOW_T, smem, s>>>(a);
+  else linf_flow_kernel<false><<<grid, FLOW_T, smem, s>>>(a);
   count_launch();
 }
 

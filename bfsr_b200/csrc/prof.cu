@@ -4,6 +4,7 @@
 #include <map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 namespace bfsr {
 
@@ -27,6 +28,50 @@ void prof_begin(int kind, double work, cudaStream_t s) {
 void prof_end(cudaStream_t s) {
   if (!g_prof_on || g_recs.empty()) return;
   cudaEventRecord(g_recs.back().b, s);
+}
+
+bool prof_enabled() { return g_prof_on; }
+
+// ------------------------------------------------------------------ CUDA-graph replay (see common.cuh)
+bool graphs_enabled() {
+  static const bool on = !(getenv("BFSR_GRAPH") && atoi(getenv("BFSR_GRAPH")) == 0);
+  return on && !g_prof_on;
+}
+void GraphCache::clear() {
+  for (auto& kv : m) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m.clear();
+}
+GraphCache::~GraphCache() { clear(); if (cap) cudaStreamDestroy(cap); }
+
+void run_graphed(GraphCache& gc, const std::vector<long long>& key, cudaStream_t s, const std::function<void(cudaStream_t)>& body) {
+  if (!graphs_enabled()) { body(s); return; }
+  if (gc.m.size() > 16 && !gc.m.count(key)) gc.clear();           // bounded: callers cycling through many shapes just re-capture
+  GraphCache::Entry& e = gc.m[key];
+  if (!e.exec) {
+    if (e.seen < 0 || e.seen++ == 0) { body(s); return; }         // first sight of a key: plain launches (one-off calls never capture)
+    if (!gc.cap) CUDA_OK(cudaStreamCreateWithFlags(&gc.cap, cudaStreamNonBlocking));
+    const long long l0 = g_launches;
+    CUDA_OK(cudaStreamBeginCapture(gc.cap, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t g = nullptr;
+    bool ok = true;
+    static const bool dbg = getenv("BFSR_GRAPH_DEBUG") && atoi(getenv("BFSR_GRAPH_DEBUG"));
+    try { body(gc.cap); } catch (const std::exception& ex) { ok = false; if (dbg) fprintf(stderr, "[bfsr graph] capture body failed: %s\n", ex.what()); }
+    const cudaError_t ce = cudaStreamEndCapture(gc.cap, &g);
+    if (ce != cudaSuccess || !g) { ok = false; if (dbg) fprintf(stderr, "[bfsr graph] end capture: %s\n", cudaGetErrorString(ce)); }
+    else if (dbg) fprintf(stderr, "[bfsr graph] captured %lld launches\n", g_launches - l0);
+    e.launches = g_launches - l0;
+    g_launches = l0;
+    if (ok && cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) { e.exec = nullptr; ok = false; }
+    if (g) cudaGraphDestroy(g);
+    if (!ok) {                                                     // not capturable: this key keeps the plain launches (errors resurface there)
+      cudaGetLastError();
+      e.seen = -1;
+      body(s);
+      return;
+    }
+  }
+  CUDA_OK(cudaGraphLaunch(e.exec, s));
+  g_launches += e.launches;
 }
 
 }  // namespace bfsr

@@ -32,7 +32,7 @@ for _ in range(3):
     out = model.lp_sr(*args, prior, (h * s, w * s))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 5
+n = 20
 e0.record()
 for _ in range(n):
     out = model.lp_sr(*args, prior, (h * s, w * s))
