@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": "HR Mpixels/sec, SRFlow-LP 4x LP inference (160x160 LR tiles)", "value": val,
         "unit": "HR-Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"SRFlow-LP 4x RRDB(nb=23,K=16,L=3) {LR_SIZE}x{LR_SIZE} LR tiles, batch {BATCH} per GPU, synthetic weights",
                    "sample": sample},
         "cpu_baseline": {"value": val, "unit": "HR-Mpix/s", "cores": torch.get_num_threads(), "kind": "port",

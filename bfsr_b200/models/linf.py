@@ -317,3 +317,56 @@ def lp_sr_mixed(model, prior, lr01, scales, world=1, rank=0, always_pad=False):
             out[i] = pred[j]
     return out
 
+
+
+# ---- stand-alone encoders under the reference's registry names (LINF-LP/models/edsr.py:168-181, rrdb.py:119-129) -------------
+class EncoderEngine(nn.Module):
+    """`models.make({'name': 'edsr-baseline' | 'rrdb', 'args': {..., 'no_upsampling': True}})`: the LR encoder of LINF on its own
+    (EDSR.forward edsr.py:134-146 / RRDBNet.forward rrdb.py:105-116, `no_upsampling` variants -- the only ones LINF uses), with the
+    encoder's own state_dict keys and `out_dim`.  Runs the `gen_feat` path of the engine (`bfsr_linf_gen_feat`)."""
+
+    def __init__(self, name, args):
+        super().__init__()
+        s = OrderedDict()
+        _encoder_shapes(s, name, dict(args))
+        param_tree.build(self, OrderedDict((k[len("encoder."):], v) for k, v in s.items()))
+        self._spec = {"name": name, "args": dict(args)}
+        self.out_dim = 64
+        self._inner = None
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._inner = None
+        return r
+
+    def cuda(self, device=None):
+        self._device = device
+        return self
+
+    def forward(self, x):
+        if self._inner is None:
+            inner = LINFEngine(encoder_spec=self._spec, device=getattr(self, "_device", None))
+            sd = inner.state_dict()
+            for k, v in self.state_dict().items():
+                sd["encoder." + k] = v
+            eye = torch.eye(3 * inner.patch_size ** 2)
+            for k in sd:                      # the query side is unused by gen_feat; its flow matrices only have to be invertible
+                if k.endswith("._weight"):
+                    sd[k] = eye.clone()
+            inner.load_state_dict(sd, strict=True)
+            self._inner = inner
+        return self._inner.gen_feat(x)
+
+
+@register('edsr-baseline')
+def make_edsr_baseline(n_resblocks=16, n_feats=64, res_scale=1, scale=2, no_upsampling=False, rgb_range=1):
+    if n_feats != 64 or res_scale != 1 or not no_upsampling:
+        raise NotImplementedError("edsr-baseline: the engine builds the LINF configuration (64 feats, res_scale 1, no_upsampling=True)")
+    return EncoderEngine("edsr-baseline", {"n_resblocks": n_resblocks, "no_upsampling": True})
+
+
+@register('rrdb')
+def make_rrdb(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, no_upsampling=True):
+    if (in_nc, out_nc, nf, gc) != (3, 3, 64, 32) or not no_upsampling:
+        raise NotImplementedError("rrdb: the engine builds the LINF configuration (3->64, gc 32, no_upsampling=True)")
+    return EncoderEngine("rrdb", {"nb": nb, "no_upsampling": True})

@@ -292,6 +292,56 @@ class SRFlowNetEngine(nn.Module):
         return out
 
 
+class SRFlowModel:
+    """The inference surface of the reference's `SRFlowModel` (SRFlow-LP/code/models/SRFlow_model.py:198-237) over the engine:
+    `get_sr`, `get_sr_with_z`, `get_encode_z`, `get_z` with the reference's argument meaning, including its quirks -- the net is
+    left in train() mode after every call (:205,221) and `get_z` reads `netG.module.flowUpsamplerNet.{C,scaleH,scaleW}`
+    (:227-229).  `SRFlow-LP/code/test.py:135-148` runs unchanged on top of it (`model.get_encode_z(...)`, `model.get_sr(...)`).
+    Host glue only: every tensor op is a call into the engine."""
+
+    def __init__(self, opt, step=0, netG=None, **kw):
+        self.opt = opt
+        self.netG = netG if netG is not None else define_Flow(opt, step, **kw)
+
+    def load_network(self, load_path_or_sd, network=None, strict=True, submodule=None):
+        """base_model.load_network (base_model.py:112-124): flat state_dict, `module.` prefixes stripped, optional submodule."""
+        sd = torch.load(load_path_or_sd, map_location="cpu") if isinstance(load_path_or_sd, str) else load_path_or_sd
+        sd = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in sd.items())
+        net = self.netG if network is None else network
+        if submodule is not None:
+            full = net.state_dict()
+            full.update({f"{submodule}.{k}": v for k, v in sd.items()})
+            sd = full
+        net.load_state_dict(sd, strict=strict)
+
+    def get_sr(self, lq, heat=None, seed=None, z=None, epses=None):
+        return self.get_sr_with_z(lq, heat, seed, z, epses)[0]
+
+    def get_encode_z(self, lq, gt, epses=None, add_gt_noise=True):
+        self.netG.eval()
+        with torch.no_grad():
+            z, _, _ = self.netG(gt=gt, lr=lq, reverse=False, epses=epses, add_gt_noise=add_gt_noise)
+        self.netG.train()
+        return z
+
+    def get_sr_with_z(self, lq, heat=None, seed=None, z=None, epses=None):
+        self.netG.eval()
+        z = self.get_z(heat, seed, batch_size=lq.shape[0], lr_shape=lq.shape) if z is None and epses is None else z
+        sr, logdet = self.netG(lr=lq, z=z, eps_std=heat, reverse=True, epses=epses, reverse_with_grad=True)
+        self.netG.train()
+        return sr, z
+
+    def get_z(self, heat, seed=None, batch_size=1, lr_shape=None):
+        if seed:
+            torch.manual_seed(seed)
+        fu = self.netG.module.flowUpsamplerNet
+        H = int(self.opt["scale"] * lr_shape[2] // fu.scaleH)
+        W = int(self.opt["scale"] * lr_shape[3] // fu.scaleW)
+        if heat and heat > 0:
+            return torch.normal(mean=0, std=heat, size=(batch_size, fu.C, H, W))
+        return torch.zeros((batch_size, fu.C, H, W))
+
+
 def define_Flow(opt, step=0, **kw):
     """networks.define_Flow (SRFlow-LP/code/models/networks.py:70-79) returning the engine."""
     n = opt["network_G"]

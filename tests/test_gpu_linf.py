@@ -137,3 +137,38 @@ def test_linf_config_shapes_vs_reference(name):
     fused = model.lp_sr(d_inp, d_coord, d_cell, d_gt, prior, d_hw)
     assert tuple(d_hw) == tuple(hw)
     assert rel_l2(g["pred"], fused) < 1e-4 and max_abs(g["pred"], fused) < 1e-3
+
+
+def test_linf_sampling_mode_temperature():
+    """f1: `query_rgb` without a latent map samples z ~ N(0, temperature^2) (linf.py:398).  temperature = 0 is the decode of the zero
+    latent (checked against the oracle); temperature > 0 is reproducible under the seed and equals the explicit-zmap call."""
+    from oracle import linf_oracle as LO
+    g, enc, sd, psd, inp, coord, cell, gt, hw = load_case("linf_edsr_synth_x4")
+    model, _ = _engines(enc, sd, psd)
+    feat = model("gen_feat", inp=inp)
+    B, qh, qw, _ = coord.shape
+    rgb0 = model("query_rgb", inp=inp, feat=feat, coord=coord, cell=cell, temperature=0)
+    ref0 = LO.query_rgb(sd, LO.gen_feat(sd, enc, inp), coord, cell, torch.zeros(B, 27, qh, qw))
+    assert rel_l2(ref0, rgb0) < 1e-4
+    torch.manual_seed(11)
+    a = model("query_rgb", inp=inp, feat=feat, coord=coord, cell=cell, temperature=0.5)
+    torch.manual_seed(11)
+    zmap = torch.randn((B, 27, qh, qw), device="cuda") * 0.5
+    b = model("query_rgb", inp=inp, feat=feat, coord=coord, cell=cell, zmap=zmap)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["edsr-baseline", "rrdb"])
+def test_standalone_encoders_by_registry_name(name):
+    """`models.make({'name': 'edsr-baseline' | 'rrdb', ...})` (the reference's encoder registry names) equals the oracle's encoder."""
+    from bfsr_b200 import models
+    from oracle import linf_oracle as LO
+    from tools import synth
+    sd = synth.synth_linf_state_dict(synth.linf_param_shapes(name, nb=2) if name == "rrdb" else synth.linf_param_shapes(name), seed=9)
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    args = {"no_upsampling": True} if name == "edsr-baseline" else {"no_upsampling": True, "nb": 2}
+    enc = models.make({"name": name, "args": args, "sd": enc_sd}, load_sd=True).cuda()
+    assert enc.out_dim == 64
+    x = (synth.img(2, 20, 16, 5) - 0.5) / 0.5
+    ref = LO.edsr_forward(sd, x) if name == "edsr-baseline" else LO.rrdb_forward(sd, x, nb=2)
+    assert rel_l2(ref, enc(x)) < 1e-4

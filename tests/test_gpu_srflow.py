@@ -468,3 +468,79 @@ def test_split2d_module_vs_reference(lib):
         assert rel_l2(g[f"l{idx}_zinv"], zo) < 1e-5
         n += 1
     assert n == 1
+
+
+# ------------------------------------------------------------------ a15 / f1: the SRFlowModel surface and the sampling mode
+def test_srflow_model_surface_runs_the_reference_test_loop():
+    """SRFlow-LP/code/test.py:135-148 written against `SRFlowModel` (get_encode_z with an in-place `epses` list, the latent
+    normalisation, `prior_model(epses)`, get_sr(lq, epses=...)) on top of the engine reproduces the reference's recorded SR; the
+    wrapper leaves the net in train() mode like the reference (SRFlow_model.py:205,221) without disturbing the packed weights."""
+    from bfsr_b200 import models
+    t, sd, usd, net, prior = _small()
+    g = golden("srflow_small")
+    model = models.SRFlowModel(t.opt(), netG=net)
+    lr_t = torch.from_numpy(g["lr"])
+    lr_up = F.interpolate(lr_t, scale_factor=4, mode="bilinear", align_corners=False)
+    epses_lr = []
+    model.get_encode_z(lr_t, lr_up, epses=epses_lr, add_gt_noise=False)
+    assert len(epses_lr) == 2 and net.training
+    epses = [e.detach() for e in epses_lr]
+    for i in range(len(epses)):
+        mean = torch.mean(epses[i], dim=[1], keepdim=True)
+        std = torch.std(epses[i], dim=[1], keepdim=True)
+        epses[i] = (epses[i] - mean) / (std + 1e-8)
+    learned = prior(epses)
+    sr_t = model.get_sr(lq=lr_t, epses=learned)
+    assert rel_l2(g["sr"], sr_t) < 1e-4 and net.training
+    z = model.get_z(0.5, seed=3, batch_size=2, lr_shape=lr_t.shape)
+    assert tuple(z.shape) == (2, 96, lr_t.shape[2] // 2, lr_t.shape[3] // 2)
+
+
+def test_sampling_mode_without_prior():
+    """f1: `get_sr(lq, heat=tau)` (SRFlow_model.py:198-237) -- z ~ N(0, tau^2) from get_z, Split2d draws its eps ~ N(0, tau^2)
+    (Split.py:66-68).  heat = 0 equals the oracle's decode of all-zero latents; heat > 0 is reproducible under the seed and equals
+    the decode of the explicitly drawn (eps, z)."""
+    from oracle import srflow_oracle as O
+    from bfsr_b200 import models
+    t, sd, usd, net, prior = _small()
+    model = models.SRFlowModel(t.opt(), netG=net)
+    lr = torch.from_numpy(golden("srflow_small")["lr"])
+    B, _, h, w = lr.shape
+    sr0 = model.get_sr(lr, heat=0)
+    ref0 = O.decode(sd, t, lr, [torch.zeros(B, 6, 2 * h, 2 * w), torch.zeros(B, 96, h // 2, w // 2)])
+    assert rel_l2(ref0, sr0) < 1e-4
+    tau = 0.3
+    sr_a = model.get_sr(lr, heat=tau, seed=5)
+    sr_b = model.get_sr(lr, heat=tau, seed=5)
+    assert torch.isfinite(sr_a).all() and torch.equal(sr_a, sr_b)
+    torch.manual_seed(5)                                           # replay the two draws: z on the host (get_z), eps on the device
+    z = torch.normal(mean=0, std=tau, size=(B, 96, h // 2, w // 2))
+    eps = torch.zeros((B, 6, 2 * h, 2 * w), device="cuda").normal_(0.0, tau)
+    sr_c, _ = net(lr=lr, reverse=True, epses=[eps, z])
+    assert torch.equal(sr_a, sr_c)
+    assert not torch.equal(sr_a, model.get_sr(lr, heat=tau, seed=6))
+
+
+def test_div2k_size_image_in_one_pass():
+    """f3: a full DIV2K-validation-size LR image (339 x 510, odd height -> reflect-padded like test.py:126-130) through
+    `sr_image` in ONE pass: the reference never tiles an image (tiling would change the result at the seams -- the RRDB trunk alone
+    has a receptive field of ~350 LR pixels), and on a 180 GB part the whole-image workspace (about 10 GB) simply fits.  Checked:
+    output geometry, finiteness, the workspace bound, and invertibility at that size."""
+    import ctypes as C
+    from tools import synth
+    from bfsr_b200 import _lib, models
+    t = synth.SRFlowTopo()
+    net = models.define_Flow(t.opt())
+    net.load_state_dict(synth.synth_srflow_state_dict(t, seed=0), strict=True)
+    usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(), seed=1)
+    prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd}, load_sd=True)
+    lr = (synth.img(1, 339, 510, 99)[0].permute(1, 2, 0) * 255).round().to(torch.uint8).numpy()
+    sr = net.sr_image(lr, prior)
+    assert sr.shape == (339 * 4, 510 * 4, 3) and sr.dtype == np.uint8
+    assert _lib.lib().bfsr_srflow_workspace_bytes(net.handle()) < 20e9
+    lr_t = synth.img(1, 340, 510, 98)
+    lr_up = F.interpolate(lr_t, scale_factor=4, mode="bilinear", align_corners=False)
+    epses = []
+    net(gt=lr_up, lr=lr_t, reverse=False, epses=epses, add_gt_noise=False)
+    rt, _ = net(lr=lr_t, reverse=True, epses=epses)
+    assert rel_l2(lr_up, rt) < 1e-4 and max_abs(lr_up, rt) < 5e-3
