@@ -121,6 +121,7 @@ struct TcArgs {
   int w_res;                             // all weight stages fit in smem: loaded once per CTA, never recycled (nw = stages per tile)
   int nacc;                              // TMEM accumulator stages (1 or 2)
   int tiles_x, tiles_y, total_tiles;     // macro tiles per image and total work tiles (incl. cout tiles, batch)
+  uint32_t m_nct, m_tx, m_ty;            // ceil(2^32 / d) for d = n_ct, tiles_x, tiles_y (tile_coord)
   uint32_t tmem_cols;
 };
 
@@ -332,13 +333,18 @@ __device__ __forceinline__ bool elect_one() {
 #endif
 
 struct TileCoord { int n, ty0, tx0, ct, ph; };
+// t / d for the small divisors of the tile walk with a host-computed reciprocal m = ceil(2^32 / d): exact while t * d < 2^32
+// (tile counts stay below 2^20, divisors below 2^12); every warp of the CTA decodes every tile, so the three runtime divisions
+// were ~90 instructions per warp per tile
+__device__ __forceinline__ uint32_t fdiv(uint32_t t, uint32_t m, uint32_t d) { return d == 1 ? t : __umulhi(t, m); }
 __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
   TileCoord c;
-  c.ct = t % a.n_ct; t /= a.n_ct;
+  uint32_t u = (uint32_t)t, qd;
+  qd = fdiv(u, a.m_nct, (uint32_t)a.n_ct); c.ct = (int)(u - qd * a.n_ct); u = qd;
   c.ph = 0;
-  if (a.phase) { c.ph = t & 3; t >>= 2; }
-  const int tx = t % a.tiles_x; t /= a.tiles_x;
-  const int ty = t % a.tiles_y; c.n = t / a.tiles_y;
+  if (a.phase) { c.ph = u & 3; u >>= 2; }
+  qd = fdiv(u, a.m_tx, (uint32_t)a.tiles_x); const int tx = (int)(u - qd * a.tiles_x); u = qd;
+  qd = fdiv(u, a.m_ty, (uint32_t)a.tiles_y); const int ty = (int)(u - qd * a.tiles_y); c.n = (int)qd;
   c.ty0 = ty * a.tile_h; c.tx0 = tx * a.tile_w;
   return c;
 }
@@ -742,11 +748,14 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
       // 32-channel blocks of this cout tile that hold real channels, and the flattened (sub-tile, block) sequence
       const int nblk = min((nt + 31) >> 5, (a.cout - co_base + 31) >> 5);
       const int nb_total = a.mt * nblk;
-      for (int b = grp; b < nb_total; b += N_GRP) {      // the warps sharing a lane quarter take alternate blocks
-        const int sub = b / nblk, n0 = (b - sub * nblk) << 5;
+      int sub = 0, blk = grp;                            // (sub-tile, block) of item b, advanced without divisions
+      for (int b = grp; b < nb_total; b += N_GRP, blk += N_GRP) {      // the warps sharing a lane quarter take alternate blocks
+        while (blk >= nblk) { blk -= nblk; ++sub; }
+        const int n0 = blk << 5;
         {
         const int idx = q * 32 + lane;                     // accumulator row = pixel of the 8 x 16 sub-tile
-        const int sy0 = tcd.ty0 + (sub / a.sx) * 16, sx0 = tcd.tx0 + (sub % a.sx) * 8;
+        const int sub_y = a.sx == 2 ? sub >> 1 : sub, sub_x = a.sx == 2 ? sub & 1 : 0;
+        const int sy0 = tcd.ty0 + sub_y * 16, sx0 = tcd.tx0 + sub_x * 8;
         const int gy = sy0 + (idx >> 3), gx = sx0 + (idx & 7);
         const bool valid = gy < a.H && gx < a.W;
         const long long p = a.phase ? ((long long)tcd.n * 2 * a.H + 2 * gy + (tcd.ph >> 1)) * (2 * a.W) + 2 * gx + (tcd.ph & 1)
@@ -1350,6 +1359,12 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.tmem_cols = cols;
   a.tiles_x = cdiv(gW, a.tile_w); a.tiles_y = cdiv(gH, a.tile_h);
   a.total_tiles = a.tiles_x * a.tiles_y * out.N * a.n_ct * (phase ? 4 : 1);
+  {
+    auto magic = [](int d) { return (uint32_t)((((uint64_t)1 << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    a.m_nct = magic(a.n_ct); a.m_tx = magic(a.tiles_x); a.m_ty = magic(a.tiles_y);
+    BFSR_CHECK((uint64_t)a.total_tiles * (uint64_t)std::max(std::max(a.n_ct, a.tiles_x), a.tiles_y) < ((uint64_t)1 << 32) && a.total_tiles < (1 << 24),
+               "conv_tc: tile count out of range for the reciprocal tile decode");
+  }
   // weight stages: as many taps per stage as fit ~48 KB (fewer barrier round trips on the MMA issue path), 2-4 stages
   a.tps = 1;
   if (a.n_pre) {

@@ -225,12 +225,16 @@ __global__ void __launch_bounds__(256) flowstep_wide_kernel(StepArgs a) {
   float* Mt = sm;                      // [ci][co]
   float* zs = sm + C * C;              // [P][ZP]
   const int tid = threadIdx.x;
-  const long long p0 = (long long)blockIdx.x * P;
   if (a.MT) {     // pre-transposed copy: straight 128-bit copy (a transposing fill is a 32-way bank conflict per store)
     for (int e = tid; e < C * C / 4; e += 256) reinterpret_cast<float4*>(Mt)[e] = __ldg(reinterpret_cast<const float4*>(a.MT) + e);
   } else {
     for (int e = tid; e < C * C; e += 256) { const int co = e / C, ci = e % C; Mt[ci * C + co] = a.M[e]; }
   }
+  // persistent over pixel tiles: the 36 KB mix matrix is staged once per CTA, not once per 64 pixels
+  const long long ntiles = (a.npix + P - 1) / P;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long p0 = tile * P;
+  __syncthreads();                       // the previous tile's phase 2 has finished reading zs
   // ---- phase 1
   for (int e = tid; e < P * C4; e += 256) {
     const int p = e / C4, k = e % C4, c = 4 * k;
@@ -306,6 +310,7 @@ __global__ void __launch_bounds__(256) flowstep_wide_kernel(StepArgs a) {
       }
     }
   }
+  }   // tile loop
 }
 
 static bool vec4_ok(const View& v) {
@@ -352,7 +357,10 @@ static void launch_step(bool inv, const StepW& w, const View& zin, bool sq_in, c
   if (wide_ok) {
     if (z1_ok) { a.z1op = *z1op; z1_done = true; }
     const size_t smem96 = (size_t)(96 * 96 + 64 * 100) * 4;
-    const int g = cdiv(a.npix, 64);
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int tiles = cdiv(a.npix, 64);
+    const int g = tiles < 3 * nsm ? tiles : 3 * nsm;       // three CTAs of 62 KB fit an SM
     if (inv) { CUDA_OK(cudaFuncSetAttribute(flowstep_wide_kernel<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem96));
                flowstep_wide_kernel<96, true><<<g, 256, smem96, s>>>(a); }
     else { CUDA_OK(cudaFuncSetAttribute(flowstep_wide_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem96));

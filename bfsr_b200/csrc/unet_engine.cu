@@ -6,6 +6,7 @@
 // (torch.cat([x2, x1]) at unet.py:96 never materialises), 1x1 OutConv.
 #include "engine.cuh"
 #include <cmath>
+#include <cstring>
 
 using namespace bfsr;
 
@@ -23,6 +24,17 @@ bfsr_unet::~bfsr_unet() {
 }
 
 namespace bfsr {
+
+// OutConv (1x1, dim -> nf) with nf = 6 / 27: padded with zero output channels to a multiple of 8 so that it is a tcgen05 conv with
+// 16-byte addressable output rows (the caller sees the first nf channels of the padded buffer); on the CUDA-core kernel the
+// 64 -> 6 conv at 320x320 cost 1.15 ms per step for 0.13 ms of HBM traffic.
+static ConvW pack_outc(const float* w, const float* b, int nf, int dim) {
+  const int np = (nf + 7) & ~7;
+  std::vector<float> wp((size_t)np * dim, 0.f), bp(np, 0.f);
+  memcpy(wp.data(), w, (size_t)nf * dim * 4); memcpy(bp.data(), b, nf * 4);
+  return pack_conv(wp.data(), np, dim, 1, bp.data(), nullptr, {});
+}
+
 
 // conv (no bias) + BatchNorm2d(eval) : W' = W*g, b' = beta - mean*g, g = gamma/sqrt(var+1e-5)   (unet.py:44-51)
 static ConvW pack_conv_bn(const Weights& W, const std::string& conv, const std::string& bn, int cout, int cin) {
@@ -82,7 +94,7 @@ void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n) {
       const int cin = dim << (depth - i), cout = (dim << (depth - i - 1)) / (i < depth - 1 ? 2 : 1);
       pack_double_conv(W, "up_layers." + std::to_string(i) + ".conv", cin, cin / 2, cout, &B.up[2 * i]);
     }
-    B.outc = pack_conv(W.data("outc.conv.weight", {B.nf, dim, 1, 1}), B.nf, dim, 1, W.data("outc.conv.bias", {B.nf}), nullptr, {});
+    B.outc = pack_outc(W.data("outc.conv.weight", {B.nf, dim, 1, 1}), W.data("outc.conv.bias", {B.nf}), B.nf, dim);
     u->br.push_back(B);
     return;
   }
@@ -102,8 +114,7 @@ void unet_build(bfsr_unet* u, const bfsr_tensor_t* weights, int n) {
       const int cin = dim << (depth - i), cout = (dim << (depth - i - 1)) / (i < depth - 1 ? 2 : 1);
       pack_double_conv(W, "up_layers" + sb + "." + std::to_string(i) + ".conv", cin, cin / 2, cout, &B.up[2 * i]);
     }
-    B.outc = pack_conv(W.data("outc" + sb + ".conv.weight", {B.nf, dim, 1, 1}), B.nf, dim, 1,
-                       W.data("outc" + sb + ".conv.bias", {B.nf}), nullptr, {});
+    B.outc = pack_outc(W.data("outc" + sb + ".conv.weight", {B.nf, dim, 1, 1}), W.data("outc" + sb + ".conv.bias", {B.nf}), B.nf, dim);
     u->br.push_back(B);
   }
 }
@@ -149,9 +160,9 @@ View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const Vie
     K_(conv2d(B.up[2 * i + 1], m, o, lrelu, IN_DIRECT, s));
     z = o;
   }
-  View out = make_view(A, N, Hs[0], Ws[0], B.outc.cout);
+  View out = make_view(A, N, Hs[0], Ws[0], B.outc.cout);      // cout = nf rounded up to a multiple of 8 (zero channels)
   K_(conv2d(B.outc, z, out, ConvEpi(), IN_DIRECT, s));
-  return out;
+  return out.slice(0, B.nf);
 }
 
 // DenseBlock_5C (unet.py:30-36): x -> dense buffer -> conv5 output (out_dim channels)
