@@ -98,7 +98,7 @@ class ClockSampler:
 
 def _top_launch_traffic():
     """dram__bytes_read+write of the top single launch from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_ftconv_full_summary.json")
+    p = os.path.join(ROOT, "profiles", "r2_ftconv_full_summary.json")
     try:
         return json.load(open(p))
     except Exception:
