@@ -307,6 +307,83 @@ def run_linf(args, rank, world, local, cfg):
         dist.destroy_process_group()
 
 
+def run_config4(args, rank, world, local):
+    """Config 4: SRFlow-LP 8x (RRDB nb=23, K=16, L=4, two Split2d, three latents) on 80x80 LR tiles, global batch 64 sharded over
+    the ranks (16 tiles per GPU at N = 4), with the three-branch generalisation of the SRFlow-LP prior (unet.py:109-181, see
+    DESIGN.md).  Synthetic weights; the prior's output convs are zero so the untrained 64-step inverse stays finite (any non-zero
+    latent overflows it: oracle/make_golden_r2.py) -- the launch sequence and the arithmetic per launch do not depend on the data."""
+    import torch.distributed as dist
+    from bfsr_b200 import _lib, models
+    from bfsr_b200.dist import shard_range
+    from tools import synth
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        saved_fd = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
+    B = args.batch if args.batch != BATCH else 64
+    S8, LR = 8, 80
+    t = synth.SRFlowTopo(scale=8, L=4)
+    net = models.define_Flow(t.opt(), device=dev, tile_chunk=args.tile_chunk, precision=args.precision)
+    net.load_state_dict(synth.synth_srflow_state_dict(t, seed=31), strict=True)
+    lat_ch = (6, 12, 192)
+    usd = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(latent_ch=lat_ch), seed=32)
+    for k in usd:
+        if k.startswith("outc"):
+            usd[k] = torch.zeros_like(usd[k])
+    prior = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True, "latent_ch": lat_ch}, "sd": usd}, load_sd=True)
+    lo, hi = shard_range(B, world, rank)
+    lr_host = synth.img(B, LR, LR, 1238)[lo:hi].contiguous().pin_memory()
+    lr = lr_host.to(dev)
+    L = _lib.lib()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        sr = net.lp_sr(lr, prior)
+    _barrier(dist, world, dev)
+    L.bfsr_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        _barrier(dist, world, dev)
+        e0.record()
+        for _ in range(args.steps):
+            sr = net.lp_sr(lr, prior)
+        e1.record()
+        _barrier(dist, world, dev)
+    launches = int(L.bfsr_launch_count(0))
+    ms = _max_over_ranks(dist, world, dev, e0.elapsed_time(e1)) / args.steps
+    hr_px_job = B * (S8 * LR) ** 2
+    value = hr_px_job / (ms * 1e-3) / 1e6
+    assert torch.isfinite(sr).all()
+    out_host = torch.empty((hi - lo, 3, S8 * LR, S8 * LR), dtype=torch.float32).pin_memory()
+    net.lp_sr_host(lr_host, prior, out=out_host)
+    _barrier(dist, world, dev)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.lp_sr_host(lr_host, prior, out=out_host)
+    _barrier(dist, world, dev)
+    e2e_ms = _max_over_ranks(dist, world, dev, (time.perf_counter() - t0) * 1e3) / args.steps
+    peaks = load_peaks()
+    # SURVEY.md 8(d): ~183 M MAC per LR pixel (flow + encoder 165.14 M, three-branch prior ~18.1 M, estimated)
+    alg_tflop = 2 * 183.2e6 * B * LR * LR / 1e12
+    if rank == 0:
+        print(json.dumps({
+            "metric": "HR Mpixels/sec, SRFlow-LP 8x LP inference (BASELINE config 4)", "value": value, "unit": "HR-Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 0 else "bf16", "data": "synthetic",
+            "config": {"workload": f"SRFlow-LP 8x RRDB(nb=23,K=16,L=4) {LR}x{LR} LR tiles, global batch {B} ({hi - lo} per GPU), three-branch prior, synthetic weights",
+                       "global_batch": B, "tiles_per_gpu": hi - lo, "l2": "per-step working set (tens of GB) >> 126 MB L2, no flush needed",
+                       "parallelism": f"dp{world} (independent tiles, no data-path collective)"},
+            "clocks": cs.summary(), "e2e": {"value": hr_px_job / (e2e_ms * 1e-3) / 1e6, "unit": "HR-Mpix/s", "h2d_bytes_per_step": lr_host.numel() * 4 * world,
+                                            "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "alg_tflop_per_step": alg_tflop,
+            "path_tensor_roofline_frac": (alg_tflop / world / (ms * 1e-3)) / peaks["tflops"], "roofline": None, "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,8 +397,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--gather", action="store_true", help="time the optional final gather of the SR tiles to rank 0 (NCCL) too")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
-                    help="BASELINE.json config: 2 = SRFlow-LP 4x (headline, default), 3 = LINF-LP EDSR 48x48 b64, 5 = LINF-LP RRDB mixed scales b256")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = SRFlow-LP 4x (headline, default), 3 = LINF-LP EDSR 48x48 b64, 4 = SRFlow-LP 8x 80x80 b64, 5 = LINF-LP RRDB mixed scales b256")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -332,6 +409,9 @@ def main():
         return
     if args.config in (3, 5):
         run_linf(args, rank, world, local, args.config)
+        return
+    if args.config == 4:
+        run_config4(args, rank, world, local)
         return
 
     import torch.distributed as dist
