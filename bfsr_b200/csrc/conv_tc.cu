@@ -108,6 +108,7 @@ struct TcArgs {
                                          // image row of 32 positions, 30 of them valid outputs): 3x fewer MMAs of 3x the width -- the
                                          // small-N floor of the MMA (A operand read from shared memory, ~40 clk) is paid once per dy
   int cb;                                // fold = 2: accumulator column stride of a dx block (16 or 32)
+  int pdl;                               // launched with programmatic stream serialisation (griddepcontrol in the kernel)
   int stg_bytes;                         // epilogue staging bytes in shared memory (0: the epilogue never stages, e.g. dx-folded head + FlowStep)
   int tile_w, tile_h;                    // output pixels of a macro tile (fold 1: 16x16 or 14x14; fold 2: 30 x 4*mt; else 8*sx x 16*sy)
   FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
@@ -378,6 +379,10 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
     const int sp = p / g;
     return (sp * 2 + cl_rank) * g + (p - sp * g);
   };
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as CTAs of this one exit, and runs its
+  // prologue (barrier init, TMEM allocation, FlowStep matrices) while our last tiles drain; it blocks at griddepcontrol.wait below
+  // until this whole grid has completed and its writes are visible.  Hides ~5-10 us of launch + prologue per conv (860 per step).
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = base;                                   // NA slots of [hi plane | lo plane]
@@ -415,6 +420,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // everything below touches activations of the previous kernel
 
   if (TMA_IN && warp == R::W_PROD0) {
     // ===================== A by TMA: the input already lives in HBM as bf16 (hi, lo) planes =====================
@@ -1458,6 +1464,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
     cfg.gridDim = dim3(grid);
     snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s-cl2 k%d %d->%d %dx%d", phase == 2 ? "-phase1p" : (fold == 2 ? "-f3" : ""), w.ks, w.cin, w.cout, out.H, out.W);
+    a.pdl = 0;
     ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
     CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 2>, a));
     count_launch();
@@ -1467,11 +1474,26 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   snprintf(g_prof_tag, sizeof g_prof_tag, "tc%s k%d %d->%d %dx%d%s", fold == 2 ? "-f3" : fold ? "-fold" : (phase == 2 ? "-phase1p" : (phase ? "-phase" : "")), w.ks, w.cin, w.cout, out.H, out.W,
            in_mode == IN_UP2 ? " up2" : "");
   ProfScope prof(PK_CONV_TC, 2.0 * (double)out.npix() * w.cin * w.ks * w.ks * w.cout, s);
+  // Programmatic dependent launch is wired (griddepcontrol in the kernel) but OFF by default: measured on the whole step it costs
+  // 3 % (batch 32: 300.3 vs 290.0 ms; batch 4: 43.7 vs 42.4 ms) -- the early-scheduled CTAs of the next conv take issue slots and
+  // barrier traffic from the draining one without shortening its tail.  BFSR_PDL=1 enables it.
+  static const bool use_pdl = getenv("BFSR_PDL") && atoi(getenv("BFSR_PDL")) == 1;
+  a.pdl = use_pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem; cfg.stream = s; cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
   if (a.tma && ew16) {
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    conv_tc_kernel<true, 1, 16><<<grid, Roles<true, 16>::NTHREADS, smem, s>>>(a);
-  } else if (a.tma) conv_tc_kernel<true><<<grid, Roles<true>::NTHREADS, smem, s>>>(a);
-  else conv_tc_kernel<false><<<grid, Roles<false>::NTHREADS, smem, s>>>(a);
+    cfg.blockDim = dim3(Roles<true, 16>::NTHREADS);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 1, 16>, a));
+  } else if (a.tma) {
+    cfg.blockDim = dim3(Roles<true>::NTHREADS);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, a));
+  } else {
+    cfg.blockDim = dim3(Roles<false>::NTHREADS);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, a));
+  }
   count_launch();
 }
 
