@@ -120,7 +120,7 @@ struct TcArgs {
   int a_plane, a_slot, w_slot;           // bytes (w_slot = one tap image)
   int tps, nw, w_stage;                  // taps per weight stage, number of stages, bytes per stage
   int w_res;                             // all weight stages fit in smem: loaded once per CTA, never recycled (nw = stages per tile)
-  int nacc;                              // TMEM accumulator stages (1 or 2)
+  int nacc;                              // TMEM accumulator stages (1, 2 or 4)
   int tiles_x, tiles_y, total_tiles;     // macro tiles per image and total work tiles (incl. cout tiles, batch)
   uint32_t m_nct, m_tx, m_ty;            // ceil(2^32 / d) for d = n_ct, tiles_x, tiles_y (tile_coord)
   uint32_t tmem_cols;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
   const uint32_t stg_smem = w_smem + a.nw * a.w_stage;            // epilogue staging (1024-aligned: every slot size is)
   const uint32_t bars = stg_smem + (uint32_t)a.stg_bytes;         // mbarriers (8 B each), then the per-warp bias copies
   const uint32_t a_full = bars, a_empty = bars + 8 * NA_MAX, w_full = bars + 16 * NA_MAX, w_empty = w_full + 8 * NW_MAX;
-  const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
+  const uint32_t acc_full = w_empty + 8 * NW_MAX, acc_empty = acc_full + 32, tmem_slot = acc_empty + 32;   // up to four accumulator stages
   unsigned char* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
   if (tid == 0) {
     for (int i = 0; i < NA_MAX; ++i) { mbar_init(a_full + 8 * i, TMA_IN ? 1 : NPROD); mbar_init(a_empty + 8 * i, a.n_iss); }
     for (int i = 0; i < NW_MAX; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, a.n_iss * CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(acc_full + 8 * i, a.n_iss); mbar_init(acc_empty + 8 * i, 32 * R::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   float* flow_s = reinterpret_cast<float*>(smem_gen + (bars + 256 + BIAS_BYTES - base));   // [C*C] mix matrix, then [C] vector
@@ -1361,6 +1361,10 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   a.a_slot = (a.fast ? 1 : 2) * a.a_plane;
   a.w_slot = 2 * a.nt * ROWB;
   a.nacc = 2 * a.mt * sub_cols <= 512 ? 2 : 1;
+  // four stages when they fit (small accumulators): a deeper MMA -> epilogue queue smooths the bubbles of the short-K convs whose
+  // three pipeline stages (TMA, MMA, epilogue) are each ~50 % busy (BFSR_TC_NACC4=1; measured neutral on the whole step, so two stages stay the default)
+  static const bool nacc4 = getenv("BFSR_TC_NACC4") && atoi(getenv("BFSR_TC_NACC4")) == 1;   // measured neutral (and worse with the smaller tiles it needs): opt-in
+  if (nacc4 && fold != 1 && 4 * a.mt * sub_cols <= 512) a.nacc = 4;
   uint32_t cols = 32; while ((int)cols < a.nacc * a.mt * sub_cols) cols <<= 1;
   a.tmem_cols = cols;
   a.tiles_x = cdiv(gW, a.tile_w); a.tiles_y = cdiv(gH, a.tile_h);
