@@ -469,9 +469,14 @@ def main():
         out = None
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        buf = torch.empty((x.shape[0], 3, SCALE * S, SCALE * S), device=dev, dtype=torch.float32)
+        for _ in range(2):
+            net.lp_sr(x, prior, out=buf)           # same buffers from here on: the plan is captured once, then replayed
+        barrier()
+        L.bfsr_launch_count(1)                     # count the launches of the timed steps only
         e0.record()
         for _ in range(steps):
-            out = net.lp_sr(x, prior)
+            out = net.lp_sr(x, prior, out=buf)
             if gather and world > 1:
                 gather_tiles(out, B if args.scaling == "strong" else B * world, dst=0)
         e1.record()
@@ -484,7 +489,6 @@ def main():
         if args.gather and world > 1:
             gather_tiles(sr, B if args.scaling == "strong" else B * world, dst=0)
     barrier()
-    L.bfsr_launch_count(1)
     with ClockSampler(local) as cs:
         ms, sr = timed(lr, args.steps, gather=args.gather)
     launches = int(L.bfsr_launch_count(0))

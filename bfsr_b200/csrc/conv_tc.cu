@@ -358,14 +358,14 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int t) {
 // convs, the dx-folded heads) are bound by their epilogue's instruction LATENCY -- ncu (profiles/r2_coupling_l1_summary.md): 19 % of
 // the warp slots occupied, 'wait' / 'short scoreboard' stalls, tensor pipe 11-22 %, DRAM 30-59 % -- so they run with four warps per
 // TMEM lane quarter instead of two.
-template <bool TMA_IN, int CL = 1, int EW = BFSR_EPI_WARPS>
+template <bool TMA_IN, int CL = 1, int EW = BFSR_EPI_WARPS, bool LEANP = (EW == 16)>
 __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   using R = Roles<TMA_IN, EW>;
   constexpr int BIAS_BYTES = bias_bytes(TMA_IN ? EW : BFSR_EPI_WARPS);
   // the 16-warp instantiation has 96 registers per thread: it carries only the epilogues of the convs that use it (no tap folding,
   // no C = 24 FlowStep, no residual / fp32 pre-activation / second-output passes; launch_tc checks the same conditions)
-  constexpr bool LEAN = EW == 16;
+  constexpr bool LEAN = LEANP;
   static_assert(CL == 1 || (CL == 2 && TMA_IN), "clusters: TMA-fed variant only");
   // persistent tile walk: CL = 1 strides the tile list by the grid; CL = 2 strides the PAIR list by the cluster count
   // (macros, not hoisted constants: the CL = 1 loops stay on the uniform datapath exactly as before)
@@ -1257,7 +1257,7 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // TMEM loads and adds a pass to an epilogue that is the bottleneck there, and halves the sub-tiles per weight stream everywhere
   // else.  BFSR_TC_WIDE=1 restores the wide form for NT <= 64.
   static const int force_wide = getenv("BFSR_TC_WIDE") ? atoi(getenv("BFSR_TC_WIDE")) : 0;
-  a.wide = (!a.fast && fold != 1 && a.nt <= 64 && force_wide == 1) ? 1 : 0;
+  a.wide = (!a.fast && fold != 1 && ((a.nt <= 64 && force_wide == 1) || (force_wide == 3 && fold == 2 && a.nt <= 128))) ? 1 : 0;
   // sixteen epilogue warps for the epilogue-latency-bound convs: TMA-fed, few (chunk, tap) MMA groups per output tile (see
   // conv_tc_kernel); the geometry below must then give at least four (sub-tile, 32-channel block) items per work tile
   static const int ew16_maxk = getenv("BFSR_TC_EW16_MAXK") ? atoi(getenv("BFSR_TC_EW16_MAXK")) : 2;
@@ -1481,6 +1481,10 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   // Programmatic dependent launch is wired (griddepcontrol in the kernel) but OFF by default: measured on the whole step it costs
   // 3 % (batch 32: 300.3 vs 290.0 ms; batch 4: 43.7 vs 42.4 ms) -- the early-scheduled CTAs of the next conv take issue slots and
   // barrier traffic from the draining one without shortening its tail.  BFSR_PDL=1 enables it.
+  // lean 8-warp instantiation (epilogue without the residual / fp32 pre-activation / second output / tap-fold / C = 24 FlowStep paths)
+  static const bool lean8_on = getenv("BFSR_TC_LEAN8") && atoi(getenv("BFSR_TC_LEAN8")) == 1;
+  const bool lean8 = lean8_on && !ew16 && a.tma && phase == 0 && fold != 1 && !epi.res1 && !epi.res2 && !epi.out2 && (!epi.pre || pre_gemm) &&
+                     (!epi.flow || epi.flow->C == 12);
   static const bool use_pdl = getenv("BFSR_PDL") && atoi(getenv("BFSR_PDL")) == 1;
   a.pdl = use_pdl ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
@@ -1491,6 +1495,10 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
     CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     cfg.blockDim = dim3(Roles<true, 16>::NTHREADS);
     CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 1, 16>, a));
+  } else if (a.tma && lean8) {
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    cfg.blockDim = dim3(Roles<true>::NTHREADS);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, 1, 8, true>, a));
   } else if (a.tma) {
     cfg.blockDim = dim3(Roles<true>::NTHREADS);
     CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, a));

@@ -255,11 +255,15 @@ class SRFlowNetEngine(nn.Module):
         return sr, torch.full((B,), float("nan"), device=lr_d.device)
 
     # ---- fused LP path (SRFlow-LP/code/test.py:135-148 in one call) ----------------------
-    def lp_sr(self, lr, prior):
-        """bilinear(lr) -> encode -> normalise -> prior -> decode, encoder and feature-only convs run once."""
+    def lp_sr(self, lr, prior, out=None):
+        """bilinear(lr) -> encode -> normalise -> prior -> decode, encoder and feature-only convs run once.  `out`: optional
+        preallocated (B,3,s*h,s*w) fp32 CUDA tensor for the result (a stable output buffer lets the engine replay one CUDA graph)."""
         lr_d = self._prep(lr)
         B, _, h, w = lr_d.shape
-        sr = torch.empty((B, 3, h * self.scale, w * self.scale), device=lr_d.device, dtype=torch.float32)
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and \
+                tuple(out.shape) == (B, 3, h * self.scale, w * self.scale) and out.device == lr_d.device
+        sr = out if out is not None else torch.empty((B, 3, h * self.scale, w * self.scale), device=lr_d.device, dtype=torch.float32)
         with torch.cuda.device(lr_d.device):
             _lib.check(_lib.lib().bfsr_srflow_lp_sr(self.handle(), prior.handle(self.device()), lr_d.data_ptr(), B, h, w,
                                                     sr.data_ptr(), _lib.stream_ptr(lr_d.device)))
