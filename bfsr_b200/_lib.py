@@ -70,6 +70,9 @@ SYMBOLS = {
     "bfsr_linf_destroy": (None, [_P]),
     "bfsr_linf_gen_feat": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "bfsr_linf_query": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "bfsr_linf_affine": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "bfsr_linf_flow": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "bfsr_op_linf_flow": (C.c_int, [C.POINTER(Tensor), _I, _I, _I, _P, _P, C.c_int64, _P, _P]),
     "bfsr_linf_lp_sr": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "bfsr_linf_build_inputs": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "bfsr_linf_lp_sr_host": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),

@@ -20,6 +20,11 @@ void linf_build(bfsr_linf* e, const bfsr_tensor_t* weights, int n);
 void linf_gen_feat(bfsr_linf* e, const float* inp, int B, int h, int w, float* feat_out, cudaStream_t s);
 void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh,
                 int qw, int mode, const float* zin, float* out, cudaStream_t s);
+void linf_affine(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh, int qw,
+                 float* aff_out, cudaStream_t s);
+void linf_flow_apply(bfsr_linf* e, const float* aff_nhwc, const float* zin, int B, int qh, int qw, int mode, float* out, cudaStream_t s);
+void op_linf_flow(const bfsr_tensor_t* weights, int n, int n_layers, bool inverse, const float* x_dev, const float* aff_dev, long long N,
+                  float* out_dev, cudaStream_t s);
 void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, int w, const float* coord, const float* cell,
                 const float* gt, int qh, int qw, int OH, int OW, float* pred, cudaStream_t s);
 }
@@ -212,6 +217,31 @@ int bfsr_linf_query(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr
   BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0 && qh > 0 && qw > 0, "bad shape");
   g_conv_mode = h->d.precision;
   linf_query(h, feat_dev, B, lr_h, lr_w, coord_dev, cell_dev, qh, qw, mode, zin_dev, out_dev, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_linf_affine(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr_h, int32_t lr_w, const float* coord_dev,
+                     const float* cell_dev, int32_t qh, int32_t qw, float* affine_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && (B == 0 || (feat_dev && coord_dev && cell_dev && affine_dev)), "null argument");
+  BFSR_CHECK(B >= 0 && lr_h > 0 && lr_w > 0 && qh > 0 && qw > 0, "bad shape");
+  g_conv_mode = h->d.precision;
+  linf_affine(h, feat_dev, B, lr_h, lr_w, coord_dev, cell_dev, qh, qw, affine_dev, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_linf_flow(bfsr_linf_t* h, const float* affine_dev, const float* zin_dev, int32_t B, int32_t qh, int32_t qw, int32_t mode,
+                   float* out_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(h && (B == 0 || (affine_dev && zin_dev && out_dev)), "null argument");
+  BFSR_CHECK(mode == 0 || mode == 1, "mode must be 0 (log_p) or 1 (rgb)");
+  BFSR_CHECK(B >= 0 && qh > 0 && qw > 0, "bad shape");
+  linf_flow_apply(h, affine_dev, zin_dev, B, qh, qw, mode, out_dev, (cudaStream_t)stream);
+  API_END
+}
+int bfsr_op_linf_flow(const bfsr_tensor_t* weights, int32_t n_weights, int32_t n_layers, int32_t inverse, const float* x_dev,
+                      const float* affine_dev, int64_t N, float* out_dev, void* stream) {
+  API_BEGIN
+  BFSR_CHECK(weights && x_dev && affine_dev && out_dev && n_layers > 0 && N > 0 && N < ((int64_t)1 << 31), "bad argument");
+  op_linf_flow(weights, n_weights, n_layers, inverse != 0, x_dev, affine_dev, N, out_dev, (cudaStream_t)stream);
   API_END
 }
 int bfsr_linf_lp_sr(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w,

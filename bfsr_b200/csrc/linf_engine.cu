@@ -197,6 +197,64 @@ void linf_query(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const
   CUDA_OK(cudaGetLastError());
 }
 
+// affine_info of a query chunk into the caller's buffer (B,qh,qw,2*D*L) NHWC fp32: the part of query_log_p / query_rgb that does
+// not depend on the latent (coef/freq conv, Fourier features, MLP; linf.py:251-321 == :327-396).  The reference recomputes it in
+// both passes and the coef/freq convs per row chunk; a caller that keeps the buffer pays for it once.
+void linf_affine(bfsr_linf* e, const float* feat_nchw, int B, int h, int w, const float* coord, const float* cell, int qh, int qw,
+                 float* aff_out, cudaStream_t s) {
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  Arena& A = e->arena;
+  for (int pass = 0; pass < 2; ++pass) {
+    A.reset(); A.plan = pass == 0; if (pass == 0) A.peak = 0;
+    View feat = make_view(A, B, h, w, 64);
+    K_(nchw_to_nhwc(feat_nchw, feat, s));
+    View aff = run_affine_info(e, A, feat, coord, cell, qh, qw, s);
+    K_(CUDA_OK(cudaMemcpyAsync(aff_out, aff.p, (size_t)aff.npix() * aff.C * 4, cudaMemcpyDeviceToDevice, s)));
+    if (pass == 0) { A.plan = false; if (ensure(A, s)) e->graphs.clear(); }
+  }
+  CUDA_OK(cudaGetLastError());
+}
+// the latent-dependent part: mode 0 = Flow.forward on gt (-> z, NCHW), 1 = Flow.inverse on zmap + fold (-> (B,3,3qh,3qw))
+void linf_flow_apply(bfsr_linf* e, const float* aff_nhwc, const float* zin, int B, int qh, int qw, int mode, float* out, cudaStream_t s) {
+  if (B == 0) return;
+  CUDA_OK(cudaSetDevice(e->device));
+  const int ps = e->d.patch_size, D = 3 * ps * ps, L = e->d.flow_layers;
+  View aff; aff.p = (void*)aff_nhwc; aff.N = B; aff.H = qh; aff.W = qw; aff.C = 2 * D * L; aff.cs = 2 * D * L;
+  if (mode == 0) linf_flow(false, e->Mf, e->fbias, L, aff, zin, B, qh, qw, out, 0, 0, nullptr, 0, 0, ps, s);
+  else linf_flow(true, e->Mi, e->fbias, L, aff, zin, B, qh, qw, out, qh * ps, qw * ps, nullptr, 0, 0, ps, s);
+  CUDA_OK(cudaGetLastError());
+}
+
+// Stand-alone Flow (LINF-LP/models/flow.py:12-63, registry name 'flow', D = 27): x (N,D) row-major, affine_info (N, 2*D*L)
+void op_linf_flow(const bfsr_tensor_t* weights, int n, int n_layers, bool inverse, const float* x_dev, const float* aff_dev, long long N,
+                  float* out_dev, cudaStream_t s) {
+  Weights W(weights, n);
+  const int D = 27;
+  std::vector<float> M((size_t)(n_layers + 1) * D * D), fb((size_t)(n_layers + 1) * D);
+  for (int i = 0; i <= n_layers; ++i) {
+    const std::string p = i < n_layers ? "linears." + std::to_string(i) : std::string("last");
+    const float* w = W.data(p + "._weight", {D, D}); const float* b = W.data(p + ".bias", {D});
+    if (!inverse) memcpy(&M[(size_t)i * D * D], w, (size_t)D * D * 4);
+    else { std::vector<double> inv = invert_f64(w, D); for (int k = 0; k < D * D; ++k) M[(size_t)i * D * D + k] = (float)inv[k]; }
+    memcpy(&fb[(size_t)i * D], b, D * 4);
+  }
+  float* dM = to_device(M); float* db = to_device(fb);
+  float *xt = nullptr, *ot = nullptr;
+  try {
+    CUDA_OK(cudaMalloc((void**)&xt, (size_t)N * D * 4 + 16)); CUDA_OK(cudaMalloc((void**)&ot, (size_t)N * D * 4 + 16));
+    // the kernel's latent layout is (B, D, qh, qw) with the query index fastest: one "image" of 1 x N queries, transposed in / out
+    View xin; xin.p = (void*)x_dev; xin.N = 1; xin.H = 1; xin.W = (int)N; xin.C = D; xin.cs = D;
+    nhwc_to_nchw(xin, xt, s);
+    View aff; aff.p = (void*)aff_dev; aff.N = 1; aff.H = 1; aff.W = (int)N; aff.C = 2 * D * n_layers; aff.cs = 2 * D * n_layers;
+    linf_flow(inverse, dM, db, n_layers, aff, xt, 1, 1, (int)N, ot, 0, 0, nullptr, 0, 0, inverse ? 0 : 3, s);
+    View o; o.p = out_dev; o.N = 1; o.H = 1; o.W = (int)N; o.C = D; o.cs = D;
+    nchw_to_nhwc(ot, o, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+  } catch (...) { cudaFree(dM); cudaFree(db); cudaFree(xt); cudaFree(ot); throw; }
+  cudaFree(dM); cudaFree(db); cudaFree(xt); cudaFree(ot);
+}
+
 // whole LP path for one chunk of images (all pointers already offset to the chunk)
 static void linf_lp_chunk(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, int w, const float* coord,
                           const float* cell, const float* gt, int qh, int qw, int OH, int OW, float* pred, cudaStream_t s) {

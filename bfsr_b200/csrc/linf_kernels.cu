@@ -227,6 +227,11 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
     }
     // fold 3x3 patches (== pixel_shuffle(3), linf.py:401-406), crop to (OH,OW), add bilinear(inp) (test.py:168-171)
     if (!live) return;
+    if (a.ps == 0) {     // stand-alone Flow.inverse: the D-vector itself, same NCHW layout as the forward output
+#pragma unroll
+      for (int o = 0; o < FD; ++o) a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = y[o];
+      return;
+    }
     const int ps = a.ps;
     for (int c = 0; c < 3; ++c)
       for (int ky = 0; ky < ps; ++ky)
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
 
 void linf_flow(bool inverse, const float* M, const float* bias, int n_layers, const View& aff, const float* zin, int B,
                int qh, int qw, float* out, int OH, int OW, const float* inp, int h, int w, int ps, cudaStream_t s) {
-  BFSR_CHECK(3 * ps * ps == FD, "linf_flow: only patch_size 3 (D = 27) is built");
+  BFSR_CHECK(ps == 0 || 3 * ps * ps == FD, "linf_flow: only patch_size 3 (D = 27) is built");
   BFSR_CHECK(aff.fmt == F32 && aff.C == 2 * FD * n_layers, "linf_flow: affine_info shape");
   FlowArgs a;
   a.M = M; a.bias = bias; a.aff = aff; a.zin = zin; a.out = out; a.inp = inp;

@@ -105,6 +105,8 @@ class LINFEngine(nn.Module):
         return self._device
 
     def _destroy(self):
+        self.__dict__["_serial"] = self.__dict__.get("_serial", 0) + 1      # cached features / affine parameters belong to the old weights
+        self.__dict__.pop("_feat_cache", None); self.__dict__.pop("_aff_cache", None)
         if self._handle is not None:
             _lib.lib().bfsr_linf_destroy(self._handle)
             self._handle = None
@@ -133,26 +135,85 @@ class LINFEngine(nn.Module):
         return t.detach().to(self.device(), torch.float32).contiguous()
 
     # ---- LINFPatch operators (linf.py:244-428) --------------------------------------------
+    # The reference's drivers call gen_feat twice per batch and query_* once per pass and per 256-row chunk, recomputing the
+    # encoder, the coef / freq convs and the MLP every time (LINF-LP/test.py:20-47).  Through the same call surface the engine
+    # remembers (a) the features of the last inputs and (b) the per-query affine parameters of the last (features, coord chunk)
+    # pairs.  A cache entry is tied to the tensor OBJECT (weak reference, so an id is never reused) and its in-place version
+    # counter, so modified or new tensors miss.  `cache_entries = 0` disables it.
+    cache_entries = 8
+
+    @staticmethod
+    def _root(t):
+        return t._base if t._base is not None else t     # row-chunk slices are fresh view objects of one live tensor
+
+    @staticmethod
+    def _key(t):
+        r = t._base if t._base is not None else t
+        return (id(r), t._version, t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+    def _cache_get(self, store, key_tensors):
+        import weakref
+        if not self.cache_entries:
+            return None, None
+        cache = self.__dict__.setdefault(store, OrderedDict())
+        key = tuple(self._key(t) for t in key_tensors) + (self._handle_serial(),)
+        hit = cache.get(key)
+        if hit is not None and all(r() is self._root(t) for r, t in zip(hit[0], key_tensors)):
+            cache.move_to_end(key)
+            return key, hit[1]
+        return key, None
+
+    def _cache_put(self, store, key, key_tensors, value):
+        import weakref
+        if key is None:
+            return
+        cache = self.__dict__.setdefault(store, OrderedDict())
+        cache[key] = ([weakref.ref(self._root(t)) for t in key_tensors], value)
+        while len(cache) > self.cache_entries:
+            cache.popitem(last=False)
+
+    def _handle_serial(self):
+        return self.__dict__.get("_serial", 0)
+
     def gen_feat(self, inp):
+        key, hit = self._cache_get("_feat_cache", [inp])
+        if hit is not None:
+            return hit
         x = self._prep(inp)
         B, _, h, w = x.shape
         feat = torch.empty((B, 64, h, w), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().bfsr_linf_gen_feat(self.handle(), x.data_ptr(), B, h, w, feat.data_ptr(),
                                                      _lib.stream_ptr(x.device)))
+        self._cache_put("_feat_cache", key, [inp], feat)
         return feat
 
+    def affine_info(self, feat, coord, cell):
+        """coef / freq conv + local Fourier features + MLP of a query chunk (linf.py:251-321): (B,qh,qw,540) NHWC, cached."""
+        key, hit = self._cache_get("_aff_cache", [feat, coord, cell])
+        if hit is not None:
+            return hit
+        f, c, ce = self._prep(feat), self._prep(coord), self._prep(cell)
+        B, _, h, w = f.shape
+        _, qh, qw, _ = c.shape
+        aff = torch.empty((B, qh, qw, 2 * 3 * self.patch_size ** 2 * self.flow_layers), device=f.device, dtype=torch.float32)
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().bfsr_linf_affine(self.handle(), f.data_ptr(), B, h, w, c.data_ptr(), ce.data_ptr(), qh, qw,
+                                                   aff.data_ptr(), _lib.stream_ptr(f.device)))
+        self._cache_put("_aff_cache", key, [feat, coord, cell], aff)
+        return aff
+
     def _query(self, feat, coord, cell, zin, mode):
-        feat, coord, cell, zin = self._prep(feat), self._prep(coord), self._prep(cell), self._prep(zin)
-        B, _, h, w = feat.shape
-        _, qh, qw, _ = coord.shape
+        aff = self.affine_info(feat, coord, cell)
+        zin = self._prep(zin)
+        B, qh, qw, _ = aff.shape
         D = 3 * self.patch_size ** 2
         assert tuple(zin.shape) == (B, D, qh, qw), (tuple(zin.shape), (B, D, qh, qw))
         shape = (B, D, qh, qw) if mode == 0 else (B, 3, qh * self.patch_size, qw * self.patch_size)
-        out = torch.empty(shape, device=feat.device, dtype=torch.float32)
-        with torch.cuda.device(feat.device):
-            _lib.check(_lib.lib().bfsr_linf_query(self.handle(), feat.data_ptr(), B, h, w, coord.data_ptr(), cell.data_ptr(),
-                                                  qh, qw, mode, zin.data_ptr(), out.data_ptr(), _lib.stream_ptr(feat.device)))
+        out = torch.empty(shape, device=aff.device, dtype=torch.float32)
+        with torch.cuda.device(aff.device):
+            _lib.check(_lib.lib().bfsr_linf_flow(self.handle(), aff.data_ptr(), zin.data_ptr(), B, qh, qw, mode, out.data_ptr(),
+                                                 _lib.stream_ptr(aff.device)))
         return out
 
     def query_log_p(self, inp, feat, coord, cell, gt):
@@ -370,3 +431,51 @@ def make_rrdb(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, no_upsampling=True):
     if (in_nc, out_nc, nf, gc) != (3, 3, 64, 32) or not no_upsampling:
         raise NotImplementedError("rrdb: the engine builds the LINF configuration (3->64, gc 32, no_upsampling=True)")
     return EncoderEngine("rrdb", {"nb": nb, "no_upsampling": True})
+
+
+# ---- stand-alone Flow under the reference's registry name (LINF-LP/models/flow.py:11-63) -------------------------------------
+@register('flow')
+class FlowEngine(nn.Module):
+    """`Flow(flow_layers=10, patch_size=3)`: forward(x, affine_info) -> (z, log_det) and inverse(z, affine_info) -> x on (N, 27)
+    vectors with (N, 54*flow_layers) affine parameters; state_dict keys `linears.<i>._weight/.bias`, `last._weight/.bias`.  The
+    log-determinant is dead on the inference path and returned as NaN.  Only 3x3 patches (D = 27) are built."""
+
+    def __init__(self, flow_layers=10, patch_size=3, name='flow'):
+        super().__init__()
+        if patch_size != 3:
+            raise NotImplementedError("flow: only patch_size 3 (D = 27) is built (the shipped checkpoints)")
+        self.n_layers, D = flow_layers, 3 * patch_size ** 2
+        s = OrderedDict()
+        for i in range(flow_layers):
+            s[f"linears.{i}.bias"] = (D,)
+            s[f"linears.{i}._weight"] = (D, D)
+        s["last.bias"] = (D,)
+        s["last._weight"] = (D, D)
+        param_tree.build(self, s)
+        for k, v in self.state_dict().items():
+            if k.endswith("._weight"):
+                v.copy_(torch.eye(D))
+
+    def cuda(self, device=None):
+        return self
+
+    def _run(self, x, affine_info, inverse):
+        dev = x.device if x.is_cuda else _lib.cuda_device(None)
+        x = x.detach().to(dev, torch.float32).contiguous()
+        a = affine_info.detach().to(dev, torch.float32).contiguous()
+        N, D = x.shape
+        assert D == 27 and tuple(a.shape) == (N, 2 * D * self.n_layers), (tuple(x.shape), tuple(a.shape))
+        out = torch.empty_like(x)
+        table, keep = _lib.tensor_table(self.state_dict())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().bfsr_op_linf_flow(table, len(table), self.n_layers, int(inverse), x.data_ptr(), a.data_ptr(), N,
+                                                    out.data_ptr(), _lib.stream_ptr(dev)))
+        del keep
+        return out
+
+    def forward(self, x, affine_info):
+        z = self._run(x, affine_info, False)
+        return z, torch.full((z.shape[0],), float("nan"), device=z.device)
+
+    def inverse(self, z, affine_info):
+        return self._run(z, affine_info, True)

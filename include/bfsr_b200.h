@@ -141,6 +141,18 @@ int bfsr_linf_gen_feat(bfsr_linf_t* h, const float* inp_dev, int32_t B, int32_t 
 int bfsr_linf_query(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr_h, int32_t lr_w, const float* coord_dev,
                     const float* cell_dev, int32_t qh, int32_t qw, int32_t mode, const float* zin_dev, float* out_dev,
                     void* stream);
+/* The two halves of a query, for callers that keep the per-query affine parameters between the log_p and the rgb pass (the
+ * reference recomputes them, and the coef / freq convs per 256-row chunk: LINF-LP/test.py:22-32,40-45):
+ * bfsr_linf_affine: coef/freq conv + local Fourier features + MLP (linf.py:251-321) -> affine (B,qh,qw,2*27*flow_layers), NHWC fp32;
+ * bfsr_linf_flow:   Flow.forward on gt (mode 0, -> z (B,27,qh,qw)) / Flow.inverse on zmap + fold (mode 1, -> (B,3,3qh,3qw)). */
+int bfsr_linf_affine(bfsr_linf_t* h, const float* feat_dev, int32_t B, int32_t lr_h, int32_t lr_w, const float* coord_dev,
+                     const float* cell_dev, int32_t qh, int32_t qw, float* affine_dev, void* stream);
+int bfsr_linf_flow(bfsr_linf_t* h, const float* affine_dev, const float* zin_dev, int32_t B, int32_t qh, int32_t qw, int32_t mode,
+                   float* out_dev, void* stream);
+/* Stand-alone Flow of LINF-LP/models/flow.py:12-63 (registry name 'flow', 3x3 patches: D = 27): x (N,27), affine_info
+ * (N, 54*n_layers) row-major device buffers; keys `linears.<i>._weight/.bias`, `last._weight/.bias`; inverse != 0 -> Flow.inverse. */
+int bfsr_op_linf_flow(const bfsr_tensor_t* weights, int32_t n_weights, int32_t n_layers, int32_t inverse, const float* x_dev,
+                      const float* affine_dev, int64_t N, float* out_dev, void* stream);
 /* The whole LP path of LINF-LP/test.py:143-171 (--patch, eval_bsize set) in one call: encoder and per-query affine
  * parameters computed once and shared by the log_p and rgb passes; returns pred cropped to (out_h,out_w) + bilinear(inp). */
 int bfsr_linf_lp_sr(bfsr_linf_t* h, bfsr_unet_t* prior, const float* inp_dev, int32_t B, int32_t lr_h, int32_t lr_w,

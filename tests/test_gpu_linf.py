@@ -172,3 +172,47 @@ def test_standalone_encoders_by_registry_name(name):
     x = (synth.img(2, 20, 16, 5) - 0.5) / 0.5
     ref = LO.edsr_forward(sd, x) if name == "edsr-baseline" else LO.rrdb_forward(sd, x, nb=2)
     assert rel_l2(ref, enc(x)) < 1e-4
+
+
+def test_reference_surface_reuses_features_and_affine_parameters(lib=None):
+    """The reference's two-pass driver (batched_predict_log_p, then batched_predict: encoder, coef / freq convs and MLP recomputed in
+    every pass and per row chunk, test.py:20-47) through the same surface: the second pass reuses the cached features and affine
+    parameters (fewer launches, identical numbers); in-place modification of the input invalidates the cache."""
+    from bfsr_b200 import _lib, models
+    g, enc, sd, psd, inp, coord, cell, gt, hw = load_case("linf_edsr_synth_x4")
+    model, prior = _engines(enc, sd, psd)
+    L = _lib.lib()
+    inp_d, coord_d, cell_d = inp.cuda(), coord.cuda(), cell.cuda()
+    L.bfsr_launch_count(1)
+    z1 = models.batched_predict_log_p(model, inp_d, coord_d, cell_d, gt)
+    n_first = int(L.bfsr_launch_count(1))
+    rgb = models.batched_predict(model, inp_d, coord_d, cell_d, 0, z1)
+    n_second = int(L.bfsr_launch_count(1))
+    assert n_second < n_first // 4                       # only the flow kernel runs in the second pass
+    model.cache_entries = 0
+    rgb_nc = models.batched_predict(model, inp_d, coord_d, cell_d, 0, z1)
+    assert torch.equal(rgb, rgb_nc)
+    model.cache_entries = 8
+    f1 = model("gen_feat", inp=inp_d)
+    assert model("gen_feat", inp=inp_d) is f1
+    inp_d.mul_(0.5)                                      # in-place change: version counter moves, cache must miss
+    f2 = model("gen_feat", inp=inp_d)
+    assert f2 is not f1 and not torch.equal(f1, f2)
+
+
+def test_standalone_flow_by_registry_name():
+    """`models.make({'name': 'flow', ...})` (LINF-LP/models/flow.py): forward / inverse on (N, 27) vectors vs the oracle, and
+    inverse(forward(x)) == x."""
+    from bfsr_b200 import models
+    from oracle import linf_oracle as LO
+    from tools import synth
+    sd = synth.synth_linf_state_dict(synth.linf_param_shapes("edsr-baseline"), seed=5)
+    fsd = {k[len("imnet."):]: v for k, v in sd.items() if k.startswith("imnet.")}
+    flow = models.make({"name": "flow", "args": {"flow_layers": 10, "patch_size": 3}, "sd": fsd}, load_sd=True).cuda()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 27, generator=gen) * 0.3
+    aff = torch.randn(1000, 540, generator=gen) * 0.5
+    z, _ = flow(x, aff)
+    assert rel_l2(LO.flow_forward(sd, x, aff), z) < 1e-5
+    xr = flow.inverse(z, aff)
+    assert rel_l2(LO.flow_inverse(sd, z.cpu(), aff), xr) < 1e-4 and max_abs(x, xr) < 1e-3
