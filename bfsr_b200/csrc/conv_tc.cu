@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
           }
           if (a.act == ACT_CROSS_SIGMOID) {
 #pragma unroll
-            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + expf(-(acc[i] + 2.f))) + a.eps;
+            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + __expf(-(acc[i] + 2.f))) + a.eps;
           } else if (a.act == ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
           }
           if (a.act == ACT_CROSS_SIGMOID) {                // co0 % 4 == 0: the odd channels are the scales
 #pragma unroll
-            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + expf(-(acc[i] + 2.f))) + a.eps;
+            for (int i = 1; i < 32; i += 2) acc[i] = __fdividef(1.f, 1.f + __expf(-(acc[i] + 2.f))) + a.eps;
           } else if (a.act == ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
       }
 #pragma unroll
       for (int c = 0; c < FD; ++c) {
-        const float scale = __fdividef(1.f, 1.f + expf(-(af[c] + 2.f))) + 1e-4f;
+        const float scale = __fdividef(1.f, 1.f + __expf(-(af[c] + 2.f))) + 1e-4f;
         x[c] = fmaf(y[c], scale, af[FD + c]);
       }
     }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
       const float* W = Ms + i * FD * FDP;
 #pragma unroll
       for (int c = 0; c < FD; ++c) {
-        const float scale = __fdividef(1.f, 1.f + expf(-(af[c] + 2.f))) + 1e-4f;
+        const float scale = __fdividef(1.f, 1.f + __expf(-(af[c] + 2.f))) + 1e-4f;
         x[c] = __fdividef(y[c] - af[FD + c], scale) - bs[i * FD + c];
       }
 #pragma unroll
