@@ -109,6 +109,7 @@ struct TcArgs {
                                          // small-N floor of the MMA (A operand read from shared memory, ~40 clk) is paid once per dy
   int cb;                                // fold = 2: accumulator column stride of a dx block (16 or 32)
   int pdl;                               // launched with programmatic stream serialisation (griddepcontrol in the kernel)
+  int dbg;                               // timing experiments only (BFSR_TC_DBG: 1 = no proxy fence, 2 = no TMA store, 4 = no hi/lo split math): WRONG results
   int stg_bytes;                         // epilogue staging bytes in shared memory (0: the epilogue never stages, e.g. dx-folded head + FlowStep)
   int tile_w, tile_h;                    // output pixels of a macro tile (fold 1: 16x16 or 14x14; fold 2: 30 x 4*mt; else 8*sx x 16*sy)
   FlowEpi flow;                          // flow.C != 0: the epilogue applies the FlowStep instead of storing the conv output
@@ -591,9 +592,9 @@ __global__ void __launch_bounds__(tc::Roles<TMA_IN, EW>::NTHREADS, 1) conv_tc_ke
             *reinterpret_cast<uint4*>(buf + 2048 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (!(a.dbg & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(a.dbg & 2)) {
         const uint32_t src = stg_u32;
         if (v.fmt == F32) tma_store_4d(tm, src, v.coff + c0, x0, y0, n);
         else { tma_store_5d(tm, src, v.coff + c0, x0, y0, n, 0); tma_store_5d(tm, src + 2048, v.coff + c0, x0, y0, n, 1); }
@@ -1485,6 +1486,8 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
   static const bool lean8_on = getenv("BFSR_TC_LEAN8") && atoi(getenv("BFSR_TC_LEAN8")) == 1;
   const bool lean8 = lean8_on && !ew16 && a.tma && phase == 0 && fold != 1 && !epi.res1 && !epi.res2 && !epi.out2 && (!epi.pre || pre_gemm) &&
                      (!epi.flow || epi.flow->C == 12);
+  static const int dbg_env = getenv("BFSR_TC_DBG") ? atoi(getenv("BFSR_TC_DBG")) : 0;
+  a.dbg = dbg_env;
   static const bool use_pdl = getenv("BFSR_PDL") && atoi(getenv("BFSR_PDL")) == 1;
   a.pdl = use_pdl ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
