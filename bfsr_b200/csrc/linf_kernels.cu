@@ -127,14 +127,20 @@ struct FlowArgs {
   long long nq;
 };
 
-__device__ __forceinline__ float dot27(const float* w, const float* x, float acc) {   // w: 28 floats, 16-byte aligned, w[27] = 0
+// y[o] (+)= sum_c W[o][c] x[c] in outer-product form: Wt holds the layer's matrix TRANSPOSED ([c][o], rows padded to 28 floats), so
+// every 16-byte broadcast load feeds four INDEPENDENT accumulators -- 27 independent FMA chains instead of one 27-long dependent
+// chain per output (the kernel is latency-bound).  Per output the products are still added in ascending c: bit-identical.
+__device__ __forceinline__ void matvec27(const float* Wt, const float* x, float* y) {
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const float4 m = *reinterpret_cast<const float4*>(w + 4 * k);
-    acc = fmaf(m.x, x[4 * k], acc); acc = fmaf(m.y, x[4 * k + 1], acc); acc = fmaf(m.z, x[4 * k + 2], acc);
-    if (4 * k + 3 < FD) acc = fmaf(m.w, x[4 * k + 3], acc);
+  for (int c = 0; c < FD; ++c) {
+    const float xc = x[c];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float4 m = *reinterpret_cast<const float4*>(Wt + c * FDP + 4 * k);
+      y[4 * k] = fmaf(m.x, xc, y[4 * k]); y[4 * k + 1] = fmaf(m.y, xc, y[4 * k + 1]); y[4 * k + 2] = fmaf(m.z, xc, y[4 * k + 2]);
+      if (4 * k + 3 < FD) y[4 * k + 3] = fmaf(m.w, xc, y[4 * k + 3]);
+    }
   }
-  return acc;
 }
 
 // 256 queries per block, two blocks per SM (<= 128 registers): the kernel is bound by instruction latency, so resident warps count
@@ -143,11 +149,13 @@ constexpr int FLOW_T = 256;
 template <bool INV>
 __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
   extern __shared__ float sm[];
-  // weight rows padded to FDP = 28 floats: a row is read as seven 16-byte broadcast loads (one shared-memory load per four FMAs
-  // instead of one per FMA -- the flow passes were bound by the load/store pipe)
+  // transposed weight rows padded to FDP = 28 floats, read as seven 16-byte broadcast loads (matvec27)
   const int nm = (a.n_layers + 1) * FD * FDP;
   float* Ms = sm; float* bs = sm + nm;
-  for (int e = threadIdx.x; e < nm; e += blockDim.x) { const int r = e / FDP, c = e - r * FDP; Ms[e] = c < FD ? a.M[r * FD + c] : 0.f; }
+  for (int e = threadIdx.x; e < nm; e += blockDim.x) {           // Ms[layer][c][o] = M[layer][o][c]
+    const int r = e / FDP, o = e - r * FDP, l = r / FD, c = r - l * FD;
+    Ms[e] = o < FD ? a.M[(l * FD + o) * FD + c] : 0.f;
+  }
   for (int e = threadIdx.x; e < (a.n_layers + 1) * FD; e += blockDim.x) bs[e] = a.bias[e];
   // per-layer affine parameters of the block's 128 queries, staged through shared memory: a query's 2*D values of a layer are
   // 216 contiguous bytes of a 2160-byte row, so the block reads them as coalesced runs (a thread walking its own row touched a
@@ -180,11 +188,8 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
       load_layer(i);
       const float* W = Ms + i * FD * FDP;
 #pragma unroll
-      for (int o = 0; o < FD; ++o) {
-        float acc = bs[i * FD + o];
-        acc = dot27(W + o * FDP, x, acc);
-        y[o] = acc;
-      }
+      for (int o = 0; o < FD; ++o) y[o] = bs[i * FD + o];
+      matvec27(W, x, y);
 #pragma unroll
       for (int c = 0; c < FD; ++c) {
         const float scale = __fdividef(1.f, 1.f + __expf(-(af[c] + 2.f))) + 1e-4f;
@@ -193,10 +198,11 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
     }
     const float* W = Ms + a.n_layers * FD * FDP;
 #pragma unroll
-    for (int o = 0; o < FD; ++o) {
-      float acc = bs[a.n_layers * FD + o];
-      acc = dot27(W + o * FDP, x, acc);
-      if (live) a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = acc;
+    for (int o = 0; o < FD; ++o) y[o] = bs[a.n_layers * FD + o];
+    matvec27(W, x, y);
+    if (live) {
+#pragma unroll
+      for (int o = 0; o < FD; ++o) a.out[(b * FD + o) * plane + (long long)qy * a.qw + qx] = y[o];
     }
   } else {
     {   // last^-1
@@ -204,11 +210,8 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
 #pragma unroll
       for (int c = 0; c < FD; ++c) x[c] -= bs[a.n_layers * FD + c];
 #pragma unroll
-      for (int o = 0; o < FD; ++o) {
-        float acc = 0.f;
-        acc = dot27(W + o * FDP, x, acc);
-        y[o] = acc;
-      }
+      for (int o = 0; o < FD; ++o) y[o] = 0.f;
+      matvec27(W, x, y);
     }
     for (int i = a.n_layers - 1; i >= 0; --i) {
       load_layer(i);
@@ -219,11 +222,8 @@ __global__ void __launch_bounds__(FLOW_T, 2) linf_flow_kernel(FlowArgs a) {
         x[c] = __fdividef(y[c] - af[FD + c], scale) - bs[i * FD + c];
       }
 #pragma unroll
-      for (int o = 0; o < FD; ++o) {
-        float acc = 0.f;
-        acc = dot27(W + o * FDP, x, acc);
-        y[o] = acc;
-      }
+      for (int o = 0; o < FD; ++o) y[o] = 0.f;
+      matvec27(W, x, y);
     }
     // fold 3x3 patches (== pixel_shuffle(3), linf.py:401-406), crop to (OH,OW), add bilinear(inp) (test.py:168-171)
     if (!live) return;
