@@ -2,6 +2,7 @@
 #include "engine.cuh"
 #include <cstring>
 #include <memory>
+#include <atomic>
 
 using namespace bfsr;
 
@@ -127,7 +128,8 @@ int bfsr_unet_create(bfsr_unet_t** out, const bfsr_unet_desc_t* desc, const bfsr
   BFSR_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
   CUDA_OK(cudaSetDevice(device));
   std::unique_ptr<bfsr_unet> u(new bfsr_unet());
-  u->d = *desc; u->device = device;
+  static std::atomic<long long> next_serial{1};
+  u->d = *desc; u->device = device; u->serial = next_serial.fetch_add(1);
   unet_build(u.get(), weights, n_weights);
   *out = u.release();
   API_END

@@ -79,6 +79,7 @@ View run_unet_body(const UNetBranchW& B, int depth, int dim, Arena& A, const Vie
 struct bfsr_unet {
   bfsr_unet_desc_t d;
   int device = 0;
+  long long serial = 0;       // unique per created handle: captured launch plans of the engines key on it (an address can be reused)
   std::vector<bfsr::UNetBranchW> br;
   bfsr::Arena arena;          // used only by the standalone forward entry point
   ~bfsr_unet();

@@ -291,7 +291,7 @@ void linf_lp_sr(bfsr_linf* e, bfsr_unet* prior, const float* inp, int B, int h, 
   const int D = 3 * e->d.patch_size * e->d.patch_size;
   // the launch sequence is fixed by (shapes, buffers, arena, precision): replayed as a CUDA graph from the third identical call on
   const std::vector<long long> key = {(long long)(uintptr_t)inp, B, h, w, (long long)(uintptr_t)coord, (long long)(uintptr_t)cell,
-                                      (long long)(uintptr_t)gt, qh, qw, OH, OW, (long long)(uintptr_t)pred, (long long)(uintptr_t)prior,
+                                      (long long)(uintptr_t)gt, qh, qw, OH, OW, (long long)(uintptr_t)pred, (prior ? prior->serial : 0),
                                       (long long)(uintptr_t)A.base, g_conv_mode, chunk};
   run_graphed(e->graphs, key, s, [&](cudaStream_t st) {
     for (int b0 = 0; b0 < B; b0 += chunk) {

@@ -707,7 +707,7 @@ void srflow_run(bfsr_srflow* e, bfsr_unet* prior, int mode_i, const float* lr, c
   }
   // fixed launch sequence per (mode, shapes, buffers, arena, precision): replayed as a CUDA graph from the third identical call on
   std::vector<long long> key = {mode_i, B, h, w, chunk, (long long)(uintptr_t)lr, (long long)(uintptr_t)gt, (long long)(uintptr_t)sr,
-                                (long long)(uintptr_t)prior, (long long)(uintptr_t)e->arena.base, g_conv_mode};
+                                (prior ? prior->serial : 0), (long long)(uintptr_t)e->arena.base, g_conv_mode};
   for (int i = 0; i < nl; ++i) { key.push_back(lat_out ? (long long)(uintptr_t)lat_out[i] : 0); key.push_back(lat_in ? (long long)(uintptr_t)lat_in[i] : 0); }
   run_graphed(e->graphs, key, s, [&](cudaStream_t st) {
     for (int b0 = 0; b0 < B; b0 += chunk) {

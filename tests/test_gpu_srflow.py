@@ -544,3 +544,29 @@ def test_div2k_size_image_in_one_pass():
     net(gt=lr_up, lr=lr_t, reverse=False, epses=epses, add_gt_noise=False)
     rt, _ = net(lr=lr_t, reverse=True, epses=epses)
     assert rel_l2(lr_up, rt) < 1e-4 and max_abs(lr_up, rt) < 5e-3
+
+
+def test_cuda_graph_replay_matches_plain_launches():
+    """The engine replays its fixed launch plan as a CUDA graph from the third identical call on (same shapes and buffers).  New
+    CONTENTS in the same buffers must give the same bits as plain launches, and a refreshed prior must never be served from a plan
+    captured with the old prior's weights."""
+    from tools import synth
+    from bfsr_b200 import models
+    t, sd, usd, net, prior = _small()
+    lr = synth.img(3, 16, 16, 501).cuda()
+    out = torch.empty(3, 3, 64, 64, device="cuda")
+    for _ in range(3):
+        net.lp_sr(lr, prior, out=out)                 # third call replays the captured plan
+    for seed in (502, 503):
+        lr.copy_(synth.img(3, 16, 16, seed))
+        net.lp_sr(lr, prior, out=out)                 # replay on new contents
+        fresh = models.define_Flow(t.opt())
+        fresh.load_state_dict(sd, strict=True)
+        assert torch.equal(out, fresh.lp_sr(lr.clone(), prior))    # first call of a new engine: plain launches
+    usd2 = synth.synth_unet_state_dict(synth.unet_srflow_param_shapes(), seed=99)
+    prior.load_state_dict(usd2)                        # new packed weights (possibly at the old address)
+    got = net.lp_sr(lr, prior, out=out).clone()
+    prior2 = models.make({"name": "unet", "args": {"depth": 3, "dim": 64, "bilinear": True}, "sd": usd2}, load_sd=True)
+    fresh = models.define_Flow(t.opt())
+    fresh.load_state_dict(sd, strict=True)
+    assert torch.equal(got, fresh.lp_sr(lr.clone(), prior2))
