@@ -19,16 +19,18 @@
 //    completing on mbarriers; one weight stage serves all MT sub-tiles of the macro tile.
 //  * fp32-accurate arithmetic on bf16 tensor cores (split-bf16 x3):
 //        x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi      (dropped term ~2^-16 relative)
-//    NT <= 64: A_hi x [W_hi;W_lo] as one N = 2*NT MMA + A_lo x W_hi (the epilogue adds the column halves); NT > 64: three
-//    N = NT MMAs into the same columns (the small-N MMA floor decides, see launch_tc).  The fast mode issues A_hi x W_hi.
+//    issued as three N = NT MMAs into the same accumulator columns (round 2: measured never slower than the round-1 "wide" form
+//    A_hi x [W_hi;W_lo] as one N = 2*NT MMA + A_lo x W_hi, which stays available with BFSR_TC_WIDE=1).  The fast mode issues A_hi x W_hi.
 //  * Accumulators live in TMEM (two stages whenever they fit 512 columns); two warps issue the MMAs (even / odd
 //    sub-tiles); tcgen05.commit arrives on the mbarriers that recycle the A / W slots and release the epilogue.
-//  * Epilogue (8 warps in the TMA variant, two per TMEM lane quarter): tcgen05.ld 32x32b -> bias / pre-activation /
+//  * Epilogue (8 warps in the TMA variant, two per TMEM lane quarter; 16 in the lean instantiation used by the short-K convs,
+//    whose epilogue is bound by instruction latency): tcgen05.ld 32x32b -> bias / pre-activation /
 //    activation / residual passes on whole rows -> swizzled staging tile -> TMA bulk tensor store (fp32 or bf16 planes,
 //    optionally a second copy); or a FlowStep applied in place of the store (FlowEpi).
 //  * Modes: phase 1/2 = conv over nearest-2x-upsampled channels evaluated per output phase with pre-summed 2x2 taps
 //    (phase 2 adds the hi-res channels as TMA parity planes in the same pass); n_pre = a BF16X2 pre-activation tensor
-//    enters the GEMM as identity K chunks; fold = nine taps folded into N with a shift-add epilogue (opt-in).
+//    enters the GEMM as identity K chunks; fold = 1: nine taps folded into N with a shared-memory shift-add epilogue (opt-in, slower);
+//    fold = 2: the three dx taps folded into N over a raster of pitch 32, shift-add by warp shuffles (default for Cout <= 32).
 //
 // Warp roles (Roles<TMA_IN>): epilogue warps, MMA issuer A (+ TMEM allocator), weight loader, TMA loader or 8 A producers,
 // MMA issuer B.
