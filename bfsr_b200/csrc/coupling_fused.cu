@@ -1,0 +1,550 @@
+// One kernel per coupling FlowStep of a C = 12 level (SRFlow level 1): the z-dependent affine sub-net
+//     fAffine.0 (3x3, z1 -> 64, + feature-only pre-activation) -> ReLU -> fAffine.2 (1x1, 64 -> 64) -> ReLU -> fAffine.4 (3x3, 64 -> 12,
+//     cross-sigmoid) -> affine coupling + the FlowStep's ActNorm / InvConv1x1 / feature-affine
+// (FlowAffineCouplingsAblation.py:78-96, 114-135; FlowStep.py:88-129) with the two 64-channel hidden maps kept in shared memory / TMEM.
+// The three-launch chain it replaces (conv_tc: z-conv, 1x1, dx-folded head + FlowEpi) moved 1.3 KB per level pixel through HBM for
+// ~450 B of compulsory traffic; here the only HBM traffic is the pre-activation (256 B), z / hF (48 + 48 + 96 B) and the z1 operand.
+//
+// Work decomposition: a work item is a vertical STRIP of 28 output columns x seg_rows output rows of one image.  The CTA marches down
+// the strip in BLOCKS of 128 raster positions = 4 rows x 32 columns (one UMMA M = 128 tile); column c of the raster is image column
+// x0 - 1 + c, so the 30 columns the head conv needs (28 outputs + 1 halo each side) are columns 0..29 and columns 30, 31 are padding.
+// Per block b (h rows yb .. yb+3):
+//   M1: acc1 = pre-activation (identity MMAs over the TMA-loaded BF16X2 tile) + conv3x3(z1): nine shifted views of the 6 x 32 z1 halo tile;
+//       z1 arrives as ONE bf16 plane [hi(8) | lo(8)] per pixel, so  z_hi.W_hi + z_lo.W_hi  is one K = 16 MMA and  z_hi.W_lo  a second one
+//   E1: h1 = relu(acc1 + b1) -> (hi, lo) bf16 planes in the UMMA K-major SWIZZLE_64B layout (activation buffer p = b & 1)
+//   M2: acc2 = h1 . W2 (split-bf16 x3)         E2: h2 = relu(acc2 + b2), zeroed outside the image (the head conv's zero padding), same buffer
+//   M3: acc3[r, tap*16 + co] = h2[r, :] . W3[tap][:, co]  -- all nine taps folded into N = 144, no halo of h2 needed in shared memory
+//   E3: out(y, x) = sum_{dy,dx} acc3[(y-1+dy, x-1+dx), tap]: the dx sum by warp shuffles (a warp holds one raster row), the dy sum through
+//       a ring of 8 row sums in shared memory (row y is complete one row after it was started, so rows are finalised with a lag of one
+//       row and carried across blocks); then bias, cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out).
+// Two blocks are in flight (software pipeline of the single MMA issuer: M1(b), M3(b-2), M2(b-1)); E1/E2 run on 8 warps, E3 on two groups
+// of 4 warps that alternate blocks.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation).
+#include "ops.cuh"
+#include "tc_ptx.cuh"
+#include <vector>
+#include <cstdlib>
+#include <cmath>
+
+namespace bfsr {
+namespace cf {
+constexpr int ROWB = 64;
+constexpr int N3 = 144;                                // 9 taps x 16 columns (12 used)
+constexpr int W1_BYTES = 9 * 64 * ROWB;                // per tap 64 rows: bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
+constexpr int W2_BYTES = 2 * 128 * ROWB;               // per 32-channel chunk [W_hi (64 rows) ; W_lo (64 rows)]
+constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;            // per chunk [W_hi (144 rows) ; W_lo (144 rows)]
+constexpr int ID_BYTES = 32 * ROWB;                    // 32 x 32 identity (pre-activation as K chunks)
+constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;   // 92160
+constexpr int PLANE = 128 * ROWB;                      // one (chunk, plane) operand tile: 128 rows x 64 B
+constexpr int ACT_BYTES = 4 * PLANE;                   // [chunk][hi, lo]
+constexpr int Z1_ROWS = 6 * 32;
+constexpr int Z1_BYTES = Z1_ROWS * ROWB;               // 12288
+constexpr int PRE_BYTES = 4 * PLANE;
+constexpr int EXCH_BYTES = 8 * 12 * 32 * 4;            // ring of 8 row sums x 12 channels x 32 lanes
+constexpr int OFF_ACT = W_BYTES, OFF_Z1 = OFF_ACT + 2 * ACT_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + PRE_BYTES,
+              OFF_BARS = OFF_EXCH + EXCH_BYTES;
+constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;      // + alignment slack
+static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
+static_assert(W_BYTES % 1024 == 0 && Z1_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+constexpr int NTHREADS = 18 * 32;                      // 8 E1/E2 warps, 8 E3 warps, MMA issuer, loader
+constexpr int W_ISSUE = 16, W_LOAD = 17;
+constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_ACC3 = 256, TM_COLS = 512;
+constexpr int OUT_W = 28;                              // output columns per strip
+// mbarrier indices
+enum { B_WFULL = 0, B_Z1FULL = 1, B_Z1EMPTY = 3, B_PREFULL = 5, B_PREEMPTY = 6, B_ACC1FULL = 7, B_H1READY = 9, B_ACC2FULL = 11,
+       B_H2READY = 13, B_ACTFREE = 15, B_ACC3FULL = 17 /* one per E3 group: a waiter must see every phase of its barrier */, B_ACC3EMPTY = 19,
+       B_BARC = 20, B_COUNT = 22 };
+}  // namespace cf
+
+struct CfArgs {
+  alignas(64) CUtensorMap tm_z1;     // (16 ch, W, H, N, 1) bf16, box = 32 ch (upper 16 zero-filled) x 32 px x 6 rows
+  alignas(64) CUtensorMap tm_pre;    // (C, W, H, N, plane) bf16 BF16X2 view, box = 32 ch x 32 px x 4 rows
+  const unsigned char* w;
+  int pre_coff;
+  int H, W, N;
+  int strips, segs, seg_rows, nblk, total_items;
+  float eps;
+  int inv, has_mix, has_hF;
+  View z_in, z_out, hF;
+  __nv_bfloat16* z1_out;             // [npix][16] = [hi(8) | lo(8)] of the first 6 output channels (next step's conv operand) or null
+  float bias1[64], bias2[64], bias3[16];
+  float M[144], cvec[12];
+};
+
+struct Blk { int n, x0, yb, y0, y1; };   // yb = image row of raster row 0 of the block; [y0, y1) = output rows of the item
+__device__ __forceinline__ Blk blk_coord(const CfArgs& a, int b) {
+  const int ii = b / a.nblk, jb = b - ii * a.nblk;
+  int item = (int)blockIdx.x + ii * (int)gridDim.x;
+  const int seg = item % a.segs; item /= a.segs;
+  const int sx = item % a.strips;
+  Blk k;
+  k.n = item / a.strips;
+  k.x0 = sx * cf::OUT_W;
+  k.y0 = seg * a.seg_rows;
+  k.y1 = min(k.y0 + a.seg_rows, a.H);
+  k.yb = k.y0 - 1 + 4 * jb;
+  return k;
+}
+
+// 32 channels of one raster row -> (hi, lo) bf16 planes of an operand tile (row r of 128, 64-byte rows, SWIZZLE_64B)
+__device__ __forceinline__ void store_act_row(unsigned char* tile_hi, int r, const float* o) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = o[8 * k + 2 * e], x1 = o[8 * k + 2 * e + 1];
+      hi[e] = pack_bf16(x0, x1);
+      lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
+    }
+    const uint32_t off = (uint32_t)r * 64u + (uint32_t)((k ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile_hi + cf::PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// FlowStep on one pixel: h = (shift, scale) pairs of the coupling (FlowEpi semantics, ops.cuh); matrices from the kernel parameters
+__device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, long long pix) {
+  constexpr int C = 12;
+  float z[C], o[C];
+  const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) { const float4 v = __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+  float4 hq[C / 2];
+  if (a.has_hF) {
+    const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) hq[k] = __ldg(fp + k);
+  }
+#pragma unroll
+  for (int j = 0; j < C / 2; ++j) {
+    if (a.inv) z[C / 2 + j] = __fdividef(z[C / 2 + j], h[2 * j + 1]) - h[2 * j];
+    else z[C / 2 + j] = (z[C / 2 + j] + h[2 * j]) * h[2 * j + 1];
+  }
+  if (a.inv && a.has_hF) {
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) {
+      z[2 * k] = __fdividef(z[2 * k], hq[k].y) - hq[k].x; z[2 * k + 1] = __fdividef(z[2 * k + 1], hq[k].w) - hq[k].z;
+    }
+  }
+  if (a.has_mix) {
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) acc = fmaf(a.M[co * C + k], z[k], acc);
+      o[co] = a.inv ? acc - a.cvec[co] : acc + a.cvec[co];
+    }
+    if (!a.inv && a.has_hF) {
+#pragma unroll
+      for (int k = 0; k < C / 2; ++k) { o[2 * k] = (o[2 * k] + hq[k].x) * hq[k].y; o[2 * k + 1] = (o[2 * k + 1] + hq[k].z) * hq[k].w; }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = z[c];
+  }
+  float4* dst = reinterpret_cast<float4*>((float*)a.z_out.p + pix * a.z_out.cs + a.z_out.coff);
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  if (a.z1_out) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = e < 3 ? o[2 * e] : 0.f, x1 = e < 3 ? o[2 * e + 1] : 0.f;
+      hi[e] = pack_bf16(x0, x1);
+      lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
+    }
+    uint4* d = reinterpret_cast<uint4*>(a.z1_out + pix * 16);
+    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const __grid_constant__ CfArgs a) {
+  using namespace cf;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sgen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w1 = base, w2 = w1 + W1_BYTES, w3 = w2 + W2_BYTES, wid = w3 + W3_BYTES;
+  const uint32_t act = base + OFF_ACT, z1s = base + OFF_Z1, pres = base + OFF_PRE, bars = base + OFF_BARS;
+  auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = bars + 8u * B_COUNT;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int n_mine = ((int)a.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NB = n_mine * a.nblk;                      // blocks this CTA streams through
+
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; ++i) {
+      uint32_t cnt = 1;
+      if (i == B_H1READY || i == B_H1READY + 1 || i == B_H2READY || i == B_H2READY + 1) cnt = 256;
+      if (i == B_ACC3EMPTY || i == B_BARC || i == B_BARC + 1) cnt = 128;
+      mbar_init(bar(i), cnt);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp == W_LOAD) {
+    // ===================== loader: resident weights once, then per block the z1 halo tile and the pre-activation tile =====================
+    if (elect_one()) {
+      mbar_expect_tx(bar(B_WFULL), W_BYTES);
+      bulk_g2s(w1, a.w, W1_BYTES, bar(B_WFULL));
+      bulk_g2s(w2, a.w + W1_BYTES, W2_BYTES, bar(B_WFULL));
+      bulk_g2s(w3, a.w + W1_BYTES + W2_BYTES, W3_BYTES, bar(B_WFULL));
+      bulk_g2s(wid, a.w + W1_BYTES + W2_BYTES + W3_BYTES, ID_BYTES, bar(B_WFULL));
+    }
+    __syncwarp();
+    for (int b = 0; b < NB; ++b) {
+      const Blk k = blk_coord(a, b);
+      const int p = b & 1, j = b >> 1;
+      mbar_wait_relaxed(bar(B_Z1EMPTY + p), (uint32_t)((j & 1) ^ 1));
+      if (elect_one()) {
+        mbar_expect_tx(bar(B_Z1FULL + p), Z1_BYTES);
+        tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_Z1FULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
+      }
+      __syncwarp();
+      mbar_wait_relaxed(bar(B_PREEMPTY), (uint32_t)((b & 1) ^ 1));
+      if (elect_one()) {
+        mbar_expect_tx(bar(B_PREFULL), PRE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+            tma_load_5d(pres + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
+      }
+      __syncwarp();
+    }
+  } else if (warp == W_ISSUE) {
+    // ===================== MMA issuer: software pipeline M1(it), M3(it-2), M2(it-1) =====================
+    const uint64_t dsc = make_desc(0, 8 * ROWB);        // K-major SWIZZLE_64B, 8-row groups 512 B apart (dense rows)
+    auto D = [&](uint32_t addr) -> uint64_t { return dsc | (uint64_t)((addr & 0x3FFFF) >> 4); };
+    const uint32_t id32 = make_idesc(32), id64 = make_idesc(64), id144 = make_idesc(N3);
+    mbar_wait(bar(B_WFULL), 0);
+    for (int it = 0; it < NB + 2; ++it) {
+      if (it < NB) {                                      // ---- M1(b): pre-activation + conv3x3(z1) -> acc1[p]
+        const int b = it, p = b & 1, j = b >> 1;
+        const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
+        mbar_wait(bar(B_PREFULL), (uint32_t)(b & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma_f16(acc + 32 * c, D(pres + (c * 2 + pl) * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
+          umma_commit(bar(B_PREEMPTY));
+        }
+        __syncwarp();
+        mbar_wait(bar(B_Z1FULL + p), (uint32_t)(j & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t zt = z1s + p * Z1_BYTES;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + tap * 64 * ROWB);
+            umma_f16(acc, A, B1, id64, 1u);
+            umma_f16(acc, A, B1 + 2, id64, 1u);          // + 32 bytes: the [W_lo | 0] half of the weight rows
+          }
+          umma_commit(bar(B_Z1EMPTY + p));
+          umma_commit(bar(B_ACC1FULL + p));
+        }
+        __syncwarp();
+      }
+      if (it >= 2) {                                      // ---- M3(b): tap-folded head, acc3[r, tap*16+co]
+        const int b = it - 2, p = b & 1, j = b >> 1;
+        mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
+        mbar_wait(bar(B_ACC3EMPTY), (uint32_t)((b & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t acc = tmem_base + TM_ACC3;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t Ah = D(act + p * ACT_BYTES + c * 2 * PLANE + ks * 32), Al = Ah + (PLANE >> 4);
+              const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
+              umma_f16(acc, Ah, Bh, id144, (c | ks) ? 1u : 0u);
+              umma_f16(acc, Ah, Bl, id144, 1u);
+              umma_f16(acc, Al, Bh, id144, 1u);
+            }
+          umma_commit(bar(B_ACC3FULL + (b & 1)));
+          umma_commit(bar(B_ACTFREE + p));
+        }
+        __syncwarp();
+      }
+      if (it >= 1 && it <= NB) {                          // ---- M2(b): 1x1, acc2[p]
+        const int b = it - 1, p = b & 1, j = b >> 1;
+        mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t acc = tmem_base + TM_ACC2 + 64 * p;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t Ah = D(act + p * ACT_BYTES + c * 2 * PLANE + ks * 32), Al = Ah + (PLANE >> 4);
+              const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
+              umma_f16(acc, Ah, Bh, id64, (c | ks) ? 1u : 0u);
+              umma_f16(acc, Ah, Bl, id64, 1u);
+              umma_f16(acc, Al, Bh, id64, 1u);
+            }
+          umma_commit(bar(B_ACC2FULL + p));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== E1 / E2: TMEM -> bias, ReLU -> (hi, lo) operand tile of the next GEMM =====================
+    const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter = raster row of the block; 32-channel half
+    const int r = q * 32 + lane;
+    for (int it = 0; it <= NB; ++it) {
+      if (it < NB) {
+        const int b = it, p = b & 1, j = b >> 1;
+        mbar_wait(bar(B_ACC1FULL + p), (uint32_t)(j & 1));
+        mbar_wait(bar(B_ACTFREE + p), (uint32_t)((j & 1) ^ 1));     // M3 of the block that used this buffer two blocks ago has retired
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v[32];
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC1 + 64 * p + 32 * half;
+        tmem_ld16(t_row, v); tmem_ld16(t_row + 16, v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + a.bias1[32 * half + i], 0.f);
+        store_act_row(sgen + OFF_ACT + p * ACT_BYTES + half * 2 * PLANE, r, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar(B_H1READY + p));
+      }
+      if (it >= 1) {
+        const int b = it - 1, p = b & 1, j = b >> 1;
+        const Blk k = blk_coord(a, b);
+        const int y = k.yb + q, x = k.x0 - 1 + lane;
+        const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
+        mbar_wait(bar(B_ACC2FULL + p), (uint32_t)(j & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v[32];
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC2 + 64 * p + 32 * half;
+        tmem_ld16(t_row, v); tmem_ld16(t_row + 16, v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = inside ? fmaxf(v[i] + a.bias2[32 * half + i], 0.f) : 0.f;
+        store_act_row(sgen + OFF_ACT + p * ACT_BYTES + half * 2 * PLANE, r, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar(B_H2READY + p));
+      }
+    }
+  } else {
+    // ===================== E3: tap sums, cross-sigmoid, FlowStep (two groups of 4 warps alternate blocks) =====================
+    const int q = warp & 3, g = (warp - 8) >> 2;
+    float* S = reinterpret_cast<float*>(sgen + OFF_EXCH);
+    for (int b = g; b < NB; b += 2) {
+      const Blk k = blk_coord(a, b);
+      const int yo = k.yb + q - 1, xo = k.x0 + lane;      // the warp holding raster row y finalises output row y - 1
+      const bool valid = lane < OUT_W && xo < a.W && yo >= k.y0 && yo < k.y1;
+      const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
+      mbar_wait(bar(B_ACC3FULL + g), (uint32_t)((b >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float u[3][12];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        float t0[16], t1[16], t2[16];
+        tmem_ld16(t_row + 48 * dy, t0); tmem_ld16(t_row + 48 * dy + 16, t1); tmem_ld16(t_row + 48 * dy + 32, t2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+          u[dy][c] = t0[c] + __shfl_down_sync(0xffffffffu, t1[c], 1) + __shfl_down_sync(0xffffffffu, t2[c], 2);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar(B_ACC3EMPTY));
+      if (b > 0) mbar_wait(bar(B_BARC + ((b - 1) & 1)), (uint32_t)(((b - 1) >> 1) & 1));   // the previous block has read its row sums
+      const int sA = q < 3 ? 4 * (b & 1) + q + 1 : 4 * ((b + 1) & 1);
+      const int sB = 4 * (b & 1) + q;
+      const int sC = q > 0 ? 4 * (b & 1) + q - 1 : 4 * ((b + 1) & 1) + 3;
+#pragma unroll
+      for (int c = 0; c < 12; ++c) S[(sA * 12 + c) * 32 + lane] = u[0][c];       // row y+1 starts with the dy = 0 tap row of row y
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+#pragma unroll
+      for (int c = 0; c < 12; ++c) S[(sB * 12 + c) * 32 + lane] += u[1][c];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      float h[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) h[c] = S[(sC * 12 + c) * 32 + lane] + u[2][c] + a.bias3[c];
+      mbar_arrive(bar(B_BARC + (b & 1)));
+#pragma unroll
+      for (int c = 1; c < 12; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
+      if (valid) flow_apply12(a, h, pix);
+    }
+  }
+  __syncthreads();
+  if (warp == W_ISSUE) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
+// z (fp32, first 6 channels) -> z1 operand plane [hi(8) | lo(8)] bf16 per pixel
+__global__ void z1_pack_kernel(const View z, __nv_bfloat16* out, long long npix) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const float* s = (const float*)z.p + p * z.cs + z.coff;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = e < 3 ? s[2 * e] : 0.f, x1 = e < 3 ? s[2 * e + 1] : 0.f;
+    hi[e] = pack_bf16(x0, x1);
+    lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
+  }
+  uint4* d = reinterpret_cast<uint4*>(out + p * 16);
+  d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+void z1_pack(const View& z, void* z1p, cudaStream_t s) {
+  BFSR_CHECK(z.fmt == F32 && z.C >= 6, "z1_pack: fp32 view with at least 6 channels expected");
+  const long long n = z.npix();
+  if (n == 0) return;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "z1_pack %dx%d", z.H, z.W);
+  ProfScope prof(PK_OTHER, (double)n * (24 + 32), s);
+  z1_pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
+  CUDA_OK(cudaGetLastError());
+  count_launch();
+}
+
+// ------------------------------------------------------------------ host side
+static void put_bf(std::vector<unsigned short>& img, size_t row0, int r, int k, unsigned short v) {   // element k (0..31) of 64-byte row r, SWIZZLE_64B
+  img[(row0 + r) * 32 + (size_t)((((k >> 3) ^ ((r >> 1) & 3)) << 3) + (k & 7))] = v;
+}
+
+bool coupling_fused_enabled() {
+  static const bool off = getenv("BFSR_FUSE_CPL") && atoi(getenv("BFSR_FUSE_CPL")) == 0;
+  return !off;
+}
+
+// Builds the resident weight image from the three packed convs of a coupling (fp32 [tap][cin_pad][cout_pad] device arrays of pack_conv).
+void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4, int C) {
+  using namespace cf;
+  fw = FusedCouplingW();
+  if (C != 12 || fA0z.cout != 64 || fA2.cin != 64 || fA2.cout != 64 || fA4.cin != 64 || fA4.cout != 12 || fA0z.cin > 8 || fA0z.ks != 3 ||
+      fA2.ks != 1 || fA4.ks != 3) return;
+  auto fetch = [](const ConvW& c, std::vector<float>& w, std::vector<float>& b) {
+    w.resize((size_t)c.ks * c.ks * c.cin_pad * c.cout_pad); b.resize(c.cout_pad);
+    CUDA_OK(cudaMemcpy(w.data(), c.w, w.size() * 4, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(b.data(), c.bias, b.size() * 4, cudaMemcpyDeviceToHost));
+  };
+  std::vector<float> wa, ba, wb, bb, wc, bc;
+  fetch(fA0z, wa, ba); fetch(fA2, wb, bb); fetch(fA4, wc, bc);
+  std::vector<unsigned short> img(W_BYTES / 2, 0);
+  auto split = [](float w, unsigned short& hi, unsigned short& lo) { hi = f2bf(w); lo = f2bf(w - bf2f(hi)); };
+  // W1: tap t, row n: k 0..7 = W_hi[ci], 8..15 = W_hi[ci], 16..23 = W_lo[ci], 24..31 = 0
+  for (int t = 0; t < 9; ++t)
+    for (int n = 0; n < 64; ++n)
+      for (int ci = 0; ci < fA0z.cin && ci < 8; ++ci) {
+        unsigned short hi, lo; split(wa[((size_t)t * fA0z.cin_pad + ci) * fA0z.cout_pad + n], hi, lo);
+        put_bf(img, (size_t)t * 64, n, ci, hi); put_bf(img, (size_t)t * 64, n, 8 + ci, hi); put_bf(img, (size_t)t * 64, n, 16 + ci, lo);
+      }
+  // W2: chunk c, rows 0..63 hi, 64..127 lo
+  const size_t r2 = W1_BYTES / ROWB;
+  for (int c = 0; c < 2; ++c)
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < 32; ++k) {
+        unsigned short hi, lo; split(wb[((size_t)(c * 32 + k)) * fA2.cout_pad + n], hi, lo);
+        put_bf(img, r2 + (size_t)c * 128, n, k, hi); put_bf(img, r2 + (size_t)c * 128, 64 + n, k, lo);
+      }
+  // W3: chunk c, rows tap*16 + co (hi), N3 + tap*16 + co (lo)
+  const size_t r3 = r2 + W2_BYTES / ROWB;
+  for (int c = 0; c < 2; ++c)
+    for (int t = 0; t < 9; ++t)
+      for (int co = 0; co < 12; ++co)
+        for (int k = 0; k < 32; ++k) {
+          unsigned short hi, lo; split(wc[((size_t)t * fA4.cin_pad + c * 32 + k) * fA4.cout_pad + co], hi, lo);
+          put_bf(img, r3 + (size_t)c * 2 * N3, t * 16 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 16 + co, k, lo);
+        }
+  const size_t r4 = r3 + W3_BYTES / ROWB;
+  for (int r = 0; r < 32; ++r) put_bf(img, r4, r, r, 0x3F80);
+  CUDA_OK(cudaMalloc(&fw.w, W_BYTES));
+  CUDA_OK(cudaMemcpy(fw.w, img.data(), W_BYTES, cudaMemcpyHostToDevice));
+  for (int i = 0; i < 64; ++i) { fw.bias1[i] = ba[i]; fw.bias2[i] = bb[i]; }
+  for (int i = 0; i < 16; ++i) fw.bias3[i] = i < 12 ? bc[i] : 0.f;
+}
+void free_fused_coupling(FusedCouplingW& fw) { if (fw.w) cudaFree(fw.w); fw.w = nullptr; }
+
+static int g_cf_sms = 0;
+
+// z1p_in / z1p_out: [N,H,W,16] bf16 planes ([hi(8) | lo(8)] of z1); pre: the BF16X2 64-channel pre-activation slice; f as for the conv
+// epilogue (z1op.p != null requests the z1 operand of the next step in z1p_out); hM / hcvec: host copies of f.M / f.cvec
+void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out, const View& pre, const FlowEpi& f, const float* hM,
+                    const float* hcvec, float eps, cudaStream_t s) {
+  using namespace cf;
+  BFSR_CHECK(fw.w && f.C == 12, "coupling_fused: weights not packed / C != 12");
+  const View& z = f.z_in;
+  BFSR_CHECK(pre.fmt == BF16X2 && pre.C == 64 && pre.cs % 8 == 0 && pre.coff % 8 == 0 && pre.plane % 8 == 0 && ((uintptr_t)pre.p % 16) == 0 &&
+             pre.N == z.N && pre.H == z.H && pre.W == z.W, "coupling_fused: pre-activation view");
+  auto v4 = [](const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; };
+  BFSR_CHECK(v4(z) && v4(f.z_out) && z.C == 12 && f.z_out.C == 12 && f.z_out.npix() == z.npix() && (!f.hF.p || (v4(f.hF) && f.hF.C == 24)) &&
+             (!f.has_mix || (hM && hcvec)) && ((uintptr_t)z1p_in % 16) == 0 && ((uintptr_t)z1p_out % 16) == 0 && (!f.z1op.p || z1p_out),
+             "coupling_fused: flow-state views");
+  if (z.npix() == 0) return;
+  if (!g_cf_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_cf_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  CfArgs a = CfArgs();
+  a.w = (const unsigned char*)fw.w; a.pre_coff = pre.coff;
+  a.H = z.H; a.W = z.W; a.N = z.N;
+  a.strips = cdiv(z.W, OUT_W);
+  // vertical segmentation: the cheapest of 1, 2, 4, ... segments per strip under one-CTA-per-SM wave quantisation (each segment recomputes
+  // two halo rows)
+  {
+    double best = 1e300; int best_ns = 1;
+    for (int ns = 1; ns <= 64 && (ns == 1 || cdiv(z.H, ns) >= 8); ns *= 2) {
+      const int rows = cdiv(z.H, ns), nsr = cdiv(z.H, rows);
+      const long long items = (long long)z.N * a.strips * nsr;
+      const double cost = (double)((items + g_cf_sms - 1) / g_cf_sms) * (cdiv(rows + 2, 4) + 1.5);
+      if (cost < best * (1.0 - 1e-9)) { best = cost; best_ns = ns; }
+    }
+    static const int ns_env = getenv("BFSR_CF_SEGS") ? atoi(getenv("BFSR_CF_SEGS")) : 0;
+    if (ns_env > 0) best_ns = ns_env;
+    a.seg_rows = cdiv(z.H, best_ns); a.segs = cdiv(z.H, a.seg_rows);
+  }
+  a.nblk = cdiv(a.seg_rows + 2, 4);
+  const long long items = (long long)z.N * a.strips * a.segs;
+  BFSR_CHECK(items < (1 << 30), "coupling_fused: too many work items");
+  a.total_items = (int)items;
+  a.eps = eps; a.inv = f.inv; a.has_mix = f.has_mix; a.has_hF = f.hF.p ? 1 : 0;
+  a.z_in = z; a.z_out = f.z_out; a.hF = f.hF;
+  a.z1_out = f.z1op.p ? (__nv_bfloat16*)z1p_out : nullptr;
+  memcpy(a.bias1, fw.bias1, sizeof a.bias1); memcpy(a.bias2, fw.bias2, sizeof a.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
+  if (f.has_mix) { memcpy(a.M, hM, sizeof a.M); memcpy(a.cvec, hcvec, sizeof a.cvec); }
+  View zv; zv.p = const_cast<void*>(z1p_in); zv.N = z.N; zv.H = z.H; zv.W = z.W; zv.C = 16; zv.cs = 16; zv.coff = 0; zv.fmt = BF16X2;
+  zv.plane = 16;   // unused second plane: the map is only ever read at plane coordinate 0
+  {
+    const cuuint64_t dims[5] = {16, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N, 1};
+    const cuuint64_t strides[4] = {32, (cuuint64_t)z.W * 32, (cuuint64_t)z.H * z.W * 32, (cuuint64_t)z.N * z.H * z.W * 32};
+    const cuuint32_t box[5] = {32, 32, 6, 1, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const CUresult r = encode_tiled()(&a.tm_z1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, zv.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BFSR_CHECK(r == CUDA_SUCCESS, "coupling_fused: cuTensorMapEncodeTiled(z1) failed (%d)", (int)r);
+  }
+  make_tmap(&a.tm_pre, pre, 32, 4);
+  CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int grid = a.total_items < g_cf_sms ? a.total_items : g_cf_sms;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "cpl-fused C12 %dx%d", z.H, z.W);
+  ProfScope prof(PK_CONV_TC, 2.0 * (double)z.npix() * (8.0 * 9 * 64 + 64.0 * 64 + 64.0 * 9 * 12), s);
+  coupling_fused_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a);
+  CUDA_OK(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace bfsr

@@ -32,6 +32,8 @@ struct FlowEpi {
   int inv = 0, C = 0, has_mix = 1;
   const float* M = nullptr;     // [C][C] row-major (out, in): Mi of this step (inverse) or Mf of the next step (forward)
   const float* cvec = nullptr;  // [C]
+  const float* hM = nullptr;    // host copies of M / cvec (fused coupling kernel: they travel as kernel parameters)
+  const float* hcvec = nullptr;
   View z_in, z_out;             // fp32, C channels, same resolution as the conv output
   View hF;                      // (shiftF, scaleF) pairs, 2C channels; p == nullptr: none
   View z1op;                    // optional BF16X2 operand copy of the first C/2 output channels (padded to a multiple of 8)
@@ -74,6 +76,22 @@ ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float*
                 const std::vector<int>& cin_map, int tc_min_cin = -1 /* smallest Cin packed for the tcgen05 path; -1 = default (32) */);
 void free_conv(ConvW& w);
 
+// ------------------------------------------------------------------ fused coupling step (coupling_fused.cu), C = 12 levels
+// fAffine.0 (z part) -> ReLU -> fAffine.2 -> ReLU -> fAffine.4 -> cross-sigmoid -> FlowStep in ONE launch, hidden maps on chip
+struct FusedCouplingW {
+  void* w = nullptr;                       // resident weight image (split-bf16, pre-swizzled); null: shape not eligible
+  float bias1[64], bias2[64], bias3[16];
+};
+bool coupling_fused_enabled();             // BFSR_FUSE_CPL=0 keeps the three-launch chain
+void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4, int C);
+void free_fused_coupling(FusedCouplingW& fw);
+// z1p_*: [N,H,W,16] bf16 = [hi(8) | lo(8)] of the conditioning half z1 (first 6 channels of z); pre: BF16X2 64-channel slice of the
+// feature-only pre-activations; f: as for the conv epilogue (f.z1op.p != null asks for the next step's z1 operand in z1p_out);
+// hM / hcvec: HOST copies of f.M / f.cvec (they travel as kernel parameters)
+void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out, const View& pre, const FlowEpi& f, const float* hM,
+                    const float* hcvec, float eps, cudaStream_t s);
+void z1_pack(const View& z, void* z1p, cudaStream_t s);
+
 // ------------------------------------------------------------------ layout / resampling
 void nchw_to_nhwc(const float* src, const View& dst, cudaStream_t s);
 void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);
@@ -89,6 +107,7 @@ struct StepW {      // one FlowStep (device pointers, fp32)
   float* Mf = nullptr;  float* cf = nullptr;   // forward: y = Mf z + cf   (W diag(e^logs), W (b*e^logs))
   float* Mi = nullptr;  float* ci = nullptr;   // inverse: z = Mi y - ci   (diag(e^-logs) W^-1, bias)
   float* MfT = nullptr; float* MiT = nullptr;  // the same matrices transposed ([in][out]) for the shared-memory tile kernels
+  std::vector<float> hMf, hcf, hMi, hci;       // host copies (the fused coupling kernel takes them as kernel parameters)
 };
 // encode half-step: [finish previous coupling with h_prev] -> actnorm -> invconv -> [ft-affine with hF]
 //   squeeze_in: z_in is the un-squeezed tensor (N,2H,2W,C/4) read through the Squeeze2d index map (flow.py:122-134)

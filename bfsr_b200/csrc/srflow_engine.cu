@@ -32,6 +32,7 @@ bfsr_srflow::~bfsr_srflow() {
     if (l.step.MfT) cudaFree(l.step.MfT);
     if (l.step.MiT) cudaFree(l.step.MiT);
     free_conv(l.cp.fF2); free_conv(l.cp.fF4); free_conv(l.cp.fA0z); free_conv(l.cp.fA2); free_conv(l.cp.fA4);
+    free_fused_coupling(l.cp.fz);
     free_conv(l.split_conv);
   }
   for (auto& l : levels) {
@@ -97,6 +98,7 @@ static StepW pack_step(const Weights& W, const std::string& p, int C, bool coupl
   std::vector<float> MfT((size_t)C * C), MiT((size_t)C * C);
   for (int o = 0; o < C; ++o) for (int i = 0; i < C; ++i) { MfT[(size_t)i * C + o] = Mf[(size_t)o * C + i]; MiT[(size_t)i * C + o] = Mi[(size_t)o * C + i]; }
   s.MfT = to_device(MfT); s.MiT = to_device(MiT);
+  s.hMf = Mf; s.hcf = cf; s.hMi = Mi; s.hci = ci;
   return s;
 }
 
@@ -191,6 +193,7 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
       l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
       l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
       l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
+      if (Hd == 64) pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C);
       e->layers.push_back(l); ++idx;
     }
     lv.fF0_all = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), {});
@@ -345,10 +348,42 @@ static bool flow_fused(const Run& r, int C) {
   static const bool off = getenv("BFSR_FUSE_FLOW") && atoi(getenv("BFSR_FUSE_FLOW")) == 0;
   return !off && z1_fused(r) && (C == 12 || C == 24);
 }
-static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z1op, bool z1_ready, const View& t1, const View& t2,
-                           const View& hout, const FlowEpi* flow = nullptr) {
+// Per-level scratch: the flow state ping-pongs between two buffers; the affine-net intermediates are reused by
+// every step of the level (all work is ordered on one stream).
+struct LevelBufs {
+  View z[2], z1op, t1, t2, h; int pp = 0;
+  void* z1p[2] = {nullptr, nullptr};   // fused coupling steps: z1 operand planes [hi(8) | lo(8)] bf16 per pixel, read with a halo while the
+  int z1p_cur = 0;                     // next step's plane is written, hence two
+  bool z1p_ready = false;              // z1p[z1p_cur] holds the operand of the current flow state
+  void alloc(Run& r, int H, int W, int C) {
+    const int Hd = r.e->d.hidden;
+    z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
+    t1 = make_view(r.A, r.B, H, W, Hd, fp32_z() ? (int)F32 : r.opfmt()); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
+    h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
+    z1op = make_view(r.A, r.B, H, W, (C / 2 + 7) & ~7, r.opfmt());
+    if (C == 12) for (int i = 0; i < 2; ++i) z1p[i] = r.A.alloc((size_t)r.B * H * W * 32);
+    pp = 0; z1p_cur = 0; z1p_ready = false;
+  }
+  View& next() { View& v = z[pp]; pp ^= 1; return v; }
+};
+
+// One-launch coupling step (coupling_fused.cu): accurate tensor-core mode, C = 12 levels, FlowStep fused (BFSR_FUSE_CPL=0: three launches)
+static bool cpl_fused(const Run& r, const LayerW& l) {
+  return coupling_fused_enabled() && g_conv_mode == 0 && l.cp.fz.w != nullptr && flow_fused(r, l.C);
+}
+// Returns true when the fused kernel ran (the z1 operand of the next step, if requested, then lives in lb.z1p, not in lb.z1op).
+static bool run_affine_net(Run& r, const LayerW& l, const View& z, LevelBufs& lb, bool z1_ready, const FlowEpi* flow = nullptr) {
   const int Hd = r.e->d.hidden;
+  const View &z1op = lb.z1op, &t1 = lb.t1, &t2 = lb.t2, &hout = lb.h;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
+  if (flow && cpl_fused(r, l)) {
+    if (!lb.z1p_ready) K_(z1_pack(z.slice(0, l.C / 2), lb.z1p[lb.z1p_cur], r.s));
+    K_(coupling_fused(l.cp.fz, lb.z1p[lb.z1p_cur], lb.z1p[lb.z1p_cur ^ 1], pre, *flow, flow->hM, flow->hcvec, ConvEpi().eps, r.s));
+    lb.z1p_ready = flow->z1op.p != nullptr;
+    if (lb.z1p_ready) lb.z1p_cur ^= 1;
+    return true;
+  }
+  lb.z1p_ready = false;
   ConvEpi e1; e1.act = ACT_RELU; e1.pre = &pre;
   // z-dependent first conv: split-bf16 x3 on the tensor cores like every other conv (products exact to ~2^-17); BFSR_FP32_Z=1
   // keeps it on the fp32 CUDA-core kernel (the round-1 default) for A/B parity runs
@@ -364,22 +399,8 @@ static void run_affine_net(Run& r, const LayerW& l, const View& z, const View& z
   ConvEpi cs; cs.act = ACT_CROSS_SIGMOID; cs.flow = flow;
   if (flow) { View none = hout; none.p = nullptr; K_(conv2d_tc(l.cp.fA4, t2, none, cs, IN_DIRECT, r.s)); }
   else K_(conv2d(l.cp.fA4, t2, hout, cs, IN_DIRECT, r.s));
+  return false;
 }
-
-// Per-level scratch: the flow state ping-pongs between two buffers; the affine-net intermediates are reused by
-// every step of the level (all work is ordered on one stream).
-struct LevelBufs {
-  View z[2], z1op, t1, t2, h; int pp = 0;
-  void alloc(Run& r, int H, int W, int C) {
-    const int Hd = r.e->d.hidden;
-    z[0] = make_view(r.A, r.B, H, W, C); z[1] = make_view(r.A, r.B, H, W, C);
-    t1 = make_view(r.A, r.B, H, W, Hd, fp32_z() ? (int)F32 : r.opfmt()); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
-    h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
-    z1op = make_view(r.A, r.B, H, W, (C / 2 + 7) & ~7, r.opfmt());
-    pp = 0;
-  }
-  View& next() { View& v = z[pp]; pp ^= 1; return v; }
-};
 
 // FlowUpsamplerNet.encode (FlowUpsamplerNet.py:217-251).  gt: (B, sh, sw, 3) NHWC.  Returns latent views.
 static std::vector<View> run_encode(Run& r, const View& gt) {
@@ -398,13 +419,14 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
       const bool sq = e->layers[i - 1].kind == 0;
       BFSR_CHECK(!(sq && pending), "internal: pending coupling across a squeeze");
       const View* hF = l.kind == 2 ? &r.hF[l.level][l.k_in_level] : nullptr;
-      const bool emit_z1 = l.kind == 2 && z1_fused(r);     // this step's output feeds its own affine net
+      const bool emit_z1 = l.kind == 2 && z1_fused(r) && !cpl_fused(r, l);     // this step's output feeds its own affine net (the one-launch coupling packs its own operand)
       const bool level_end = (i + 1 == e->layers.size()) || e->layers[i + 1].kind == 0 || e->layers[i + 1].kind == 3;
       if (!premixed) {
         View zo = lb.next();
         K_(flowstep_fwd(l.step, z, sq, pending ? &lb.h : nullptr, hF, zo, r.s, emit_z1 ? &lb.z1op : nullptr));
         pending = false;
         z = zo;
+        lb.z1p_ready = false;
       }
       const bool z1_have = emit_z1;      // premixed steps received their z1 copy from the previous coupling's epilogue
       premixed = false;
@@ -415,12 +437,13 @@ static std::vector<View> run_encode(Run& r, const View& gt) {
           const LayerW& nx = e->layers[i + 1];
           BFSR_CHECK(nx.kind == 2 && nx.level == l.level, "internal: coupling followed by a non-coupling step inside a level");
           f.has_mix = 1; f.M = nx.step.Mf; f.cvec = nx.step.cf; f.hF = r.hF[nx.level][nx.k_in_level]; f.z1op = lb.z1op;
+          f.hM = nx.step.hMf.data(); f.hcvec = nx.step.hcf.data();
         } else f.has_mix = 0;
-        run_affine_net(r, l, z, lb.z1op, z1_have, lb.t1, lb.t2, lb.h, &f);
+        run_affine_net(r, l, z, lb, z1_have, &f);
         z = f.z_out;
         premixed = !level_end;
       } else {
-        if (l.kind == 2) { run_affine_net(r, l, z, lb.z1op, z1_have, lb.t1, lb.t2, lb.h); pending = true; }
+        if (l.kind == 2) { run_affine_net(r, l, z, lb, z1_have); pending = true; }
         if (level_end && pending) { K_(coupling_finish(z, lb.h, z, r.s)); pending = false; }   // in place
       }
     } else {   // Split2d forward (Split.py:49-61)
@@ -455,7 +478,7 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
       View zo = make_view(r.A, r.B, H, W, l.C);
       K_(conv2d_fp32(l.split_conv, z, hs, ConvEpi(), IN_DIRECT, r.s));
       K_(split_inv(z, hs, lat[li], zo, r.s));
-      --li; z = zo; z1_ready = false;
+      --li; z = zo; z1_ready = false; lb.z1p_ready = false;
       continue;
     }
     if (l.level != cur_level) { lb.alloc(r, H, W, l.C); cur_level = l.level; }
@@ -463,18 +486,23 @@ static View run_decode(Run& r, const std::vector<View>& lat) {
     View zo = unsq ? make_view(r.A, r.B, 2 * H, 2 * W, l.C / 4) : lb.next();
     // the step's output is the input of the next processed layer: if that is a coupling of the same level, emit its z1 copy
     const bool next_cpl = i > 0 && e->layers[i - 1].kind == 2 && e->layers[i - 1].level == l.level && !unsq && z1_fused(r);
+    // a one-launch coupling next packs / receives its operand in lb.z1p: the step kernels need not emit the BF16X2 copy for it
+    const bool next_one = next_cpl && cpl_fused(r, e->layers[i - 1]) && !(i > 1 && e->layers[i - 2].kind == 0);
+    bool one = false;
     if (l.kind == 2 && flow_fused(r, l.C) && !unsq) {
       FlowEpi f; f.inv = 1; f.C = l.C; f.z_in = z; f.z_out = zo; f.has_mix = 1; f.M = l.step.Mi; f.cvec = l.step.ci;
+      f.hM = l.step.hMi.data(); f.hcvec = l.step.hci.data();
       f.hF = r.hF[l.level][l.k_in_level];
       if (next_cpl) f.z1op = lb.z1op;
-      run_affine_net(r, l, z, lb.z1op, z1_ready, lb.t1, lb.t2, lb.h, &f);
+      one = run_affine_net(r, l, z, lb, z1_ready, &f);
     } else if (l.kind == 2) {
-      run_affine_net(r, l, z, lb.z1op, z1_ready, lb.t1, lb.t2, lb.h);
-      K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s, next_cpl ? &lb.z1op : nullptr));
+      run_affine_net(r, l, z, lb, z1_ready);
+      K_(flowstep_inv(l.step, z, &lb.h, &r.hF[l.level][l.k_in_level], zo, unsq, r.s, next_cpl && !next_one ? &lb.z1op : nullptr));
     } else {
-      K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s, next_cpl ? &lb.z1op : nullptr));
+      K_(flowstep_inv(l.step, z, nullptr, nullptr, zo, unsq, r.s, next_cpl && !next_one ? &lb.z1op : nullptr));
+      lb.z1p_ready = false;
     }
-    z1_ready = next_cpl;
+    z1_ready = next_cpl && !one && !next_one;
     z = zo;
   }
   BFSR_CHECK(z.C == 3, "decode: final tensor has %d channels", z.C);
@@ -498,6 +526,7 @@ static void pack_coupling(const Weights& W, const std::string& p, int C, int Hd,
   l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
   l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
   l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
+  if (Hd == 64) pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C);
 }
 
 // One FlowStep of the reference (FlowStep.py:88-129) through exactly the kernels the engine uses for that step: the feature-only
@@ -547,17 +576,20 @@ void op_flowstep(const bfsr_tensor_t* weights, int n, const char* prefix, int C,
         K_(flowstep_fwd(L.step, z, false, nullptr, coupling ? &hF : nullptr, zo, s, emit_z1 ? &lb.z1op : nullptr));
         if (coupling && flow_fused(r, C)) {
           FlowEpi f; f.inv = 0; f.C = C; f.z_in = zo; f.z_out = zo2; f.has_mix = 0;
-          run_affine_net(r, L, zo, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h, &f);
+          lb.z1p_ready = false;
+          run_affine_net(r, L, zo, lb, emit_z1, &f);
         } else if (coupling) {
-          run_affine_net(r, L, zo, lb.z1op, emit_z1, lb.t1, lb.t2, lb.h);
+          run_affine_net(r, L, zo, lb, emit_z1);
           K_(coupling_finish(zo, lb.h, zo2, s));
         } else K_(resample(zo, zo2, RS_COPY, s));
       } else {
         if (coupling && flow_fused(r, C)) {
           FlowEpi f; f.inv = 1; f.C = C; f.z_in = z; f.z_out = zo2; f.has_mix = 1; f.M = L.step.Mi; f.cvec = L.step.ci; f.hF = hF;
-          run_affine_net(r, L, z, lb.z1op, false, lb.t1, lb.t2, lb.h, &f);
+          f.hM = L.step.hMi.data(); f.hcvec = L.step.hci.data();
+          lb.z1p_ready = false;
+          run_affine_net(r, L, z, lb, false, &f);
         } else if (coupling) {
-          run_affine_net(r, L, z, lb.z1op, false, lb.t1, lb.t2, lb.h);
+          run_affine_net(r, L, z, lb, false);
           K_(flowstep_inv(L.step, z, &lb.h, &hF, zo2, false, s, nullptr));
         } else K_(flowstep_inv(L.step, z, nullptr, nullptr, zo2, false, s, nullptr));
       }
