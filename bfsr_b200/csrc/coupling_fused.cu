@@ -11,48 +11,62 @@
 // Per block b (h rows yb .. yb+3):
 //   M1: acc1 = pre-activation (identity MMAs over the TMA-loaded BF16X2 tile) + conv3x3(z1): nine shifted views of the 6 x 32 z1 halo tile;
 //       z1 arrives as ONE bf16 plane [hi(8) | lo(8)] per pixel, so  z_hi.W_hi + z_lo.W_hi  is one K = 16 MMA and  z_hi.W_lo  a second one
-//   E1: h1 = relu(acc1 + b1) -> (hi, lo) bf16 planes in the UMMA K-major SWIZZLE_64B layout (activation buffer p = b & 1)
-//   M2: acc2 = h1 . W2 (split-bf16 x3)         E2: h2 = relu(acc2 + b2), zeroed outside the image (the head conv's zero padding), same buffer
-//   M3: acc3[r, tap*16 + co] = h2[r, :] . W3[tap][:, co]  -- all nine taps folded into N = 144, no halo of h2 needed in shared memory
-//   E3: out(y, x) = sum_{dy,dx} acc3[(y-1+dy, x-1+dx), tap]: the dx sum by warp shuffles (a warp holds one raster row), the dy sum through
-//       a ring of 8 row sums in shared memory (row y is complete one row after it was started, so rows are finalised with a lag of one
-//       row and carried across blocks); then bias, cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out).
-// Two blocks are in flight (software pipeline of the single MMA issuer: M1(b), M3(b-2), M2(b-1)); E1/E2 run on 8 warps, E3 on two groups
-// of 4 warps that alternate blocks.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation).
+//   E1: h1 = relu(acc1 + b1) -> packed bf16 (hi, lo) written back to TENSOR MEMORY (tcgen05.st) as the A operand of the next GEMM: the
+//       hidden maps never touch shared memory.  (First version: operand tiles in shared memory -- 4550 clk per block, bound by shared-memory
+//       bandwidth: every SS-mode MMA re-reads its 4 KB A slice, 440 KB per block; with A in TMEM an MMA only reads its weights.)
+//   M2: acc2 = h1 . W2 (split-bf16 x3, A from TMEM)   E2: h2 = relu(acc2 + b2), zeroed outside the image (the head conv's zero padding), same columns
+//   M3: acc3[r, tap*12 + co] = h2[r, :] . W3[tap][:, co]  -- all nine taps folded into N = 112, no halo of h2 needed anywhere
+//   E3: out(y, x) = sum_{dy,dx} acc3[(y-1+dy, x-1+dx), tap]: the dx sum by warp shuffles (a warp holds one raster row); the dy = 0 and dy = 1
+//       tap-row sums of every raster row go to a 16-row ring in shared memory, and the warp holding row y finalises output row y - 1 from the
+//       rings (rows y-2, y-1) and its own dy = 2 sums -- rows are finalised with a lag of one row and carried across blocks; then bias,
+//       cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out).
+// Two blocks are in flight (software pipeline of the single MMA issuer: M1(b), M3(b-2), M2(b-1)); E1/E2 run on 8 warps, E3 on three groups
+// of 4 warps that take blocks in rotation.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation).
 #include "ops.cuh"
 #include "tc_ptx.cuh"
 #include <vector>
 #include <cstdlib>
 #include <cmath>
 
+#ifdef BFSR_TC_TRACE
+#define TR_DECL(...) long long __VA_ARGS__
+#define TR_T(x) const long long x = clock64()
+#define TR_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define TR_DECL(...)
+#define TR_T(x)
+#define TR_ADD(acc, t0)
+#endif
+
 namespace bfsr {
 namespace cf {
 constexpr int ROWB = 64;
-constexpr int N3 = 144;                                // 9 taps x 16 columns (12 used)
+constexpr int N3 = 112;                                // 9 taps x 12 columns (+ 4 padding columns)
 constexpr int W1_BYTES = 9 * 64 * ROWB;                // per tap 64 rows: bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
 constexpr int W2_BYTES = 2 * 128 * ROWB;               // per 32-channel chunk [W_hi (64 rows) ; W_lo (64 rows)]
-constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;            // per chunk [W_hi (144 rows) ; W_lo (144 rows)]
+constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;            // per chunk [W_hi (112 rows) ; W_lo (112 rows)]
 constexpr int ID_BYTES = 32 * ROWB;                    // 32 x 32 identity (pre-activation as K chunks)
-constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;   // 92160
+constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;   // 83968
 constexpr int PLANE = 128 * ROWB;                      // one (chunk, plane) operand tile: 128 rows x 64 B
-constexpr int ACT_BYTES = 4 * PLANE;                   // [chunk][hi, lo]
 constexpr int Z1_ROWS = 6 * 32;
 constexpr int Z1_BYTES = Z1_ROWS * ROWB;               // 12288
-constexpr int PRE_BYTES = 4 * PLANE;
-constexpr int EXCH_BYTES = 8 * 12 * 32 * 4;            // ring of 8 row sums x 12 channels x 32 lanes
-constexpr int OFF_ACT = W_BYTES, OFF_Z1 = OFF_ACT + 2 * ACT_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + PRE_BYTES,
-              OFF_BARS = OFF_EXCH + EXCH_BYTES;
-constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;      // + alignment slack
+constexpr int PRE_BYTES = 4 * PLANE;                   // [chunk][hi, lo]
+constexpr int RING = 16;                               // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0 and dy = 1)
+constexpr int EXCH_BYTES = 2 * RING * 12 * 32 * 4;     // [dy][row & 15][12 channels][32 lanes] fp32
+constexpr int OFF_Z1 = W_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + 2 * PRE_BYTES, OFF_BARS = OFF_EXCH + EXCH_BYTES;
+constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;      // + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
 static_assert(W_BYTES % 1024 == 0 && Z1_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
-constexpr int NTHREADS = 18 * 32;                      // 8 E1/E2 warps, 8 E3 warps, MMA issuer, loader
-constexpr int W_ISSUE = 16, W_LOAD = 17;
-constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_ACC3 = 256, TM_COLS = 512;
+constexpr int NG = 3;                                  // E3 groups (4 warps each)
+constexpr int W_ISSUE = 8 + 4 * NG, W_LOAD = W_ISSUE + 1;
+constexpr int NTHREADS = (W_LOAD + 1) * 32;            // 8 E1/E2 warps, 12 E3 warps, MMA issuer, loader
+// tensor memory: fp32 accumulators of the three GEMMs and the packed bf16 A operand (h1, then h2) of block parity p
+constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_A = 256, TM_ACC3 = 384, TM_COLS = 512;
 constexpr int OUT_W = 28;                              // output columns per strip
 // mbarrier indices
-enum { B_WFULL = 0, B_Z1FULL = 1, B_Z1EMPTY = 3, B_PREFULL = 5, B_PREEMPTY = 6, B_ACC1FULL = 7, B_H1READY = 9, B_ACC2FULL = 11,
-       B_H2READY = 13, B_ACTFREE = 15, B_ACC3FULL = 17 /* one per E3 group: a waiter must see every phase of its barrier */, B_ACC3EMPTY = 19,
-       B_BARC = 20, B_COUNT = 22 };
+enum { B_WFULL = 0, B_Z1FULL = 1, B_Z1EMPTY = 3, B_PREFULL = 5, B_PREEMPTY = 7, B_ACC1FULL = 9, B_H1READY = 11, B_ACC2FULL = 13,
+       B_H2READY = 15, B_ACTFREE = 17, B_ACC3FULL = 19 /* one per E3 group: a waiter must see every phase of its barrier */,
+       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 1 /* tap-row sums of a block written */, B_COUNT = B_BARW + NG };
 }  // namespace cf
 
 struct CfArgs {
@@ -63,12 +77,28 @@ struct CfArgs {
   int H, W, N;
   int strips, segs, seg_rows, nblk, total_items;
   float eps;
+  int dbg;                           // timing experiments only (BFSR_CF_DBG bit mask: skip 1 = conv taps, 2 = identity, 4 = M2, 8 = M3 MMAs, 16 = flow epilogue): WRONG results
   int inv, has_mix, has_hF;
   View z_in, z_out, hF;
   __nv_bfloat16* z1_out;             // [npix][16] = [hi(8) | lo(8)] of the first 6 output channels (next step's conv operand) or null
-  float bias1[64], bias2[64], bias3[16];
+  float bias12[128], bias3[16];      // [bias of fAffine.0 (z part: zeros) | bias of fAffine.2], bias of fAffine.4
   float M[144], cvec[12];
 };
+
+// wait of an epilogue role: a short fixed sleep between polls -- 20 warps spinning on try_wait take the issue slots the working warps need
+// (the kernel is close to instruction-issue bound), while the 64..512 ns back-off of mbar_wait_relaxed is too coarse for the hand-offs
+// on the M1 -> E1 -> M2 -> E2 -> M3 chain
+__device__ __forceinline__ void mbar_wait_nap(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(32);
+    if (clock64() - t0 > 8000000000LL) {
+      printf("bfsr coupling_fused: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+      __trap();
+    }
+  }
+}
 
 struct Blk { int n, x0, yb, y0, y1; };   // yb = image row of raster row 0 of the block; [y0, y1) = output rows of the item
 __device__ __forceinline__ Blk blk_coord(const CfArgs& a, int b) {
@@ -85,36 +115,43 @@ __device__ __forceinline__ Blk blk_coord(const CfArgs& a, int b) {
   return k;
 }
 
-// 32 channels of one raster row -> (hi, lo) bf16 planes of an operand tile (row r of 128, 64-byte rows, SWIZZLE_64B)
-__device__ __forceinline__ void store_act_row(unsigned char* tile_hi, int r, const float* o) {
+// 32 channels of one accumulator row -> packed bf16 (hi, lo) words: word i = channels (2i, 2i+1), even channel in the low half
+__device__ __forceinline__ void split_pack32(const float* o, uint32_t* hi, uint32_t* lo) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = o[8 * k + 2 * e], x1 = o[8 * k + 2 * e + 1];
-      hi[e] = pack_bf16(x0, x1);
-      lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
-    }
-    const uint32_t off = (uint32_t)r * 64u + (uint32_t)((k ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(tile_hi + cf::PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  for (int i = 0; i < 16; ++i) {
+    const float x0 = o[2 * i], x1 = o[2 * i + 1];
+    hi[i] = pack_bf16(x0, x1);
+    lo[i] = pack_bf16(x0 - __uint_as_float(hi[i] << 16), x1 - __uint_as_float(hi[i] & 0xffff0000u));
   }
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+// A operand from tensor memory (128 lanes x 8 columns of packed bf16 pairs per K = 16 step), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
 // FlowStep on one pixel: h = (shift, scale) pairs of the coupling (FlowEpi semantics, ops.cuh); matrices from the kernel parameters
-__device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, long long pix) {
+__device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, long long pix, const float4* zq, const float4* hq) {
   constexpr int C = 12;
   float z[C], o[C];
-  const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) { const float4 v = __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
-  float4 hq[C / 2];
-  if (a.has_hF) {
-    const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
-#pragma unroll
-    for (int k = 0; k < C / 2; ++k) hq[k] = __ldg(fp + k);
-  }
+  for (int k = 0; k < C / 4; ++k) { const float4 v = zq[k]; z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
 #pragma unroll
   for (int j = 0; j < C / 2; ++j) {
     if (a.inv) z[C / 2 + j] = __fdividef(z[C / 2 + j], h[2 * j + 1]) - h[2 * j];
@@ -165,7 +202,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sgen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w1 = base, w2 = w1 + W1_BYTES, w3 = w2 + W2_BYTES, wid = w3 + W3_BYTES;
-  const uint32_t act = base + OFF_ACT, z1s = base + OFF_Z1, pres = base + OFF_PRE, bars = base + OFF_BARS;
+  const uint32_t z1s = base + OFF_Z1, pres = base + OFF_PRE, bars = base + OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bars + 8u * B_COUNT;
 
@@ -178,7 +215,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     for (int i = 0; i < B_COUNT; ++i) {
       uint32_t cnt = 1;
       if (i == B_H1READY || i == B_H1READY + 1 || i == B_H2READY || i == B_H2READY + 1) cnt = 256;
-      if (i == B_ACC3EMPTY || i == B_BARC || i == B_BARC + 1) cnt = 128;
+      if (i == B_ACC3EMPTY || (i >= B_BARW && i < B_BARW + NG)) cnt = 128;
       mbar_init(bar(i), cnt);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -204,59 +241,79 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       bulk_g2s(wid, a.w + W1_BYTES + W2_BYTES + W3_BYTES, ID_BYTES, bar(B_WFULL));
     }
     __syncwarp();
+    TR_DECL(tr_z1 = 0, tr_pre = 0); TR_T(tr_start);
     for (int b = 0; b < NB; ++b) {
       const Blk k = blk_coord(a, b);
       const int p = b & 1, j = b >> 1;
+      TR_T(tr0);
       mbar_wait_relaxed(bar(B_Z1EMPTY + p), (uint32_t)((j & 1) ^ 1));
+      TR_ADD(tr_z1, tr0);
       if (elect_one()) {
         mbar_expect_tx(bar(B_Z1FULL + p), Z1_BYTES);
         tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_Z1FULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
       }
       __syncwarp();
-      mbar_wait_relaxed(bar(B_PREEMPTY), (uint32_t)((b & 1) ^ 1));
+      TR_T(tr1);
+      mbar_wait_relaxed(bar(B_PREEMPTY + p), (uint32_t)((j & 1) ^ 1));
+      TR_ADD(tr_pre, tr1);
       if (elect_one()) {
-        mbar_expect_tx(bar(B_PREFULL), PRE_BYTES);
+        mbar_expect_tx(bar(B_PREFULL + p), PRE_BYTES);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)
-            tma_load_5d(pres + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
+            tma_load_5d(pres + p * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL + p), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
       }
       __syncwarp();
     }
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] loader: total %lld wait_z1_empty %lld wait_pre_empty %lld (blocks %d)\n", clock64() - tr_start, tr_z1, tr_pre, NB);
+#endif
   } else if (warp == W_ISSUE) {
     // ===================== MMA issuer: software pipeline M1(it), M3(it-2), M2(it-1) =====================
     const uint64_t dsc = make_desc(0, 8 * ROWB);        // K-major SWIZZLE_64B, 8-row groups 512 B apart (dense rows)
     auto D = [&](uint32_t addr) -> uint64_t { return dsc | (uint64_t)((addr & 0x3FFFF) >> 4); };
-    const uint32_t id32 = make_idesc(32), id64 = make_idesc(64), id144 = make_idesc(N3);
+    const uint32_t id32 = make_idesc(32), id64 = make_idesc(64), idn3 = make_idesc(N3);
     mbar_wait(bar(B_WFULL), 0);
+    TR_DECL(tr_pre = 0, tr_z1 = 0, tr_h2 = 0, tr_a3 = 0, tr_h1 = 0); TR_T(tr_start);
     for (int it = 0; it < NB + 2; ++it) {
       if (it < NB) {                                      // ---- M1(b): pre-activation + conv3x3(z1) -> acc1[p]
         const int b = it, p = b & 1, j = b >> 1;
         const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
-        mbar_wait(bar(B_PREFULL), (uint32_t)(b & 1));
+        TR_T(tr0);
+        mbar_wait(bar(B_PREFULL + p), (uint32_t)(j & 1));
+        TR_ADD(tr_pre, tr0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // (the issue loops are rolled: the kernel's hot code must stay inside the instruction caches -- the fully unrolled first version
+        // spent half of its issue slots of every role waiting for instruction fetches)
         if (elect_one()) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t pt = pres + p * PRE_BYTES + c * 2 * PLANE;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
-                umma_f16(acc + 32 * c, D(pres + (c * 2 + pl) * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
-          umma_commit(bar(B_PREEMPTY));
+                if (!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
+          }
+          umma_commit(bar(B_PREEMPTY + p));
         }
         __syncwarp();
+        TR_T(tr1);
         mbar_wait(bar(B_Z1FULL + p), (uint32_t)(j & 1));
+        TR_ADD(tr_z1, tr1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t zt = z1s + p * Z1_BYTES;
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            if (a.dbg & 1) continue;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - 3 * dy;
-            const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + tap * 64 * ROWB);
-            umma_f16(acc, A, B1, id64, 1u);
-            umma_f16(acc, A, B1 + 2, id64, 1u);          // + 32 bytes: the [W_lo | 0] half of the weight rows
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)(dy * 3 + dx) * 64 * ROWB);
+              umma_f16(acc, A, B1, id64, 1u);
+              umma_f16(acc, A, B1 + 2, id64, 1u);        // + 32 bytes: the [W_lo | 0] half of the weight rows
+            }
           }
           umma_commit(bar(B_Z1EMPTY + p));
           umma_commit(bar(B_ACC1FULL + p));
@@ -265,129 +322,177 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       }
       if (it >= 2) {                                      // ---- M3(b): tap-folded head, acc3[r, tap*16+co]
         const int b = it - 2, p = b & 1, j = b >> 1;
+        TR_T(tr2);
         mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
+        TR_ADD(tr_h2, tr2); TR_T(tr3);
         mbar_wait(bar(B_ACC3EMPTY), (uint32_t)((b & 1) ^ 1));
+        TR_ADD(tr_a3, tr3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC3;
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t Ah = D(act + p * ACT_BYTES + c * 2 * PLANE + ks * 32), Al = Ah + (PLANE >> 4);
+          const uint32_t acc = tmem_base + TM_ACC3, At = tmem_base + TM_A + 64 * p;
+#pragma unroll 1
+          for (int ck = 0; ck < 4; ++ck) {
+              const int c = ck >> 1, ks = ck & 1;
+              const uint32_t Ah = At + 8 * ck, Al = Ah + 32;      // 16 channels = 8 columns of packed pairs; lo plane 32 columns on
               const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
-              umma_f16(acc, Ah, Bh, id144, (c | ks) ? 1u : 0u);
-              umma_f16(acc, Ah, Bl, id144, 1u);
-              umma_f16(acc, Al, Bh, id144, 1u);
+              umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
+              if (a.dbg & 8) continue;
+              umma_f16_ts(acc, Ah, Bl, idn3, 1u);
+              umma_f16_ts(acc, Al, Bh, idn3, 1u);
             }
-          umma_commit(bar(B_ACC3FULL + (b & 1)));
+          umma_commit(bar(B_ACC3FULL + b % NG));
           umma_commit(bar(B_ACTFREE + p));
         }
         __syncwarp();
       }
       if (it >= 1 && it <= NB) {                          // ---- M2(b): 1x1, acc2[p]
         const int b = it - 1, p = b & 1, j = b >> 1;
+        TR_T(tr4);
         mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
+        TR_ADD(tr_h1, tr4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC2 + 64 * p;
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t Ah = D(act + p * ACT_BYTES + c * 2 * PLANE + ks * 32), Al = Ah + (PLANE >> 4);
+          const uint32_t acc = tmem_base + TM_ACC2 + 64 * p, At = tmem_base + TM_A + 64 * p;
+#pragma unroll 1
+          for (int ck = 0; ck < 4; ++ck) {
+              const int c = ck >> 1, ks = ck & 1;
+              const uint32_t Ah = At + 8 * ck, Al = Ah + 32;
               const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
-              umma_f16(acc, Ah, Bh, id64, (c | ks) ? 1u : 0u);
-              umma_f16(acc, Ah, Bl, id64, 1u);
-              umma_f16(acc, Al, Bh, id64, 1u);
+              umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
+              if (a.dbg & 4) continue;
+              umma_f16_ts(acc, Ah, Bl, id64, 1u);
+              umma_f16_ts(acc, Al, Bh, id64, 1u);
             }
           umma_commit(bar(B_ACC2FULL + p));
         }
         __syncwarp();
       }
     }
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] issuer: total %lld wait pre_full %lld z1_full %lld h2_ready %lld acc3_empty %lld h1_ready %lld (blocks %d)\n", clock64() - tr_start, tr_pre, tr_z1, tr_h2, tr_a3, tr_h1, NB);
+#endif
   } else if (warp < 8) {
-    // ===================== E1 / E2: TMEM -> bias, ReLU -> (hi, lo) operand tile of the next GEMM =====================
+    // ===================== E1 / E2: TMEM -> bias, ReLU -> packed (hi, lo) A operand of the next GEMM, back into TMEM =====================
     const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter = raster row of the block; 32-channel half
-    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    TR_DECL(tr_a1 = 0, tr_af = 0, tr_a2 = 0); TR_T(tr_start);
     for (int it = 0; it <= NB; ++it) {
-      if (it < NB) {
-        const int b = it, p = b & 1, j = b >> 1;
-        mbar_wait(bar(B_ACC1FULL + p), (uint32_t)(j & 1));
-        mbar_wait(bar(B_ACTFREE + p), (uint32_t)((j & 1) ^ 1));     // M3 of the block that used this buffer two blocks ago has retired
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ++ph) {                    // ph 0: E1 of block it, ph 1: E2 of block it - 1 (one code path: instruction-cache footprint)
+        const int b = it - ph;
+        if (b < 0 || b >= NB) continue;
+        const int p = b & 1, j = b >> 1;
+        bool inside = true;
+        if (ph == 0) {
+          TR_T(tr0);
+          mbar_wait_nap(bar(B_ACC1FULL + p), (uint32_t)(j & 1));
+          TR_ADD(tr_a1, tr0); TR_T(tr1);
+          mbar_wait_nap(bar(B_ACTFREE + p), (uint32_t)((j & 1) ^ 1));     // M3 of the block that used these A columns two blocks ago has retired
+          TR_ADD(tr_af, tr1);
+        } else {
+          const Blk k = blk_coord(a, b);
+          const int y = k.yb + q, x = k.x0 - 1 + lane;
+          inside = y >= 0 && y < a.H && x >= 0 && x < a.W;  // h2 outside the image is the head conv's zero padding
+          TR_T(tr2);
+          mbar_wait_nap(bar(B_ACC2FULL + p), (uint32_t)(j & 1));
+          TR_ADD(tr_a2, tr2);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v[32];
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC1 + 64 * p + 32 * half;
-        tmem_ld16(t_row, v); tmem_ld16(t_row + 16, v + 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t src = lane_base + (ph ? TM_ACC2 : TM_ACC1) + 64 * p + 32 * half;
+        const uint32_t dst = lane_base + TM_A + 64 * p + 16 * half;
+        const int boff = 64 * ph + 32 * half;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          float v[16];
+          tmem_ld16(src + 16 * g, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + a.bias1[32 * half + i], 0.f);
-        store_act_row(sgen + OFF_ACT + p * ACT_BYTES + half * 2 * PLANE, r, v);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          for (int i = 0; i < 8; ++i) {
+            float x0 = fmaxf(v[2 * i] + a.bias12[boff + 16 * g + 2 * i], 0.f), x1 = fmaxf(v[2 * i + 1] + a.bias12[boff + 16 * g + 2 * i + 1], 0.f);
+            if (!inside) { x0 = 0.f; x1 = 0.f; }
+            hi[i] = pack_bf16(x0, x1);
+            lo[i] = pack_bf16(x0 - __uint_as_float(hi[i] << 16), x1 - __uint_as_float(hi[i] & 0xffff0000u));
+          }
+          tmem_st8(dst + 8 * g, hi); tmem_st8(dst + 32 + 8 * g, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(bar(B_H1READY + p));
-      }
-      if (it >= 1) {
-        const int b = it - 1, p = b & 1, j = b >> 1;
-        const Blk k = blk_coord(a, b);
-        const int y = k.yb + q, x = k.x0 - 1 + lane;
-        const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
-        mbar_wait(bar(B_ACC2FULL + p), (uint32_t)(j & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v[32];
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC2 + 64 * p + 32 * half;
-        tmem_ld16(t_row, v); tmem_ld16(t_row + 16, v + 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = inside ? fmaxf(v[i] + a.bias2[32 * half + i], 0.f) : 0.f;
-        store_act_row(sgen + OFF_ACT + p * ACT_BYTES + half * 2 * PLANE, r, v);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(bar(B_H2READY + p));
+        mbar_arrive(bar((ph ? B_H2READY : B_H1READY) + p));
       }
     }
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && tid == 0) printf("[cf trace] E12: total %lld wait acc1_full %lld act_free %lld acc2_full %lld\n", clock64() - tr_start, tr_a1, tr_af, tr_a2);
+#endif
   } else {
-    // ===================== E3: tap sums, cross-sigmoid, FlowStep (two groups of 4 warps alternate blocks) =====================
+    // ===================== E3: tap sums, cross-sigmoid, FlowStep (NG groups of 4 warps take blocks in rotation) =====================
     const int q = warp & 3, g = (warp - 8) >> 2;
     float* S = reinterpret_cast<float*>(sgen + OFF_EXCH);
-    for (int b = g; b < NB; b += 2) {
+    TR_DECL(tr_a3 = 0, tr_bc = 0, tr_ld = 0, tr_ex = 0, tr_fl = 0); TR_T(tr_start);
+    for (int b = g; b < NB; b += NG) {
       const Blk k = blk_coord(a, b);
       const int yo = k.yb + q - 1, xo = k.x0 + lane;      // the warp holding raster row y finalises output row y - 1
       const bool valid = lane < OUT_W && xo < a.W && yo >= k.y0 && yo < k.y1;
       const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
-      mbar_wait(bar(B_ACC3FULL + g), (uint32_t)((b >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float u[3][12];
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3;
+      float4 zq[3];
+      if (valid) {                                        // flow state of the pixel: in flight while the accumulator is awaited / summed
+        const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        float t0[16], t1[16], t2[16];
-        tmem_ld16(t_row + 48 * dy, t0); tmem_ld16(t_row + 48 * dy + 16, t1); tmem_ld16(t_row + 48 * dy + 32, t2);
+        for (int i = 0; i < 3; ++i) zq[i] = __ldg(zp + i);
+      }
+      TR_T(tr0);
+      mbar_wait_nap(bar(B_ACC3FULL + g), (uint32_t)((b / NG) & 1));
+      TR_ADD(tr_a3, tr0); TR_T(tr1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float u2[12];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3;
+      const int R = 4 * b + q;                            // running raster row of the CTA's block stream; ring slot = row & 15
+#pragma unroll 1
+      for (int dy = 0; dy < 2; ++dy) {                     // needed by the rows below: y + 1 (dy = 0), y (dy = 1)
+        float t[36];                                      // columns 36 dy + 12 dx + co
+        tmem_ld16(t_row + 36 * dy, t); tmem_ld16(t_row + 36 * dy + 16, t + 16); tmem_ld4(t_row + 36 * dy + 32, t + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* Sd = S + (dy * RING + (R & (RING - 1))) * 12 * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+          Sd[c * 32] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+      }
+      {
+        float t[36];
+        tmem_ld16(t_row + 72, t); tmem_ld16(t_row + 72 + 16, t + 16); tmem_ld4(t_row + 72 + 32, t + 32);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 12; ++c)
-          u[dy][c] = t0[c] + __shfl_down_sync(0xffffffffu, t1[c], 1) + __shfl_down_sync(0xffffffffu, t2[c], 2);
+          u2[c] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
       }
+      TR_ADD(tr_ld, tr1); TR_T(tr2);
+      // the previous block's sums are in the ring (awaited BEFORE the accumulator is released: no E3 group can then run two blocks ahead
+      // of a waiter, so every waiter sees every phase of the barriers it polls)
+      if (b > 0) mbar_wait_nap(bar(B_BARW + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar(B_ACC3EMPTY));
-      if (b > 0) mbar_wait(bar(B_BARC + ((b - 1) & 1)), (uint32_t)(((b - 1) >> 1) & 1));   // the previous block has read its row sums
-      const int sA = q < 3 ? 4 * (b & 1) + q + 1 : 4 * ((b + 1) & 1);
-      const int sB = 4 * (b & 1) + q;
-      const int sC = q > 0 ? 4 * (b & 1) + q - 1 : 4 * ((b + 1) & 1) + 3;
+      mbar_arrive(bar(B_BARW + g));
+      float4 hq[6];
+      if (valid && a.has_hF) {
+        const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
-      for (int c = 0; c < 12; ++c) S[(sA * 12 + c) * 32 + lane] = u[0][c];       // row y+1 starts with the dy = 0 tap row of row y
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-#pragma unroll
-      for (int c = 0; c < 12; ++c) S[(sB * 12 + c) * 32 + lane] += u[1][c];
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        for (int i = 0; i < 6; ++i) hq[i] = __ldg(fp + i);
+      }
+      mbar_wait_nap(bar(B_BARW + g), (uint32_t)((b / NG) & 1));
+      TR_ADD(tr_bc, tr2); TR_T(tr3);
       float h[12];
 #pragma unroll
-      for (int c = 0; c < 12; ++c) h[c] = S[(sC * 12 + c) * 32 + lane] + u[2][c] + a.bias3[c];
-      mbar_arrive(bar(B_BARC + (b & 1)));
+      for (int c = 0; c < 12; ++c)
+        h[c] = S[((((R + RING - 2) & (RING - 1))) * 12 + c) * 32 + lane] + S[((RING + ((R + RING - 1) & (RING - 1))) * 12 + c) * 32 + lane] + u2[c] + a.bias3[c];
+      TR_ADD(tr_ex, tr3); TR_T(tr4);
 #pragma unroll
       for (int c = 1; c < 12; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
-      if (valid) flow_apply12(a, h, pix);
+      if (valid && !(a.dbg & 16)) flow_apply12(a, h, pix, zq, hq);
+      TR_ADD(tr_fl, tr4);
     }
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0 && q == 0) printf("[cf trace] E3 g%d: total %lld wait acc3_full %lld ld+shuffle %lld wait barC %lld exchange %lld sigmoid+flow %lld\n", g, clock64() - tr_start, tr_a3, tr_ld, tr_bc, tr_ex, tr_fl);
+#endif
   }
   __syncthreads();
   if (warp == W_ISSUE) {
@@ -464,14 +569,14 @@ void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2
         unsigned short hi, lo; split(wb[((size_t)(c * 32 + k)) * fA2.cout_pad + n], hi, lo);
         put_bf(img, r2 + (size_t)c * 128, n, k, hi); put_bf(img, r2 + (size_t)c * 128, 64 + n, k, lo);
       }
-  // W3: chunk c, rows tap*16 + co (hi), N3 + tap*16 + co (lo)
+  // W3: chunk c, rows tap*12 + co (hi), N3 + tap*12 + co (lo)
   const size_t r3 = r2 + W2_BYTES / ROWB;
   for (int c = 0; c < 2; ++c)
     for (int t = 0; t < 9; ++t)
       for (int co = 0; co < 12; ++co)
         for (int k = 0; k < 32; ++k) {
           unsigned short hi, lo; split(wc[((size_t)t * fA4.cin_pad + c * 32 + k) * fA4.cout_pad + co], hi, lo);
-          put_bf(img, r3 + (size_t)c * 2 * N3, t * 16 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 16 + co, k, lo);
+          put_bf(img, r3 + (size_t)c * 2 * N3, t * 12 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 12 + co, k, lo);
         }
   const size_t r4 = r3 + W3_BYTES / ROWB;
   for (int r = 0; r < 32; ++r) put_bf(img, r4, r, r, 0x3F80);
@@ -521,10 +626,12 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   const long long items = (long long)z.N * a.strips * a.segs;
   BFSR_CHECK(items < (1 << 30), "coupling_fused: too many work items");
   a.total_items = (int)items;
+  static const int dbg_env = getenv("BFSR_CF_DBG") ? atoi(getenv("BFSR_CF_DBG")) : 0;
+  a.dbg = dbg_env;
   a.eps = eps; a.inv = f.inv; a.has_mix = f.has_mix; a.has_hF = f.hF.p ? 1 : 0;
   a.z_in = z; a.z_out = f.z_out; a.hF = f.hF;
   a.z1_out = f.z1op.p ? (__nv_bfloat16*)z1p_out : nullptr;
-  memcpy(a.bias1, fw.bias1, sizeof a.bias1); memcpy(a.bias2, fw.bias2, sizeof a.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
+  memcpy(a.bias12, fw.bias1, sizeof fw.bias1); memcpy(a.bias12 + 64, fw.bias2, sizeof fw.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
   if (f.has_mix) { memcpy(a.M, hM, sizeof a.M); memcpy(a.cvec, hcvec, sizeof a.cvec); }
   View zv; zv.p = const_cast<void*>(z1p_in); zv.N = z.N; zv.H = z.H; zv.W = z.W; zv.C = 16; zv.cs = 16; zv.coff = 0; zv.fmt = BF16X2;
   zv.plane = 16;   // unused second plane: the map is only ever read at plane coordinate 0
