@@ -20,7 +20,7 @@
 //       tap-row sums of every raster row go to a 16-row ring in shared memory, and the warp holding row y finalises output row y - 1 from the
 //       rings (rows y-2, y-1) and its own dy = 2 sums -- rows are finalised with a lag of one row and carried across blocks; then bias,
 //       cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out).
-// Two blocks are in flight (software pipeline of the single MMA issuer: M1(b), M3(b-2), M2(b-1)); E1/E2 run on 8 warps, E3 on three groups
+// Two blocks are in flight; issuer A runs M1 up to two blocks ahead, issuer B interleaves M2(b), M3(b-1); E1/E2 run on 8 warps, E3 on three groups
 // of 4 warps that take blocks in rotation.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation).
 #include "ops.cuh"
 #include "tc_ptx.cuh"
@@ -58,15 +58,16 @@ constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;      // + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
 static_assert(W_BYTES % 1024 == 0 && Z1_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 constexpr int NG = 3;                                  // E3 groups (4 warps each)
-constexpr int W_ISSUE = 8 + 4 * NG, W_LOAD = W_ISSUE + 1;
-constexpr int NTHREADS = (W_LOAD + 1) * 32;            // 8 E1/E2 warps, 12 E3 warps, MMA issuer, loader
-// tensor memory: fp32 accumulators of the three GEMMs and the packed bf16 A operand (h1, then h2) of block parity p
-constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_A = 256, TM_ACC3 = 384, TM_COLS = 512;
+constexpr int W_ISSUE_A = 8 + 4 * NG, W_ISSUE_B = W_ISSUE_A + 1, W_LOAD = W_ISSUE_B + 1;
+constexpr int NTHREADS = (W_LOAD + 1) * 32;            // 8 E1/E2 warps, 12 E3 warps, two MMA issuers, loader
+// tensor memory: fp32 accumulators of the three GEMMs (two stages each).  E1 / E2 convert an accumulator IN PLACE into the packed bf16
+// A operand of the next GEMM: the 16 fp32 columns of a 16-channel group become 8 columns of (hi, hi) pairs + 8 columns of (lo, lo) pairs
+constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_ACC3 = 256, TM_COLS = 512;
 constexpr int OUT_W = 28;                              // output columns per strip
 // mbarrier indices
-enum { B_WFULL = 0, B_Z1FULL = 1, B_Z1EMPTY = 3, B_PREFULL = 5, B_PREEMPTY = 7, B_ACC1FULL = 9, B_H1READY = 11, B_ACC2FULL = 13,
-       B_H2READY = 15, B_ACTFREE = 17, B_ACC3FULL = 19 /* one per E3 group: a waiter must see every phase of its barrier */,
-       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 1 /* tap-row sums of a block written */, B_COUNT = B_BARW + NG };
+enum { B_WFULL = 0, B_INFULL = 1, B_ACC1FULL = 3, B_H1READY = 5, B_ACC2FULL = 7, B_H2READY = 9,
+       B_ACC3FULL = 11 /* one per E3 group: a waiter must see every phase of a barrier it polls */,
+       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 2 /* tap-row sums of a block written */, B_COUNT = B_BARW + NG };
 }  // namespace cf
 
 struct CfArgs {
@@ -81,7 +82,7 @@ struct CfArgs {
   int inv, has_mix, has_hF;
   View z_in, z_out, hF;
   __nv_bfloat16* z1_out;             // [npix][16] = [hi(8) | lo(8)] of the first 6 output channels (next step's conv operand) or null
-  float bias12[128], bias3[16];      // [bias of fAffine.0 (z part: zeros) | bias of fAffine.2], bias of fAffine.4
+  float bias2[64], bias3[16];        // biases of fAffine.2 and fAffine.4 (fAffine.0's rides in the pre-activation: its z part has none)
   float M[144], cvec[12];
 };
 
@@ -114,6 +115,17 @@ __device__ __forceinline__ Blk blk_coord(const CfArgs& a, int b) {
   k.yb = k.y0 - 1 + 4 * jb;
   return k;
 }
+
+// Walks the CTA's block stream without per-block divisions (each role steps through it in order; the three runtime divisions of
+// blk_coord were ~150 instructions per block per warp in a kernel that is close to instruction-issue bound)
+struct BlkIter {
+  int ii = 0, jb = 0; Blk k;
+  __device__ __forceinline__ void init(const CfArgs& a, int b) { ii = b / a.nblk; jb = b - ii * a.nblk; k = blk_coord(a, b); }
+  __device__ __forceinline__ void advance(const CfArgs& a, int n) {
+    jb += n; k.yb += 4 * n;
+    if (jb >= a.nblk) { while (jb >= a.nblk) { jb -= a.nblk; ++ii; } k = blk_coord(a, ii * a.nblk + jb); }
+  }
+};
 
 // 32 channels of one accumulator row -> packed bf16 (hi, lo) words: word i = channels (2i, 2i+1), even channel in the low half
 __device__ __forceinline__ void split_pack32(const float* o, uint32_t* hi, uint32_t* lo) {
@@ -215,12 +227,12 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     for (int i = 0; i < B_COUNT; ++i) {
       uint32_t cnt = 1;
       if (i == B_H1READY || i == B_H1READY + 1 || i == B_H2READY || i == B_H2READY + 1) cnt = 256;
-      if (i == B_ACC3EMPTY || (i >= B_BARW && i < B_BARW + NG)) cnt = 128;
+      if (i == B_ACC3EMPTY || i == B_ACC3EMPTY + 1 || (i >= B_BARW && i < B_BARW + NG)) cnt = 128;
       mbar_init(bar(i), cnt);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == W_ISSUE) {
+  if (warp == W_ISSUE_A) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -241,142 +253,143 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       bulk_g2s(wid, a.w + W1_BYTES + W2_BYTES + W3_BYTES, ID_BYTES, bar(B_WFULL));
     }
     __syncwarp();
-    TR_DECL(tr_z1 = 0, tr_pre = 0); TR_T(tr_start);
-    for (int b = 0; b < NB; ++b) {
-      const Blk k = blk_coord(a, b);
+    TR_DECL(tr_in = 0); TR_T(tr_start);
+    BlkIter bi; bi.init(a, 0);
+    for (int b = 0; b < NB; ++b, bi.advance(a, 1)) {
+      const Blk& k = bi.k;
       const int p = b & 1, j = b >> 1;
       TR_T(tr0);
-      mbar_wait_relaxed(bar(B_Z1EMPTY + p), (uint32_t)((j & 1) ^ 1));
-      TR_ADD(tr_z1, tr0);
+      mbar_wait_relaxed(bar(B_ACC1FULL + p), (uint32_t)((j & 1) ^ 1));    // M1 of the block that used stage p two blocks ago has retired
+      TR_ADD(tr_in, tr0);
       if (elect_one()) {
-        mbar_expect_tx(bar(B_Z1FULL + p), Z1_BYTES);
-        tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_Z1FULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
-      }
-      __syncwarp();
-      TR_T(tr1);
-      mbar_wait_relaxed(bar(B_PREEMPTY + p), (uint32_t)((j & 1) ^ 1));
-      TR_ADD(tr_pre, tr1);
-      if (elect_one()) {
-        mbar_expect_tx(bar(B_PREFULL + p), PRE_BYTES);
+        mbar_expect_tx(bar(B_INFULL + p), Z1_BYTES + PRE_BYTES);
+        tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_INFULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)
-            tma_load_5d(pres + p * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL + p), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
+            tma_load_5d(pres + p * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_INFULL + p), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
       }
       __syncwarp();
     }
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] loader: total %lld wait_z1_empty %lld wait_pre_empty %lld (blocks %d)\n", clock64() - tr_start, tr_z1, tr_pre, NB);
+    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] loader: total %lld wait stage free %lld (blocks %d)\n", clock64() - tr_start, tr_in, NB);
 #endif
-  } else if (warp == W_ISSUE) {
-    // ===================== MMA issuer: software pipeline M1(it), M3(it-2), M2(it-1) =====================
+  } else if (warp == W_ISSUE_A) {
+    // ===================== MMA issuer A: M1(b) = pre-activation + conv3x3(z1) -> acc1[p], up to two blocks ahead of the epilogues ==========
+    // (one thread sustains a tcgen05.mma per ~40-50 clk and every barrier poll / commit costs it ~100 clk more: with a single issuer the
+    // 50 MMAs + 10 barrier operations of a block took 3700 clk and bounded the kernel)
     const uint64_t dsc = make_desc(0, 8 * ROWB);        // K-major SWIZZLE_64B, 8-row groups 512 B apart (dense rows)
     auto D = [&](uint32_t addr) -> uint64_t { return dsc | (uint64_t)((addr & 0x3FFFF) >> 4); };
-    const uint32_t id32 = make_idesc(32), id64 = make_idesc(64), idn3 = make_idesc(N3);
+    const uint32_t id32 = make_idesc(32), id64 = make_idesc(64);
     mbar_wait(bar(B_WFULL), 0);
-    TR_DECL(tr_pre = 0, tr_z1 = 0, tr_h2 = 0, tr_a3 = 0, tr_h1 = 0); TR_T(tr_start);
-    for (int it = 0; it < NB + 2; ++it) {
-      if (it < NB) {                                      // ---- M1(b): pre-activation + conv3x3(z1) -> acc1[p]
+    TR_DECL(tr_in = 0, tr_h1 = 0); TR_T(tr_start);
+    for (int b = 0; b < NB; ++b) {
+      const int p = b & 1, j = b >> 1;
+      const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
+      TR_T(tr0);
+      mbar_wait(bar(B_INFULL + p), (uint32_t)(j & 1));
+      TR_ADD(tr_in, tr0); TR_T(tr1);
+      mbar_wait(bar(B_ACC2FULL + p), (uint32_t)((j & 1) ^ 1));            // M2 of block b - 2 has consumed h1, which lives in the columns of acc1[p]
+      TR_ADD(tr_h1, tr1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // (the issue loops are rolled: the kernel's hot code must stay inside the instruction caches -- the fully unrolled first version
+      // spent half of its issue slots of every role waiting for instruction fetches)
+      if (elect_one()) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t pt = pres + p * PRE_BYTES + c * 2 * PLANE;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              if (!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
+        }
+        const uint32_t zt = z1s + p * Z1_BYTES;
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+          if (a.dbg & 1) continue;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)(dy * 3 + dx) * 64 * ROWB);
+            umma_f16(acc, A, B1, id64, 1u);
+            umma_f16(acc, A, B1 + 2, id64, 1u);          // + 32 bytes: the [W_lo | 0] half of the weight rows
+          }
+        }
+        umma_commit(bar(B_ACC1FULL + p));                 // releases E1 and, two blocks later, the loader's stage p
+      }
+      __syncwarp();
+    }
+#ifdef BFSR_TC_TRACE
+    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] issuer A: total %lld wait in_full %lld acc2_full(b-2) %lld (blocks %d)\n", clock64() - tr_start, tr_in, tr_h1, NB);
+#endif
+  } else if (warp == W_ISSUE_B) {
+    // ===================== MMA issuer B: M2(it) = 1x1, then M3(it-1) = tap-folded head (E2 of block it-1 runs under M3(it-2) / M2(it)),
+    // both with the A operand in tensor memory =====================
+    const uint64_t dsc = make_desc(0, 8 * ROWB);
+    auto D = [&](uint32_t addr) -> uint64_t { return dsc | (uint64_t)((addr & 0x3FFFF) >> 4); };
+    const uint32_t id64 = make_idesc(64), idn3 = make_idesc(N3);
+    mbar_wait(bar(B_WFULL), 0);
+    TR_DECL(tr_h2 = 0, tr_a3 = 0, tr_h1 = 0); TR_T(tr_start);
+    for (int it = 0; it <= NB; ++it) {
+      if (it < NB) {                                      // ---- M2(b): 1x1, acc2[p]
         const int b = it, p = b & 1, j = b >> 1;
-        const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
-        TR_T(tr0);
-        mbar_wait(bar(B_PREFULL + p), (uint32_t)(j & 1));
-        TR_ADD(tr_pre, tr0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // (the issue loops are rolled: the kernel's hot code must stay inside the instruction caches -- the fully unrolled first version
-        // spent half of its issue slots of every role waiting for instruction fetches)
-        if (elect_one()) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t pt = pres + p * PRE_BYTES + c * 2 * PLANE;
-#pragma unroll
-            for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks)
-                if (!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
-          }
-          umma_commit(bar(B_PREEMPTY + p));
-        }
-        __syncwarp();
-        TR_T(tr1);
-        mbar_wait(bar(B_Z1FULL + p), (uint32_t)(j & 1));
-        TR_ADD(tr_z1, tr1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t zt = z1s + p * Z1_BYTES;
-#pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy) {
-            if (a.dbg & 1) continue;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)(dy * 3 + dx) * 64 * ROWB);
-              umma_f16(acc, A, B1, id64, 1u);
-              umma_f16(acc, A, B1 + 2, id64, 1u);        // + 32 bytes: the [W_lo | 0] half of the weight rows
-            }
-          }
-          umma_commit(bar(B_Z1EMPTY + p));
-          umma_commit(bar(B_ACC1FULL + p));
-        }
-        __syncwarp();
-      }
-      if (it >= 2) {                                      // ---- M3(b): tap-folded head, acc3[r, tap*16+co]
-        const int b = it - 2, p = b & 1, j = b >> 1;
-        TR_T(tr2);
-        mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
-        TR_ADD(tr_h2, tr2); TR_T(tr3);
-        mbar_wait(bar(B_ACC3EMPTY), (uint32_t)((b & 1) ^ 1));
-        TR_ADD(tr_a3, tr3);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC3, At = tmem_base + TM_A + 64 * p;
-#pragma unroll 1
-          for (int ck = 0; ck < 4; ++ck) {
-              const int c = ck >> 1, ks = ck & 1;
-              const uint32_t Ah = At + 8 * ck, Al = Ah + 32;      // 16 channels = 8 columns of packed pairs; lo plane 32 columns on
-              const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
-              umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
-              if (a.dbg & 8) continue;
-              umma_f16_ts(acc, Ah, Bl, idn3, 1u);
-              umma_f16_ts(acc, Al, Bh, idn3, 1u);
-            }
-          umma_commit(bar(B_ACC3FULL + b % NG));
-          umma_commit(bar(B_ACTFREE + p));
-        }
-        __syncwarp();
-      }
-      if (it >= 1 && it <= NB) {                          // ---- M2(b): 1x1, acc2[p]
-        const int b = it - 1, p = b & 1, j = b >> 1;
         TR_T(tr4);
         mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
         TR_ADD(tr_h1, tr4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC2 + 64 * p, At = tmem_base + TM_A + 64 * p;
+          const uint32_t acc = tmem_base + TM_ACC2 + 64 * p, At = tmem_base + TM_ACC1 + 64 * p;   // h1 sits where acc1 was
 #pragma unroll 1
           for (int ck = 0; ck < 4; ++ck) {
-              const int c = ck >> 1, ks = ck & 1;
-              const uint32_t Ah = At + 8 * ck, Al = Ah + 32;
-              const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
-              umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
-              if (a.dbg & 4) continue;
-              umma_f16_ts(acc, Ah, Bl, id64, 1u);
-              umma_f16_ts(acc, Al, Bh, id64, 1u);
-            }
+            const int c = ck >> 1, ks = ck & 1;
+            const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
+            const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
+            umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
+            if (a.dbg & 4) continue;
+            umma_f16_ts(acc, Ah, Bl, id64, 1u);
+            umma_f16_ts(acc, Al, Bh, id64, 1u);
+          }
           umma_commit(bar(B_ACC2FULL + p));
+        }
+        __syncwarp();
+      }
+      if (it >= 1) {                                      // ---- M3(b): acc3[r, tap*12+co]
+        const int b = it - 1, p = b & 1, j = b >> 1;
+        TR_T(tr2);
+        mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
+        TR_ADD(tr_h2, tr2); TR_T(tr3);
+        mbar_wait(bar(B_ACC3EMPTY + p), (uint32_t)((j & 1) ^ 1));
+        TR_ADD(tr_a3, tr3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t acc = tmem_base + TM_ACC3 + N3 * p, At = tmem_base + TM_ACC2 + 64 * p;    // h2 sits where acc2 was
+#pragma unroll 1
+          for (int ck = 0; ck < 4; ++ck) {
+            const int c = ck >> 1, ks = ck & 1;
+            const uint32_t Ah = At + 16 * ck, Al = Ah + 8;
+            const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
+            umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
+            if (a.dbg & 8) continue;
+            umma_f16_ts(acc, Ah, Bl, idn3, 1u);
+            umma_f16_ts(acc, Al, Bh, idn3, 1u);
+          }
+          umma_commit(bar(B_ACC3FULL + b % NG));
         }
         __syncwarp();
       }
     }
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] issuer: total %lld wait pre_full %lld z1_full %lld h2_ready %lld acc3_empty %lld h1_ready %lld (blocks %d)\n", clock64() - tr_start, tr_pre, tr_z1, tr_h2, tr_a3, tr_h1, NB);
+    if (blockIdx.x == 0 && lane == 0) printf("[cf trace] issuer B: total %lld wait h2_ready %lld acc3_empty %lld h1_ready %lld (blocks %d)\n", clock64() - tr_start, tr_h2, tr_a3, tr_h1, NB);
 #endif
   } else if (warp < 8) {
     // ===================== E1 / E2: TMEM -> bias, ReLU -> packed (hi, lo) A operand of the next GEMM, back into TMEM =====================
     const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter = raster row of the block; 32-channel half
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    TR_DECL(tr_a1 = 0, tr_af = 0, tr_a2 = 0); TR_T(tr_start);
+    TR_DECL(tr_a1 = 0, tr_a2 = 0); TR_T(tr_start);
+    BlkIter bi; bi.init(a, 0);                          // block it - 1 (E2's coordinates)
     for (int it = 0; it <= NB; ++it) {
+      if (it >= 2) bi.advance(a, 1);
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {                    // ph 0: E1 of block it, ph 1: E2 of block it - 1 (one code path: instruction-cache footprint)
         const int b = it - ph;
@@ -386,11 +399,9 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
         if (ph == 0) {
           TR_T(tr0);
           mbar_wait_nap(bar(B_ACC1FULL + p), (uint32_t)(j & 1));
-          TR_ADD(tr_a1, tr0); TR_T(tr1);
-          mbar_wait_nap(bar(B_ACTFREE + p), (uint32_t)((j & 1) ^ 1));     // M3 of the block that used these A columns two blocks ago has retired
-          TR_ADD(tr_af, tr1);
+          TR_ADD(tr_a1, tr0);
         } else {
-          const Blk k = blk_coord(a, b);
+          const Blk& k = bi.k;
           const int y = k.yb + q, x = k.x0 - 1 + lane;
           inside = y >= 0 && y < a.H && x >= 0 && x < a.W;  // h2 outside the image is the head conv's zero padding
           TR_T(tr2);
@@ -398,23 +409,29 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
           TR_ADD(tr_a2, tr2);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t src = lane_base + (ph ? TM_ACC2 : TM_ACC1) + 64 * p + 32 * half;
-        const uint32_t dst = lane_base + TM_A + 64 * p + 16 * half;
-        const int boff = 64 * ph + 32 * half;
-#pragma unroll 1
+        const uint32_t src = lane_base + (ph ? TM_ACC2 : TM_ACC1) + 64 * p + 32 * half;   // this warp's two 16-channel groups, converted in place
+        float v[32];
+        tmem_ld16(src, v); tmem_ld16(src + 16, v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ph) {                                          // fAffine.2's bias (fAffine.0's rides in the pre-activation)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += a.bias2[32 * half + i];
+        }
+        const bool all_in = __all_sync(0xffffffffu, inside);
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
-          float v[16];
-          tmem_ld16(src + 16 * g, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x0 = fmaxf(v[2 * i] + a.bias12[boff + 16 * g + 2 * i], 0.f), x1 = fmaxf(v[2 * i + 1] + a.bias12[boff + 16 * g + 2 * i + 1], 0.f);
-            if (!inside) { x0 = 0.f; x1 = 0.f; }
+            const float x0 = fmaxf(v[16 * g + 2 * i], 0.f), x1 = fmaxf(v[16 * g + 2 * i + 1], 0.f);
             hi[i] = pack_bf16(x0, x1);
             lo[i] = pack_bf16(x0 - __uint_as_float(hi[i] << 16), x1 - __uint_as_float(hi[i] & 0xffff0000u));
           }
-          tmem_st8(dst + 8 * g, hi); tmem_st8(dst + 32 + 8 * g, lo);
+          if (!all_in) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hi[i] = inside ? hi[i] : 0u; lo[i] = inside ? lo[i] : 0u; }
+          }
+          tmem_st8(src + 16 * g, hi); tmem_st8(src + 16 * g + 8, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -422,15 +439,16 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       }
     }
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && tid == 0) printf("[cf trace] E12: total %lld wait acc1_full %lld act_free %lld acc2_full %lld\n", clock64() - tr_start, tr_a1, tr_af, tr_a2);
+    if (blockIdx.x == 0 && tid == 0) printf("[cf trace] E12: total %lld wait acc1_full %lld acc2_full %lld\n", clock64() - tr_start, tr_a1, tr_a2);
 #endif
   } else {
     // ===================== E3: tap sums, cross-sigmoid, FlowStep (NG groups of 4 warps take blocks in rotation) =====================
     const int q = warp & 3, g = (warp - 8) >> 2;
     float* S = reinterpret_cast<float*>(sgen + OFF_EXCH);
     TR_DECL(tr_a3 = 0, tr_bc = 0, tr_ld = 0, tr_ex = 0, tr_fl = 0); TR_T(tr_start);
-    for (int b = g; b < NB; b += NG) {
-      const Blk k = blk_coord(a, b);
+    BlkIter bi; bi.init(a, g < NB ? g : 0);
+    for (int b = g; b < NB; b += NG, bi.advance(a, NG)) {
+      const Blk& k = bi.k;
       const int yo = k.yb + q - 1, xo = k.x0 + lane;      // the warp holding raster row y finalises output row y - 1
       const bool valid = lane < OUT_W && xo < a.W && yo >= k.y0 && yo < k.y1;
       const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
@@ -445,7 +463,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       TR_ADD(tr_a3, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float u2[12];
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3 + N3 * (b & 1);
       const int R = 4 * b + q;                            // running raster row of the CTA's block stream; ring slot = row & 15
 #pragma unroll 1
       for (int dy = 0; dy < 2; ++dy) {                     // needed by the rows below: y + 1 (dy = 0), y (dy = 1)
@@ -470,7 +488,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       // of a waiter, so every waiter sees every phase of the barriers it polls)
       if (b > 0) mbar_wait_nap(bar(B_BARW + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar(B_ACC3EMPTY));
+      mbar_arrive(bar(B_ACC3EMPTY + (b & 1)));
       mbar_arrive(bar(B_BARW + g));
       float4 hq[6];
       if (valid && a.has_hF) {
@@ -495,7 +513,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 #endif
   }
   __syncthreads();
-  if (warp == W_ISSUE) {
+  if (warp == W_ISSUE_A) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TM_COLS) : "memory");
   }
@@ -631,7 +649,8 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   a.eps = eps; a.inv = f.inv; a.has_mix = f.has_mix; a.has_hF = f.hF.p ? 1 : 0;
   a.z_in = z; a.z_out = f.z_out; a.hF = f.hF;
   a.z1_out = f.z1op.p ? (__nv_bfloat16*)z1p_out : nullptr;
-  memcpy(a.bias12, fw.bias1, sizeof fw.bias1); memcpy(a.bias12 + 64, fw.bias2, sizeof fw.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
+  for (int i = 0; i < 64; ++i) BFSR_CHECK(fw.bias1[i] == 0.f, "coupling_fused: the z part of fAffine.0 must be packed without a bias");
+  memcpy(a.bias2, fw.bias2, sizeof a.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
   if (f.has_mix) { memcpy(a.M, hM, sizeof a.M); memcpy(a.cvec, hcvec, sizeof a.cvec); }
   View zv; zv.p = const_cast<void*>(z1p_in); zv.N = z.N; zv.H = z.H; zv.W = z.W; zv.C = 16; zv.cs = 16; zv.coff = 0; zv.fmt = BF16X2;
   zv.plane = 16;   // unused second plane: the map is only ever read at plane coordinate 0
