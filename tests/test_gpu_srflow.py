@@ -354,6 +354,27 @@ def test_cluster_multicast_variant_subprocess():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_one_launch_coupling_vs_three_launch_chain(tmp_path):
+    """coupling_fused_kernel (C = 12 levels: z-conv -> 1x1 -> tap-folded head -> FlowStep in one launch, hidden maps in tensor memory)
+    against the three conv_tc launches it replaces, through bfsr_op_flowstep in both directions: ragged strips / rows, batch > 1,
+    several vertical segments per strip (forced with BFSR_CF_SEGS as well).  Same split-bf16 products, different summation order:
+    <= 5e-6 rel-L2.  The switches are read once per process, hence the subprocesses (tools/cpl_check.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from tools import cpl_check
+    outs = {}
+    for name, env in (("chain", {"BFSR_FUSE_CPL": "0"}), ("fused", {"BFSR_FUSE_CPL": "1"}), ("fused_s3", {"BFSR_FUSE_CPL": "1", "BFSR_CF_SEGS": "3"})):
+        path = str(tmp_path / f"{name}.pt")
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "cpl_check.py"), "run", path], env=dict(os.environ, **env), cwd=root,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[name] = path
+    assert cpl_check.cmp(outs["chain"], outs["fused"], tol=5e-6) == 0
+    assert cpl_check.cmp(outs["chain"], outs["fused_s3"], tol=5e-6) == 0
+
+
 # ------------------------------------------------------------------ reference-recorded pins at the BASELINE shapes (round 2)
 def test_config2_tile_vs_reference_golden():
     """BASELINE config 2 geometry: tile 0 of the bench batch (160x160 LR, shipped topology) through the engine -- fused LP path,

@@ -30,7 +30,7 @@ def run(path):
     print("saved", path, {k: float(v.abs().mean()) for k, v in out.items()})
 
 
-def cmp(pa, pb):
+def cmp(pa, pb, tol=2e-5):
     a, b = torch.load(pa), torch.load(pb)
     bad = 0
     for k in a:
@@ -38,7 +38,7 @@ def cmp(pa, pb):
         rel = float(d.norm() / a[k].double().norm())
         mx = float(d.abs().max())
         print(f"{k:20s} rel-L2 {rel:.3e} max-abs {mx:.3e} finite {bool(torch.isfinite(b[k]).all())}")
-        if not (rel < 2e-5):
+        if not (rel < tol) or not bool(torch.isfinite(b[k]).all()):
             bad += 1
             idx = (d.abs() > 1e-3).nonzero()
             print("   first bad indices:", idx[:8].tolist(), " count", idx.shape[0])
