@@ -41,37 +41,51 @@
 namespace bfsr {
 namespace cf {
 constexpr int ROWB = 64;
-constexpr int N3 = 112;                                // 9 taps x 12 columns (+ 4 padding columns)
-constexpr int W1_BYTES = 9 * 64 * ROWB;                // per tap 64 rows: bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
-constexpr int W2_BYTES = 2 * 128 * ROWB;               // per 32-channel chunk [W_hi (64 rows) ; W_lo (64 rows)]
-constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;            // per chunk [W_hi (112 rows) ; W_lo (112 rows)]
-constexpr int ID_BYTES = 32 * ROWB;                    // 32 x 32 identity (pre-activation as K chunks)
-constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;   // 83968
 constexpr int PLANE = 128 * ROWB;                      // one (chunk, plane) operand tile: 128 rows x 64 B
 constexpr int Z1_ROWS = 6 * 32;
 constexpr int Z1_BYTES = Z1_ROWS * ROWB;               // 12288
 constexpr int PRE_BYTES = 4 * PLANE;                   // [chunk][hi, lo]
-constexpr int RING = 16;                               // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0 and dy = 1)
-constexpr int EXCH_BYTES = 2 * RING * 12 * 32 * 4;     // [dy][row & 15][12 channels][32 lanes] fp32
-constexpr int OFF_Z1 = W_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + 2 * PRE_BYTES, OFF_BARS = OFF_EXCH + EXCH_BYTES;
-constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;      // + alignment slack
-static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
-static_assert(W_BYTES % 1024 == 0 && Z1_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+constexpr int W2_BYTES = 2 * 128 * ROWB;               // per 32-channel chunk [W_hi (64 rows) ; W_lo (64 rows)]
+constexpr int ID_BYTES = 32 * ROWB;                    // 32 x 32 identity (pre-activation as K chunks)
 constexpr int NG = 3;                                  // E3 groups (4 warps each)
 constexpr int W_ISSUE_A = 8 + 4 * NG, W_ISSUE_B = W_ISSUE_A + 1, W_LOAD = W_ISSUE_B + 1;
 constexpr int NTHREADS = (W_LOAD + 1) * 32;            // 8 E1/E2 warps, 12 E3 warps, two MMA issuers, loader
-// tensor memory: fp32 accumulators of the three GEMMs (two stages each).  E1 / E2 convert an accumulator IN PLACE into the packed bf16
+// tensor memory: fp32 accumulators of the three GEMMs.  E1 / E2 convert an accumulator IN PLACE into the packed bf16
 // A operand of the next GEMM: the 16 fp32 columns of a 16-channel group become 8 columns of (hi, hi) pairs + 8 columns of (lo, lo) pairs
 constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_ACC3 = 256, TM_COLS = 512;
 constexpr int OUT_W = 28;                              // output columns per strip
 // mbarrier indices
-enum { B_WFULL = 0, B_INFULL = 1, B_ACC1FULL = 3, B_H1READY = 5, B_ACC2FULL = 7, B_H2READY = 9,
-       B_ACC3FULL = 11 /* one per E3 group: a waiter must see every phase of a barrier it polls */,
-       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 2 /* tap-row sums of a block written */, B_COUNT = B_BARW + NG };
+enum { B_WFULL = 0, B_INFULL = 1, B_PREFULL = 3, B_PREEMPTY = 5, B_ACC1FULL = 6, B_H1READY = 8, B_ACC2FULL = 10, B_H2READY = 12,
+       B_ACC3FULL = 14 /* one per E3 group: a waiter must see every phase of a barrier it polls */,
+       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 2 /* tap-row sums of a block written */,
+       B_BARR = B_BARW + NG /* ... and read (C = 24: the small ring is recycled block by block) */, B_COUNT = B_BARR + NG };
+// Per level: C = 12 (z1: 6 channels -> one K = 16 step [hi(8) | lo(8)], head N = 9 x 12 -> 112, two accumulator / pre-activation stages,
+// 16-row tap-sum ring) or C = 24 (z1: 12 channels -> K = 32 [hi(16) | lo(16)], head N = 9 x 24 -> 224 in ONE accumulator stage, one
+// pre-activation stage and a 6-row ring recycled block by block: its 130 KB of weights leave no more shared memory)
+template <int C> struct Cfg {
+  static_assert(C == 12 || C == 24, "coupling_fused: C = 12 or 24");
+  static constexpr int ZP = C == 12 ? 8 : 16;                      // z1 channels, padded
+  static constexpr int N3 = C == 12 ? 112 : 224;                   // 9 taps x C columns (+ padding to a multiple of 16)
+  // W1: C = 12: per tap 64 rows, bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
+  //     C = 24: per tap 64 rows [W_hi(16) | W_hi(16)], then five images holding [W_lo(16)] of two taps per row (bytes 0..31 / 32..63)
+  static constexpr int W1_BYTES = C == 12 ? 9 * 64 * ROWB : (9 + 5) * 64 * ROWB;
+  static constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;               // per 32-channel chunk [W_hi (N3 rows) ; W_lo (N3 rows)]
+  static constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;
+  static constexpr int NPRE = C == 12 ? 2 : 1;                     // pre-activation stages
+  static constexpr int NACC3 = C == 12 ? 2 : 1;                    // head accumulator stages
+  static constexpr int RING = C == 12 ? 16 : 6;                    // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0, 1)
+  static constexpr bool CHAIN = C != 12;                           // ring too small to run ahead: block b writes after block b-1 has read
+  static constexpr int EXCH_BYTES = 2 * RING * C * 32 * 4;         // [dy][row % RING][C channels][32 lanes] fp32
+  static constexpr int OFF_Z1 = W_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + NPRE * PRE_BYTES, OFF_BARS = OFF_EXCH + EXCH_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;         // + alignment slack
+  static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
+  static_assert(W_BYTES % 1024 == 0 && OFF_PRE % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+  static_assert(TM_ACC3 + NACC3 * N3 <= TM_COLS, "coupling_fused: tensor memory budget");
+};
 }  // namespace cf
 
 struct CfArgs {
-  alignas(64) CUtensorMap tm_z1;     // (16 ch, W, H, N, 1) bf16, box = 32 ch (upper 16 zero-filled) x 32 px x 6 rows
+  alignas(64) CUtensorMap tm_z1;     // (2 ZP ch, W, H, N, 1) bf16, box = 32 ch (zero-filled past 2 ZP) x 32 px x 6 rows
   alignas(64) CUtensorMap tm_pre;    // (C, W, H, N, plane) bf16 BF16X2 view, box = 32 ch x 32 px x 4 rows
   const unsigned char* w;
   int pre_coff;
@@ -81,9 +95,9 @@ struct CfArgs {
   int dbg;                           // timing experiments only (BFSR_CF_DBG bit mask: skip 1 = conv taps, 2 = identity, 4 = M2, 8 = M3 MMAs, 16 = flow epilogue): WRONG results
   int inv, has_mix, has_hF;
   View z_in, z_out, hF;
-  __nv_bfloat16* z1_out;             // [npix][16] = [hi(8) | lo(8)] of the first 6 output channels (next step's conv operand) or null
-  float bias2[64], bias3[16];        // biases of fAffine.2 and fAffine.4 (fAffine.0's rides in the pre-activation: its z part has none)
-  float M[144], cvec[12];
+  __nv_bfloat16* z1_out;             // [npix][2 ZP] = [hi(ZP) | lo(ZP)] of the first C/2 output channels (next step's conv operand) or null
+  float bias2[64], bias3[32];        // biases of fAffine.2 and fAffine.4 (fAffine.0's rides in the pre-activation: its z part has none)
+  float M[576], cvec[24];            // [C][C] row-major, [C]
 };
 
 // wait of an epilogue role: a short fixed sleep between polls -- 20 warps spinning on try_wait take the issue slots the working warps need
@@ -145,6 +159,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
                ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -158,12 +179,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
-// FlowStep on one pixel: h = (shift, scale) pairs of the coupling (FlowEpi semantics, ops.cuh); matrices from the kernel parameters
-__device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, long long pix, const float4* zq, const float4* hq) {
-  constexpr int C = 12;
+// FlowStep on one pixel: h = (shift, scale) pairs of the coupling (FlowEpi semantics, ops.cuh); matrices from the kernel parameters.
+// PRE: z / hF of the pixel were prefetched by the caller (C = 12); otherwise they are loaded here, hF piecewise (register budget).
+template <int C, bool PRE>
+__device__ __forceinline__ void flow_apply(const CfArgs& a, const float* h, long long pix, const float4* zq, const float4* hq) {
   float z[C], o[C];
+  const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
+  const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) { const float4 v = zq[k]; z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+  for (int k = 0; k < C / 4; ++k) { const float4 v = PRE ? zq[k] : __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
 #pragma unroll
   for (int j = 0; j < C / 2; ++j) {
     if (a.inv) z[C / 2 + j] = __fdividef(z[C / 2 + j], h[2 * j + 1]) - h[2 * j];
@@ -172,7 +196,8 @@ __device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, lo
   if (a.inv && a.has_hF) {
 #pragma unroll
     for (int k = 0; k < C / 2; ++k) {
-      z[2 * k] = __fdividef(z[2 * k], hq[k].y) - hq[k].x; z[2 * k + 1] = __fdividef(z[2 * k + 1], hq[k].w) - hq[k].z;
+      const float4 v = PRE ? hq[k] : __ldg(fp + k);
+      z[2 * k] = __fdividef(z[2 * k], v.y) - v.x; z[2 * k + 1] = __fdividef(z[2 * k + 1], v.w) - v.z;
     }
   }
   if (a.has_mix) {
@@ -185,7 +210,10 @@ __device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, lo
     }
     if (!a.inv && a.has_hF) {
 #pragma unroll
-      for (int k = 0; k < C / 2; ++k) { o[2 * k] = (o[2 * k] + hq[k].x) * hq[k].y; o[2 * k + 1] = (o[2 * k + 1] + hq[k].z) * hq[k].w; }
+      for (int k = 0; k < C / 2; ++k) {
+        const float4 v = PRE ? hq[k] : __ldg(fp + k);
+        o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w;
+      }
     }
   } else {
 #pragma unroll
@@ -195,26 +223,33 @@ __device__ __forceinline__ void flow_apply12(const CfArgs& a, const float* h, lo
 #pragma unroll
   for (int k = 0; k < C / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
   if (a.z1_out) {
-    uint32_t hi[4], lo[4];
+    constexpr int ZP = cf::Cfg<C>::ZP;
+    uint32_t hi[ZP / 2], lo[ZP / 2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = e < 3 ? o[2 * e] : 0.f, x1 = e < 3 ? o[2 * e + 1] : 0.f;
+    for (int e = 0; e < ZP / 2; ++e) {
+      const float x0 = 2 * e < C / 2 ? o[2 * e] : 0.f, x1 = 2 * e + 1 < C / 2 ? o[2 * e + 1] : 0.f;
       hi[e] = pack_bf16(x0, x1);
       lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
     }
-    uint4* d = reinterpret_cast<uint4*>(a.z1_out + pix * 16);
-    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    uint4* d = reinterpret_cast<uint4*>(a.z1_out + pix * (2 * ZP));
+#pragma unroll
+    for (int e = 0; e < ZP / 8; ++e) {
+      d[e] = make_uint4(hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+      d[ZP / 8 + e] = make_uint4(lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+    }
   }
 }
 
+template <int C>
 __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const __grid_constant__ CfArgs a) {
   using namespace cf;
+  using K = Cfg<C>;
+  constexpr int N3 = K::N3;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sgen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t w1 = base, w2 = w1 + W1_BYTES, w3 = w2 + W2_BYTES, wid = w3 + W3_BYTES;
-  const uint32_t z1s = base + OFF_Z1, pres = base + OFF_PRE, bars = base + OFF_BARS;
+  const uint32_t w1 = base, w2 = w1 + K::W1_BYTES, w3 = w2 + W2_BYTES, wid = w3 + K::W3_BYTES;
+  const uint32_t z1s = base + K::OFF_Z1, pres = base + K::OFF_PRE, bars = base + K::OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bars + 8u * B_COUNT;
 
@@ -227,7 +262,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     for (int i = 0; i < B_COUNT; ++i) {
       uint32_t cnt = 1;
       if (i == B_H1READY || i == B_H1READY + 1 || i == B_H2READY || i == B_H2READY + 1) cnt = 256;
-      if (i == B_ACC3EMPTY || i == B_ACC3EMPTY + 1 || (i >= B_BARW && i < B_BARW + NG)) cnt = 128;
+      if (i == B_ACC3EMPTY || i == B_ACC3EMPTY + 1 || (i >= B_BARW && i < B_BARR + NG)) cnt = 128;
       mbar_init(bar(i), cnt);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -246,11 +281,11 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
   if (warp == W_LOAD) {
     // ===================== loader: resident weights once, then per block the z1 halo tile and the pre-activation tile =====================
     if (elect_one()) {
-      mbar_expect_tx(bar(B_WFULL), W_BYTES);
-      bulk_g2s(w1, a.w, W1_BYTES, bar(B_WFULL));
-      bulk_g2s(w2, a.w + W1_BYTES, W2_BYTES, bar(B_WFULL));
-      bulk_g2s(w3, a.w + W1_BYTES + W2_BYTES, W3_BYTES, bar(B_WFULL));
-      bulk_g2s(wid, a.w + W1_BYTES + W2_BYTES + W3_BYTES, ID_BYTES, bar(B_WFULL));
+      mbar_expect_tx(bar(B_WFULL), K::W_BYTES);
+      bulk_g2s(w1, a.w, K::W1_BYTES, bar(B_WFULL));
+      bulk_g2s(w2, a.w + K::W1_BYTES, W2_BYTES, bar(B_WFULL));
+      bulk_g2s(w3, a.w + K::W1_BYTES + W2_BYTES, K::W3_BYTES, bar(B_WFULL));
+      bulk_g2s(wid, a.w + K::W1_BYTES + W2_BYTES + K::W3_BYTES, ID_BYTES, bar(B_WFULL));
     }
     __syncwarp();
     TR_DECL(tr_in = 0); TR_T(tr_start);
@@ -262,13 +297,19 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       mbar_wait_relaxed(bar(B_ACC1FULL + p), (uint32_t)((j & 1) ^ 1));    // M1 of the block that used stage p two blocks ago has retired
       TR_ADD(tr_in, tr0);
       if (elect_one()) {
-        mbar_expect_tx(bar(B_INFULL + p), Z1_BYTES + PRE_BYTES);
+        mbar_expect_tx(bar(B_INFULL + p), Z1_BYTES);
         tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_INFULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
+      }
+      __syncwarp();
+      const int ps = b % K::NPRE;
+      if (K::NPRE == 1) mbar_wait_relaxed(bar(B_PREEMPTY), (uint32_t)((b & 1) ^ 1));   // single stage: the identity MMAs of block b - 1 have retired
+      if (elect_one()) {
+        mbar_expect_tx(bar(B_PREFULL + ps), PRE_BYTES);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)
-            tma_load_5d(pres + p * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_INFULL + p), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
+            tma_load_5d(pres + ps * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL + ps), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
       }
       __syncwarp();
     }
@@ -287,36 +328,50 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     for (int b = 0; b < NB; ++b) {
       const int p = b & 1, j = b >> 1;
       const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
-      TR_T(tr0);
-      mbar_wait(bar(B_INFULL + p), (uint32_t)(j & 1));
-      TR_ADD(tr_in, tr0); TR_T(tr1);
+      const int ps = b % K::NPRE;
+      TR_T(tr1);
       mbar_wait(bar(B_ACC2FULL + p), (uint32_t)((j & 1) ^ 1));            // M2 of block b - 2 has consumed h1, which lives in the columns of acc1[p]
-      TR_ADD(tr_h1, tr1);
+      TR_ADD(tr_h1, tr1); TR_T(tr0);
+      mbar_wait(bar(B_PREFULL + ps), (uint32_t)((b / K::NPRE) & 1));
+      TR_ADD(tr_in, tr0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // (the issue loops are rolled: the kernel's hot code must stay inside the instruction caches -- the fully unrolled first version
       // spent half of its issue slots of every role waiting for instruction fetches)
       if (elect_one()) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-          const uint32_t pt = pres + p * PRE_BYTES + c * 2 * PLANE;
+          const uint32_t pt = pres + ps * PRE_BYTES + c * 2 * PLANE;
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
               if (!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
         }
+        if (K::NPRE == 1) umma_commit(bar(B_PREEMPTY));
+      }
+      __syncwarp();
+      mbar_wait(bar(B_INFULL + p), (uint32_t)(j & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint32_t zt = z1s + p * Z1_BYTES;
 #pragma unroll 1
         for (int dy = 0; dy < 3; ++dy) {
           if (a.dbg & 1) continue;
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)(dy * 3 + dx) * 64 * ROWB);
-            umma_f16(acc, A, B1, id64, 1u);
-            umma_f16(acc, A, B1 + 2, id64, 1u);          // + 32 bytes: the [W_lo | 0] half of the weight rows
+            const int tap = dy * 3 + dx;
+            const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)tap * 64 * ROWB);
+            if (C == 12) {
+              umma_f16(acc, A, B1, id64, 1u);                // [z_hi | z_lo] . [W_hi | W_hi]
+              umma_f16(acc, A, B1 + 2, id64, 1u);            // + 32 bytes: [z_hi | z_lo] . [W_lo | 0]
+            } else {
+              umma_f16(acc, A, B1, id64, 1u);                // z_hi . W_hi
+              umma_f16(acc, A + 2, B1 + 2, id64, 1u);        // z_lo . W_hi
+              umma_f16(acc, A, D(w1 + (uint32_t)(9 + (tap >> 1)) * 64 * ROWB) + 2 * (tap & 1), id64, 1u);   // z_hi . W_lo
+            }
           }
         }
-        umma_commit(bar(B_ACC1FULL + p));                 // releases E1 and, two blocks later, the loader's stage p
+        umma_commit(bar(B_ACC1FULL + p));                 // releases E1 and, two blocks later, the loader's z1 stage p
       }
       __syncwarp();
     }
@@ -359,11 +414,11 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
         TR_T(tr2);
         mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
         TR_ADD(tr_h2, tr2); TR_T(tr3);
-        mbar_wait(bar(B_ACC3EMPTY + p), (uint32_t)((j & 1) ^ 1));
+        mbar_wait(bar(B_ACC3EMPTY + b % K::NACC3), (uint32_t)(((b / K::NACC3) & 1) ^ 1));
         TR_ADD(tr_a3, tr3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC3 + N3 * p, At = tmem_base + TM_ACC2 + 64 * p;    // h2 sits where acc2 was
+          const uint32_t acc = tmem_base + TM_ACC3 + N3 * (b % K::NACC3), At = tmem_base + TM_ACC2 + 64 * p;    // h2 sits where acc2 was
 #pragma unroll 1
           for (int ck = 0; ck < 4; ++ck) {
             const int c = ck >> 1, ks = ck & 1;
@@ -444,7 +499,8 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
   } else {
     // ===================== E3: tap sums, cross-sigmoid, FlowStep (NG groups of 4 warps take blocks in rotation) =====================
     const int q = warp & 3, g = (warp - 8) >> 2;
-    float* S = reinterpret_cast<float*>(sgen + OFF_EXCH);
+    constexpr int RING = K::RING, NH = C / 12;            // the tap sums are taken 12 channels at a time (36 accumulator columns in registers)
+    float* S = reinterpret_cast<float*>(sgen + K::OFF_EXCH);
     TR_DECL(tr_a3 = 0, tr_bc = 0, tr_ld = 0, tr_ex = 0, tr_fl = 0); TR_T(tr_start);
     BlkIter bi; bi.init(a, g < NB ? g : 0);
     for (int b = g; b < NB; b += NG, bi.advance(a, NG)) {
@@ -453,59 +509,72 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       const bool valid = lane < OUT_W && xo < a.W && yo >= k.y0 && yo < k.y1;
       const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
       float4 zq[3];
-      if (valid) {                                        // flow state of the pixel: in flight while the accumulator is awaited / summed
+      if (C == 12 && valid) {                             // flow state of the pixel: in flight while the accumulator is awaited / summed
         const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
 #pragma unroll
         for (int i = 0; i < 3; ++i) zq[i] = __ldg(zp + i);
       }
       TR_T(tr0);
       mbar_wait_nap(bar(B_ACC3FULL + g), (uint32_t)((b / NG) & 1));
+      // small ring (C = 24): the previous block has read its rows before this one overwrites the slots they alias
+      if (K::CHAIN && b > 0) mbar_wait_nap(bar(B_BARR + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
       TR_ADD(tr_a3, tr0); TR_T(tr1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float u2[12];
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3 + N3 * (b & 1);
-      const int R = 4 * b + q;                            // running raster row of the CTA's block stream; ring slot = row & 15
+      float u2[C];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3 + N3 * (b % K::NACC3);
+      const int R = 4 * b + q;                            // running raster row of the CTA's block stream; ring slot = row % RING
+      // accumulator columns: 3 C dy + C dx + co
 #pragma unroll 1
       for (int dy = 0; dy < 2; ++dy) {                     // needed by the rows below: y + 1 (dy = 0), y (dy = 1)
-        float t[36];                                      // columns 36 dy + 12 dx + co
-        tmem_ld16(t_row + 36 * dy, t); tmem_ld16(t_row + 36 * dy + 16, t + 16); tmem_ld4(t_row + 36 * dy + 32, t + 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* Sd = S + (dy * RING + (R & (RING - 1))) * 12 * 32 + lane;
+        float* Sd = S + (dy * RING + R % RING) * C * 32 + lane;
 #pragma unroll
-        for (int c = 0; c < 12; ++c)
-          Sd[c * 32] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+        for (int hc = 0; hc < NH; ++hc) {
+          float t[36];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 3 * C * dy + C * dx + 12 * hc, t + 12 * dx); tmem_ld4(t_row + 3 * C * dy + C * dx + 12 * hc + 8, t + 12 * dx + 8); }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 12; ++c)
+            Sd[(12 * hc + c) * 32] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+        }
       }
-      {
+#pragma unroll
+      for (int hc = 0; hc < NH; ++hc) {
         float t[36];
-        tmem_ld16(t_row + 72, t); tmem_ld16(t_row + 72 + 16, t + 16); tmem_ld4(t_row + 72 + 32, t + 32);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 6 * C + C * dx + 12 * hc, t + 12 * dx); tmem_ld4(t_row + 6 * C + C * dx + 12 * hc + 8, t + 12 * dx + 8); }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 12; ++c)
-          u2[c] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+          u2[12 * hc + c] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
       }
       TR_ADD(tr_ld, tr1); TR_T(tr2);
       // the previous block's sums are in the ring (awaited BEFORE the accumulator is released: no E3 group can then run two blocks ahead
       // of a waiter, so every waiter sees every phase of the barriers it polls)
       if (b > 0) mbar_wait_nap(bar(B_BARW + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar(B_ACC3EMPTY + (b & 1)));
+      mbar_arrive(bar(B_ACC3EMPTY + b % K::NACC3));
       mbar_arrive(bar(B_BARW + g));
       float4 hq[6];
-      if (valid && a.has_hF) {
+      if (C == 12 && valid && a.has_hF) {
         const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
         for (int i = 0; i < 6; ++i) hq[i] = __ldg(fp + i);
       }
       mbar_wait_nap(bar(B_BARW + g), (uint32_t)((b / NG) & 1));
       TR_ADD(tr_bc, tr2); TR_T(tr3);
-      float h[12];
+      float h[C];
+      {
+        const float* S0 = S + ((R + RING - 2) % RING) * C * 32 + lane;
+        const float* S1 = S + (RING + (R + RING - 1) % RING) * C * 32 + lane;
 #pragma unroll
-      for (int c = 0; c < 12; ++c)
-        h[c] = S[((((R + RING - 2) & (RING - 1))) * 12 + c) * 32 + lane] + S[((RING + ((R + RING - 1) & (RING - 1))) * 12 + c) * 32 + lane] + u2[c] + a.bias3[c];
+        for (int c = 0; c < C; ++c) h[c] = S0[c * 32] + S1[c * 32] + u2[c] + a.bias3[c];
+      }
+      if (K::CHAIN) mbar_arrive(bar(B_BARR + g));
       TR_ADD(tr_ex, tr3); TR_T(tr4);
 #pragma unroll
-      for (int c = 1; c < 12; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
-      if (valid && !(a.dbg & 16)) flow_apply12(a, h, pix, zq, hq);
+      for (int c = 1; c < C; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
+      if (valid && !(a.dbg & 16)) flow_apply<C, C == 12>(a, h, pix, zq, hq);
       TR_ADD(tr_fl, tr4);
     }
 #ifdef BFSR_TC_TRACE
@@ -519,30 +588,36 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
   }
 }
 
-// z (fp32, first 6 channels) -> z1 operand plane [hi(8) | lo(8)] bf16 per pixel
+// z (fp32, first C/2 channels) -> z1 operand plane [hi(ZP) | lo(ZP)] bf16 per pixel
+template <int C>
 __global__ void z1_pack_kernel(const View z, __nv_bfloat16* out, long long npix) {
+  constexpr int ZP = cf::Cfg<C>::ZP;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const float* s = (const float*)z.p + p * z.cs + z.coff;
-  uint32_t hi[4], lo[4];
+  uint32_t hi[ZP / 2], lo[ZP / 2];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float x0 = e < 3 ? s[2 * e] : 0.f, x1 = e < 3 ? s[2 * e + 1] : 0.f;
+  for (int e = 0; e < ZP / 2; ++e) {
+    const float x0 = 2 * e < C / 2 ? s[2 * e] : 0.f, x1 = 2 * e + 1 < C / 2 ? s[2 * e + 1] : 0.f;
     hi[e] = pack_bf16(x0, x1);
     lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
   }
-  uint4* d = reinterpret_cast<uint4*>(out + p * 16);
-  d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  uint4* d = reinterpret_cast<uint4*>(out + p * (2 * ZP));
+#pragma unroll
+  for (int e = 0; e < ZP / 8; ++e) {
+    d[e] = make_uint4(hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+    d[ZP / 8 + e] = make_uint4(lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+  }
 }
 
-void z1_pack(const View& z, void* z1p, cudaStream_t s) {
-  BFSR_CHECK(z.fmt == F32 && z.C >= 6, "z1_pack: fp32 view with at least 6 channels expected");
+void z1_pack(const View& z, void* z1p, int C, cudaStream_t s) {
+  BFSR_CHECK(z.fmt == F32 && (C == 12 || C == 24) && z.C >= C / 2, "z1_pack: fp32 view with the C/2 conditioning channels expected (C = 12 or 24)");
   const long long n = z.npix();
   if (n == 0) return;
-  snprintf(g_prof_tag, sizeof g_prof_tag, "z1_pack %dx%d", z.H, z.W);
-  ProfScope prof(PK_OTHER, (double)n * (24 + 32), s);
-  z1_pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
+  snprintf(g_prof_tag, sizeof g_prof_tag, "z1_pack C%d %dx%d", C, z.H, z.W);
+  ProfScope prof(PK_OTHER, (double)n * (2 * C + (C == 12 ? 32 : 64)), s);
+  if (C == 12) z1_pack_kernel<12><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
+  else z1_pack_kernel<24><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
   CUDA_OK(cudaGetLastError());
   count_launch();
 }
@@ -558,11 +633,11 @@ bool coupling_fused_enabled() {
 }
 
 // Builds the resident weight image from the three packed convs of a coupling (fp32 [tap][cin_pad][cout_pad] device arrays of pack_conv).
-void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4, int C) {
+template <int C>
+static void pack_fused_t(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4) {
   using namespace cf;
-  fw = FusedCouplingW();
-  if (C != 12 || fA0z.cout != 64 || fA2.cin != 64 || fA2.cout != 64 || fA4.cin != 64 || fA4.cout != 12 || fA0z.cin > 8 || fA0z.ks != 3 ||
-      fA2.ks != 1 || fA4.ks != 3) return;
+  using K = Cfg<C>;
+  constexpr int N3 = K::N3, ZP = K::ZP;
   auto fetch = [](const ConvW& c, std::vector<float>& w, std::vector<float>& b) {
     w.resize((size_t)c.ks * c.ks * c.cin_pad * c.cout_pad); b.resize(c.cout_pad);
     CUDA_OK(cudaMemcpy(w.data(), c.w, w.size() * 4, cudaMemcpyDeviceToHost));
@@ -570,54 +645,66 @@ void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2
   };
   std::vector<float> wa, ba, wb, bb, wc, bc;
   fetch(fA0z, wa, ba); fetch(fA2, wb, bb); fetch(fA4, wc, bc);
-  std::vector<unsigned short> img(W_BYTES / 2, 0);
+  std::vector<unsigned short> img(K::W_BYTES / 2, 0);
   auto split = [](float w, unsigned short& hi, unsigned short& lo) { hi = f2bf(w); lo = f2bf(w - bf2f(hi)); };
-  // W1: tap t, row n: k 0..7 = W_hi[ci], 8..15 = W_hi[ci], 16..23 = W_lo[ci], 24..31 = 0
+  // W1 (see Cfg): the A operand of a tap is the z1 row [hi(ZP) | lo(ZP)]
   for (int t = 0; t < 9; ++t)
     for (int n = 0; n < 64; ++n)
-      for (int ci = 0; ci < fA0z.cin && ci < 8; ++ci) {
+      for (int ci = 0; ci < fA0z.cin && ci < ZP; ++ci) {
         unsigned short hi, lo; split(wa[((size_t)t * fA0z.cin_pad + ci) * fA0z.cout_pad + n], hi, lo);
-        put_bf(img, (size_t)t * 64, n, ci, hi); put_bf(img, (size_t)t * 64, n, 8 + ci, hi); put_bf(img, (size_t)t * 64, n, 16 + ci, lo);
+        put_bf(img, (size_t)t * 64, n, ci, hi); put_bf(img, (size_t)t * 64, n, ZP + ci, hi);
+        if (C == 12) put_bf(img, (size_t)t * 64, n, 16 + ci, lo);
+        else put_bf(img, (size_t)(9 + (t >> 1)) * 64, n, 16 * (t & 1) + ci, lo);
       }
   // W2: chunk c, rows 0..63 hi, 64..127 lo
-  const size_t r2 = W1_BYTES / ROWB;
+  const size_t r2 = K::W1_BYTES / ROWB;
   for (int c = 0; c < 2; ++c)
     for (int n = 0; n < 64; ++n)
       for (int k = 0; k < 32; ++k) {
         unsigned short hi, lo; split(wb[((size_t)(c * 32 + k)) * fA2.cout_pad + n], hi, lo);
         put_bf(img, r2 + (size_t)c * 128, n, k, hi); put_bf(img, r2 + (size_t)c * 128, 64 + n, k, lo);
       }
-  // W3: chunk c, rows tap*12 + co (hi), N3 + tap*12 + co (lo)
+  // W3: chunk c, rows tap*C + co (hi), N3 + tap*C + co (lo)
   const size_t r3 = r2 + W2_BYTES / ROWB;
   for (int c = 0; c < 2; ++c)
     for (int t = 0; t < 9; ++t)
-      for (int co = 0; co < 12; ++co)
+      for (int co = 0; co < C; ++co)
         for (int k = 0; k < 32; ++k) {
           unsigned short hi, lo; split(wc[((size_t)t * fA4.cin_pad + c * 32 + k) * fA4.cout_pad + co], hi, lo);
-          put_bf(img, r3 + (size_t)c * 2 * N3, t * 12 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 12 + co, k, lo);
+          put_bf(img, r3 + (size_t)c * 2 * N3, t * C + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * C + co, k, lo);
         }
-  const size_t r4 = r3 + W3_BYTES / ROWB;
+  const size_t r4 = r3 + K::W3_BYTES / ROWB;
   for (int r = 0; r < 32; ++r) put_bf(img, r4, r, r, 0x3F80);
-  CUDA_OK(cudaMalloc(&fw.w, W_BYTES));
-  CUDA_OK(cudaMemcpy(fw.w, img.data(), W_BYTES, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&fw.w, K::W_BYTES));
+  CUDA_OK(cudaMemcpy(fw.w, img.data(), K::W_BYTES, cudaMemcpyHostToDevice));
+  fw.C = C;
   for (int i = 0; i < 64; ++i) { fw.bias1[i] = ba[i]; fw.bias2[i] = bb[i]; }
-  for (int i = 0; i < 16; ++i) fw.bias3[i] = i < 12 ? bc[i] : 0.f;
+  for (int i = 0; i < 32; ++i) fw.bias3[i] = i < C ? bc[i] : 0.f;
+}
+void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4, int C) {
+  fw = FusedCouplingW();
+  static const int max_c = getenv("BFSR_FUSE_CPL_MAXC") ? atoi(getenv("BFSR_FUSE_CPL_MAXC")) : 24;   // 12: keep the C = 24 level on the three-launch chain
+  if ((C != 12 && C != 24) || C > max_c || fA0z.cout != 64 || fA2.cin != 64 || fA2.cout != 64 || fA4.cin != 64 || fA4.cout != C ||
+      fA0z.cin > cf::Cfg<24>::ZP || (C == 12 && fA0z.cin > 8) || fA0z.ks != 3 || fA2.ks != 1 || fA4.ks != 3) return;
+  if (C == 12) pack_fused_t<12>(fw, fA0z, fA2, fA4); else pack_fused_t<24>(fw, fA0z, fA2, fA4);
 }
 void free_fused_coupling(FusedCouplingW& fw) { if (fw.w) cudaFree(fw.w); fw.w = nullptr; }
 
 static int g_cf_sms = 0;
 
-// z1p_in / z1p_out: [N,H,W,16] bf16 planes ([hi(8) | lo(8)] of z1); pre: the BF16X2 64-channel pre-activation slice; f as for the conv
+// z1p_in / z1p_out: [N,H,W,2 ZP] bf16 planes ([hi(ZP) | lo(ZP)] of z1); pre: the BF16X2 64-channel pre-activation slice; f as for the conv
 // epilogue (z1op.p != null requests the z1 operand of the next step in z1p_out); hM / hcvec: host copies of f.M / f.cvec
 void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out, const View& pre, const FlowEpi& f, const float* hM,
                     const float* hcvec, float eps, cudaStream_t s) {
   using namespace cf;
-  BFSR_CHECK(fw.w && f.C == 12, "coupling_fused: weights not packed / C != 12");
+  const int C = f.C;
+  BFSR_CHECK(fw.w && (C == 12 || C == 24) && fw.C == C, "coupling_fused: weights not packed for C = %d", C);
+  const int ZP = C == 12 ? 8 : 16;
   const View& z = f.z_in;
   BFSR_CHECK(pre.fmt == BF16X2 && pre.C == 64 && pre.cs % 8 == 0 && pre.coff % 8 == 0 && pre.plane % 8 == 0 && ((uintptr_t)pre.p % 16) == 0 &&
              pre.N == z.N && pre.H == z.H && pre.W == z.W, "coupling_fused: pre-activation view");
   auto v4 = [](const View& v) { return v.fmt == F32 && v.cs % 4 == 0 && v.coff % 4 == 0 && ((uintptr_t)v.p % 16) == 0; };
-  BFSR_CHECK(v4(z) && v4(f.z_out) && z.C == 12 && f.z_out.C == 12 && f.z_out.npix() == z.npix() && (!f.hF.p || (v4(f.hF) && f.hF.C == 24)) &&
+  BFSR_CHECK(v4(z) && v4(f.z_out) && z.C == C && f.z_out.C == C && f.z_out.npix() == z.npix() && (!f.hF.p || (v4(f.hF) && f.hF.C == 2 * C)) &&
              (!f.has_mix || (hM && hcvec)) && ((uintptr_t)z1p_in % 16) == 0 && ((uintptr_t)z1p_out % 16) == 0 && (!f.z1op.p || z1p_out),
              "coupling_fused: flow-state views");
   if (z.npix() == 0) return;
@@ -651,24 +738,28 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   a.z1_out = f.z1op.p ? (__nv_bfloat16*)z1p_out : nullptr;
   for (int i = 0; i < 64; ++i) BFSR_CHECK(fw.bias1[i] == 0.f, "coupling_fused: the z part of fAffine.0 must be packed without a bias");
   memcpy(a.bias2, fw.bias2, sizeof a.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
-  if (f.has_mix) { memcpy(a.M, hM, sizeof a.M); memcpy(a.cvec, hcvec, sizeof a.cvec); }
-  View zv; zv.p = const_cast<void*>(z1p_in); zv.N = z.N; zv.H = z.H; zv.W = z.W; zv.C = 16; zv.cs = 16; zv.coff = 0; zv.fmt = BF16X2;
-  zv.plane = 16;   // unused second plane: the map is only ever read at plane coordinate 0
+  if (f.has_mix) { memcpy(a.M, hM, (size_t)C * C * 4); memcpy(a.cvec, hcvec, (size_t)C * 4); }
   {
-    const cuuint64_t dims[5] = {16, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N, 1};
-    const cuuint64_t strides[4] = {32, (cuuint64_t)z.W * 32, (cuuint64_t)z.H * z.W * 32, (cuuint64_t)z.N * z.H * z.W * 32};
+    const cuuint64_t px = (cuuint64_t)ZP * 4;      // bytes per pixel of the z1 plane
+    const cuuint64_t dims[5] = {(cuuint64_t)(2 * ZP), (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N, 1};
+    const cuuint64_t strides[4] = {px, (cuuint64_t)z.W * px, (cuuint64_t)z.H * z.W * px, (cuuint64_t)z.N * z.H * z.W * px};
     const cuuint32_t box[5] = {32, 32, 6, 1, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    const CUresult r = encode_tiled()(&a.tm_z1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, zv.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = encode_tiled()(&a.tm_z1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(z1p_in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BFSR_CHECK(r == CUDA_SUCCESS, "coupling_fused: cuTensorMapEncodeTiled(z1) failed (%d)", (int)r);
   }
   make_tmap(&a.tm_pre, pre, 32, 4);
-  CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int grid = a.total_items < g_cf_sms ? a.total_items : g_cf_sms;
-  snprintf(g_prof_tag, sizeof g_prof_tag, "cpl-fused C12 %dx%d", z.H, z.W);
-  ProfScope prof(PK_CONV_TC, 2.0 * (double)z.npix() * (8.0 * 9 * 64 + 64.0 * 64 + 64.0 * 9 * 12), s);
-  coupling_fused_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(a);
+  snprintf(g_prof_tag, sizeof g_prof_tag, "cpl-fused C%d %dx%d", C, z.H, z.W);
+  ProfScope prof(PK_CONV_TC, 2.0 * (double)z.npix() * (ZP * 9.0 * 64 + 64.0 * 64 + 64.0 * 9 * C), s);
+  if (C == 12) {
+    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<12>::SMEM_BYTES));
+    coupling_fused_kernel<12><<<grid, NTHREADS, Cfg<12>::SMEM_BYTES, s>>>(a);
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<24>::SMEM_BYTES));
+    coupling_fused_kernel<24><<<grid, NTHREADS, Cfg<24>::SMEM_BYTES, s>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   count_launch();
 }

@@ -76,21 +76,22 @@ ConvW pack_conv(const float* w_oihw, int cout, int cin_src, int ks, const float*
                 const std::vector<int>& cin_map, int tc_min_cin = -1 /* smallest Cin packed for the tcgen05 path; -1 = default (32) */);
 void free_conv(ConvW& w);
 
-// ------------------------------------------------------------------ fused coupling step (coupling_fused.cu), C = 12 levels
+// ------------------------------------------------------------------ fused coupling step (coupling_fused.cu), C = 12 / 24 levels
 // fAffine.0 (z part) -> ReLU -> fAffine.2 -> ReLU -> fAffine.4 -> cross-sigmoid -> FlowStep in ONE launch, hidden maps on chip
 struct FusedCouplingW {
   void* w = nullptr;                       // resident weight image (split-bf16, pre-swizzled); null: shape not eligible
-  float bias1[64], bias2[64], bias3[16];
+  int C = 0;                               // 12 or 24
+  float bias1[64], bias2[64], bias3[32];
 };
 bool coupling_fused_enabled();             // BFSR_FUSE_CPL=0 keeps the three-launch chain
 void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2, const ConvW& fA4, int C);
 void free_fused_coupling(FusedCouplingW& fw);
-// z1p_*: [N,H,W,16] bf16 = [hi(8) | lo(8)] of the conditioning half z1 (first 6 channels of z); pre: BF16X2 64-channel slice of the
+// z1p_*: [N,H,W,2 ZP] bf16 = [hi(ZP) | lo(ZP)] of the conditioning half z1 (first C/2 channels of z, ZP = 8 / 16); pre: BF16X2 64-channel slice of the
 // feature-only pre-activations; f: as for the conv epilogue (f.z1op.p != null asks for the next step's z1 operand in z1p_out);
 // hM / hcvec: HOST copies of f.M / f.cvec (they travel as kernel parameters)
 void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out, const View& pre, const FlowEpi& f, const float* hM,
                     const float* hcvec, float eps, cudaStream_t s);
-void z1_pack(const View& z, void* z1p, cudaStream_t s);
+void z1_pack(const View& z, void* z1p, int C, cudaStream_t s);
 
 // ------------------------------------------------------------------ layout / resampling
 void nchw_to_nhwc(const float* src, const View& dst, cudaStream_t s);

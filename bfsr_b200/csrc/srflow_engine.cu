@@ -361,13 +361,13 @@ struct LevelBufs {
     t1 = make_view(r.A, r.B, H, W, Hd, fp32_z() ? (int)F32 : r.opfmt()); t2 = make_view(r.A, r.B, H, W, Hd, r.opfmt());
     h = make_view(r.A, r.B, H, W, (C - C / 2) * 2);
     z1op = make_view(r.A, r.B, H, W, (C / 2 + 7) & ~7, r.opfmt());
-    if (C == 12) for (int i = 0; i < 2; ++i) z1p[i] = r.A.alloc((size_t)r.B * H * W * 32);
+    if (C == 12 || C == 24) for (int i = 0; i < 2; ++i) z1p[i] = r.A.alloc((size_t)r.B * H * W * (C == 12 ? 32 : 64));
     pp = 0; z1p_cur = 0; z1p_ready = false;
   }
   View& next() { View& v = z[pp]; pp ^= 1; return v; }
 };
 
-// One-launch coupling step (coupling_fused.cu): accurate tensor-core mode, C = 12 levels, FlowStep fused (BFSR_FUSE_CPL=0: three launches)
+// One-launch coupling step (coupling_fused.cu): accurate tensor-core mode, C = 12 / 24 levels, FlowStep fused (BFSR_FUSE_CPL=0: three launches)
 static bool cpl_fused(const Run& r, const LayerW& l) {
   return coupling_fused_enabled() && g_conv_mode == 0 && l.cp.fz.w != nullptr && flow_fused(r, l.C);
 }
@@ -377,7 +377,7 @@ static bool run_affine_net(Run& r, const LayerW& l, const View& z, LevelBufs& lb
   const View &z1op = lb.z1op, &t1 = lb.t1, &t2 = lb.t2, &hout = lb.h;
   View pre = r.bufA[l.level].slice(l.k_in_level * Hd, Hd);
   if (flow && cpl_fused(r, l)) {
-    if (!lb.z1p_ready) K_(z1_pack(z.slice(0, l.C / 2), lb.z1p[lb.z1p_cur], r.s));
+    if (!lb.z1p_ready) K_(z1_pack(z.slice(0, l.C / 2), lb.z1p[lb.z1p_cur], l.C, r.s));
     K_(coupling_fused(l.cp.fz, lb.z1p[lb.z1p_cur], lb.z1p[lb.z1p_cur ^ 1], pre, *flow, flow->hM, flow->hcvec, ConvEpi().eps, r.s));
     lb.z1p_ready = flow->z1op.p != nullptr;
     if (lb.z1p_ready) lb.z1p_cur ^= 1;

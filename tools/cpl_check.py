@@ -16,16 +16,17 @@ def run(path):
     table, keep = _lib.tensor_table(sd)
     L = _lib.lib()
     out = {}
-    for (B, H, W) in ((2, 24, 20), (1, 96, 80), (3, 61, 45), (2, 320, 320)):
-        g = torch.Generator().manual_seed(H * 1000 + W)
-        z = torch.randn(B, 12, H, W, generator=g).cuda()
-        ft = (torch.randn(B, 320, H, W, generator=g) * 0.5).cuda()
-        for rev in (0, 1):
-            o = torch.empty_like(z)
-            _lib.check(L.bfsr_op_flowstep(table, len(table), b"flowUpsamplerNet.layers.3", 12, 1, rev, z.data_ptr(), ft.data_ptr(), B, H, W,
-                                          o.data_ptr(), 0, 1, None))
-            torch.cuda.synchronize()
-            out[f"{B}x{H}x{W}_rev{rev}"] = o.cpu()
+    for C, layer, shapes in ((12, 3, ((2, 24, 20), (1, 96, 80), (3, 61, 45), (2, 320, 320))), (24, 8, ((2, 24, 20), (3, 61, 45), (4, 160, 160)))):
+        for (B, H, W) in shapes:
+            g = torch.Generator().manual_seed(H * 1000 + W + C)
+            z = torch.randn(B, C, H, W, generator=g).cuda()
+            ft = (torch.randn(B, 320, H, W, generator=g) * 0.5).cuda()
+            for rev in (0, 1):
+                o = torch.empty_like(z)
+                _lib.check(L.bfsr_op_flowstep(table, len(table), f"flowUpsamplerNet.layers.{layer}".encode(), C, 1, rev, z.data_ptr(), ft.data_ptr(),
+                                              B, H, W, o.data_ptr(), 0, 1, None))
+                torch.cuda.synchronize()
+                out[f"C{C}_{B}x{H}x{W}_rev{rev}"] = o.cpu()
     torch.save(out, path)
     print("saved", path, {k: float(v.abs().mean()) for k, v in out.items()})
 
