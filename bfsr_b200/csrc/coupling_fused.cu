@@ -180,14 +180,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 
 // FlowStep on one pixel: h = (shift, scale) pairs of the coupling (FlowEpi semantics, ops.cuh); matrices from the kernel parameters.
-// PRE: z / hF of the pixel were prefetched by the caller (C = 12); otherwise they are loaded here, hF piecewise (register budget).
-template <int C, bool PRE>
+// zq: the pixel's z, prefetched by the caller; hq: the first NHQ of its C/2 hF quads, prefetched too (the rest is loaded here: register budget).
+template <int C, int NHQ>
 __device__ __forceinline__ void flow_apply(const CfArgs& a, const float* h, long long pix, const float4* zq, const float4* hq) {
   float z[C], o[C];
-  const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
   const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) { const float4 v = PRE ? zq[k] : __ldg(zp + k); z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
+  for (int k = 0; k < C / 4; ++k) { const float4 v = zq[k]; z[4 * k] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w; }
 #pragma unroll
   for (int j = 0; j < C / 2; ++j) {
     if (a.inv) z[C / 2 + j] = __fdividef(z[C / 2 + j], h[2 * j + 1]) - h[2 * j];
@@ -196,22 +195,22 @@ __device__ __forceinline__ void flow_apply(const CfArgs& a, const float* h, long
   if (a.inv && a.has_hF) {
 #pragma unroll
     for (int k = 0; k < C / 2; ++k) {
-      const float4 v = PRE ? hq[k] : __ldg(fp + k);
+      const float4 v = k < NHQ ? hq[k] : __ldg(fp + k);
       z[2 * k] = __fdividef(z[2 * k], v.y) - v.x; z[2 * k + 1] = __fdividef(z[2 * k + 1], v.w) - v.z;
     }
   }
   if (a.has_mix) {
 #pragma unroll
-    for (int co = 0; co < C; ++co) {
-      float acc = 0.f;
+    for (int co = 0; co < C; ++co) {                      // packed fp32x2 FMAs (sm_100 FFMA2): even / odd k partial sums
+      float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < C; ++k) acc = fmaf(a.M[co * C + k], z[k], acc);
-      o[co] = a.inv ? acc - a.cvec[co] : acc + a.cvec[co];
+      for (int k = 0; k < C; k += 2) acc = __ffma2_rn(make_float2(a.M[co * C + k], a.M[co * C + k + 1]), make_float2(z[k], z[k + 1]), acc);
+      o[co] = a.inv ? (acc.x + acc.y) - a.cvec[co] : (acc.x + acc.y) + a.cvec[co];
     }
     if (!a.inv && a.has_hF) {
 #pragma unroll
       for (int k = 0; k < C / 2; ++k) {
-        const float4 v = PRE ? hq[k] : __ldg(fp + k);
+        const float4 v = k < NHQ ? hq[k] : __ldg(fp + k);
         o[2 * k] = (o[2 * k] + v.x) * v.y; o[2 * k + 1] = (o[2 * k + 1] + v.z) * v.w;
       }
     }
@@ -508,11 +507,11 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       const int yo = k.yb + q - 1, xo = k.x0 + lane;      // the warp holding raster row y finalises output row y - 1
       const bool valid = lane < OUT_W && xo < a.W && yo >= k.y0 && yo < k.y1;
       const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
-      float4 zq[3];
+      float4 zq[C / 4];
+      const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
       if (C == 12 && valid) {                             // flow state of the pixel: in flight while the accumulator is awaited / summed
-        const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) zq[i] = __ldg(zp + i);
+        for (int i = 0; i < C / 4; ++i) zq[i] = __ldg(zp + i);
       }
       TR_T(tr0);
       mbar_wait_nap(bar(B_ACC3FULL + g), (uint32_t)((b / NG) & 1));
@@ -555,11 +554,16 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar(B_ACC3EMPTY + b % K::NACC3));
       mbar_arrive(bar(B_BARW + g));
-      float4 hq[6];
-      if (C == 12 && valid && a.has_hF) {
+      if (C != 12 && valid) {                             // C = 24: no registers for it during the tap sums; in flight across the ring hand-off
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) zq[i] = __ldg(zp + i);
+      }
+      constexpr int NHQ = C == 12 ? 6 : 4;
+      float4 hq[NHQ];
+      if (valid && a.has_hF) {
         const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) hq[i] = __ldg(fp + i);
+        for (int i = 0; i < NHQ; ++i) hq[i] = __ldg(fp + i);
       }
       mbar_wait_nap(bar(B_BARW + g), (uint32_t)((b / NG) & 1));
       TR_ADD(tr_bc, tr2); TR_T(tr3);
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       TR_ADD(tr_ex, tr3); TR_T(tr4);
 #pragma unroll
       for (int c = 1; c < C; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
-      if (valid && !(a.dbg & 16)) flow_apply<C, C == 12>(a, h, pix, zq, hq);
+      if (valid && !(a.dbg & 16)) flow_apply<C, NHQ>(a, h, pix, zq, hq);
       TR_ADD(tr_fl, tr4);
     }
 #ifdef BFSR_TC_TRACE
