@@ -537,7 +537,22 @@ def main():
         tms, work, cnt = C.c_double(), C.c_double(), C.c_int64()
         L.bfsr_prof_summary(kind, C.byref(tms), C.byref(work), C.byref(cnt))
         cls[name] = {"ms": tms.value, "work": work.value, "launches": cnt.value}
+    dump = C.create_string_buffer(1 << 20)
+    L.bfsr_prof_dump(dump, len(dump))
     L.bfsr_prof_enable(0)
+    # one-launch coupling steps (coupling_fused.cu): HBM-side view -- compulsory bytes per level pixel (pre-activation 256 + z 48/96 in
+    # and out + hF 96/192 + z1 operand 32/64 in and out) x pixels / device time, against the measured copy bandwidth
+    cpl_roof = None
+    for ln in dump.value.decode().splitlines():
+        tag, n, tms_, _work = ln.split("\t")
+        if tag.startswith("cpl-fused C12") and float(tms_) > 0 and not args.tile_chunk:
+            hw = tag.split()[-1].split("x")
+            px = B_local * int(hw[0]) * int(hw[1])
+            byt = (256 + 48 + 96 + 32 + 48 + 32) * px * int(n)
+            ach = byt / (float(tms_) * 1e-3) / 1e9
+            cpl_roof = {"bound": "hbm", "kernel": "coupling_fused_kernel<12> (" + tag + ")", "achieved": ach, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "launches": int(n), "kernel_ms_per_step": float(tms_),
+                        "algorithmic_bytes_per_pixel": 512}
     conv_name = max(("conv_fp32", "conv_tcgen05"), key=lambda k: cls[k]["ms"])
     cv = cls[conv_name]
     if cv["ms"] > 0:
@@ -601,7 +616,7 @@ def main():
                        "global_batch": tiles_job, "tiles_per_gpu": B_local, "gather_in_timed_region": bool(args.gather and world > 1), "precision_mode": {0: "fp32-accurate (split-bf16 x3 on tcgen05, fp32 accumulate)", 1: "bf16-fast", 2: "fp32 CUDA cores"}[args.precision],
                        "l2": "per-step working set (tens of GB of activations) >> 126 MB L2, no flush needed",
                        "parallelism": f"dp{world} (independent tiles, no data-path collective)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_flowstep": flow_roof,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_flowstep": flow_roof, "roofline_coupling": cpl_roof,
             "kernel_classes_ms_per_step": {k: round(v["ms"], 3) for k, v in cls.items()},
             "alg_tflop_per_step": ALG_FLOP_PER_LR_PX * tiles_job * S * S / 1e12,
             "path_tensor_roofline_frac": (ALG_FLOP_PER_LR_PX * tiles_job * S * S / world / (ms * 1e-3) / 1e12) / peaks["tflops"],
