@@ -92,6 +92,7 @@ struct CfArgs {
   int H, W, N;
   int strips, segs, seg_rows, nblk, total_items;
   float eps;
+  int fast;                          // bf16 single-pass mode (precision 1): only the hi x hi products; z1 / h1 / h2 carry zero lo halves
   int dbg;                           // timing experiments only (BFSR_CF_DBG bit mask: skip 1 = conv taps, 2 = identity, 4 = M2, 8 = M3 MMAs, 16 = flow epilogue): WRONG results
   int inv, has_mix, has_hF;
   View z_in, z_out, hF;
@@ -228,7 +229,7 @@ __device__ __forceinline__ void flow_apply(const CfArgs& a, const float* h, long
     for (int e = 0; e < ZP / 2; ++e) {
       const float x0 = 2 * e < C / 2 ? o[2 * e] : 0.f, x1 = 2 * e + 1 < C / 2 ? o[2 * e + 1] : 0.f;
       hi[e] = pack_bf16(x0, x1);
-      lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
+      lo[e] = a.fast ? 0u : pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
     }
     uint4* d = reinterpret_cast<uint4*>(a.z1_out + pix * (2 * ZP));
 #pragma unroll
@@ -303,12 +304,12 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       const int ps = b % K::NPRE;
       if (K::NPRE == 1) mbar_wait_relaxed(bar(B_PREEMPTY), (uint32_t)((b & 1) ^ 1));   // single stage: the identity MMAs of block b - 1 have retired
       if (elect_one()) {
-        mbar_expect_tx(bar(B_PREFULL + ps), PRE_BYTES);
+        mbar_expect_tx(bar(B_PREFULL + ps), a.fast ? PRE_BYTES / 2 : PRE_BYTES);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)
-            tma_load_5d(pres + ps * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL + ps), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
+            if (!(a.fast && pl)) tma_load_5d(pres + ps * PRE_BYTES + (c * 2 + pl) * PLANE, &a.tm_pre, bar(B_PREFULL + ps), a.pre_coff + 32 * c, k.x0 - 1, k.yb, k.n, pl);
       }
       __syncwarp();
     }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
           for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              if (!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
+              if ((!(a.dbg & 2) || (c == 0 && (pl | ks) == 0)) && !(a.fast && pl)) umma_f16(acc + 32 * c, D(pt + pl * PLANE + ks * 32), D(wid + ks * 32), id32, (pl | ks) ? 1u : 0u);
         }
         if (K::NPRE == 1) umma_commit(bar(B_PREEMPTY));
       }
@@ -361,12 +362,14 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
             const int tap = dy * 3 + dx;
             const uint64_t A = D(zt + (uint32_t)(dy * 32 + dx) * ROWB), B1 = D(w1 + (uint32_t)tap * 64 * ROWB);
             if (C == 12) {
-              umma_f16(acc, A, B1, id64, 1u);                // [z_hi | z_lo] . [W_hi | W_hi]
-              umma_f16(acc, A, B1 + 2, id64, 1u);            // + 32 bytes: [z_hi | z_lo] . [W_lo | 0]
+              umma_f16(acc, A, B1, id64, 1u);                // [z_hi | z_lo] . [W_hi | W_hi]   (fast mode: z_lo = 0)
+              if (!a.fast) umma_f16(acc, A, B1 + 2, id64, 1u);   // + 32 bytes: [z_hi | z_lo] . [W_lo | 0]
             } else {
               umma_f16(acc, A, B1, id64, 1u);                // z_hi . W_hi
-              umma_f16(acc, A + 2, B1 + 2, id64, 1u);        // z_lo . W_hi
-              umma_f16(acc, A, D(w1 + (uint32_t)(9 + (tap >> 1)) * 64 * ROWB) + 2 * (tap & 1), id64, 1u);   // z_hi . W_lo
+              if (!a.fast) {
+                umma_f16(acc, A + 2, B1 + 2, id64, 1u);      // z_lo . W_hi
+                umma_f16(acc, A, D(w1 + (uint32_t)(9 + (tap >> 1)) * 64 * ROWB) + 2 * (tap & 1), id64, 1u);   // z_hi . W_lo
+              }
             }
           }
         }
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
             const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
             const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
             umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
-            if (a.dbg & 4) continue;
+            if ((a.dbg & 4) || a.fast) continue;
             umma_f16_ts(acc, Ah, Bl, id64, 1u);
             umma_f16_ts(acc, Al, Bh, id64, 1u);
           }
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
             const uint32_t Ah = At + 16 * ck, Al = Ah + 8;
             const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
             umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
-            if (a.dbg & 8) continue;
+            if ((a.dbg & 8) || a.fast) continue;
             umma_f16_ts(acc, Ah, Bl, idn3, 1u);
             umma_f16_ts(acc, Al, Bh, idn3, 1u);
           }
@@ -485,7 +488,8 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 #pragma unroll
             for (int i = 0; i < 8; ++i) { hi[i] = inside ? hi[i] : 0u; lo[i] = inside ? lo[i] : 0u; }
           }
-          tmem_st8(src + 16 * g, hi); tmem_st8(src + 16 * g + 8, lo);
+          tmem_st8(src + 16 * g, hi);
+          if (!a.fast) tmem_st8(src + 16 * g + 8, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 
 // z (fp32, first C/2 channels) -> z1 operand plane [hi(ZP) | lo(ZP)] bf16 per pixel
 template <int C>
-__global__ void z1_pack_kernel(const View z, __nv_bfloat16* out, long long npix) {
+__global__ void z1_pack_kernel(const View z, __nv_bfloat16* out, long long npix, int fast) {
   constexpr int ZP = cf::Cfg<C>::ZP;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
@@ -604,7 +608,7 @@ __global__ void z1_pack_kernel(const View z, __nv_bfloat16* out, long long npix)
   for (int e = 0; e < ZP / 2; ++e) {
     const float x0 = 2 * e < C / 2 ? s[2 * e] : 0.f, x1 = 2 * e + 1 < C / 2 ? s[2 * e + 1] : 0.f;
     hi[e] = pack_bf16(x0, x1);
-    lo[e] = pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
+    lo[e] = fast ? 0u : pack_bf16(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xffff0000u));
   }
   uint4* d = reinterpret_cast<uint4*>(out + p * (2 * ZP));
 #pragma unroll
@@ -620,8 +624,9 @@ void z1_pack(const View& z, void* z1p, int C, cudaStream_t s) {
   if (n == 0) return;
   snprintf(g_prof_tag, sizeof g_prof_tag, "z1_pack C%d %dx%d", C, z.H, z.W);
   ProfScope prof(PK_OTHER, (double)n * (2 * C + (C == 12 ? 32 : 64)), s);
-  if (C == 12) z1_pack_kernel<12><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
-  else z1_pack_kernel<24><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n);
+  const int fast = g_conv_mode == 1;
+  if (C == 12) z1_pack_kernel<12><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n, fast);
+  else z1_pack_kernel<24><<<cdiv(n, 256), 256, 0, s>>>(z, (__nv_bfloat16*)z1p, n, fast);
   CUDA_OK(cudaGetLastError());
   count_launch();
 }
@@ -737,6 +742,7 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   a.total_items = (int)items;
   static const int dbg_env = getenv("BFSR_CF_DBG") ? atoi(getenv("BFSR_CF_DBG")) : 0;
   a.dbg = dbg_env;
+  a.fast = g_conv_mode == 1 ? 1 : 0;
   a.eps = eps; a.inv = f.inv; a.has_mix = f.has_mix; a.has_hF = f.hF.p ? 1 : 0;
   a.z_in = z; a.z_out = f.z_out; a.hF = f.hF;
   a.z1_out = f.z1op.p ? (__nv_bfloat16*)z1p_out : nullptr;

@@ -367,9 +367,9 @@ struct LevelBufs {
   View& next() { View& v = z[pp]; pp ^= 1; return v; }
 };
 
-// One-launch coupling step (coupling_fused.cu): accurate tensor-core mode, C = 12 / 24 levels, FlowStep fused (BFSR_FUSE_CPL=0: three launches)
+// One-launch coupling step (coupling_fused.cu): tensor-core modes (accurate and bf16 single-pass), C = 12 / 24 levels, FlowStep fused (BFSR_FUSE_CPL=0: three launches)
 static bool cpl_fused(const Run& r, const LayerW& l) {
-  return coupling_fused_enabled() && g_conv_mode == 0 && l.cp.fz.w != nullptr && flow_fused(r, l.C);
+  return coupling_fused_enabled() && g_conv_mode != 2 && l.cp.fz.w != nullptr && flow_fused(r, l.C);
 }
 // Returns true when the fused kernel ran (the z1 operand of the next step, if requested, then lives in lb.z1p, not in lb.z1op).
 static bool run_affine_net(Run& r, const LayerW& l, const View& z, LevelBufs& lb, bool z1_ready, const FlowEpi* flow = nullptr) {

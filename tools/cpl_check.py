@@ -15,6 +15,8 @@ def run(path):
     sd = synth.synth_srflow_state_dict(t, seed=3)
     table, keep = _lib.tensor_table(sd)
     L = _lib.lib()
+    import os
+    prec = int(os.environ.get("BFSR_CPL_CHECK_PREC", "0"))
     out = {}
     for C, layer, shapes in ((12, 3, ((2, 24, 20), (1, 96, 80), (3, 61, 45), (2, 320, 320))), (24, 8, ((2, 24, 20), (3, 61, 45), (4, 160, 160)))):
         for (B, H, W) in shapes:
@@ -24,7 +26,7 @@ def run(path):
             for rev in (0, 1):
                 o = torch.empty_like(z)
                 _lib.check(L.bfsr_op_flowstep(table, len(table), f"flowUpsamplerNet.layers.{layer}".encode(), C, 1, rev, z.data_ptr(), ft.data_ptr(),
-                                              B, H, W, o.data_ptr(), 0, 1, None))
+                                              B, H, W, o.data_ptr(), prec, 1, None))
                 torch.cuda.synchronize()
                 out[f"C{C}_{B}x{H}x{W}_rev{rev}"] = o.cpu()
     torch.save(out, path)
