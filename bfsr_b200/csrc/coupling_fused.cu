@@ -62,21 +62,24 @@ enum { B_WFULL = 0, B_INFULL = 1, B_PREFULL = 3, B_PREEMPTY = 5, B_ACC1FULL = 6,
 // Per level: C = 12 (z1: 6 channels -> one K = 16 step [hi(8) | lo(8)], head N = 9 x 12 -> 112, two accumulator / pre-activation stages,
 // 16-row tap-sum ring) or C = 24 (z1: 12 channels -> K = 32 [hi(16) | lo(16)], head N = 9 x 24 -> 224 in ONE accumulator stage, one
 // pre-activation stage and a 6-row ring recycled block by block: its 130 KB of weights leave no more shared memory)
-template <int C> struct Cfg {
+// TAIL: the feature-only tail of a coupling (fFeatures.2 1x1 -> ReLU -> fFeatures.4 3x3 -> cross-sigmoid = the (shiftF, scaleF) pairs hF of
+// a level's step) runs through the same machinery without M1 / E1 and without the FlowStep: C = the tail's 2 x C_level output channels.
+template <int C, bool TAIL = false> struct Cfg {
   static_assert(C == 12 || C == 24, "coupling_fused: C = 12 or 24");
+  static_assert(!TAIL || C == 24, "coupling_fused: the tail variant is built for 24 output channels (C = 12 levels)");
   static constexpr int ZP = C == 12 ? 8 : 16;                      // z1 channels, padded
   static constexpr int N3 = C == 12 ? 112 : 224;                   // 9 taps x C columns (+ padding to a multiple of 16)
   // W1: C = 12: per tap 64 rows, bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
   //     C = 24: per tap 64 rows [W_hi(16) | W_hi(16)], then five images holding [W_lo(16)] of two taps per row (bytes 0..31 / 32..63)
-  static constexpr int W1_BYTES = C == 12 ? 9 * 64 * ROWB : (9 + 5) * 64 * ROWB;
+  static constexpr int W1_BYTES = TAIL ? 0 : (C == 12 ? 9 * 64 * ROWB : (9 + 5) * 64 * ROWB);
   static constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;               // per 32-channel chunk [W_hi (N3 rows) ; W_lo (N3 rows)]
   static constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;
-  static constexpr int NPRE = C == 12 ? 2 : 1;                     // pre-activation stages
+  static constexpr int NPRE = (C == 12 || TAIL) ? 2 : 1;           // pre-activation (TAIL: input) stages
   static constexpr int NACC3 = C == 12 ? 2 : 1;                    // head accumulator stages
-  static constexpr int RING = C == 12 ? 16 : 6;                    // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0, 1)
-  static constexpr bool CHAIN = C != 12;                           // ring too small to run ahead: block b writes after block b-1 has read
+  static constexpr int RING = C == 12 ? 16 : (TAIL ? 14 : 6);      // (14: the smallest ring whose aliasing blocks are three apart = same E3 group)                    // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0, 1)
+  static constexpr bool CHAIN = C != 12 && !TAIL;                           // ring too small to run ahead: block b writes after block b-1 has read
   static constexpr int EXCH_BYTES = 2 * RING * C * 32 * 4;         // [dy][row % RING][C channels][32 lanes] fp32
-  static constexpr int OFF_Z1 = W_BYTES, OFF_PRE = OFF_Z1 + 2 * Z1_BYTES, OFF_EXCH = OFF_PRE + NPRE * PRE_BYTES, OFF_BARS = OFF_EXCH + EXCH_BYTES;
+  static constexpr int OFF_Z1 = W_BYTES, OFF_PRE = OFF_Z1 + (TAIL ? 0 : 2 * Z1_BYTES), OFF_EXCH = OFF_PRE + NPRE * PRE_BYTES, OFF_BARS = OFF_EXCH + EXCH_BYTES;
   static constexpr int SMEM_BYTES = OFF_BARS + 512 + 1024;         // + alignment slack
   static_assert(SMEM_BYTES <= 227 * 1024, "coupling_fused: shared memory budget");
   static_assert(W_BYTES % 1024 == 0 && OFF_PRE % 1024 == 0, "operand tiles must stay 1024-byte aligned");
@@ -240,10 +243,10 @@ __device__ __forceinline__ void flow_apply(const CfArgs& a, const float* h, long
   }
 }
 
-template <int C>
+template <int C, bool TAIL>
 __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const __grid_constant__ CfArgs a) {
   using namespace cf;
-  using K = Cfg<C>;
+  using K = Cfg<C, TAIL>;
   constexpr int N3 = K::N3;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     // ===================== loader: resident weights once, then per block the z1 halo tile and the pre-activation tile =====================
     if (elect_one()) {
       mbar_expect_tx(bar(B_WFULL), K::W_BYTES);
-      bulk_g2s(w1, a.w, K::W1_BYTES, bar(B_WFULL));
+      if (!TAIL) bulk_g2s(w1, a.w, K::W1_BYTES, bar(B_WFULL));
       bulk_g2s(w2, a.w + K::W1_BYTES, W2_BYTES, bar(B_WFULL));
       bulk_g2s(w3, a.w + K::W1_BYTES + W2_BYTES, K::W3_BYTES, bar(B_WFULL));
       bulk_g2s(wid, a.w + K::W1_BYTES + W2_BYTES + K::W3_BYTES, ID_BYTES, bar(B_WFULL));
@@ -294,9 +297,10 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       const Blk& k = bi.k;
       const int p = b & 1, j = b >> 1;
       TR_T(tr0);
-      mbar_wait_relaxed(bar(B_ACC1FULL + p), (uint32_t)((j & 1) ^ 1));    // M1 of the block that used stage p two blocks ago has retired
+      // M1 (TAIL: the 1x1) of the block that used stage p two blocks ago has retired
+      mbar_wait_relaxed(bar((TAIL ? B_ACC2FULL : B_ACC1FULL) + p), (uint32_t)((j & 1) ^ 1));
       TR_ADD(tr_in, tr0);
-      if (elect_one()) {
+      if (!TAIL && elect_one()) {
         mbar_expect_tx(bar(B_INFULL + p), Z1_BYTES);
         tma_load_5d(z1s + p * Z1_BYTES, &a.tm_z1, bar(B_INFULL + p), 0, k.x0 - 2, k.yb - 1, k.n, 0);
       }
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     const uint32_t id32 = make_idesc(32), id64 = make_idesc(64);
     mbar_wait(bar(B_WFULL), 0);
     TR_DECL(tr_in = 0, tr_h1 = 0); TR_T(tr_start);
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < (TAIL ? 0 : NB); ++b) {     // TAIL: no M1 (issuer B runs the 1x1 from shared memory)
       const int p = b & 1, j = b >> 1;
       const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
       const int ps = b % K::NPRE;
@@ -392,7 +396,8 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       if (it < NB) {                                      // ---- M2(b): 1x1, acc2[p]
         const int b = it, p = b & 1, j = b >> 1;
         TR_T(tr4);
-        mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
+        if (TAIL) mbar_wait(bar(B_PREFULL + p), (uint32_t)(j & 1));          // the 64-channel input tile (BF16X2, TMA) is the A operand
+        else mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
         TR_ADD(tr_h1, tr4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -400,14 +405,22 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 #pragma unroll 1
           for (int ck = 0; ck < 4; ++ck) {
             const int c = ck >> 1, ks = ck & 1;
-            const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
             const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
-            umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
-            if ((a.dbg & 4) || a.fast) continue;
-            umma_f16_ts(acc, Ah, Bl, id64, 1u);
-            umma_f16_ts(acc, Al, Bh, id64, 1u);
+            if (TAIL) {
+              const uint64_t Sh = D(pres + p * PRE_BYTES + c * 2 * PLANE + ks * 32), Sl = Sh + (PLANE >> 4);
+              umma_f16(acc, Sh, Bh, id64, ck ? 1u : 0u);
+              if ((a.dbg & 4) || a.fast) continue;
+              umma_f16(acc, Sh, Bl, id64, 1u);
+              umma_f16(acc, Sl, Bh, id64, 1u);
+            } else {
+              const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
+              umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
+              if ((a.dbg & 4) || a.fast) continue;
+              umma_f16_ts(acc, Ah, Bl, id64, 1u);
+              umma_f16_ts(acc, Al, Bh, id64, 1u);
+            }
           }
-          umma_commit(bar(B_ACC2FULL + p));
+          umma_commit(bar(B_ACC2FULL + p));                   // (TAIL: also frees the input stage for the loader)
         }
         __syncwarp();
       }
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {                    // ph 0: E1 of block it, ph 1: E2 of block it - 1 (one code path: instruction-cache footprint)
         const int b = it - ph;
-        if (b < 0 || b >= NB) continue;
+        if (b < 0 || b >= NB || (TAIL && ph == 0)) continue;
         const int p = b & 1, j = b >> 1;
         bool inside = true;
         if (ph == 0) {
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       const long long pix = ((long long)k.n * a.H + yo) * a.W + xo;
       float4 zq[C / 4];
       const float4* zp = reinterpret_cast<const float4*>((const float*)a.z_in.p + pix * a.z_in.cs + a.z_in.coff);
-      if (C == 12 && valid) {                             // flow state of the pixel: in flight while the accumulator is awaited / summed
+      if (!TAIL && C == 12 && valid) {                             // flow state of the pixel: in flight while the accumulator is awaited / summed
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) zq[i] = __ldg(zp + i);
       }
@@ -558,13 +571,13 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar(B_ACC3EMPTY + b % K::NACC3));
       mbar_arrive(bar(B_BARW + g));
-      if (C != 12 && valid) {                             // C = 24: no registers for it during the tap sums; in flight across the ring hand-off
+      if (!TAIL && C != 12 && valid) {                    // C = 24: no registers for it during the tap sums; in flight across the ring hand-off
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) zq[i] = __ldg(zp + i);
       }
       constexpr int NHQ = C == 12 ? 6 : 4;
       float4 hq[NHQ];
-      if (valid && a.has_hF) {
+      if (!TAIL && valid && a.has_hF) {
         const float4* fp = reinterpret_cast<const float4*>((const float*)a.hF.p + pix * a.hF.cs + a.hF.coff);
 #pragma unroll
         for (int i = 0; i < NHQ; ++i) hq[i] = __ldg(fp + i);
@@ -582,7 +595,13 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       TR_ADD(tr_ex, tr3); TR_T(tr4);
 #pragma unroll
       for (int c = 1; c < C; c += 2) h[c] = __fdividef(1.f, 1.f + __expf(-(h[c] + 2.f))) + a.eps;
-      if (valid && !(a.dbg & 16)) flow_apply<C, NHQ>(a, h, pix, zq, hq);
+      if (TAIL) {                                         // the level's (shiftF, scaleF) pairs: stored, consumed by the FlowSteps of both directions
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>((float*)a.z_out.p + pix * a.z_out.cs + a.z_out.coff);
+#pragma unroll
+          for (int i = 0; i < C / 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+      } else if (valid && !(a.dbg & 16)) flow_apply<C, NHQ>(a, h, pix, zq, hq);
       TR_ADD(tr_fl, tr4);
     }
 #ifdef BFSR_TC_TRACE
@@ -697,9 +716,70 @@ void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2
       fA0z.cin > cf::Cfg<24>::ZP || (C == 12 && fA0z.cin > 8) || fA0z.ks != 3 || fA2.ks != 1 || fA4.ks != 3) return;
   if (C == 12) pack_fused_t<12>(fw, fA0z, fA2, fA4); else pack_fused_t<24>(fw, fA0z, fA2, fA4);
 }
+// Feature-only tail of a C = 12 level's coupling: fFeatures.2 (1x1 64 -> 64, ReLU) and fFeatures.4 (3x3 64 -> 24, cross-sigmoid)
+void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4) {
+  using namespace cf;
+  using K = Cfg<24, true>;
+  constexpr int N3 = K::N3;
+  fw = FusedCouplingW();
+  static const bool off = getenv("BFSR_FUSE_TAIL") && atoi(getenv("BFSR_FUSE_TAIL")) == 0;
+  if (off || fF2.ks != 1 || fF2.cin != 64 || fF2.cout != 64 || fF4.ks != 3 || fF4.cin != 64 || fF4.cout != 24) return;
+  auto fetch = [](const ConvW& c, std::vector<float>& w, std::vector<float>& b) {
+    w.resize((size_t)c.ks * c.ks * c.cin_pad * c.cout_pad); b.resize(c.cout_pad);
+    CUDA_OK(cudaMemcpy(w.data(), c.w, w.size() * 4, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(b.data(), c.bias, b.size() * 4, cudaMemcpyDeviceToHost));
+  };
+  std::vector<float> wb, bb, wc, bc;
+  fetch(fF2, wb, bb); fetch(fF4, wc, bc);
+  std::vector<unsigned short> img(K::W_BYTES / 2, 0);
+  auto split = [](float w, unsigned short& hi, unsigned short& lo) { hi = f2bf(w); lo = f2bf(w - bf2f(hi)); };
+  for (int c = 0; c < 2; ++c)
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < 32; ++k) {
+        unsigned short hi, lo; split(wb[((size_t)(c * 32 + k)) * fF2.cout_pad + n], hi, lo);
+        put_bf(img, (size_t)c * 128, n, k, hi); put_bf(img, (size_t)c * 128, 64 + n, k, lo);
+      }
+  const size_t r3 = W2_BYTES / ROWB;
+  for (int c = 0; c < 2; ++c)
+    for (int t = 0; t < 9; ++t)
+      for (int co = 0; co < 24; ++co)
+        for (int k = 0; k < 32; ++k) {
+          unsigned short hi, lo; split(wc[((size_t)t * fF4.cin_pad + c * 32 + k) * fF4.cout_pad + co], hi, lo);
+          put_bf(img, r3 + (size_t)c * 2 * N3, t * 24 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 24 + co, k, lo);
+        }
+  CUDA_OK(cudaMalloc(&fw.w, K::W_BYTES));
+  CUDA_OK(cudaMemcpy(fw.w, img.data(), K::W_BYTES, cudaMemcpyHostToDevice));
+  fw.C = 24;
+  for (int i = 0; i < 64; ++i) { fw.bias1[i] = 0.f; fw.bias2[i] = bb[i]; }
+  for (int i = 0; i < 32; ++i) fw.bias3[i] = i < 24 ? bc[i] : 0.f;
+}
 void free_fused_coupling(FusedCouplingW& fw) { if (fw.w) cudaFree(fw.w); fw.w = nullptr; }
 
 static int g_cf_sms = 0;
+
+// strips x vertical segments of the tiles -> work items
+static void cf_decompose(CfArgs& a, int N, int H, int W) {
+  using namespace cf;
+  a.strips = cdiv(W, OUT_W);
+  // vertical segmentation: the cheapest number of segments per strip under one-CTA-per-SM wave quantisation (each segment recomputes
+  // two halo rows; 32 tiles of 320x320: 5 segments of 64 rows = 13 rounds x 17 blocks instead of 3 x 81)
+  {
+    double best = 1e300; int best_ns = 1;
+    for (int ns = 1; ns <= 64 && (ns == 1 || cdiv(H, ns) >= 8); ++ns) {
+      const int rows = cdiv(H, ns), nsr = cdiv(H, rows);
+      const long long items = (long long)N * a.strips * nsr;
+      const double cost = (double)((items + g_cf_sms - 1) / g_cf_sms) * (cdiv(rows + 2, 4) + 0.5);
+      if (cost < best * (1.0 - 1e-9)) { best = cost; best_ns = ns; }
+    }
+    static const int ns_env = getenv("BFSR_CF_SEGS") ? atoi(getenv("BFSR_CF_SEGS")) : 0;
+    if (ns_env > 0) best_ns = ns_env;
+    a.seg_rows = cdiv(H, best_ns); a.segs = cdiv(H, a.seg_rows);
+  }
+  a.nblk = cdiv(a.seg_rows + 2, 4);
+  const long long items = (long long)N * a.strips * a.segs;
+  BFSR_CHECK(items < (1 << 30), "coupling_fused: too many work items");
+  a.total_items = (int)items;
+}
 
 // z1p_in / z1p_out: [N,H,W,2 ZP] bf16 planes ([hi(ZP) | lo(ZP)] of z1); pre: the BF16X2 64-channel pre-activation slice; f as for the conv
 // epilogue (z1op.p != null requests the z1 operand of the next step in z1p_out); hM / hcvec: host copies of f.M / f.cvec
@@ -721,25 +801,7 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   CfArgs a = CfArgs();
   a.w = (const unsigned char*)fw.w; a.pre_coff = pre.coff;
   a.H = z.H; a.W = z.W; a.N = z.N;
-  a.strips = cdiv(z.W, OUT_W);
-  // vertical segmentation: the cheapest number of segments per strip under one-CTA-per-SM wave quantisation (each segment recomputes
-  // two halo rows; 32 tiles of 320x320: 5 segments of 64 rows = 13 rounds x 17 blocks instead of 3 x 81)
-  {
-    double best = 1e300; int best_ns = 1;
-    for (int ns = 1; ns <= 64 && (ns == 1 || cdiv(z.H, ns) >= 8); ++ns) {
-      const int rows = cdiv(z.H, ns), nsr = cdiv(z.H, rows);
-      const long long items = (long long)z.N * a.strips * nsr;
-      const double cost = (double)((items + g_cf_sms - 1) / g_cf_sms) * (cdiv(rows + 2, 4) + 0.5);
-      if (cost < best * (1.0 - 1e-9)) { best = cost; best_ns = ns; }
-    }
-    static const int ns_env = getenv("BFSR_CF_SEGS") ? atoi(getenv("BFSR_CF_SEGS")) : 0;
-    if (ns_env > 0) best_ns = ns_env;
-    a.seg_rows = cdiv(z.H, best_ns); a.segs = cdiv(z.H, a.seg_rows);
-  }
-  a.nblk = cdiv(a.seg_rows + 2, 4);
-  const long long items = (long long)z.N * a.strips * a.segs;
-  BFSR_CHECK(items < (1 << 30), "coupling_fused: too many work items");
-  a.total_items = (int)items;
+  cf_decompose(a, z.N, z.H, z.W);
   static const int dbg_env = getenv("BFSR_CF_DBG") ? atoi(getenv("BFSR_CF_DBG")) : 0;
   a.dbg = dbg_env;
   a.fast = g_conv_mode == 1 ? 1 : 0;
@@ -764,12 +826,43 @@ void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out,
   snprintf(g_prof_tag, sizeof g_prof_tag, "cpl-fused C%d %dx%d", C, z.H, z.W);
   ProfScope prof(PK_CONV_TC, 2.0 * (double)z.npix() * (ZP * 9.0 * 64 + 64.0 * 64 + 64.0 * 9 * C), s);
   if (C == 12) {
-    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<12>::SMEM_BYTES));
-    coupling_fused_kernel<12><<<grid, NTHREADS, Cfg<12>::SMEM_BYTES, s>>>(a);
+    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<12>::SMEM_BYTES));
+    coupling_fused_kernel<12, false><<<grid, NTHREADS, Cfg<12>::SMEM_BYTES, s>>>(a);
   } else {
-    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<24>::SMEM_BYTES));
-    coupling_fused_kernel<24><<<grid, NTHREADS, Cfg<24>::SMEM_BYTES, s>>>(a);
+    CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<24>::SMEM_BYTES));
+    coupling_fused_kernel<24, false><<<grid, NTHREADS, Cfg<24>::SMEM_BYTES, s>>>(a);
   }
+  CUDA_OK(cudaGetLastError());
+  count_launch();
+}
+
+// hF = cross_sigmoid(conv3x3(relu(conv1x1(in)))) for one step of a C = 12 level: in = BF16X2 64-channel slice of the level's fFeatures.0
+// outputs, out = fp32 24-channel (shiftF, scaleF) pairs
+void tail_fused(const FusedCouplingW& fw, const View& in, const View& out, float eps, cudaStream_t s) {
+  using namespace cf;
+  using K = Cfg<24, true>;
+  BFSR_CHECK(fw.w && fw.C == 24, "tail_fused: weights not packed");
+  BFSR_CHECK(in.fmt == BF16X2 && in.C == 64 && in.cs % 8 == 0 && in.coff % 8 == 0 && in.plane % 8 == 0 && ((uintptr_t)in.p % 16) == 0 &&
+             out.fmt == F32 && out.C == 24 && out.cs % 4 == 0 && out.coff % 4 == 0 && ((uintptr_t)out.p % 16) == 0 && in.N == out.N &&
+             in.H == out.H && in.W == out.W, "tail_fused: operand views");
+  if (in.npix() == 0) return;
+  if (!g_cf_sms) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&g_cf_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  CfArgs a = CfArgs();
+  a.w = (const unsigned char*)fw.w; a.pre_coff = in.coff;
+  a.H = in.H; a.W = in.W; a.N = in.N;
+  cf_decompose(a, in.N, in.H, in.W);
+  static const int dbg_env = getenv("BFSR_CF_DBG") ? atoi(getenv("BFSR_CF_DBG")) : 0;
+  a.dbg = dbg_env;
+  a.fast = g_conv_mode == 1 ? 1 : 0;
+  a.eps = eps;
+  a.z_in = out; a.z_out = out;
+  memcpy(a.bias2, fw.bias2, sizeof a.bias2); memcpy(a.bias3, fw.bias3, sizeof a.bias3);
+  make_tmap(&a.tm_pre, in, 32, 4);
+  const int grid = a.total_items < g_cf_sms ? a.total_items : g_cf_sms;
+  snprintf(g_prof_tag, sizeof g_prof_tag, "tail-fused 64->64->24 %dx%d", in.H, in.W);
+  ProfScope prof(PK_CONV_TC, 2.0 * (double)in.npix() * (64.0 * 64 + 64.0 * 9 * 24), s);
+  CUDA_OK(cudaFuncSetAttribute(coupling_fused_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+  coupling_fused_kernel<24, true><<<grid, NTHREADS, K::SMEM_BYTES, s>>>(a);
   CUDA_OK(cudaGetLastError());
   count_launch();
 }

@@ -373,14 +373,15 @@ def test_one_launch_coupling_vs_three_launch_chain(tmp_path):
         outs[name] = path
     assert cpl_check.cmp(outs["chain"], outs["fused"], tol=5e-6) == 0
     assert cpl_check.cmp(outs["chain"], outs["fused_s3"], tol=5e-6) == 0
-    # bf16 single-pass mode (precision 1): same hi x hi products in both forms
+    # bf16 single-pass mode (precision 1): same hi x hi products in both forms; a 1e-7 difference of summation order flips the bf16
+    # rounding of a hidden value now and then (2^-9 relative at that point), hence the wider gate (the mode itself is a 5e-3 class)
     for name, env in (("chain_fast", {"BFSR_FUSE_CPL": "0", "BFSR_CPL_CHECK_PREC": "1"}), ("fused_fast", {"BFSR_FUSE_CPL": "1", "BFSR_CPL_CHECK_PREC": "1"})):
         path = str(tmp_path / f"{name}.pt")
         r = subprocess.run([sys.executable, os.path.join(root, "tools", "cpl_check.py"), "run", path], env=dict(os.environ, **env), cwd=root,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs[name] = path
-    assert cpl_check.cmp(outs["chain_fast"], outs["fused_fast"], tol=2e-5) == 0
+    assert cpl_check.cmp(outs["chain_fast"], outs["fused_fast"], tol=1e-4) == 0
 
 
 # ------------------------------------------------------------------ reference-recorded pins at the BASELINE shapes (round 2)
