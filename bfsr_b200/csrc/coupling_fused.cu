@@ -56,8 +56,8 @@ constexpr int TM_ACC1 = 0, TM_ACC2 = 128, TM_ACC3 = 256, TM_COLS = 512;
 constexpr int OUT_W = 28;                              // output columns per strip
 // mbarrier indices
 enum { B_WFULL = 0, B_INFULL = 1, B_PREFULL = 3, B_PREEMPTY = 5, B_ACC1FULL = 6, B_H1READY = 8, B_ACC2FULL = 10, B_H2READY = 12,
-       B_ACC3FULL = 14 /* one per E3 group: a waiter must see every phase of a barrier it polls */,
-       B_ACC3EMPTY = B_ACC3FULL + NG, B_BARW = B_ACC3EMPTY + 2 /* tap-row sums of a block written */,
+       B_ACC3FULL = 14 /* one per (E3 group, head group): a waiter must see every phase of a barrier it polls */,
+       B_ACC3EMPTY = B_ACC3FULL + 2 * NG, B_BARW = B_ACC3EMPTY + 2 /* tap-row sums of a block written */,
        B_BARR = B_BARW + NG /* ... and read (C = 24: the small ring is recycled block by block) */, B_COUNT = B_BARR + NG };
 // Per level: C = 12 (z1: 6 channels -> one K = 16 step [hi(8) | lo(8)], head N = 9 x 12 -> 112, two accumulator / pre-activation stages,
 // 16-row tap-sum ring) or C = 24 (z1: 12 channels -> K = 32 [hi(16) | lo(16)], head N = 9 x 24 -> 224 in ONE accumulator stage, one
@@ -68,14 +68,18 @@ template <int C, bool TAIL = false> struct Cfg {
   static_assert(C == 12 || C == 24, "coupling_fused: C = 12 or 24");
   static_assert(!TAIL || C == 24, "coupling_fused: the tail variant is built for 24 output channels (C = 12 levels)");
   static constexpr int ZP = C == 12 ? 8 : 16;                      // z1 channels, padded
-  static constexpr int N3 = C == 12 ? 112 : 224;                   // 9 taps x C columns (+ padding to a multiple of 16)
+  static constexpr int NSUB = TAIL ? 2 : 1;                        // head MMA groups per block (TAIL: two halves of 12 output channels, each with its
+                                                                   // own accumulator slot, released as soon as E3 has summed it: the next block's head
+                                                                   // MMAs run under the other half's sums)
+  static constexpr int CH = C / NSUB;                              // output channels per head group / accumulator slot
+  static constexpr int N3 = CH == 12 ? 112 : 224;                  // 9 taps x CH columns (+ padding to a multiple of 16)
   // W1: C = 12: per tap 64 rows, bytes 0..31 = [W_hi | W_hi], bytes 32..63 = [W_lo | 0]
   //     C = 24: per tap 64 rows [W_hi(16) | W_hi(16)], then five images holding [W_lo(16)] of two taps per row (bytes 0..31 / 32..63)
   static constexpr int W1_BYTES = TAIL ? 0 : (C == 12 ? 9 * 64 * ROWB : (9 + 5) * 64 * ROWB);
-  static constexpr int W3_BYTES = 2 * 2 * N3 * ROWB;               // per 32-channel chunk [W_hi (N3 rows) ; W_lo (N3 rows)]
+  static constexpr int W3_BYTES = 2 * NSUB * 2 * N3 * ROWB;        // per 32-channel chunk and head group [W_hi (N3 rows) ; W_lo (N3 rows)]
   static constexpr int W_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ID_BYTES;
   static constexpr int NPRE = (C == 12 || TAIL) ? 2 : 1;           // pre-activation (TAIL: input) stages
-  static constexpr int NACC3 = C == 12 ? 2 : 1;                    // head accumulator stages
+  static constexpr int NACC3 = (C == 12 || TAIL) ? 2 : 1;          // head accumulator slots of N3 columns (C = 12: block parity; TAIL: head half)
   static constexpr int RING = C == 12 ? 16 : (TAIL ? 14 : 6);      // (14: the smallest ring whose aliasing blocks are three apart = same E3 group)                    // rows of tap-row sums kept for the neighbouring rows (two arrays: dy = 0, 1)
   static constexpr bool CHAIN = C != 12 && !TAIL;                           // ring too small to run ahead: block b writes after block b-1 has read
   static constexpr int EXCH_BYTES = 2 * RING * C * 32 * 4;         // [dy][row % RING][C channels][32 lanes] fp32
@@ -329,7 +333,29 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     const uint32_t id32 = make_idesc(32), id64 = make_idesc(64);
     mbar_wait(bar(B_WFULL), 0);
     TR_DECL(tr_in = 0, tr_h1 = 0); TR_T(tr_start);
-    for (int b = 0; b < (TAIL ? 0 : NB); ++b) {     // TAIL: no M1 (issuer B runs the 1x1 from shared memory)
+    for (int b = 0; TAIL && b < NB; ++b) {             // TAIL: this issuer runs the 1x1 straight from the TMA-loaded input tile (SS mode)
+      const int p = b & 1, j = b >> 1;
+      mbar_wait(bar(B_PREFULL + p), (uint32_t)(j & 1));
+      // acc2[p] still holds h2 of block b - 2 until its head MMAs (both halves; the second is committed last) have retired
+      if (b >= 2) mbar_wait(bar(B_ACC3FULL + 2 * ((b - 2) % NG) + K::NSUB - 1), (uint32_t)(((b - 2) / NG) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t acc = tmem_base + TM_ACC2 + 64 * p;
+#pragma unroll 1
+        for (int ck = 0; ck < 4; ++ck) {
+          const int c = ck >> 1, ks = ck & 1;
+          const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
+          const uint64_t Sh = D(pres + p * PRE_BYTES + c * 2 * PLANE + ks * 32), Sl = Sh + (PLANE >> 4);
+          umma_f16(acc, Sh, Bh, id64, ck ? 1u : 0u);
+          if ((a.dbg & 4) || a.fast) continue;
+          umma_f16(acc, Sh, Bl, id64, 1u);
+          umma_f16(acc, Sl, Bh, id64, 1u);
+        }
+        umma_commit(bar(B_ACC2FULL + p));                 // releases E2 and, two blocks later, the loader's input stage p
+      }
+      __syncwarp();
+    }
+    for (int b = 0; b < (TAIL ? 0 : NB); ++b) {
       const int p = b & 1, j = b >> 1;
       const uint32_t acc = tmem_base + TM_ACC1 + 64 * p;
       const int ps = b % K::NPRE;
@@ -393,11 +419,10 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
     mbar_wait(bar(B_WFULL), 0);
     TR_DECL(tr_h2 = 0, tr_a3 = 0, tr_h1 = 0); TR_T(tr_start);
     for (int it = 0; it <= NB; ++it) {
-      if (it < NB) {                                      // ---- M2(b): 1x1, acc2[p]
+      if (it < NB && !TAIL) {                             // ---- M2(b): 1x1, acc2[p]
         const int b = it, p = b & 1, j = b >> 1;
         TR_T(tr4);
-        if (TAIL) mbar_wait(bar(B_PREFULL + p), (uint32_t)(j & 1));          // the 64-channel input tile (BF16X2, TMA) is the A operand
-        else mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
+        mbar_wait(bar(B_H1READY + p), (uint32_t)(j & 1));
         TR_ADD(tr_h1, tr4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -406,21 +431,13 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
           for (int ck = 0; ck < 4; ++ck) {
             const int c = ck >> 1, ks = ck & 1;
             const uint64_t Bh = D(w2 + c * 128 * ROWB + ks * 32), Bl = Bh + ((64 * ROWB) >> 4);
-            if (TAIL) {
-              const uint64_t Sh = D(pres + p * PRE_BYTES + c * 2 * PLANE + ks * 32), Sl = Sh + (PLANE >> 4);
-              umma_f16(acc, Sh, Bh, id64, ck ? 1u : 0u);
-              if ((a.dbg & 4) || a.fast) continue;
-              umma_f16(acc, Sh, Bl, id64, 1u);
-              umma_f16(acc, Sl, Bh, id64, 1u);
-            } else {
-              const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
-              umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
-              if ((a.dbg & 4) || a.fast) continue;
-              umma_f16_ts(acc, Ah, Bl, id64, 1u);
-              umma_f16_ts(acc, Al, Bh, id64, 1u);
-            }
+            const uint32_t Ah = At + 16 * ck, Al = Ah + 8;          // 16-channel group: 8 columns of hi pairs, then 8 of lo pairs
+            umma_f16_ts(acc, Ah, Bh, id64, ck ? 1u : 0u);
+            if ((a.dbg & 4) || a.fast) continue;
+            umma_f16_ts(acc, Ah, Bl, id64, 1u);
+            umma_f16_ts(acc, Al, Bh, id64, 1u);
           }
-          umma_commit(bar(B_ACC2FULL + p));                   // (TAIL: also frees the input stage for the loader)
+          umma_commit(bar(B_ACC2FULL + p));
         }
         __syncwarp();
       }
@@ -428,25 +445,30 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
         const int b = it - 1, p = b & 1, j = b >> 1;
         TR_T(tr2);
         mbar_wait(bar(B_H2READY + p), (uint32_t)(j & 1));
-        TR_ADD(tr_h2, tr2); TR_T(tr3);
-        mbar_wait(bar(B_ACC3EMPTY + b % K::NACC3), (uint32_t)(((b / K::NACC3) & 1) ^ 1));
-        TR_ADD(tr_a3, tr3);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t acc = tmem_base + TM_ACC3 + N3 * (b % K::NACC3), At = tmem_base + TM_ACC2 + 64 * p;    // h2 sits where acc2 was
+        TR_ADD(tr_h2, tr2);
 #pragma unroll 1
-          for (int ck = 0; ck < 4; ++ck) {
-            const int c = ck >> 1, ks = ck & 1;
-            const uint32_t Ah = At + 16 * ck, Al = Ah + 8;
-            const uint64_t Bh = D(w3 + c * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
-            umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
-            if ((a.dbg & 8) || a.fast) continue;
-            umma_f16_ts(acc, Ah, Bl, idn3, 1u);
-            umma_f16_ts(acc, Al, Bh, idn3, 1u);
+        for (int hc = 0; hc < K::NSUB; ++hc) {
+          const int slot = TAIL ? hc : (C == 12 ? p : 0);   // accumulator slot: head half (TAIL), block parity (C = 12), the only one (C = 24)
+          TR_T(tr3);
+          mbar_wait(bar(B_ACC3EMPTY + slot), (uint32_t)(((C == 12 && !TAIL ? j : b) & 1) ^ 1));
+          TR_ADD(tr_a3, tr3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint32_t acc = tmem_base + TM_ACC3 + N3 * slot, At = tmem_base + TM_ACC2 + 64 * p;    // h2 sits where acc2 was
+#pragma unroll 1
+            for (int ck = 0; ck < 4; ++ck) {
+              const int c = ck >> 1, ks = ck & 1;
+              const uint32_t Ah = At + 16 * ck, Al = Ah + 8;
+              const uint64_t Bh = D(w3 + (c * K::NSUB + hc) * 2 * N3 * ROWB + ks * 32), Bl = Bh + ((N3 * ROWB) >> 4);
+              umma_f16_ts(acc, Ah, Bh, idn3, ck ? 1u : 0u);
+              if ((a.dbg & 8) || a.fast) continue;
+              umma_f16_ts(acc, Ah, Bl, idn3, 1u);
+              umma_f16_ts(acc, Al, Bh, idn3, 1u);
+            }
+            umma_commit(bar(B_ACC3FULL + 2 * (b % NG) + hc));
           }
-          umma_commit(bar(B_ACC3FULL + b % NG));
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
 #ifdef BFSR_TC_TRACE
@@ -515,7 +537,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
   } else {
     // ===================== E3: tap sums, cross-sigmoid, FlowStep (NG groups of 4 warps take blocks in rotation) =====================
     const int q = warp & 3, g = (warp - 8) >> 2;
-    constexpr int RING = K::RING, NH = C / 12;            // the tap sums are taken 12 channels at a time (36 accumulator columns in registers)
+    constexpr int RING = K::RING;
     float* S = reinterpret_cast<float*>(sgen + K::OFF_EXCH);
     TR_DECL(tr_a3 = 0, tr_bc = 0, tr_ld = 0, tr_ex = 0, tr_fl = 0); TR_T(tr_start);
     BlkIter bi; bi.init(a, g < NB ? g : 0);
@@ -530,46 +552,53 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
 #pragma unroll
         for (int i = 0; i < C / 4; ++i) zq[i] = __ldg(zp + i);
       }
-      TR_T(tr0);
-      mbar_wait_nap(bar(B_ACC3FULL + g), (uint32_t)((b / NG) & 1));
-      // small ring (C = 24): the previous block has read its rows before this one overwrites the slots they alias
-      if (K::CHAIN && b > 0) mbar_wait_nap(bar(B_BARR + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
-      TR_ADD(tr_a3, tr0); TR_T(tr1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float u2[C];
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3 + N3 * (b % K::NACC3);
       const int R = 4 * b + q;                            // running raster row of the CTA's block stream; ring slot = row % RING
-      // accumulator columns: 3 C dy + C dx + co
-#pragma unroll 1
-      for (int dy = 0; dy < 2; ++dy) {                     // needed by the rows below: y + 1 (dy = 0), y (dy = 1)
-        float* Sd = S + (dy * RING + R % RING) * C * 32 + lane;
+      constexpr int CH = K::CH;
+      // accumulator columns of a slot: 3 CH dy + CH dx + co; the tap sums are taken 12 channels at a time (36 columns in registers)
 #pragma unroll
-        for (int hc = 0; hc < NH; ++hc) {
+      for (int hc = 0; hc < K::NSUB; ++hc) {
+        const int slot = TAIL ? hc : (C == 12 ? (b & 1) : 0);
+        TR_T(tr0);
+        mbar_wait_nap(bar(B_ACC3FULL + 2 * g + hc), (uint32_t)((b / NG) & 1));
+        // small ring (C = 24): the previous block has read its rows before this one overwrites the slots they alias
+        if (K::CHAIN && hc == 0 && b > 0) mbar_wait_nap(bar(B_BARR + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
+        TR_ADD(tr_a3, tr0); TR_T(tr1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC3 + N3 * slot;
+#pragma unroll 1
+        for (int dy = 0; dy < 2; ++dy) {                   // needed by the rows below: y + 1 (dy = 0), y (dy = 1)
+          float* Sd = S + ((dy * RING + R % RING) * C + CH * hc) * 32 + lane;
+#pragma unroll
+          for (int h2 = 0; h2 < CH / 12; ++h2) {
+            float t[36];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 3 * CH * dy + CH * dx + 12 * h2, t + 12 * dx); tmem_ld4(t_row + 3 * CH * dy + CH * dx + 12 * h2 + 8, t + 12 * dx + 8); }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+              Sd[(12 * h2 + c) * 32] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+          }
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < CH / 12; ++h2) {
           float t[36];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 3 * C * dy + C * dx + 12 * hc, t + 12 * dx); tmem_ld4(t_row + 3 * C * dy + C * dx + 12 * hc + 8, t + 12 * dx + 8); }
+          for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 6 * CH + CH * dx + 12 * h2, t + 12 * dx); tmem_ld4(t_row + 6 * CH + CH * dx + 12 * h2 + 8, t + 12 * dx + 8); }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int c = 0; c < 12; ++c)
-            Sd[(12 * hc + c) * 32] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
+            u2[CH * hc + 12 * h2 + c] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
         }
+        TR_ADD(tr_ld, tr1); TR_T(tr2);
+        // the previous block's sums are in the ring (awaited BEFORE the accumulator is released: no E3 group can then run two blocks ahead
+        // of a waiter, so every waiter sees every phase of the barriers it polls)
+        if (b > 0) mbar_wait_nap(bar(B_BARW + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar(B_ACC3EMPTY + slot));
+        TR_ADD(tr_bc, tr2);
       }
-#pragma unroll
-      for (int hc = 0; hc < NH; ++hc) {
-        float t[36];
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) { tmem_ld8(t_row + 6 * C + C * dx + 12 * hc, t + 12 * dx); tmem_ld4(t_row + 6 * C + C * dx + 12 * hc + 8, t + 12 * dx + 8); }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 12; ++c)
-          u2[12 * hc + c] = t[c] + __shfl_down_sync(0xffffffffu, t[12 + c], 1) + __shfl_down_sync(0xffffffffu, t[24 + c], 2);
-      }
-      TR_ADD(tr_ld, tr1); TR_T(tr2);
-      // the previous block's sums are in the ring (awaited BEFORE the accumulator is released: no E3 group can then run two blocks ahead
-      // of a waiter, so every waiter sees every phase of the barriers it polls)
-      if (b > 0) mbar_wait_nap(bar(B_BARW + (b - 1) % NG), (uint32_t)(((b - 1) / NG) & 1));
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar(B_ACC3EMPTY + b % K::NACC3));
+      TR_T(tr2);
       mbar_arrive(bar(B_BARW + g));
       if (!TAIL && C != 12 && valid) {                    // C = 24: no registers for it during the tap sums; in flight across the ring hand-off
 #pragma unroll
@@ -745,7 +774,8 @@ void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4) {
       for (int co = 0; co < 24; ++co)
         for (int k = 0; k < 32; ++k) {
           unsigned short hi, lo; split(wc[((size_t)t * fF4.cin_pad + c * 32 + k) * fF4.cout_pad + co], hi, lo);
-          put_bf(img, r3 + (size_t)c * 2 * N3, t * 24 + co, k, hi); put_bf(img, r3 + (size_t)c * 2 * N3, N3 + t * 24 + co, k, lo);
+          const size_t base = r3 + (size_t)(c * K::NSUB + co / K::CH) * 2 * N3;
+          put_bf(img, base, t * K::CH + co % K::CH, k, hi); put_bf(img, base, N3 + t * K::CH + co % K::CH, k, lo);
         }
   CUDA_OK(cudaMalloc(&fw.w, K::W_BYTES));
   CUDA_OK(cudaMemcpy(fw.w, img.data(), K::W_BYTES, cudaMemcpyHostToDevice));
