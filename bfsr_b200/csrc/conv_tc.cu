@@ -1348,7 +1348,12 @@ static void launch_tc(const ConvW& w, const View& in, const View& out, const Con
                      (!epi.flow || epi.flow->C == 12);
   static const int dbg_env = getenv("BFSR_TC_DBG") ? atoi(getenv("BFSR_TC_DBG")) : 0;
   a.dbg = dbg_env;
-  static const bool use_pdl = getenv("BFSR_PDL") && atoi(getenv("BFSR_PDL")) == 1;
+  // BFSR_PDL_SMALL=<pixels>: programmatic dependent launch only for launches with at most that many output pixels (the level-3 convs of
+  // 80x80 tiles are dominated by launch + prologue latency; on the big convs PDL costs more than it hides)
+  static const bool pdl_all = getenv("BFSR_PDL") && atoi(getenv("BFSR_PDL")) == 1;
+  // Measured on the whole config-2 step: <= 1 M pixels (everything but the 320x320 launches) 257.6 -> 255.8 ms; all launches: 3 % slower.
+  static const long long pdl_small = getenv("BFSR_PDL_SMALL") ? atoll(getenv("BFSR_PDL_SMALL")) : 1000000;
+  const bool use_pdl = pdl_all || (pdl_small > 0 && out.npix() <= pdl_small);
   a.pdl = use_pdl ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute at[1];
