@@ -745,14 +745,15 @@ void pack_fused_coupling(FusedCouplingW& fw, const ConvW& fA0z, const ConvW& fA2
       fA0z.cin > cf::Cfg<24>::ZP || (C == 12 && fA0z.cin > 8) || fA0z.ks != 3 || fA2.ks != 1 || fA4.ks != 3) return;
   if (C == 12) pack_fused_t<12>(fw, fA0z, fA2, fA4); else pack_fused_t<24>(fw, fA0z, fA2, fA4);
 }
-// Feature-only tail of a C = 12 level's coupling: fFeatures.2 (1x1 64 -> 64, ReLU) and fFeatures.4 (3x3 64 -> 24, cross-sigmoid)
-void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4) {
+// Feature-only tail of a coupling: fFeatures.2 (1x1 64 -> 64, ReLU) and 24 output channels [co0, co0 + 24) of fFeatures.4 (3x3, cross-sigmoid):
+// the whole tail of a C = 12 level, half of it for C = 24 (two launches, each recomputing the cheap 1x1)
+void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4, int co0) {
   using namespace cf;
   using K = Cfg<24, true>;
   constexpr int N3 = K::N3;
   fw = FusedCouplingW();
   static const bool off = getenv("BFSR_FUSE_TAIL") && atoi(getenv("BFSR_FUSE_TAIL")) == 0;
-  if (off || fF2.ks != 1 || fF2.cin != 64 || fF2.cout != 64 || fF4.ks != 3 || fF4.cin != 64 || fF4.cout != 24) return;
+  if (off || fF2.ks != 1 || fF2.cin != 64 || fF2.cout != 64 || fF4.ks != 3 || fF4.cin != 64 || co0 % 24 != 0 || co0 + 24 > fF4.cout) return;
   auto fetch = [](const ConvW& c, std::vector<float>& w, std::vector<float>& b) {
     w.resize((size_t)c.ks * c.ks * c.cin_pad * c.cout_pad); b.resize(c.cout_pad);
     CUDA_OK(cudaMemcpy(w.data(), c.w, w.size() * 4, cudaMemcpyDeviceToHost));
@@ -773,7 +774,7 @@ void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4) {
     for (int t = 0; t < 9; ++t)
       for (int co = 0; co < 24; ++co)
         for (int k = 0; k < 32; ++k) {
-          unsigned short hi, lo; split(wc[((size_t)t * fF4.cin_pad + c * 32 + k) * fF4.cout_pad + co], hi, lo);
+          unsigned short hi, lo; split(wc[((size_t)t * fF4.cin_pad + c * 32 + k) * fF4.cout_pad + co0 + co], hi, lo);
           const size_t base = r3 + (size_t)(c * K::NSUB + co / K::CH) * 2 * N3;
           put_bf(img, base, t * K::CH + co % K::CH, k, hi); put_bf(img, base, N3 + t * K::CH + co % K::CH, k, lo);
         }
@@ -781,7 +782,7 @@ void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4) {
   CUDA_OK(cudaMemcpy(fw.w, img.data(), K::W_BYTES, cudaMemcpyHostToDevice));
   fw.C = 24;
   for (int i = 0; i < 64; ++i) { fw.bias1[i] = 0.f; fw.bias2[i] = bb[i]; }
-  for (int i = 0; i < 32; ++i) fw.bias3[i] = i < 24 ? bc[i] : 0.f;
+  for (int i = 0; i < 32; ++i) fw.bias3[i] = i < 24 ? bc[co0 + i] : 0.f;
 }
 void free_fused_coupling(FusedCouplingW& fw) { if (fw.w) cudaFree(fw.w); fw.w = nullptr; }
 

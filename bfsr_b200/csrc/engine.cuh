@@ -32,7 +32,7 @@ struct CouplingW {
   ConvW fF2, fF4;          // fFeatures tail (per step): 1x1 64->64 (+ReLU), 3x3 64->2C (cross-sigmoid)
   ConvW fA0z, fA2, fA4;    // fAffine: z-part of the first conv, 1x1, 3x3 64->C (cross-sigmoid)
   FusedCouplingW fz;       // the same three convs packed for the one-launch coupling step (C = 12 / 24 levels)
-  FusedCouplingW ftail;    // fF2 + fF4 packed for the one-launch feature-only tail (C = 12 levels)
+  FusedCouplingW ftail, ftail2;   // fF2 + 24 output channels of fF4 packed for the one-launch feature-only tail (C = 12: all of hF; C = 24: two halves)
 };
 struct LayerW {
   int kind = 0;            // 0 squeeze, 1 nocoupling, 2 coupling, 3 split

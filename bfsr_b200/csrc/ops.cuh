@@ -92,8 +92,8 @@ void free_fused_coupling(FusedCouplingW& fw);
 void coupling_fused(const FusedCouplingW& fw, const void* z1p_in, void* z1p_out, const View& pre, const FlowEpi& f, const float* hM,
                     const float* hcvec, float eps, cudaStream_t s);
 void z1_pack(const View& z, void* z1p, int C, cudaStream_t s);
-// feature-only tail of a C = 12 level's coupling in one launch: hF = cross_sigmoid(conv3x3(relu(conv1x1(in)))) (fFeatures.2 / .4)
-void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4);
+// feature-only tail of a coupling, 24 output channels per launch: hF = cross_sigmoid(conv3x3(relu(conv1x1(in)))) (fFeatures.2 / .4)
+void pack_fused_tail(FusedCouplingW& fw, const ConvW& fF2, const ConvW& fF4, int co0 = 0);   // output channels [co0, co0 + 24) of fF4
 void tail_fused(const FusedCouplingW& fw, const View& in, const View& out, float eps, cudaStream_t s);
 
 // ------------------------------------------------------------------ layout / resampling

@@ -32,7 +32,7 @@ bfsr_srflow::~bfsr_srflow() {
     if (l.step.MfT) cudaFree(l.step.MfT);
     if (l.step.MiT) cudaFree(l.step.MiT);
     free_conv(l.cp.fF2); free_conv(l.cp.fF4); free_conv(l.cp.fA0z); free_conv(l.cp.fA2); free_conv(l.cp.fA4);
-    free_fused_coupling(l.cp.fz); free_fused_coupling(l.cp.ftail);
+    free_fused_coupling(l.cp.fz); free_fused_coupling(l.cp.ftail); free_fused_coupling(l.cp.ftail2);
     free_conv(l.split_conv);
   }
   for (auto& l : levels) {
@@ -193,7 +193,7 @@ static void build_srflow(bfsr_srflow* e, const Weights& W) {
       l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
       l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
       l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
-      if (Hd == 64) { pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C); if (C == 12) pack_fused_tail(l.cp.ftail, l.cp.fF2, l.cp.fF4); }
+      if (Hd == 64) { pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C); if (C == 12 || C == 24) pack_fused_tail(l.cp.ftail, l.cp.fF2, l.cp.fF4, 0); if (C == 24) pack_fused_tail(l.cp.ftail2, l.cp.fF2, l.cp.fF4, 24); }
       e->layers.push_back(l); ++idx;
     }
     lv.fF0_all = pack_conv(wF.data(), d.K * Hd, 320, 3, bF.data(), sF.data(), {});
@@ -301,9 +301,9 @@ static void run_encoder(Run& r, const View& x) {
 }
 
 static bool fp32_z() { static const bool v = getenv("BFSR_FP32_Z") && atoi(getenv("BFSR_FP32_Z")); return v; }
-// one-launch feature-only tail (coupling_fused.cu, TAIL variant): tensor-core modes, C = 12 levels
+// one-launch feature-only tail (coupling_fused.cu, TAIL variant): tensor-core modes, C = 12 levels (C = 24: two launches of 24 outputs)
 static bool tail_one(const Run& r, const LayerW& l) {
-  return coupling_fused_enabled() && g_conv_mode != 2 && r.opfmt() == BF16X2 && l.cp.ftail.w != nullptr;
+  return coupling_fused_enabled() && g_conv_mode != 2 && r.opfmt() == BF16X2 && l.cp.ftail.w != nullptr && (l.C == 12 || l.cp.ftail2.w != nullptr);
 }
 // feature-only halves of every coupling step of every level
 static void run_ft_convs(Run& r) {
@@ -337,7 +337,12 @@ static void run_ft_convs(Run& r) {
     }
     for (const LayerW& l : e->layers) {
       if (l.kind != 2 || l.level != lv) continue;
-      if (tail_one(r, l)) { K_(tail_fused(l.cp.ftail, bufF.slice(l.k_in_level * Hd, Hd), r.hF[lv][l.k_in_level], cs.eps, r.s)); continue; }
+      if (tail_one(r, l)) {
+        const View in = bufF.slice(l.k_in_level * Hd, Hd), &o = r.hF[lv][l.k_in_level];
+        K_(tail_fused(l.cp.ftail, in, o.slice(0, 24), cs.eps, r.s));
+        if (l.C == 24) K_(tail_fused(l.cp.ftail2, in, o.slice(24, 24), cs.eps, r.s));
+        continue;
+      }
       K_(conv2d(l.cp.fF2, bufF.slice(l.k_in_level * Hd, Hd), t, relu, IN_DIRECT, r.s));
       K_(conv2d(l.cp.fF4, t, r.hF[lv][l.k_in_level], cs, IN_DIRECT, r.s));
     }
@@ -531,7 +536,7 @@ static void pack_coupling(const Weights& W, const std::string& p, int C, int Hd,
   l.cp.fF4 = pack_conv_zeros(W, p + ".affine.fFeatures.4", 2 * C, Hd);
   l.cp.fA2 = pack_conv_actnorm(W, p + ".affine.fAffine.2", Hd, Hd, 1, {}, true);
   l.cp.fA4 = pack_conv_zeros(W, p + ".affine.fAffine.4", 2 * Cc, Hd);
-  if (Hd == 64) { pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C); if (C == 12) pack_fused_tail(l.cp.ftail, l.cp.fF2, l.cp.fF4); }
+  if (Hd == 64) { pack_fused_coupling(l.cp.fz, l.cp.fA0z, l.cp.fA2, l.cp.fA4, C); if (C == 12 || C == 24) pack_fused_tail(l.cp.ftail, l.cp.fF2, l.cp.fF4, 0); if (C == 24) pack_fused_tail(l.cp.ftail2, l.cp.fF2, l.cp.fF4, 24); }
 }
 
 // One FlowStep of the reference (FlowStep.py:88-129) through exactly the kernels the engine uses for that step: the feature-only
@@ -569,7 +574,10 @@ void op_flowstep(const bfsr_tensor_t* weights, int n, const char* prefix, int C,
       ConvEpi cs; cs.act = ACT_CROSS_SIGMOID;
       K_(conv2d(fF0, ft, bufF, relu, IN_DIRECT, s));
       K_(conv2d(fA0ft, ft, r.bufA[1], ConvEpi(), IN_DIRECT, s));
-      if (tail_one(r, l)) K_(tail_fused(l.cp.ftail, bufF, hF, cs.eps, s));
+      if (tail_one(r, l)) {
+        K_(tail_fused(l.cp.ftail, bufF, hF.slice(0, 24), cs.eps, s));
+        if (l.C == 24) K_(tail_fused(l.cp.ftail2, bufF, hF.slice(24, 24), cs.eps, s));
+      }
       else {
         K_(conv2d(l.cp.fF2, bufF, t, relu, IN_DIRECT, s));
         K_(conv2d(l.cp.fF4, t, hF, cs, IN_DIRECT, s));
