@@ -340,8 +340,11 @@ def run_config4(args, rank, world, local):
     lr = lr_host.to(dev)
     L = _lib.lib()
     warm = max(args.warmup, 3)
+    # one output buffer for every call, as in the config-2 loop: the engine replays its captured launch plan only while the buffers
+    # stay the same (a fresh torch.empty per call alternates between two addresses = two plans)
+    sr_buf = torch.empty((hi - lo, 3, S8 * LR, S8 * LR), device=dev, dtype=torch.float32)
     for _ in range(warm):
-        sr = net.lp_sr(lr, prior)
+        sr = net.lp_sr(lr, prior, out=sr_buf)
     _barrier(dist, world, dev)
     L.bfsr_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,7 +352,7 @@ def run_config4(args, rank, world, local):
         _barrier(dist, world, dev)
         e0.record()
         for _ in range(args.steps):
-            sr = net.lp_sr(lr, prior)
+            sr = net.lp_sr(lr, prior, out=sr_buf)
         e1.record()
         _barrier(dist, world, dev)
     launches = int(L.bfsr_launch_count(0))
