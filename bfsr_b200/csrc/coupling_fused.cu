@@ -1,27 +1,30 @@
-// One kernel per coupling FlowStep of a C = 12 level (SRFlow level 1): the z-dependent affine sub-net
-//     fAffine.0 (3x3, z1 -> 64, + feature-only pre-activation) -> ReLU -> fAffine.2 (1x1, 64 -> 64) -> ReLU -> fAffine.4 (3x3, 64 -> 12,
+// One kernel per coupling FlowStep of a C = 12 or C = 24 level (SRFlow levels 1 and 2): the z-dependent affine sub-net
+//     fAffine.0 (3x3, z1 -> 64, + feature-only pre-activation) -> ReLU -> fAffine.2 (1x1, 64 -> 64) -> ReLU -> fAffine.4 (3x3, 64 -> C,
 //     cross-sigmoid) -> affine coupling + the FlowStep's ActNorm / InvConv1x1 / feature-affine
-// (FlowAffineCouplingsAblation.py:78-96, 114-135; FlowStep.py:88-129) with the two 64-channel hidden maps kept in shared memory / TMEM.
+// (FlowAffineCouplingsAblation.py:78-96, 114-135; FlowStep.py:88-129) with the two 64-channel hidden maps kept in TENSOR MEMORY, and -- TAIL
+// variant -- the feature-only tail fFeatures.2 (1x1) -> ReLU -> fFeatures.4 (3x3, cross-sigmoid) = hF through the same machinery.
 // The three-launch chain it replaces (conv_tc: z-conv, 1x1, dx-folded head + FlowEpi) moved 1.3 KB per level pixel through HBM for
-// ~450 B of compulsory traffic; here the only HBM traffic is the pre-activation (256 B), z / hF (48 + 48 + 96 B) and the z1 operand.
+// ~450 B of compulsory traffic; here the only HBM traffic is the pre-activation (256 B), z / hF (48 + 48 + 96 B) and the z1 operand (C = 12).
 //
 // Work decomposition: a work item is a vertical STRIP of 28 output columns x seg_rows output rows of one image.  The CTA marches down
 // the strip in BLOCKS of 128 raster positions = 4 rows x 32 columns (one UMMA M = 128 tile); column c of the raster is image column
 // x0 - 1 + c, so the 30 columns the head conv needs (28 outputs + 1 halo each side) are columns 0..29 and columns 30, 31 are padding.
-// Per block b (h rows yb .. yb+3):
+// Per block b (h rows yb .. yb+3), C = 12 numbers:
 //   M1: acc1 = pre-activation (identity MMAs over the TMA-loaded BF16X2 tile) + conv3x3(z1): nine shifted views of the 6 x 32 z1 halo tile;
 //       z1 arrives as ONE bf16 plane [hi(8) | lo(8)] per pixel, so  z_hi.W_hi + z_lo.W_hi  is one K = 16 MMA and  z_hi.W_lo  a second one
-//   E1: h1 = relu(acc1 + b1) -> packed bf16 (hi, lo) written back to TENSOR MEMORY (tcgen05.st) as the A operand of the next GEMM: the
-//       hidden maps never touch shared memory.  (First version: operand tiles in shared memory -- 4550 clk per block, bound by shared-memory
-//       bandwidth: every SS-mode MMA re-reads its 4 KB A slice, 440 KB per block; with A in TMEM an MMA only reads its weights.)
-//   M2: acc2 = h1 . W2 (split-bf16 x3, A from TMEM)   E2: h2 = relu(acc2 + b2), zeroed outside the image (the head conv's zero padding), same columns
-//   M3: acc3[r, tap*12 + co] = h2[r, :] . W3[tap][:, co]  -- all nine taps folded into N = 112, no halo of h2 needed anywhere
+//   E1: h1 = relu(acc1) -> packed bf16 (hi, lo) written back IN PLACE into the accumulator's own tensor-memory columns (tcgen05.st): the A
+//       operand of the next GEMM; the hidden maps never touch shared memory.  (First version: operand tiles in shared memory -- 4550 clk per
+//       block, bound by shared-memory bandwidth: every SS-mode MMA re-reads its 4 KB A slice, 440 KB per block; with A in TMEM an MMA only
+//       reads its weights.)
+//   M2: acc2 = h1 . W2 (split-bf16 x3, A from TMEM)   E2: h2 = relu(acc2 + b2), zeroed outside the image (the head conv's zero padding), in place
+//   M3: acc3[r, tap*12 + co] = h2[r, :] . W3[tap][:, co]  -- all nine taps folded into N = 112 (C = 24: 224), no halo of h2 needed anywhere
 //   E3: out(y, x) = sum_{dy,dx} acc3[(y-1+dy, x-1+dx), tap]: the dx sum by warp shuffles (a warp holds one raster row); the dy = 0 and dy = 1
-//       tap-row sums of every raster row go to a 16-row ring in shared memory, and the warp holding row y finalises output row y - 1 from the
+//       tap-row sums of every raster row go to a ring in shared memory, and the warp holding row y finalises output row y - 1 from the
 //       rings (rows y-2, y-1) and its own dy = 2 sums -- rows are finalised with a lag of one row and carried across blocks; then bias,
-//       cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out).
+//       cross-sigmoid, and the FlowStep epilogue per pixel (z, hF in; z, z1 operand out) or, TAIL, the store of hF.
 // Two blocks are in flight; issuer A runs M1 up to two blocks ahead, issuer B interleaves M2(b), M3(b-1); E1/E2 run on 8 warps, E3 on three groups
-// of 4 warps that take blocks in rotation.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation).
+// of 4 warps that take blocks in rotation.  Arithmetic is that of the three-launch chain (same split-bf16 products, fp32 accumulation; in the
+// bf16 single-pass mode only the hi x hi products).  Measurements and the path to this form: profiles/r2_coupling_fused_summary.md.
 #include "ops.cuh"
 #include "tc_ptx.cuh"
 #include <vector>
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(cf::NTHREADS, 1) coupling_fused_kernel(const _
       TR_ADD(tr_fl, tr4);
     }
 #ifdef BFSR_TC_TRACE
-    if (blockIdx.x == 0 && lane == 0 && q == 0) printf("[cf trace] E3 g%d: total %lld wait acc3_full %lld ld+shuffle %lld wait barC %lld exchange %lld sigmoid+flow %lld\n", g, clock64() - tr_start, tr_a3, tr_ld, tr_bc, tr_ex, tr_fl);
+    if (blockIdx.x == 0 && lane == 0 && q == 0) printf("[cf trace] E3 g%d: total %lld wait acc3_full %lld ld+shuffle %lld wait ring barriers %lld exchange %lld sigmoid+flow %lld\n", g, clock64() - tr_start, tr_a3, tr_ld, tr_bc, tr_ex, tr_fl);
 #endif
   }
   __syncthreads();
